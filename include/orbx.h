@@ -1,0 +1,182 @@
+/* orbx.h — C ABI of the B200-native ORB front end (liborbx.so).
+ *
+ * Drop-in boundary for the hot path of kpmrozowski/wut-cuda-orb-slam3 (an ORB-SLAM3 v1.0 fork):
+ * ORB_SLAM3::ORBextractor (pyramid -> FAST -> octree -> orientation -> blur -> rBRIEF -> packing),
+ * ORBmatcher::DescriptorDistance / brute-force 2-NN Hamming matching, and Frame::ComputeStereoMatches.
+ * The reference has no FFI layer (the boundary is a C++ class linked into libORB_SLAM3.so), so the entry
+ * points below are what a maintainer's thin C++ adapter binds; the adapter with the reference's exact
+ * signatures is wut_cuda_orb_slam3_b200/csrc/adapter/ORBextractor.h.
+ *
+ * Every entry point cites the reference interface it replaces (paths relative to the reference root).
+ * POD only: plain pointers and sizes, no OpenCV / torch types.  All functions return ORBX_OK (0) or a
+ * negative orbx_status; none aborts the process (the reference exit(1)s on OpenCL init failure,
+ * src/OpenCL/Manager.cpp:13-20, and throws on launch failure, src/ORBextractor.cc:498,861,973,1212).
+ * There is NO CPU fallback: compute entry points fail with ORBX_ERR_NO_DEVICE without a CUDA device.
+ *
+ * Threading: one extractor handle is used by one thread at a time; different handles may be used
+ * concurrently (the reference runs the left/right extractors on two std::threads, src/Frame.cc:124-127).
+ */
+#ifndef ORBX_H_
+#define ORBX_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ORBX_VERSION 100 /* 0.1.0 */
+#define ORBX_MAX_LEVELS 16
+#define ORBX_EDGE_THRESHOLD 19 /* src/ORBextractor.cc:101 */
+#define ORBX_DESC_BYTES 32
+
+typedef enum orbx_status {
+    ORBX_OK = 0,
+    ORBX_ERR_EMPTY_IMAGE = -1, /* ORBextractor::operator() returns -1 on an empty image (src/ORBextractor.cc:1231-1232) */
+    ORBX_ERR_INVALID_ARG = -2,
+    ORBX_ERR_NO_DEVICE = -3,
+    ORBX_ERR_CUDA = -4,
+    ORBX_ERR_CAPACITY = -5,    /* caller's output buffer too small; *n_out holds the needed count */
+    ORBX_ERR_UNSUPPORTED = -6, /* image larger than 4128 px per side, > ORBX_MAX_LEVELS levels, ... */
+    ORBX_ERR_OOM = -7
+} orbx_status;
+
+/* cv::KeyPoint == key_point_t, 28-byte POD (include/OpenCL/Kernel/key_point.hpp:22-29; the reference relies on
+ * the reinterpret-cast equivalence at src/ORBextractor.cc:839-841). */
+typedef struct orbx_keypoint {
+    float x, y;      /* pt, in level-0 pixel coordinates */
+    float size;      /* (float)(int)(31 * mvScaleFactor[octave]) */
+    float angle;     /* degrees, [0,360) */
+    float response;  /* FAST score */
+    int32_t octave;
+    int32_t class_id; /* -1 */
+} orbx_keypoint;
+
+typedef struct orbx_extractor orbx_extractor; /* opaque; owns a CUDA stream + device workspace */
+
+/* Thread-local description of the last error on the calling thread ("" if none). */
+const char* orbx_last_error(void);
+int orbx_version(void);
+/* Number of visible CUDA devices (0 without a driver/GPU; never fails). */
+int orbx_device_count(void);
+
+/* ---- construction / accessors -------------------------------------------------------------------------- */
+
+/* ORBextractor::ORBextractor(nfeatures, scaleFactor, nlevels, iniThFAST, minThFAST) — include/ORBextractor.h:58-59,
+ * src/ORBextractor.cc:410-468.  `device` = CUDA ordinal.  max_cols/max_rows/max_batch pre-size the workspace
+ * (0 = size lazily on first use; the workspace grows on demand either way). */
+int orbx_create(int nfeatures, float scaleFactor, int nlevels, int iniThFAST, int minThFAST, int device,
+                int max_cols, int max_rows, int max_batch, orbx_extractor** out);
+void orbx_destroy(orbx_extractor* ex);
+
+/* GetLevels / GetScaleFactor — include/ORBextractor.h:70-74. */
+int orbx_get_levels(const orbx_extractor* ex);
+float orbx_get_scale_factor(const orbx_extractor* ex);
+/* GetScaleFactors / GetInverseScaleFactors / GetScaleSigmaSquares / GetInverseScaleSigmaSquares (include/ORBextractor.h:76-90)
+ * plus mnFeaturesPerLevel (src/ORBextractor.cc:436-447).  Any output pointer may be NULL; arrays hold nlevels entries. */
+int orbx_get_tables(const orbx_extractor* ex, float* scale, float* inv_scale, float* sigma2, float* inv_sigma2,
+                    int* nfeatures_per_level);
+/* Same tables without a handle or a GPU (host arithmetic of src/ORBextractor.cc:418-447). */
+int orbx_compute_tables(int nfeatures, float scaleFactor, int nlevels, float* scale, float* inv_scale, float* sigma2,
+                        float* inv_sigma2, int* nfeatures_per_level);
+/* Level size for an input of cols x rows: cvRound(cols * mvInvScaleFactor[level]) (src/ORBextractor.cc:1312-1313). */
+int orbx_level_size(const orbx_extractor* ex, int cols, int rows, int level, int* level_cols, int* level_rows);
+/* Upper bound on keypoints per frame (sum over levels of mnFeaturesPerLevel + 3): size outputs with this. */
+int orbx_max_keypoints(const orbx_extractor* ex);
+
+/* ---- extraction ------------------------------------------------------------------------------------------ */
+
+/* int ORBextractor::operator()(image, mask, keypoints, descriptors, vLappingArea) — include/ORBextractor.h:66-68,
+ * src/ORBextractor.cc:1227-1307.  image: CV_8UC1 rows x cols, `step` bytes per row, HOST memory.  (lap0, lap1) =
+ * vLappingArea.  Writes *n_out keypoints (28 B) + descriptors (32 B) in the reference's packing order (non-lapping
+ * from the front, lapping from the back) and *n_mono = the reference's return value (monoIndex).
+ * Returns ORBX_ERR_EMPTY_IMAGE for a NULL/empty image. */
+int orbx_extract(orbx_extractor* ex, const uint8_t* image, int rows, int cols, size_t step, int lap0, int lap1,
+                 orbx_keypoint* keypoints, uint8_t* descriptors, int capacity, int* n_out, int* n_mono);
+
+/* Batched operator(): n_frames HOST images of identical shape (images[i] -> rows x cols, `step` bytes per row).
+ * Outputs are [n_frames][capacity] slabs; n_out / n_mono are [n_frames].  Host<->device copies are pipelined
+ * against compute when the host buffers are page-locked. */
+int orbx_extract_batch(orbx_extractor* ex, const uint8_t* const* images, int n_frames, int rows, int cols, size_t step,
+                       int lap0, int lap1, orbx_keypoint* keypoints, uint8_t* descriptors, int capacity, int* n_out,
+                       int* n_mono);
+
+/* Device-resident batched operator(): frame f starts at d_images + f*frame_stride, `pitch` bytes per row; all
+ * output pointers are DEVICE memory with the same slab layout.  Asynchronous on `stream` (a cudaStream_t, or NULL
+ * for the extractor's own stream); call orbx_sync to wait. */
+int orbx_extract_batch_device(orbx_extractor* ex, const uint8_t* d_images, size_t frame_stride, int n_frames, int rows,
+                              int cols, size_t pitch, int lap0, int lap1, orbx_keypoint* d_keypoints,
+                              uint8_t* d_descriptors, int capacity, int* d_n_out, int* d_n_mono, void* stream);
+int orbx_sync(orbx_extractor* ex);
+
+/* std::vector<cv::Mat> mvImagePyramid (include/ORBextractor.h:92), read by Frame::ComputeStereoMatches
+ * (src/Frame.cc:848,938-953): lazy device->host copy of one level of frame `frame` of the LAST call.
+ * with_border = 0: interior (level_rows x level_cols); 1: the whole (rows+38) x (cols+38) bordered buffer. */
+int orbx_get_pyramid_level(orbx_extractor* ex, int frame, int level, uint8_t* dst, size_t dst_step, int with_border);
+
+/* Stage probes for parity tests (results of the LAST call, copied to host):
+ *  blurred level (cv::GaussianBlur 7x7 sigma 2, src/ORBextractor.cc:1270-1273),
+ *  FAST candidates handed to DistributeOctTree (vToDistributeKeys, src/ORBextractor.cc:867-950; window-relative),
+ *  per-level keypoints after octree + orientation (allKeypoints[level], level coordinates) and their descriptors. */
+int orbx_get_blurred_level(orbx_extractor* ex, int frame, int level, uint8_t* dst, size_t dst_step);
+int orbx_get_candidates(orbx_extractor* ex, int frame, int level, int* xs, int* ys, int* scores, int capacity);
+int orbx_get_level_keypoints(orbx_extractor* ex, int frame, int level, orbx_keypoint* keypoints, uint8_t* descriptors,
+                             int capacity);
+
+/* Stand-alone DistributeOctTree (src/ORBextractor.cc:584-774) on host candidate arrays, run on the GPU kernel:
+ * returns in out_idx the indices (into the input) of the retained keypoints in the reference's output order. */
+int orbx_distribute_octree(int device, const int* xs, const int* ys, const int* scores, int n, int minX, int maxX,
+                           int minY, int maxY, int nFeatures, int* out_idx, int capacity, int* n_out);
+
+/* ---- matching -------------------------------------------------------------------------------------------- */
+
+/* static int ORBmatcher::DescriptorDistance(a, b) — include/ORBmatcher.h:43, src/ORBmatcher3.cc:637-653.
+ * Host inline popcount (a GPU launch per pair would be absurd); pure and re-entrant. */
+int orbx_descriptor_distance(const uint8_t* a, const uint8_t* b);
+
+/* Brute-force 2-NN (cv::BFMatcher(NORM_HAMMING).knnMatch(k=2), src/Frame.cc:45,1174; identical (d1,i1,d2) to the
+ * strict-'<' best/second scan of src/ORBmatcher1.cc:283-300 and src/ORBmatcher2.cc:84-118 over the whole set).
+ * HOST buffers; idx/dist are [nq][2], ascending distance, ties -> lower database index; missing = (-1, INT32_MAX). */
+int orbx_knn2(int device, const uint8_t* queries, int nq, const uint8_t* database, int64_t ndb, int32_t* idx,
+              int32_t* dist);
+/* Device-resident variant on `stream`; database rows are numbered index_base + row (for sharded databases). */
+int orbx_knn2_device(int device, const uint8_t* d_queries, int nq, const uint8_t* d_database, int64_t ndb,
+                     int32_t index_base, int32_t* d_idx, int32_t* d_dist, void* stream);
+/* Merge per-shard 2-NN candidates (e.g. after an NCCL all-gather): inputs [n_shards][nq][2]; lexicographic
+ * (distance, index) order reproduces the single-GPU / BFMatcher tie rule exactly. */
+int orbx_knn2_merge_device(int device, const int32_t* d_idx_shards, const int32_t* d_dist_shards, int n_shards, int nq,
+                           int32_t* d_idx, int32_t* d_dist, void* stream);
+/* Ratio-test acceptance on 2-NN output, host: mode 0 = src/ORBmatcher1.cc:329-333 (d1 <= th_low && (float)d1 <
+ * ratio*(float)d2), mode 1 = src/ORBmatcher2.cc:120-125 (d1 < th_low && ...), mode 2 = src/Frame.cc:1181
+ * (d1 < d2 * ratio, no gate).  accept[i] = 0/1. */
+int orbx_ratio_test(const int32_t* dist, int nq, float ratio, int th_low, int mode, uint8_t* accept);
+
+/* void Frame::ComputeStereoMatches() — src/Frame.cc:841-1011.  Uses the un-blurred pyramids of frame `frameL` /
+ * `frameR` of the LAST calls on exL / exR (which must live on the same device; they may be the same handle) and
+ * HOST keypoints/descriptors as returned by orbx_extract.  bf = mbf; maxD = mbf/mb is explicit because the
+ * reference reads mb before it is assigned (src/Frame.cc:143 vs 176).  Outputs mvuRight / mvDepth (-1 = no match). */
+int orbx_stereo_match(orbx_extractor* exL, int frameL, orbx_extractor* exR, int frameR, const orbx_keypoint* kpL,
+                      const uint8_t* descL, int nL, const orbx_keypoint* kpR, const uint8_t* descR, int nR, float bf,
+                      float maxD, float* uRight, float* depth);
+
+/* ---- measurement helpers ----------------------------------------------------------------------------------- */
+
+/* POPC.b32 issue-rate microbenchmark on `device`: returns popc instructions (per 32-bit lane) per second. */
+int orbx_measure_popc_peak(int device, double* popc_per_second);
+/* Number of kernel launches issued by this library on the calling process since load (for bench gpu_launches). */
+int64_t orbx_launch_count(void);
+
+/* ---- synthetic inputs (integer-only, bit-identical on host and device; csrc/synth.h) ----------------------- */
+void orbx_synth_image_host(uint32_t seed, int view, int cols, int rows, int max_disp, uint8_t* dst, size_t step);
+int orbx_synth_images_device(int device, uint32_t seed0, int view, int n_frames, int cols, int rows, int max_disp,
+                             uint8_t* d_dst, size_t pitch, size_t frame_stride, void* stream);
+void orbx_synth_descriptors_host(uint32_t seed, int is_query, int64_t first_row, int64_t n_rows, int64_t ndb,
+                                 int plant_every, uint8_t* dst);
+int orbx_synth_descriptors_device(int device, uint32_t seed, int is_query, int64_t first_row, int64_t n_rows,
+                                  int64_t ndb, int plant_every, uint8_t* d_dst, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ORBX_H_ */

@@ -1,0 +1,237 @@
+"""ctypes binding of the CPU oracle (oracle/orb_oracle.cpp).  TEST INFRASTRUCTURE ONLY.
+
+Nothing in the product package imports this module; only tests/, __graft_entry__.smoke() and bench.py's
+cpu_baseline / --impl reference legs do.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SO = os.path.join(ROOT, "oracle", "_build", "liborb_oracle.so")
+
+KP_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4"), ("response", "<f4"),
+                     ("octave", "<i4"), ("class_id", "<i4")])
+assert KP_DTYPE.itemsize == 28
+
+_vp = C.c_void_p
+_sz = C.c_size_t
+
+
+def build():
+    subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle")])
+
+
+def _ptr(a):
+    return a.ctypes.data_as(_vp)
+
+
+class Oracle:
+    def __init__(self, lib):
+        self.lib = lib
+        L = lib
+        L.orbo_create.restype = _vp
+        L.orbo_create.argtypes = [C.c_int, C.c_float, C.c_int, C.c_int, C.c_int]
+        L.orbo_destroy.argtypes = [_vp]
+        L.orbo_extract.argtypes = [_vp, _vp, C.c_int, C.c_int, _sz, C.c_int, C.c_int, _vp, _vp, C.c_int, _vp, _vp]
+        L.orbo_level_size.argtypes = [_vp, C.c_int, _vp, _vp]
+        L.orbo_get_pyramid_level.argtypes = [_vp, C.c_int, _vp, _sz, C.c_int]
+        L.orbo_get_blurred_level.argtypes = [_vp, C.c_int, _vp, _sz]
+        L.orbo_get_candidates.argtypes = [_vp, C.c_int, _vp, _vp, _vp, C.c_int]
+        L.orbo_get_level_keypoints.argtypes = [_vp, C.c_int, _vp, _vp, C.c_int]
+        L.orbo_tables.argtypes = [C.c_int, C.c_float, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp]
+        L.orbo_resize_linear_u8.argtypes = [_vp, C.c_int, C.c_int, _sz, _vp, C.c_int, C.c_int, _sz]
+        L.orbo_fill_border_reflect101.argtypes = [_vp, C.c_int, C.c_int, _sz, C.c_int]
+        L.orbo_fast9.argtypes = [_vp, C.c_int, C.c_int, _sz, C.c_int, C.c_int, _vp, _vp, _vp, C.c_int]
+        L.orbo_cell_fast.argtypes = [_vp, C.c_int, C.c_int, _sz, C.c_int, C.c_int, _vp, _vp, _vp, C.c_int]
+        L.orbo_octree.argtypes = [_vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp, C.c_int]
+        L.orbo_fast_atan2.restype = C.c_float
+        L.orbo_fast_atan2.argtypes = [C.c_float, C.c_float]
+        L.orbo_ic_angle.restype = C.c_float
+        L.orbo_ic_angle.argtypes = [_vp, _sz, C.c_int, C.c_int]
+        L.orbo_gaussian_blur7.argtypes = [_vp, C.c_int, C.c_int, _sz, _vp, _sz]
+        L.orbo_descriptor.argtypes = [_vp, _sz, C.c_int, C.c_int, C.c_float, _vp]
+        L.orbo_hamming.argtypes = [_vp, _vp]
+        L.orbo_hamming_swar.argtypes = [_vp, _vp]
+        L.orbo_knn2.argtypes = [_vp, C.c_int, _vp, C.c_int, _vp, _vp, C.c_int]
+        L.orbo_ratio_accept.argtypes = [C.c_int, C.c_int, C.c_float, C.c_int]
+        L.orbo_std_sort_hi40.argtypes = [_vp, C.c_int]
+        L.orbo_stereo_match.argtypes = [_vp, _vp, C.c_int, _vp, _vp, C.c_int, _vp, _vp, _vp, _vp, C.c_int, _vp, _vp,
+                                        C.c_float, C.c_float, _vp, _vp]
+
+    def std_sort_hi40(self, items):
+        items = np.ascontiguousarray(items, np.uint64).copy()
+        self.lib.orbo_std_sort_hi40(_ptr(items), len(items))
+        return items
+
+    # ---- primitives -------------------------------------------------------------------------
+    def tables(self, nfeatures, scale_factor, nlevels):
+        sc = np.zeros(nlevels, np.float32); inv = sc.copy(); s2 = sc.copy(); is2 = sc.copy()
+        nf = np.zeros(nlevels, np.int32); umax = np.zeros(16, np.int32)
+        self.lib.orbo_tables(nfeatures, scale_factor, nlevels, _ptr(sc), _ptr(inv), _ptr(s2), _ptr(is2), _ptr(nf), _ptr(umax))
+        return dict(scale=sc, inv=inv, sigma2=s2, invsigma2=is2, nfeat=nf, umax=umax)
+
+    def resize(self, src, dw, dh):
+        src = np.ascontiguousarray(src)
+        dst = np.zeros((dh, dw), np.uint8)
+        self.lib.orbo_resize_linear_u8(_ptr(src), src.shape[1], src.shape[0], src.strides[0], _ptr(dst), dw, dh, dst.strides[0])
+        return dst
+
+    def make_border(self, img, border=19):
+        h, w = img.shape
+        buf = np.zeros((h + 2 * border, w + 2 * border), np.uint8)
+        buf[border:border + h, border:border + w] = img
+        interior = buf.ctypes.data + border * buf.strides[0] + border
+        self.lib.orbo_fill_border_reflect101(_vp(interior), w, h, buf.strides[0], border)
+        return buf
+
+    def fast9(self, img, threshold, nms=True):
+        img = np.ascontiguousarray(img)
+        cap = img.size
+        xs = np.zeros(cap, np.int32); ys = np.zeros(cap, np.int32); sc = np.zeros(cap, np.int32)
+        n = self.lib.orbo_fast9(_ptr(img), img.shape[1], img.shape[0], img.strides[0], threshold, int(nms), _ptr(xs), _ptr(ys), _ptr(sc), cap)
+        return xs[:n].copy(), ys[:n].copy(), sc[:n].copy()
+
+    def cell_fast(self, img, ini_th=20, min_th=7):
+        img = np.ascontiguousarray(img)
+        cap = img.size
+        xs = np.zeros(cap, np.int32); ys = np.zeros(cap, np.int32); sc = np.zeros(cap, np.int32)
+        n = self.lib.orbo_cell_fast(_ptr(img), img.shape[1], img.shape[0], img.strides[0], ini_th, min_th, _ptr(xs), _ptr(ys), _ptr(sc), cap)
+        return xs[:n].copy(), ys[:n].copy(), sc[:n].copy()
+
+    def octree(self, xs, ys, sc, min_x, max_x, min_y, max_y, n_features):
+        xs = np.ascontiguousarray(xs, np.int32); ys = np.ascontiguousarray(ys, np.int32); sc = np.ascontiguousarray(sc, np.int32)
+        cap = len(xs) + 8
+        out = np.zeros(cap, np.int32)
+        m = self.lib.orbo_octree(_ptr(xs), _ptr(ys), _ptr(sc), len(xs), min_x, max_x, min_y, max_y, n_features, _ptr(out), cap)
+        return out[:m].copy()
+
+    def fast_atan2(self, y, x):
+        return self.lib.orbo_fast_atan2(float(y), float(x))
+
+    def ic_angle(self, img, x, y):
+        return self.lib.orbo_ic_angle(_ptr(img), img.strides[0], int(x), int(y))
+
+    def blur(self, img):
+        img = np.ascontiguousarray(img)
+        dst = np.zeros_like(img)
+        self.lib.orbo_gaussian_blur7(_ptr(img), img.shape[1], img.shape[0], img.strides[0], _ptr(dst), dst.strides[0])
+        return dst
+
+    def descriptor(self, blurred, x, y, angle_deg):
+        out = np.zeros(32, np.uint8)
+        self.lib.orbo_descriptor(_ptr(blurred), blurred.strides[0], int(x), int(y), float(angle_deg), _ptr(out))
+        return out
+
+    def hamming(self, a, b, swar=False):
+        f = self.lib.orbo_hamming_swar if swar else self.lib.orbo_hamming
+        return f(_ptr(a), _ptr(b))
+
+    def knn2(self, q, db, swar=False):
+        q = np.ascontiguousarray(q, np.uint8); db = np.ascontiguousarray(db, np.uint8)
+        idx = np.zeros((len(q), 2), np.int32); dist = np.zeros((len(q), 2), np.int32)
+        self.lib.orbo_knn2(_ptr(q), len(q), _ptr(db), len(db), _ptr(idx), _ptr(dist), int(swar))
+        return idx, dist
+
+    def ratio_accept(self, d1, d2, ratio, th_low):
+        return bool(self.lib.orbo_ratio_accept(int(d1), int(d2), float(ratio), int(th_low)))
+
+    # ---- extractor --------------------------------------------------------------------------
+    def extractor(self, nfeatures=1000, scale_factor=1.2, nlevels=8, ini_th=20, min_th=7):
+        return OracleExtractor(self, nfeatures, scale_factor, nlevels, ini_th, min_th)
+
+    def stereo_match(self, exL, exR, kpL, descL, kpR, descR, mbf, max_d):
+        nlev = exL.nlevels
+        pyrL = [exL.pyramid_level(l, with_border=True) for l in range(nlev)]
+        pyrR = [exR.pyramid_level(l, with_border=True) for l in range(nlev)]
+        return self.stereo_match_raw(kpL, descL, kpR, descR, pyrL, pyrR, exL.tables["scale"], exL.tables["inv"], mbf, max_d)
+
+    def stereo_match_raw(self, kpL, descL, kpR, descR, pyrL_bordered, pyrR_bordered, scale, inv, mbf, max_d, border=19):
+        nlev = len(pyrL_bordered)
+        PL = (C.c_void_p * nlev)(); PR = (C.c_void_p * nlev)()
+        steps = (C.c_size_t * nlev)(); widths = (C.c_int * nlev)()
+        for l in range(nlev):
+            a, b = pyrL_bordered[l], pyrR_bordered[l]
+            PL[l] = a.ctypes.data + border * a.strides[0] + border
+            PR[l] = b.ctypes.data + border * b.strides[0] + border
+            assert a.strides[0] == b.strides[0]
+            steps[l] = a.strides[0]
+            widths[l] = a.shape[1] - 2 * border
+        n_rows = pyrL_bordered[0].shape[0] - 2 * border
+        kpL = np.ascontiguousarray(kpL); kpR = np.ascontiguousarray(kpR)
+        descL = np.ascontiguousarray(descL); descR = np.ascontiguousarray(descR)
+        scale = np.ascontiguousarray(scale, np.float32); inv = np.ascontiguousarray(inv, np.float32)
+        u = np.zeros(len(kpL), np.float32); d = np.zeros(len(kpL), np.float32)
+        kept = self.lib.orbo_stereo_match(_ptr(kpL), _ptr(descL), len(kpL), _ptr(kpR), _ptr(descR), len(kpR), PL, PR, steps,
+                                          widths, n_rows, _ptr(scale), _ptr(inv), float(mbf), float(max_d), _ptr(u), _ptr(d))
+        return u, d, kept
+
+
+class OracleExtractor:
+    def __init__(self, o, nfeatures, scale_factor, nlevels, ini_th, min_th):
+        self.o = o
+        self.nfeatures, self.nlevels = nfeatures, nlevels
+        self.h = o.lib.orbo_create(nfeatures, scale_factor, nlevels, ini_th, min_th)
+        self.tables = o.tables(nfeatures, scale_factor, nlevels)
+
+    def __del__(self):
+        try:
+            self.o.lib.orbo_destroy(self.h)
+        except Exception:
+            pass
+
+    def extract(self, img, lapping=(0, 0)):
+        img = np.ascontiguousarray(img)
+        cap = self.nfeatures * 2 + 64 * self.nlevels
+        kps = np.zeros(cap, KP_DTYPE); desc = np.zeros((cap, 32), np.uint8)
+        n = C.c_int(0); nm = C.c_int(0)
+        rc = self.o.lib.orbo_extract(self.h, _ptr(img), img.shape[0], img.shape[1], img.strides[0], lapping[0], lapping[1],
+                                     _ptr(kps), _ptr(desc), cap, C.byref(n), C.byref(nm))
+        assert rc == 0, rc
+        return kps[:n.value].copy(), desc[:n.value].copy(), nm.value
+
+    def level_size(self, level):
+        w = C.c_int(0); h = C.c_int(0)
+        self.o.lib.orbo_level_size(self.h, level, C.byref(w), C.byref(h))
+        return w.value, h.value
+
+    def pyramid_level(self, level, with_border=False):
+        w, h = self.level_size(level)
+        b = 38 if with_border else 0
+        out = np.zeros((h + b, w + b), np.uint8)
+        self.o.lib.orbo_get_pyramid_level(self.h, level, _ptr(out), out.strides[0], int(with_border))
+        return out
+
+    def blurred_level(self, level):
+        w, h = self.level_size(level)
+        out = np.zeros((h, w), np.uint8)
+        self.o.lib.orbo_get_blurred_level(self.h, level, _ptr(out), out.strides[0])
+        return out
+
+    def candidates(self, level):
+        w, h = self.level_size(level)
+        cap = w * h
+        xs = np.zeros(cap, np.int32); ys = np.zeros(cap, np.int32); sc = np.zeros(cap, np.int32)
+        n = self.o.lib.orbo_get_candidates(self.h, level, _ptr(xs), _ptr(ys), _ptr(sc), cap)
+        return xs[:n].copy(), ys[:n].copy(), sc[:n].copy()
+
+    def level_keypoints(self, level):
+        cap = self.nfeatures * 2 + 64
+        kps = np.zeros(cap, KP_DTYPE); desc = np.zeros((cap, 32), np.uint8)
+        n = self.o.lib.orbo_get_level_keypoints(self.h, level, _ptr(kps), _ptr(desc), cap)
+        return kps[:n].copy(), desc[:n].copy()
+
+
+_cached = None
+
+
+def load():
+    global _cached
+    if _cached is None:
+        src = os.path.join(ROOT, "oracle", "orb_oracle.cpp")
+        if not os.path.exists(SO) or (os.path.exists(src) and os.path.getmtime(src) > os.path.getmtime(SO)):
+            build()
+        _cached = Oracle(C.CDLL(SO))
+    return _cached

@@ -1,0 +1,56 @@
+"""The octree kernel's single-lane replay of libstdc++ std::sort (csrc/introsort_replay.h) must reproduce std::sort's
+permutation exactly, including among elements the comparator cannot distinguish.  CPU only:
+the replay is host+device code; here its host instantiation is compared with the real std::sort in the oracle."""
+import numpy as np
+
+from wut_cuda_orb_slam3_b200.capi import lib, ptr
+
+
+def replay(items):
+    a = np.ascontiguousarray(items, np.uint64).copy()
+    lib().orbx_debug_sort_replay(ptr(a), len(a))
+    return a
+
+
+def make(keys):
+    keys = np.asarray(keys, np.uint64)
+    return (keys << np.uint64(24)) | np.arange(len(keys), dtype=np.uint64)   # payload = original index
+
+
+def test_random_with_many_ties(oracle):
+    rng = np.random.default_rng(0)
+    for n in list(range(0, 40)) + [63, 64, 65, 100, 217, 434, 1000, 5000]:
+        for nkeys in (1, 2, 3, 7, 50, 10 ** 6):
+            items = make(rng.integers(0, nkeys, n))
+            assert np.array_equal(replay(items), oracle.std_sort_hi40(items)), (n, nkeys)
+
+
+def test_structured_inputs(oracle):
+    for n in (17, 33, 128, 1025, 4096):
+        for keys in (np.arange(n), np.arange(n)[::-1], np.zeros(n), np.arange(n) % 2, np.arange(n) // 3,
+                     np.concatenate([np.arange(n // 2), np.arange(n - n // 2)])):
+            items = make(keys)
+            assert np.array_equal(replay(items), oracle.std_sort_hi40(items))
+
+
+def test_median_of_three_killer_hits_heapsort_fallback(oracle):
+    # classic anti-quicksort sequence for median-of-3 pivots: forces the depth limit -> heap-sort fallback
+    n = 4096
+    k = n // 2
+    keys = np.zeros(n, np.int64)
+    for i in range(1, k + 1):
+        if i % 2 == 1:
+            keys[i - 1] = i
+            keys[i] = k + i
+        keys[k + i - 1] = 2 * i
+    items = make(keys)
+    assert np.array_equal(replay(items), oracle.std_sort_hi40(items))
+
+
+def test_octree_like_keys(oracle):
+    rng = np.random.default_rng(1)
+    for n in (20, 60, 150, 400):
+        cnt = rng.integers(2, 12, n).astype(np.uint64)
+        ulx = (rng.integers(0, 8, n) * 45).astype(np.uint64)
+        items = make((cnt << np.uint64(13)) | ulx)
+        assert np.array_equal(replay(items), oracle.std_sort_hi40(items))

@@ -1,0 +1,13 @@
+"""B200-native ORB front end (pyramid -> FAST -> octree -> orientation -> blur -> rBRIEF -> Hamming matching).
+
+Host-side mirror of the reference's interface for this path (ORB_SLAM3::ORBextractor / ORBmatcher) over the C-ABI
+library liborbx.so (include/orbx.h).  The compute path is hand-written sm_100a CUDA; importing this package without
+the built library raises (no CPU fallback).
+"""
+from . import capi, synth  # noqa: F401
+from .capi import KP_DTYPE, OrbxError, lib  # noqa: F401
+from .extractor import ORBextractor, compute_tables, distribute_octree  # noqa: F401
+from .matcher import (ORBmatcher, compute_stereo_matches, knn2_device, knn2_merge_device,  # noqa: F401
+                      measure_popc_peak)
+
+lib()  # fail loudly at import time if the CUDA extension is missing

@@ -1,0 +1,110 @@
+"""ctypes binding of liborbx.so (include/orbx.h).  No torch types cross this boundary: pointers and sizes only.
+
+The library is built in-tree by `make -C wut_cuda_orb_slam3_b200/csrc` (see __graft_entry__.build()).  If it is
+missing the import fails loudly — there is no Python/CPU fallback for any compute entry point.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SO_PATH = os.path.join(HERE, "liborbx.so")
+
+KP_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4"), ("response", "<f4"),
+                     ("octave", "<i4"), ("class_id", "<i4")])
+assert KP_DTYPE.itemsize == 28
+
+ORBX_OK = 0
+ORBX_ERR_EMPTY_IMAGE = -1
+ORBX_ERR_INVALID_ARG = -2
+ORBX_ERR_NO_DEVICE = -3
+ORBX_ERR_CUDA = -4
+ORBX_ERR_CAPACITY = -5
+ORBX_ERR_UNSUPPORTED = -6
+ORBX_ERR_OOM = -7
+
+_vp, _sz, _i, _f = C.c_void_p, C.c_size_t, C.c_int, C.c_float
+_i64, _u32 = C.c_int64, C.c_uint32
+
+# name -> (restype, argtypes); every symbol declared in include/orbx.h
+SIGNATURES = {
+    "orbx_last_error": (C.c_char_p, []),
+    "orbx_version": (_i, []),
+    "orbx_device_count": (_i, []),
+    "orbx_create": (_i, [_i, _f, _i, _i, _i, _i, _i, _i, _i, C.POINTER(_vp)]),
+    "orbx_destroy": (None, [_vp]),
+    "orbx_get_levels": (_i, [_vp]),
+    "orbx_get_scale_factor": (_f, [_vp]),
+    "orbx_get_tables": (_i, [_vp, _vp, _vp, _vp, _vp, _vp]),
+    "orbx_compute_tables": (_i, [_i, _f, _i, _vp, _vp, _vp, _vp, _vp]),
+    "orbx_level_size": (_i, [_vp, _i, _i, _i, _vp, _vp]),
+    "orbx_max_keypoints": (_i, [_vp]),
+    "orbx_extract": (_i, [_vp, _vp, _i, _i, _sz, _i, _i, _vp, _vp, _i, _vp, _vp]),
+    "orbx_extract_batch": (_i, [_vp, _vp, _i, _i, _i, _sz, _i, _i, _vp, _vp, _i, _vp, _vp]),
+    "orbx_extract_batch_device": (_i, [_vp, _vp, _sz, _i, _i, _i, _sz, _i, _i, _vp, _vp, _i, _vp, _vp, _vp]),
+    "orbx_sync": (_i, [_vp]),
+    "orbx_get_pyramid_level": (_i, [_vp, _i, _i, _vp, _sz, _i]),
+    "orbx_get_blurred_level": (_i, [_vp, _i, _i, _vp, _sz]),
+    "orbx_get_candidates": (_i, [_vp, _i, _i, _vp, _vp, _vp, _i]),
+    "orbx_get_level_keypoints": (_i, [_vp, _i, _i, _vp, _vp, _i]),
+    "orbx_distribute_octree": (_i, [_i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _i, _vp]),
+    "orbx_descriptor_distance": (_i, [_vp, _vp]),
+    "orbx_knn2": (_i, [_i, _vp, _i, _vp, _i64, _vp, _vp]),
+    "orbx_knn2_device": (_i, [_i, _vp, _i, _vp, _i64, C.c_int32, _vp, _vp, _vp]),
+    "orbx_knn2_merge_device": (_i, [_i, _vp, _vp, _i, _i, _vp, _vp, _vp]),
+    "orbx_ratio_test": (_i, [_vp, _i, _f, _i, _i, _vp]),
+    "orbx_stereo_match": (_i, [_vp, _i, _vp, _i, _vp, _vp, _i, _vp, _vp, _i, _f, _f, _vp, _vp]),
+    "orbx_measure_popc_peak": (_i, [_i, C.POINTER(C.c_double)]),
+    "orbx_launch_count": (_i64, []),
+    "orbx_synth_image_host": (None, [_u32, _i, _i, _i, _i, _vp, _sz]),
+    "orbx_synth_images_device": (_i, [_i, _u32, _i, _i, _i, _i, _i, _vp, _sz, _sz, _vp]),
+    "orbx_synth_descriptors_host": (None, [_u32, _i, _i64, _i64, _i64, _i, _vp]),
+    "orbx_synth_descriptors_device": (_i, [_i, _u32, _i, _i64, _i64, _i64, _i, _vp, _vp]),
+}
+
+
+class OrbxError(RuntimeError):
+    def __init__(self, code, message):
+        super().__init__("orbx error %d: %s" % (code, message))
+        self.code = code
+
+
+_lib = None
+
+
+def lib():
+    """Load liborbx.so (once).  Raises if the CUDA extension has not been built: no fallback exists."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(SO_PATH):
+            raise ImportError("liborbx.so not built: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                              "(nvcc, sm_100a).  The ORB front end has no CPU fallback.")
+        L = C.CDLL(SO_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(L, name)          # AttributeError here = header and library disagree
+            fn.restype = res
+            fn.argtypes = args
+        L.orbx_debug_sort_replay.restype = None
+        L.orbx_debug_sort_replay.argtypes = [_vp, _i]
+        _lib = L
+    return _lib
+
+
+def check(rc):
+    if rc != ORBX_OK:
+        raise OrbxError(rc, lib().orbx_last_error().decode("utf-8", "replace"))
+    return rc
+
+
+def ptr(a):
+    """Raw address of a numpy array / torch tensor / int."""
+    if a is None:
+        return None
+    if isinstance(a, int):
+        return _vp(a)
+    if isinstance(a, np.ndarray):
+        return _vp(a.ctypes.data)
+    if hasattr(a, "data_ptr"):
+        return _vp(a.data_ptr())
+    raise TypeError(type(a))

@@ -1,0 +1,886 @@
+// api.cu — host side of liborbx.so: the C ABI of include/orbx.h over the sm_100a kernels.
+//
+// One orbx_extractor == one ORB_SLAM3::ORBextractor instance (reference include/ORBextractor.h:52-120): parameters,
+// scale tables, a private CUDA stream and a device workspace sized for the current image shape.  There is no CPU
+// fallback anywhere in this file: without a CUDA device every compute entry point returns ORBX_ERR_NO_DEVICE.
+#include <atomic>
+#include <cfloat>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "orbx_internal.cuh"
+#include "introsort_replay.h"
+#include "synth.h"
+
+namespace orbx {
+
+static thread_local std::string t_err;
+static std::atomic<long long> g_launches{0};
+
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+static int fail(int code, const char* fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    t_err = buf;
+    return code;
+}
+
+#define CU(call)                                                                                         \
+    do {                                                                                                 \
+        cudaError_t e__ = (call);                                                                        \
+        if (e__ != cudaSuccess)                                                                          \
+            return fail(e__ == cudaErrorMemoryAllocation ? ORBX_ERR_OOM : ORBX_ERR_CUDA, "%s failed: %s", #call, \
+                        cudaGetErrorString(e__));                                                        \
+    } while (0)
+
+static inline int cvRoundF(float v) { return (int)lrintf(v); }
+static inline int cvRoundD(double v) { return (int)lrint(v); }
+static inline int cvFloorF(float v) { int i = (int)v; return i - (i > v); }
+static inline int reflect101(int i, int n)
+{
+    if (n == 1) return 0;
+    while (i < 0 || i >= n) i = i < 0 ? -i : 2 * (n - 1) - i;
+    return i;
+}
+static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+struct Tables {
+    std::vector<float> scale, inv, sigma2, invsigma2;
+    std::vector<int> nfeat;
+};
+
+// ORBextractor::ORBextractor — reference src/ORBextractor.cc:410-447 (scaleFactor is stored as double, include/ORBextractor.h:105).
+static void make_tables(Tables& t, int nfeatures, float scaleFactorF, int nlevels)
+{
+    const double scaleFactor = scaleFactorF;
+    t.scale.assign(nlevels, 1.f); t.sigma2.assign(nlevels, 1.f);
+    for (int i = 1; i < nlevels; ++i) {
+        t.scale[i] = (float)(t.scale[i - 1] * scaleFactor);
+        t.sigma2[i] = t.scale[i] * t.scale[i];
+    }
+    t.inv.resize(nlevels); t.invsigma2.resize(nlevels);
+    for (int i = 0; i < nlevels; ++i) { t.inv[i] = 1.0f / t.scale[i]; t.invsigma2[i] = 1.0f / t.sigma2[i]; }
+    t.nfeat.assign(nlevels, 0);
+    const float factor = (float)(1.0f / scaleFactor);
+    float nDesired = nfeatures * (1 - factor) / (1 - (float)pow((double)factor, (double)nlevels));
+    int sum = 0;
+    for (int level = 0; level < nlevels - 1; ++level) {
+        t.nfeat[level] = cvRoundF(nDesired);
+        sum += t.nfeat[level];
+        nDesired *= factor;
+    }
+    t.nfeat[nlevels - 1] = std::max(nfeatures - sum, 0);
+}
+
+struct Slot {
+    Workspace ws{};
+    cudaStream_t stream = nullptr;
+    int cap_frames = 0;
+    // staging for the host-buffer API
+    uint8_t* d_in = nullptr; size_t d_in_bytes = 0;
+    orbx_keypoint* d_kps = nullptr; uint8_t* d_desc = nullptr; int* d_n = nullptr; int* d_nm = nullptr; int out_cap = 0;
+    std::vector<void*> allocs;
+};
+
+}  // namespace orbx
+
+using namespace orbx;
+
+struct orbx_extractor {
+    int nfeatures, nlevels, iniTh, minTh, device;
+    float scaleFactorF;
+    Tables tab;
+    FrameGeom fg{};
+    bool geom_valid = false;
+    uint2* d_tables = nullptr;     // resize tables
+    size_t per_frame_pyr = 0, per_frame_blur = 0;
+    int max_batch = 0;
+    static const int kSlots = 3;
+    Slot slots[kSlots];
+    int last_frames = 0;           // frames of the last call that are probe-able (slot 0)
+    int max_kp = 0;
+};
+
+namespace orbx {
+
+static int set_device(int device)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0) {
+        cudaGetLastError();
+        return fail(ORBX_ERR_NO_DEVICE, "no CUDA device visible: liborbx has no CPU fallback");
+    }
+    if (device < 0 || device >= n) return fail(ORBX_ERR_INVALID_ARG, "device %d out of range (%d visible)", device, n);
+    CU(cudaSetDevice(device));
+    return ORBX_OK;
+}
+
+static void free_slot(Slot& s)
+{
+    for (void* p : s.allocs) cudaFree(p);
+    s.allocs.clear();
+    s.ws = Workspace{};
+    s.cap_frames = 0;
+    s.d_in = nullptr; s.d_in_bytes = 0; s.d_kps = nullptr; s.d_desc = nullptr; s.d_n = nullptr; s.d_nm = nullptr; s.out_cap = 0;
+}
+
+template <typename T>
+static int dev_alloc(Slot& s, T** out, size_t count)
+{
+    void* p = nullptr;
+    CU(cudaMalloc(&p, std::max<size_t>(count * sizeof(T), 16)));
+    s.allocs.push_back(p);
+    *out = (T*)p;
+    return ORBX_OK;
+}
+
+// Geometry for an image of rows x cols: level sizes (src/ORBextractor.cc:1312-1313), buffer layout, FAST cell grid
+// (873-886), octree parameters (589-591), resize coefficient tables (OpenCV resizeLinear, 8U fixed point).
+static int configure(orbx_extractor* ex, int rows, int cols)
+{
+    if (ex->geom_valid && ex->fg.rows == rows && ex->fg.cols == cols) return ORBX_OK;
+    if (cols > kMaxDim || rows > kMaxDim) return fail(ORBX_ERR_UNSUPPORTED, "image %dx%d exceeds %d px per side", cols, rows, kMaxDim);
+    for (int i = 0; i < orbx_extractor::kSlots; ++i) {
+        if (ex->slots[i].stream) cudaStreamSynchronize(ex->slots[i].stream);
+        cudaStream_t st = ex->slots[i].stream;
+        free_slot(ex->slots[i]);
+        ex->slots[i].stream = st;
+    }
+    if (ex->d_tables) { cudaFree(ex->d_tables); ex->d_tables = nullptr; }
+    FrameGeom& fg = ex->fg;
+    memset(&fg, 0, sizeof fg);
+    fg.nlevels = ex->nlevels; fg.rows = rows; fg.cols = cols; fg.iniTh = ex->iniTh; fg.minTh = ex->minTh;
+    size_t pyr_off = 0, blur_off = 0;
+    unsigned long long cand_off = 0, oct_off = 0;
+    int cell_base = 0, kp_base = 0;
+    std::vector<uint2> tables;
+    std::vector<size_t> xtab_off(ex->nlevels, 0), ytab_off(ex->nlevels, 0);
+    for (int l = 0; l < ex->nlevels; ++l) {
+        LevelGeom& g = fg.L[l];
+        const float scale = ex->tab.inv[l];
+        g.w = cvRoundF((float)cols * scale);
+        g.h = cvRoundF((float)rows * scale);
+        if (g.w <= 0 || g.h <= 0) return fail(ORBX_ERR_UNSUPPORTED, "level %d of a %dx%d image is empty", l, cols, rows);
+        g.pitch = (int)align_up((size_t)kXPad + g.w + kEdge, 16);
+        g.rows_alloc = g.h + 2 * kEdge;
+        g.pyr_off = pyr_off;
+        g.pyr_frame_stride = align_up((size_t)g.pitch * g.rows_alloc, 256);
+        pyr_off += 0;   // level slabs are laid out after the batch size is known (see ensure_slot)
+        g.bpitch = (int)align_up((size_t)g.w, 16);
+        g.blur_off = blur_off;
+        g.blur_frame_stride = align_up((size_t)g.bpitch * g.h, 256);
+        g.scale = ex->tab.scale[l];
+        g.inv_scale = ex->tab.inv[l];
+        g.kp_size = (float)(int)(31 * ex->tab.scale[l]);           // PATCH_SIZE * mvScaleFactor[level] (src 1017)
+        // FAST grid
+        const int maxBX = g.w - kEdge + 3, maxBY = g.h - kEdge + 3;
+        const float width = (float)(maxBX - kWinBorder), height = (float)(maxBY - kWinBorder);
+        const float W = 35;
+        g.nCols = width > 0 ? (int)(width / W) : 0;
+        g.nRows = height > 0 ? (int)(height / W) : 0;
+        if (g.nCols > 0 && g.nRows > 0) {
+            g.wCell = (int)ceil(width / g.nCols);
+            g.hCell = (int)ceil(height / g.nRows);
+        } else {
+            g.nCols = g.nRows = 0; g.wCell = g.hCell = 1;       // reference divides by zero here; we return no keypoints
+        }
+        if (g.wCell > kMaxCellDim || g.hCell > kMaxCellDim) return fail(ORBX_ERR_UNSUPPORTED, "cell %dx%d too large", g.wCell, g.hCell);
+        g.cell_base = cell_base;
+        cell_base += g.nCols * g.nRows;
+        g.cell_cap = ((g.wCell + 1) / 2) * ((g.hCell + 1) / 2);
+        g.cand_off = cand_off;
+        g.cand_max = g.nCols * g.nRows * g.cell_cap;
+        cand_off += (unsigned long long)g.cand_max;
+        g.oct_off = oct_off;
+        oct_off += 4ull * g.cand_max + (unsigned long long)(g.nCols * g.nRows) + 16;
+        // octree
+        g.nfeat = ex->tab.nfeat[l];
+        g.nIni = (width > 0 && height > 0) ? (int)round(width / height) : 0;   // src 589
+        if (g.nIni > 64) return fail(ORBX_ERR_UNSUPPORTED, "aspect ratio %d:1 not supported", g.nIni);
+        g.hX = g.nIni > 0 ? width / g.nIni : 1.f;                               // src 591
+        {
+            int maxRootW = 1;
+            for (int i = 0; i < g.nIni; ++i) {
+                const int ulx = (int)(g.hX * (float)i), urx = (int)(g.hX * (float)(i + 1));
+                maxRootW = std::max(maxRootW, urx - ulx);
+            }
+            auto clog2 = [](int v) { int b = 0; while ((1 << b) < v) ++b; return b; };
+            g.depth = std::max(clog2(maxRootW) + 1, clog2(std::max((int)height, 1))) + 1;
+            g.root_bits = clog2(std::max(g.nIni, 1));
+            if (2 * g.depth + g.root_bits > 32) return fail(ORBX_ERR_UNSUPPORTED, "quadtree path code needs %d bits", 2 * g.depth + g.root_bits);
+        }
+        g.kp_base = kp_base;
+        g.kp_cap = std::max(g.nfeat + 4, 4 * g.nIni + 1);
+        kp_base += g.kp_cap;
+        // resize tables, indexed by bordered coordinates
+        if (l > 0) {
+            const LevelGeom& p = fg.L[l - 1];
+            const double scale_x = 1. / ((double)g.w / p.w), scale_y = 1. / ((double)g.h / p.h);
+            const int iscale_x = cvRoundD(scale_x), iscale_y = cvRoundD(scale_y);
+            const bool area_fast = std::abs(scale_x - iscale_x) < DBL_EPSILON && std::abs(scale_y - iscale_y) < DBL_EPSILON;
+            g.area2x = (area_fast && iscale_x == 2 && iscale_y == 2) ? 1 : 0;
+            auto entry = [&](int d, double sc, int n) -> uint2 {
+                if (g.area2x) return make_uint2((uint32_t)(2 * d) | ((uint32_t)(2 * d + 1) << 16), 1u | (1u << 16));
+                float f = (float)((d + 0.5) * sc - 0.5);
+                int s = cvFloorF(f);
+                f -= s;
+                if (s < 0) { s = 0; f = 0.f; }
+                if (s >= n - 1) { s = n - 1; f = 0.f; }
+                const int c0 = (short)cvRoundF((1.f - f) * 2048.f), c1 = (short)cvRoundF(f * 2048.f);
+                const int s1 = std::min(s + 1, n - 1);
+                return make_uint2((uint32_t)s | ((uint32_t)s1 << 16), (uint32_t)c0 | ((uint32_t)c1 << 16));
+            };
+            xtab_off[l] = tables.size();
+            for (int bc = 0; bc < g.w + 2 * kEdge; ++bc) tables.push_back(entry(reflect101(bc - kEdge, g.w), scale_x, p.w));
+            ytab_off[l] = tables.size();
+            for (int br = 0; br < g.h + 2 * kEdge; ++br) tables.push_back(entry(reflect101(br - kEdge, g.h), scale_y, p.h));
+        }
+    }
+    fg.total_cells = cell_base;
+    fg.kp_slots = kp_base;
+    fg.cand_frame_stride = cand_off + 16;
+    fg.oct_frame_stride = oct_off + 16;
+    ex->max_kp = kp_base;
+    if (!tables.empty()) {
+        CU(cudaMalloc((void**)&ex->d_tables, tables.size() * sizeof(uint2)));
+        CU(cudaMemcpy(ex->d_tables, tables.data(), tables.size() * sizeof(uint2), cudaMemcpyHostToDevice));
+        for (int l = 1; l < ex->nlevels; ++l) {
+            fg.L[l].xtab = ex->d_tables + xtab_off[l];
+            fg.L[l].ytab = ex->d_tables + ytab_off[l];
+        }
+    }
+    const size_t smem = octree_smem_bytes([&] { int M = 0; for (int l = 0; l < fg.nlevels; ++l) M = std::max(M, fg.L[l].kp_cap); return M; }());
+    if (smem > 200 * 1024) return fail(ORBX_ERR_UNSUPPORTED, "nfeatures too large for the octree kernel (%zu B shared memory)", smem);
+    CU(octree_prepare());
+    ex->geom_valid = true;
+    return ORBX_OK;
+}
+
+// (Re)allocate a slot's workspace for `frames` frames.  Level slabs are [level][frame].
+static int ensure_slot(orbx_extractor* ex, Slot& s, int frames)
+{
+    if (!s.stream) CU(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+    if (s.cap_frames >= frames) return ORBX_OK;
+    cudaStreamSynchronize(s.stream);
+    free_slot(s);
+    FrameGeom& fg = ex->fg;
+    // offsets depend on the slot capacity; all slots of an extractor share one capacity so fg is consistent
+    size_t pyr = 0, blur = 0;
+    for (int l = 0; l < fg.nlevels; ++l) {
+        fg.L[l].pyr_off = pyr; pyr += fg.L[l].pyr_frame_stride * (size_t)frames;
+        fg.L[l].blur_off = blur; blur += fg.L[l].blur_frame_stride * (size_t)frames;
+    }
+    int rc;
+    if ((rc = dev_alloc(s, &s.ws.pyr, pyr + 256))) return rc;
+    if ((rc = dev_alloc(s, &s.ws.blur, blur + 256))) return rc;
+    if ((rc = dev_alloc(s, &s.ws.cand, (size_t)fg.cand_frame_stride * frames))) return rc;
+    if ((rc = dev_alloc(s, &s.ws.cell_count, (size_t)std::max(fg.total_cells, 1) * frames))) return rc;
+    if ((rc = dev_alloc(s, &s.ws.oct, (size_t)fg.oct_frame_stride * frames))) return rc;
+    if ((rc = dev_alloc(s, &s.ws.lvl_kp, (size_t)fg.kp_slots * frames))) return rc;
+    if ((rc = dev_alloc(s, &s.ws.lvl_n, (size_t)fg.nlevels * frames))) return rc;
+    if ((rc = dev_alloc(s, &s.ws.lvl_ncand, (size_t)fg.nlevels * frames))) return rc;
+    if ((rc = dev_alloc(s, &s.ws.lvl_angle, (size_t)fg.kp_slots * frames))) return rc;
+    if ((rc = dev_alloc(s, &s.ws.lvl_desc, (size_t)fg.kp_slots * frames * 32))) return rc;
+    CU(cudaMemsetAsync(s.ws.pyr, 0, pyr + 256, s.stream));
+    CU(cudaMemsetAsync(s.ws.lvl_n, 0, sizeof(int) * (size_t)fg.nlevels * frames, s.stream));
+    CU(cudaStreamSynchronize(s.stream));
+    s.cap_frames = frames;
+    return ORBX_OK;
+}
+
+// All slots must share one capacity because level offsets live in the (shared) FrameGeom.
+static int ensure_capacity(orbx_extractor* ex, int frames, int nslots)
+{
+    int cap = ex->slots[0].cap_frames;
+    bool grow = frames > cap;
+    if (grow) {
+        for (int i = 0; i < orbx_extractor::kSlots; ++i) {
+            cudaStream_t st = ex->slots[i].stream;
+            if (st) cudaStreamSynchronize(st);
+            free_slot(ex->slots[i]);
+            ex->slots[i].stream = st;
+        }
+        cap = frames;
+    }
+    for (int i = 0; i < nslots; ++i) {
+        int rc = ensure_slot(ex, ex->slots[i], cap);
+        if (rc) return rc;
+    }
+    return ORBX_OK;
+}
+
+static int ensure_host_staging(Slot& s, size_t in_bytes, int frames, int capacity)
+{
+    int rc;
+    if (s.d_in_bytes < in_bytes) {
+        if ((rc = dev_alloc(s, &s.d_in, in_bytes))) return rc;
+        s.d_in_bytes = in_bytes;
+    }
+    if (s.out_cap < frames * capacity || !s.d_kps) {
+        if ((rc = dev_alloc(s, &s.d_kps, (size_t)frames * capacity))) return rc;
+        if ((rc = dev_alloc(s, &s.d_desc, (size_t)frames * capacity * 32))) return rc;
+        if ((rc = dev_alloc(s, &s.d_n, (size_t)frames))) return rc;
+        if ((rc = dev_alloc(s, &s.d_nm, (size_t)frames))) return rc;
+        s.out_cap = frames * capacity;
+    }
+    return ORBX_OK;
+}
+
+// The whole per-chunk pipeline on one stream.
+static int run_chunk(orbx_extractor* ex, Slot& s, const uint8_t* d_images, size_t frame_stride, size_t pitch, int frames,
+                     int lap0, int lap1, orbx_keypoint* d_kps, uint8_t* d_desc, int capacity, int* d_n, int* d_nm,
+                     cudaStream_t st)
+{
+    const FrameGeom& fg = ex->fg;
+    CU(launch_pyramid(fg, s.ws, d_images, frame_stride, pitch, frames, st));
+    CU(launch_fast(fg, s.ws, frames, st));
+    CU(launch_blur(fg, s.ws, frames, st));
+    CU(launch_octree(fg, s.ws, frames, st));
+    CU(launch_orient_describe(fg, s.ws, frames, st));
+    CU(launch_pack(fg, s.ws, frames, lap0, lap1, d_kps, d_desc, capacity, d_n, d_nm, st));
+    return ORBX_OK;
+}
+
+}  // namespace orbx
+
+// =====================================================================================================================
+extern "C" {
+
+const char* orbx_last_error(void) { return t_err.c_str(); }
+int orbx_version(void) { return ORBX_VERSION; }
+
+int orbx_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int64_t orbx_launch_count(void) { return g_launches.load(); }
+
+int orbx_compute_tables(int nfeatures, float scaleFactor, int nlevels, float* scale, float* inv_scale, float* sigma2,
+                        float* inv_sigma2, int* nfeatures_per_level)
+{
+    if (nlevels <= 0 || nlevels > ORBX_MAX_LEVELS || nfeatures < 0 || !(scaleFactor > 1.0f))
+        return fail(ORBX_ERR_INVALID_ARG, "bad extractor parameters (nfeatures=%d scaleFactor=%g nlevels=%d)", nfeatures, scaleFactor, nlevels);
+    Tables t;
+    make_tables(t, nfeatures, scaleFactor, nlevels);
+    for (int i = 0; i < nlevels; ++i) {
+        if (scale) scale[i] = t.scale[i];
+        if (inv_scale) inv_scale[i] = t.inv[i];
+        if (sigma2) sigma2[i] = t.sigma2[i];
+        if (inv_sigma2) inv_sigma2[i] = t.invsigma2[i];
+        if (nfeatures_per_level) nfeatures_per_level[i] = t.nfeat[i];
+    }
+    return ORBX_OK;
+}
+
+int orbx_create(int nfeatures, float scaleFactor, int nlevels, int iniThFAST, int minThFAST, int device, int max_cols,
+                int max_rows, int max_batch, orbx_extractor** out)
+{
+    if (!out) return fail(ORBX_ERR_INVALID_ARG, "out is NULL");
+    *out = nullptr;
+    if (nlevels <= 0 || nlevels > ORBX_MAX_LEVELS || nfeatures <= 0 || !(scaleFactor > 1.0f) || iniThFAST < 1 || minThFAST < 1 ||
+        iniThFAST > 255 || minThFAST > iniThFAST)
+        return fail(ORBX_ERR_INVALID_ARG, "bad extractor parameters (nfeatures=%d scaleFactor=%g nlevels=%d ini=%d min=%d)", nfeatures,
+                    scaleFactor, nlevels, iniThFAST, minThFAST);
+    int rc = set_device(device);
+    if (rc) return rc;
+    orbx_extractor* ex = new orbx_extractor();
+    ex->nfeatures = nfeatures; ex->nlevels = nlevels; ex->iniTh = iniThFAST; ex->minTh = minThFAST; ex->device = device;
+    ex->scaleFactorF = scaleFactor;
+    ex->max_batch = max_batch > 0 ? max_batch : 0;
+    make_tables(ex->tab, nfeatures, scaleFactor, nlevels);
+    int kp = 0;
+    for (int l = 0; l < nlevels; ++l) kp += ex->tab.nfeat[l] + 4;
+    ex->max_kp = kp;
+    if (max_cols > 0 && max_rows > 0) {
+        rc = configure(ex, max_rows, max_cols);
+        if (!rc) rc = ensure_capacity(ex, std::max(max_batch, 1), 1);
+        if (rc) { orbx_destroy(ex); return rc; }
+    }
+    *out = ex;
+    return ORBX_OK;
+}
+
+void orbx_destroy(orbx_extractor* ex)
+{
+    if (!ex) return;
+    cudaSetDevice(ex->device);
+    for (int i = 0; i < orbx_extractor::kSlots; ++i) {
+        if (ex->slots[i].stream) cudaStreamSynchronize(ex->slots[i].stream);
+        free_slot(ex->slots[i]);
+        if (ex->slots[i].stream) cudaStreamDestroy(ex->slots[i].stream);
+    }
+    if (ex->d_tables) cudaFree(ex->d_tables);
+    delete ex;
+}
+
+int orbx_get_levels(const orbx_extractor* ex) { return ex ? ex->nlevels : 0; }
+float orbx_get_scale_factor(const orbx_extractor* ex) { return ex ? (float)(double)ex->scaleFactorF : 0.f; }
+
+int orbx_get_tables(const orbx_extractor* ex, float* scale, float* inv_scale, float* sigma2, float* inv_sigma2,
+                    int* nfeatures_per_level)
+{
+    if (!ex) return fail(ORBX_ERR_INVALID_ARG, "extractor is NULL");
+    for (int i = 0; i < ex->nlevels; ++i) {
+        if (scale) scale[i] = ex->tab.scale[i];
+        if (inv_scale) inv_scale[i] = ex->tab.inv[i];
+        if (sigma2) sigma2[i] = ex->tab.sigma2[i];
+        if (inv_sigma2) inv_sigma2[i] = ex->tab.invsigma2[i];
+        if (nfeatures_per_level) nfeatures_per_level[i] = ex->tab.nfeat[i];
+    }
+    return ORBX_OK;
+}
+
+int orbx_level_size(const orbx_extractor* ex, int cols, int rows, int level, int* level_cols, int* level_rows)
+{
+    if (!ex || level < 0 || level >= ex->nlevels) return fail(ORBX_ERR_INVALID_ARG, "bad level");
+    const float scale = ex->tab.inv[level];
+    if (level_cols) *level_cols = cvRoundF((float)cols * scale);
+    if (level_rows) *level_rows = cvRoundF((float)rows * scale);
+    return ORBX_OK;
+}
+
+int orbx_max_keypoints(const orbx_extractor* ex) { return ex ? ex->max_kp : 0; }
+
+int orbx_sync(orbx_extractor* ex)
+{
+    if (!ex) return fail(ORBX_ERR_INVALID_ARG, "extractor is NULL");
+    CU(cudaSetDevice(ex->device));
+    for (int i = 0; i < orbx_extractor::kSlots; ++i)
+        if (ex->slots[i].stream) CU(cudaStreamSynchronize(ex->slots[i].stream));
+    return ORBX_OK;
+}
+
+int orbx_extract_batch_device(orbx_extractor* ex, const uint8_t* d_images, size_t frame_stride, int n_frames, int rows,
+                              int cols, size_t pitch, int lap0, int lap1, orbx_keypoint* d_keypoints,
+                              uint8_t* d_descriptors, int capacity, int* d_n_out, int* d_n_mono, void* stream)
+{
+    if (!ex) return fail(ORBX_ERR_INVALID_ARG, "extractor is NULL");
+    if (!d_images || rows <= 0 || cols <= 0 || n_frames <= 0) return fail(ORBX_ERR_EMPTY_IMAGE, "empty image");
+    if (!d_keypoints || !d_descriptors || !d_n_out || !d_n_mono || capacity <= 0 || pitch < (size_t)cols)
+        return fail(ORBX_ERR_INVALID_ARG, "bad output buffers / pitch");
+    int rc = set_device(ex->device);
+    if (rc) return rc;
+    if ((rc = configure(ex, rows, cols))) return rc;
+    const int chunk = ex->max_batch > 0 ? std::min(ex->max_batch, n_frames) : std::min(n_frames, 256);
+    if ((rc = ensure_capacity(ex, chunk, 1))) return rc;
+    Slot& s = ex->slots[0];
+    cudaStream_t st = stream ? (cudaStream_t)stream : s.stream;
+    for (int f0 = 0; f0 < n_frames; f0 += chunk) {
+        const int nf = std::min(chunk, n_frames - f0);
+        rc = run_chunk(ex, s, d_images + (size_t)f0 * frame_stride, frame_stride, pitch, nf, lap0, lap1,
+                       d_keypoints + (size_t)f0 * capacity, d_descriptors + (size_t)f0 * capacity * 32, capacity, d_n_out + f0,
+                       d_n_mono + f0, st);
+        if (rc) return rc;
+        ex->last_frames = nf;
+    }
+    return ORBX_OK;
+}
+
+int orbx_extract_batch(orbx_extractor* ex, const uint8_t* const* images, int n_frames, int rows, int cols, size_t step,
+                       int lap0, int lap1, orbx_keypoint* keypoints, uint8_t* descriptors, int capacity, int* n_out,
+                       int* n_mono)
+{
+    if (!ex) return fail(ORBX_ERR_INVALID_ARG, "extractor is NULL");
+    if (!images || rows <= 0 || cols <= 0 || n_frames <= 0) return fail(ORBX_ERR_EMPTY_IMAGE, "empty image");
+    for (int i = 0; i < n_frames; ++i)
+        if (!images[i]) return fail(ORBX_ERR_EMPTY_IMAGE, "image %d is NULL", i);
+    if (!keypoints || !descriptors || !n_out || !n_mono || capacity <= 0 || step < (size_t)cols)
+        return fail(ORBX_ERR_INVALID_ARG, "bad output buffers / step");
+    int rc = set_device(ex->device);
+    if (rc) return rc;
+    if ((rc = configure(ex, rows, cols))) return rc;
+    const int chunk = ex->max_batch > 0 ? std::min(ex->max_batch, n_frames) : std::min(n_frames, 64);
+    const int nchunks = (n_frames + chunk - 1) / chunk;
+    const int nslots = std::min(nchunks, (int)orbx_extractor::kSlots);
+    if ((rc = ensure_capacity(ex, chunk, nslots))) return rc;
+    const size_t dpitch = (size_t)cols;
+    const size_t dframe = dpitch * rows;
+    for (int i = 0; i < nslots; ++i)
+        if ((rc = ensure_host_staging(ex->slots[i], dframe * chunk, chunk, capacity))) return rc;
+    for (int c = 0; c < nchunks; ++c) {
+        Slot& s = ex->slots[c % nslots];
+        const int f0 = c * chunk, nf = std::min(chunk, n_frames - f0);
+        // stream order makes reuse of the slot's staging safe: the previous D2H on this stream precedes these H2D copies
+        bool contiguous = step == (size_t)cols;
+        for (int f = 1; f < nf && contiguous; ++f) contiguous = images[f0 + f] == images[f0 + f - 1] + dframe;
+        if (contiguous) {
+            CU(cudaMemcpyAsync(s.d_in, images[f0], dframe * nf, cudaMemcpyHostToDevice, s.stream));
+        } else {
+            for (int f = 0; f < nf; ++f)
+                CU(cudaMemcpy2DAsync(s.d_in + (size_t)f * dframe, dpitch, images[f0 + f], step, cols, rows, cudaMemcpyHostToDevice, s.stream));
+        }
+        if ((rc = run_chunk(ex, s, s.d_in, dframe, dpitch, nf, lap0, lap1, s.d_kps, s.d_desc, capacity, s.d_n, s.d_nm, s.stream))) return rc;
+        CU(cudaMemcpyAsync(keypoints + (size_t)f0 * capacity, s.d_kps, sizeof(orbx_keypoint) * (size_t)nf * capacity, cudaMemcpyDeviceToHost, s.stream));
+        CU(cudaMemcpyAsync(descriptors + (size_t)f0 * capacity * 32, s.d_desc, (size_t)nf * capacity * 32, cudaMemcpyDeviceToHost, s.stream));
+        CU(cudaMemcpyAsync(n_out + f0, s.d_n, sizeof(int) * nf, cudaMemcpyDeviceToHost, s.stream));
+        CU(cudaMemcpyAsync(n_mono + f0, s.d_nm, sizeof(int) * nf, cudaMemcpyDeviceToHost, s.stream));
+        if (c % nslots == 0) ex->last_frames = nf;
+    }
+    for (int i = 0; i < nslots; ++i) CU(cudaStreamSynchronize(ex->slots[i].stream));
+    for (int f = 0; f < n_frames; ++f)
+        if (n_out[f] > capacity) return fail(ORBX_ERR_CAPACITY, "frame %d has %d keypoints, capacity %d", f, n_out[f], capacity);
+    return ORBX_OK;
+}
+
+int orbx_extract(orbx_extractor* ex, const uint8_t* image, int rows, int cols, size_t step, int lap0, int lap1,
+                 orbx_keypoint* keypoints, uint8_t* descriptors, int capacity, int* n_out, int* n_mono)
+{
+    const uint8_t* imgs[1] = {image};
+    if (!image) return fail(ORBX_ERR_EMPTY_IMAGE, "empty image");
+    return orbx_extract_batch(ex, imgs, 1, rows, cols, step, lap0, lap1, keypoints, descriptors, capacity, n_out, n_mono);
+}
+
+// ---- probes ---------------------------------------------------------------------------------------------------------
+static int probe_check(orbx_extractor* ex, int frame, int level)
+{
+    if (!ex || !ex->geom_valid) return fail(ORBX_ERR_INVALID_ARG, "no extraction has run on this handle");
+    if (level < 0 || level >= ex->nlevels || frame < 0 || frame >= ex->slots[0].cap_frames)
+        return fail(ORBX_ERR_INVALID_ARG, "frame/level out of range");
+    int rc = set_device(ex->device);
+    if (rc) return rc;
+    return orbx_sync(ex);
+}
+
+int orbx_get_pyramid_level(orbx_extractor* ex, int frame, int level, uint8_t* dst, size_t dst_step, int with_border)
+{
+    int rc = probe_check(ex, frame, level);
+    if (rc) return rc;
+    const LevelGeom& g = ex->fg.L[level];
+    const uint8_t* base = ex->slots[0].ws.pyr + g.pyr_off + (size_t)frame * g.pyr_frame_stride;
+    if (with_border)
+        CU(cudaMemcpy2D(dst, dst_step, base + (kXPad - kEdge), g.pitch, g.w + 2 * kEdge, g.h + 2 * kEdge, cudaMemcpyDeviceToHost));
+    else
+        CU(cudaMemcpy2D(dst, dst_step, base + (size_t)kEdge * g.pitch + kXPad, g.pitch, g.w, g.h, cudaMemcpyDeviceToHost));
+    return ORBX_OK;
+}
+
+int orbx_get_blurred_level(orbx_extractor* ex, int frame, int level, uint8_t* dst, size_t dst_step)
+{
+    int rc = probe_check(ex, frame, level);
+    if (rc) return rc;
+    const LevelGeom& g = ex->fg.L[level];
+    CU(cudaMemcpy2D(dst, dst_step, ex->slots[0].ws.blur + g.blur_off + (size_t)frame * g.blur_frame_stride, g.bpitch, g.w, g.h,
+                    cudaMemcpyDeviceToHost));
+    return ORBX_OK;
+}
+
+int orbx_get_candidates(orbx_extractor* ex, int frame, int level, int* xs, int* ys, int* scores, int capacity)
+{
+    int rc = probe_check(ex, frame, level);
+    if (rc) return rc;
+    const FrameGeom& fg = ex->fg;
+    const LevelGeom& g = fg.L[level];
+    const int ncells = g.nCols * g.nRows;
+    if (ncells == 0) return 0;
+    std::vector<int> counts(ncells);
+    CU(cudaMemcpy(counts.data(), ex->slots[0].ws.cell_count + (size_t)frame * fg.total_cells + g.cell_base, sizeof(int) * ncells,
+                  cudaMemcpyDeviceToHost));
+    std::vector<uint32_t> cand((size_t)g.cand_max);
+    CU(cudaMemcpy(cand.data(), ex->slots[0].ws.cand + (size_t)frame * fg.cand_frame_stride + g.cand_off, sizeof(uint32_t) * cand.size(),
+                  cudaMemcpyDeviceToHost));
+    int n = 0;
+    for (int c = 0; c < ncells; ++c)
+        for (int i = 0; i < counts[c]; ++i, ++n)
+            if (n < capacity) {
+                const uint32_t k = cand[(size_t)c * g.cell_cap + i];
+                xs[n] = (int)(k & 0xfff); ys[n] = (int)((k >> 12) & 0xfff); scores[n] = (int)(k >> 24);
+            }
+    return n;
+}
+
+int orbx_get_level_keypoints(orbx_extractor* ex, int frame, int level, orbx_keypoint* keypoints, uint8_t* descriptors, int capacity)
+{
+    int rc = probe_check(ex, frame, level);
+    if (rc) return rc;
+    const FrameGeom& fg = ex->fg;
+    const LevelGeom& g = fg.L[level];
+    const Workspace& ws = ex->slots[0].ws;
+    int n = 0;
+    CU(cudaMemcpy(&n, ws.lvl_n + (size_t)frame * fg.nlevels + level, sizeof(int), cudaMemcpyDeviceToHost));
+    if (n <= 0) return 0;
+    std::vector<uint32_t> keys(n);
+    std::vector<float> ang(n);
+    CU(cudaMemcpy(keys.data(), ws.lvl_kp + (size_t)frame * fg.kp_slots + g.kp_base, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(ang.data(), ws.lvl_angle + (size_t)frame * fg.kp_slots + g.kp_base, sizeof(float) * n, cudaMemcpyDeviceToHost));
+    const int m = std::min(n, capacity);
+    if (descriptors)
+        CU(cudaMemcpy(descriptors, ws.lvl_desc + ((size_t)frame * fg.kp_slots + g.kp_base) * 32, (size_t)m * 32, cudaMemcpyDeviceToHost));
+    for (int i = 0; i < m; ++i) {
+        orbx_keypoint& k = keypoints[i];
+        k.x = (float)((int)(keys[i] & 0xfff) + kWinBorder);
+        k.y = (float)((int)((keys[i] >> 12) & 0xfff) + kWinBorder);
+        k.size = g.kp_size; k.angle = ang[i]; k.response = (float)(keys[i] >> 24); k.octave = level; k.class_id = -1;
+    }
+    return n;
+}
+
+// ---- stand-alone octree (parity tests drive the kernel with hand-built candidate sets) --------------------------------
+int orbx_distribute_octree(int device, const int* xs, const int* ys, const int* scores, int n, int minX, int maxX, int minY,
+                           int maxY, int nFeatures, int* out_idx, int capacity, int* n_out)
+{
+    if (!n_out || n < 0 || (n > 0 && (!xs || !ys || !scores))) return fail(ORBX_ERR_INVALID_ARG, "bad arguments");
+    int rc = set_device(device);
+    if (rc) return rc;
+    *n_out = 0;
+    const int width = maxX - minX, height = maxY - minY;
+    if (width <= 0 || height <= 0 || width > 4095 || height > 4095) return fail(ORBX_ERR_UNSUPPORTED, "window %dx%d", width, height);
+    // Build a one-level geometry whose single "cell" holds all candidates in the given order.
+    FrameGeom fg;
+    memset(&fg, 0, sizeof fg);
+    fg.nlevels = 1; fg.total_cells = 1;
+    LevelGeom& g = fg.L[0];
+    g.w = width + 2 * kWinBorder; g.h = height + 2 * kWinBorder;
+    g.nCols = 1; g.nRows = 1; g.wCell = 1; g.hCell = 1; g.cell_base = 0; g.cell_cap = std::max(n, 1); g.cand_off = 0; g.cand_max = std::max(n, 1);
+    g.oct_off = 0; g.nfeat = nFeatures;
+    g.nIni = (int)round((float)width / (float)height);
+    if (g.nIni > 64) return fail(ORBX_ERR_UNSUPPORTED, "aspect ratio");
+    g.hX = g.nIni > 0 ? (float)width / g.nIni : 1.f;
+    {
+        int maxRootW = 1;
+        for (int i = 0; i < g.nIni; ++i) maxRootW = std::max(maxRootW, (int)(g.hX * (float)(i + 1)) - (int)(g.hX * (float)i));
+        auto clog2 = [](int v) { int b = 0; while ((1 << b) < v) ++b; return b; };
+        g.depth = std::max(clog2(maxRootW) + 1, clog2(std::max(height, 1))) + 1;
+        g.root_bits = clog2(std::max(g.nIni, 1));
+        if (2 * g.depth + g.root_bits > 32) return fail(ORBX_ERR_UNSUPPORTED, "path code too long");
+    }
+    g.kp_base = 0; g.kp_cap = std::max(nFeatures + 4, 4 * g.nIni + 1);
+    fg.kp_slots = g.kp_cap; fg.cand_frame_stride = g.cand_max; fg.oct_frame_stride = 4ull * g.cand_max + 32;
+    if (octree_smem_bytes(g.kp_cap) > 200 * 1024) return fail(ORBX_ERR_UNSUPPORTED, "nFeatures too large");
+    CU(octree_prepare());
+    std::vector<uint32_t> packed(std::max(n, 1));
+    for (int i = 0; i < n; ++i) {
+        if (xs[i] < 0 || xs[i] > 4095 || ys[i] < 0 || ys[i] > 4095 || scores[i] < 0 || scores[i] > 255)
+            return fail(ORBX_ERR_INVALID_ARG, "candidate %d out of range", i);
+        packed[i] = (uint32_t)xs[i] | ((uint32_t)ys[i] << 12) | ((uint32_t)scores[i] << 24);
+    }
+    Slot s;
+    Workspace& ws = s.ws;
+    int one = n;
+    auto cleanup = [&] { free_slot(s); };
+    if ((rc = dev_alloc(s, &ws.cand, packed.size())) || (rc = dev_alloc(s, &ws.cell_count, 1)) ||
+        (rc = dev_alloc(s, &ws.oct, (size_t)fg.oct_frame_stride)) || (rc = dev_alloc(s, &ws.lvl_kp, (size_t)fg.kp_slots)) ||
+        (rc = dev_alloc(s, &ws.lvl_n, 1)) || (rc = dev_alloc(s, &ws.lvl_ncand, 1))) { cleanup(); return rc; }
+    cudaMemcpy(ws.cand, packed.data(), sizeof(uint32_t) * packed.size(), cudaMemcpyHostToDevice);
+    cudaMemcpy(ws.cell_count, &one, sizeof(int), cudaMemcpyHostToDevice);
+    cudaError_t e = launch_octree(fg, ws, 1, 0);
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) { cleanup(); return fail(ORBX_ERR_CUDA, "octree kernel: %s", cudaGetErrorString(e)); }
+    int m = 0;
+    cudaMemcpy(&m, ws.lvl_n, sizeof(int), cudaMemcpyDeviceToHost);
+    std::vector<uint32_t> keys(std::max(m, 1));
+    cudaMemcpy(keys.data(), ws.lvl_kp, sizeof(uint32_t) * m, cudaMemcpyDeviceToHost);
+    cleanup();
+    *n_out = m;
+    if (m > capacity) return fail(ORBX_ERR_CAPACITY, "need %d slots", m);
+    // map retained keys back to input indices (pixel positions are unique)
+    std::unordered_map<uint32_t, int> lut;
+    lut.reserve((size_t)n * 2);
+    for (int i = 0; i < n; ++i) lut[(uint32_t)ys[i] * 4096u + (uint32_t)xs[i]] = i;
+    for (int i = 0; i < m; ++i) out_idx[i] = lut[((keys[i] >> 12) & 0xfff) * 4096u + (keys[i] & 0xfff)];
+    return ORBX_OK;
+}
+
+// ---- matching ---------------------------------------------------------------------------------------------------------
+int orbx_descriptor_distance(const uint8_t* a, const uint8_t* b)
+{
+    uint64_t x[4], y[4];
+    memcpy(x, a, 32); memcpy(y, b, 32);
+    return __builtin_popcountll(x[0] ^ y[0]) + __builtin_popcountll(x[1] ^ y[1]) + __builtin_popcountll(x[2] ^ y[2]) +
+           __builtin_popcountll(x[3] ^ y[3]);
+}
+
+int orbx_knn2_device(int device, const uint8_t* d_queries, int nq, const uint8_t* d_database, int64_t ndb, int32_t index_base,
+                     int32_t* d_idx, int32_t* d_dist, void* stream)
+{
+    if (nq < 0 || ndb < 0 || (nq > 0 && (!d_queries || !d_idx || !d_dist)) || (ndb > 0 && !d_database))
+        return fail(ORBX_ERR_INVALID_ARG, "bad arguments");
+    if (ndb + (int64_t)index_base > 0x7fffffffLL) return fail(ORBX_ERR_UNSUPPORTED, "database rows must fit int32");
+    int rc = set_device(device);
+    if (rc) return rc;
+    CU(launch_knn2(d_queries, nq, d_database, ndb, index_base, d_idx, d_dist, (cudaStream_t)stream));
+    return ORBX_OK;
+}
+
+int orbx_knn2_merge_device(int device, const int32_t* d_idx_shards, const int32_t* d_dist_shards, int n_shards, int nq,
+                           int32_t* d_idx, int32_t* d_dist, void* stream)
+{
+    if (n_shards <= 0 || nq < 0) return fail(ORBX_ERR_INVALID_ARG, "bad arguments");
+    int rc = set_device(device);
+    if (rc) return rc;
+    CU(launch_knn2_merge(d_idx_shards, d_dist_shards, n_shards, nq, d_idx, d_dist, (cudaStream_t)stream));
+    return ORBX_OK;
+}
+
+int orbx_knn2(int device, const uint8_t* queries, int nq, const uint8_t* database, int64_t ndb, int32_t* idx, int32_t* dist)
+{
+    if (nq < 0 || ndb < 0 || (nq > 0 && (!queries || !idx || !dist)) || (ndb > 0 && !database))
+        return fail(ORBX_ERR_INVALID_ARG, "bad arguments");
+    if (nq == 0) return ORBX_OK;
+    int rc = set_device(device);
+    if (rc) return rc;
+    uint8_t *dq = nullptr, *ddb = nullptr;
+    int32_t *di = nullptr, *dd = nullptr;
+    auto cleanup = [&] { cudaFree(dq); cudaFree(ddb); cudaFree(di); cudaFree(dd); };
+    cudaError_t e;
+    if ((e = cudaMalloc(&dq, (size_t)nq * 32)) || (e = cudaMalloc(&ddb, std::max<size_t>((size_t)ndb * 32, 32))) ||
+        (e = cudaMalloc(&di, (size_t)nq * 8)) || (e = cudaMalloc(&dd, (size_t)nq * 8))) {
+        cleanup();
+        return fail(ORBX_ERR_OOM, "cudaMalloc: %s", cudaGetErrorString(e));
+    }
+    cudaMemcpy(dq, queries, (size_t)nq * 32, cudaMemcpyHostToDevice);
+    if (ndb > 0) cudaMemcpy(ddb, database, (size_t)ndb * 32, cudaMemcpyHostToDevice);
+    e = launch_knn2(dq, nq, ddb, ndb, 0, di, dd, 0);
+    if (e == cudaSuccess) e = cudaMemcpy(idx, di, (size_t)nq * 8, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) e = cudaMemcpy(dist, dd, (size_t)nq * 8, cudaMemcpyDeviceToHost);
+    cleanup();
+    if (e != cudaSuccess) return fail(ORBX_ERR_CUDA, "knn2: %s", cudaGetErrorString(e));
+    return ORBX_OK;
+}
+
+int orbx_ratio_test(const int32_t* dist, int nq, float ratio, int th_low, int mode, uint8_t* accept)
+{
+    if (!dist || !accept || nq < 0) return fail(ORBX_ERR_INVALID_ARG, "bad arguments");
+    for (int i = 0; i < nq; ++i) {
+        const int d1 = dist[2 * i], d2 = dist[2 * i + 1];
+        bool ok;
+        if (mode == 0) ok = d1 <= th_low && (float)d1 < ratio * (float)d2;          // src/ORBmatcher1.cc:329-333
+        else if (mode == 1) ok = d1 < th_low && (float)d1 < ratio * (float)d2;      // src/ORBmatcher2.cc:120-125
+        else ok = (float)d1 < (float)d2 * (double)ratio;                            // src/Frame.cc:1181
+        accept[i] = ok ? 1 : 0;
+    }
+    return ORBX_OK;
+}
+
+int orbx_stereo_match(orbx_extractor* exL, int frameL, orbx_extractor* exR, int frameR, const orbx_keypoint* kpL,
+                      const uint8_t* descL, int nL, const orbx_keypoint* kpR, const uint8_t* descR, int nR, float bf, float maxD,
+                      float* uRight, float* depth)
+{
+    if (!exL || !exR || !exL->geom_valid || !exR->geom_valid) return fail(ORBX_ERR_INVALID_ARG, "extractors have not run");
+    if (exL->device != exR->device || exL->fg.rows != exR->fg.rows || exL->fg.cols != exR->fg.cols || exL->nlevels != exR->nlevels)
+        return fail(ORBX_ERR_INVALID_ARG, "left/right extractors must share device, image shape and levels");
+    if (nL < 0 || nR < 0 || (nL > 0 && (!kpL || !descL || !uRight || !depth)) || (nR > 0 && (!kpR || !descR)))
+        return fail(ORBX_ERR_INVALID_ARG, "bad arguments");
+    if (frameL < 0 || frameL >= exL->slots[0].cap_frames || frameR < 0 || frameR >= exR->slots[0].cap_frames)
+        return fail(ORBX_ERR_INVALID_ARG, "frame out of range");
+    if (nR >= (1 << 20)) return fail(ORBX_ERR_UNSUPPORTED, "too many right keypoints");
+    if (nL == 0) return ORBX_OK;
+    int rc = set_device(exL->device);
+    if (rc) return rc;
+    if ((rc = orbx_sync(exL)) || (rc = orbx_sync(exR))) return rc;
+    for (int i = 0; i < nL; ++i)
+        if (kpL[i].octave < 0 || kpL[i].octave >= exL->nlevels) return fail(ORBX_ERR_INVALID_ARG, "left keypoint %d octave", i);
+    for (int i = 0; i < nR; ++i)
+        if (kpR[i].octave < 0 || kpR[i].octave >= exL->nlevels) return fail(ORBX_ERR_INVALID_ARG, "right keypoint %d octave", i);
+    Slot tmp;
+    StereoArgs A{};
+    orbx_keypoint *dkL = nullptr, *dkR = nullptr;
+    uint8_t *ddL = nullptr, *ddR = nullptr;
+    auto cleanup = [&] { free_slot(tmp); };
+    if ((rc = dev_alloc(tmp, &dkL, (size_t)nL)) || (rc = dev_alloc(tmp, &ddL, (size_t)nL * 32)) ||
+        (rc = dev_alloc(tmp, &dkR, (size_t)std::max(nR, 1))) || (rc = dev_alloc(tmp, &ddR, (size_t)std::max(nR, 1) * 32)) ||
+        (rc = dev_alloc(tmp, &A.uRight, (size_t)nL)) || (rc = dev_alloc(tmp, &A.depth, (size_t)nL)) || (rc = dev_alloc(tmp, &A.sad, (size_t)nL))) {
+        cleanup();
+        return rc;
+    }
+    cudaMemcpy(dkL, kpL, sizeof(orbx_keypoint) * nL, cudaMemcpyHostToDevice);
+    cudaMemcpy(ddL, descL, (size_t)nL * 32, cudaMemcpyHostToDevice);
+    if (nR > 0) {
+        cudaMemcpy(dkR, kpR, sizeof(orbx_keypoint) * nR, cudaMemcpyHostToDevice);
+        cudaMemcpy(ddR, descR, (size_t)nR * 32, cudaMemcpyHostToDevice);
+    }
+    A.pyrL = exL->slots[0].ws.pyr; A.pyrR = exR->slots[0].ws.pyr; A.frameL = frameL; A.frameR = frameR;
+    A.kpL = dkL; A.descL = ddL; A.nL = nL; A.kpR = dkR; A.descR = ddR; A.nR = nR; A.bf = bf; A.maxD = maxD;
+    cudaError_t e = launch_stereo(exL->fg, A, 0);
+    if (e == cudaSuccess) e = cudaMemcpy(uRight, A.uRight, sizeof(float) * nL, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) e = cudaMemcpy(depth, A.depth, sizeof(float) * nL, cudaMemcpyDeviceToHost);
+    cleanup();
+    if (e != cudaSuccess) return fail(ORBX_ERR_CUDA, "stereo: %s", cudaGetErrorString(e));
+    return ORBX_OK;
+}
+
+// ---- measurement ------------------------------------------------------------------------------------------------------
+int orbx_measure_popc_peak(int device, double* popc_per_second)
+{
+    if (!popc_per_second) return fail(ORBX_ERR_INVALID_ARG, "NULL output");
+    int rc = set_device(device);
+    if (rc) return rc;
+    unsigned long long* sink = nullptr;
+    CU(cudaMalloc(&sink, 8));
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    const int blocks = sms * 8, iters = 4096;
+    launch_popc_bench(sink, 256, blocks, 0);   // warm-up
+    double best = 0;
+    for (int rep = 0; rep < 5; ++rep) {
+        cudaEventRecord(e0, 0);
+        launch_popc_bench(sink, iters, blocks, 0);
+        cudaEventRecord(e1, 0);
+        cudaEventSynchronize(e1);
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e0, e1);
+        const double ops = (double)blocks * 256.0 * iters * 8.0;
+        if (ms > 0) best = std::max(best, ops / (ms * 1e-3));
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cudaFree(sink);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(ORBX_ERR_CUDA, "popc bench: %s", cudaGetErrorString(e));
+    *popc_per_second = best;
+    return ORBX_OK;
+}
+
+// ---- synthetic inputs -----------------------------------------------------------------------------------------------------
+void orbx_synth_image_host(uint32_t seed, int view, int cols, int rows, int max_disp, uint8_t* dst, size_t step)
+{
+    for (int y = 0; y < rows; ++y)
+        for (int x = 0; x < cols; ++x) dst[(size_t)y * step + x] = orbx_synth::image_pixel(seed, view, x, y, max_disp);
+}
+
+int orbx_synth_images_device(int device, uint32_t seed0, int view, int n_frames, int cols, int rows, int max_disp, uint8_t* d_dst,
+                             size_t pitch, size_t frame_stride, void* stream)
+{
+    int rc = set_device(device);
+    if (rc) return rc;
+    if (!d_dst || cols <= 0 || rows <= 0 || n_frames <= 0 || max_disp < 2) return fail(ORBX_ERR_INVALID_ARG, "bad arguments");
+    CU(launch_synth_images(seed0, view, n_frames, cols, rows, max_disp, d_dst, pitch, frame_stride, (cudaStream_t)stream));
+    return ORBX_OK;
+}
+
+void orbx_synth_descriptors_host(uint32_t seed, int is_query, int64_t first_row, int64_t n_rows, int64_t ndb, int plant_every, uint8_t* dst)
+{
+    uint32_t* w = reinterpret_cast<uint32_t*>(dst);
+    for (int64_t r = 0; r < n_rows; ++r)
+        for (uint32_t k = 0; k < 8; ++k)
+            w[r * 8 + k] = is_query ? orbx_synth::query_word(seed, (uint32_t)(first_row + r), k, (uint32_t)ndb, (uint32_t)plant_every)
+                                    : orbx_synth::desc_word(seed, (uint32_t)(first_row + r), k);
+}
+
+int orbx_synth_descriptors_device(int device, uint32_t seed, int is_query, int64_t first_row, int64_t n_rows, int64_t ndb,
+                                  int plant_every, uint8_t* d_dst, void* stream)
+{
+    int rc = set_device(device);
+    if (rc) return rc;
+    CU(launch_synth_desc(seed, is_query, first_row, n_rows, ndb, plant_every, d_dst, (cudaStream_t)stream));
+    return ORBX_OK;
+}
+
+// Test hook: the std::sort replay used by the octree kernel, on the host (tests/test_introsort.py).
+void orbx_debug_sort_replay(unsigned long long* items, int n) { orbx_sort::sort_replay(items, n); }
+
+}  // extern "C"

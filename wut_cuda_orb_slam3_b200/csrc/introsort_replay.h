@@ -1,0 +1,168 @@
+// introsort_replay.h — exact replay of libstdc++'s std::sort (GCC 13 bits/stl_algo.h, bits/stl_heap.h) on an array
+// of 64-bit items compared by their high 40 bits only (the low 24 bits are payload carried along).
+//
+// Why: DistributeOctTree sorts its expandable nodes with std::sort(compareNodes) (reference
+// src/ORBextractor.cc:569-582, 709), whose comparator orders only by (count, UL.x).  Ties are broken by whatever
+// permutation introsort happens to produce, and that permutation decides which nodes are split before the
+// `size >= N` break and the order children are pushed — i.e. the keypoint set and order.
+// So the GPU octree replays the algorithm step for step: introsort loop with threshold 16 and depth limit
+// 2*floor(log2 n), median-of-three of (first+1, mid, last-1) moved to first, unguarded Hoare partition, heap-sort
+// fallback, then the final insertion sort (guarded for the first 16, unguarded afterwards).
+// tests/test_introsort.py checks the replay against std::sort.
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define ORBX_SORT_HD __host__ __device__ inline
+#else
+#define ORBX_SORT_HD inline
+#endif
+
+namespace orbx_sort {
+
+typedef unsigned long long item_t;
+
+constexpr int kPayloadBits = 24;
+ORBX_SORT_HD item_t make_item(item_t key, uint32_t payload) { return (key << kPayloadBits) | (payload & 0xffffffu); }
+ORBX_SORT_HD uint32_t payload(item_t v) { return (uint32_t)(v & 0xffffffu); }
+ORBX_SORT_HD bool lt(item_t a, item_t b) { return (a >> kPayloadBits) < (b >> kPayloadBits); }
+ORBX_SORT_HD void swp(item_t* a, item_t* b) { item_t t = *a; *a = *b; *b = t; }
+
+ORBX_SORT_HD void push_heap_(item_t* first, int hole, int top, item_t value)
+{
+    int parent = (hole - 1) / 2;
+    while (hole > top && lt(first[parent], value)) {
+        first[hole] = first[parent];
+        hole = parent;
+        parent = (hole - 1) / 2;
+    }
+    first[hole] = value;
+}
+
+ORBX_SORT_HD void adjust_heap_(item_t* first, int hole, int len, item_t value)
+{
+    const int top = hole;
+    int second = hole;
+    while (second < (len - 1) / 2) {
+        second = 2 * (second + 1);
+        if (lt(first[second], first[second - 1])) second--;
+        first[hole] = first[second];
+        hole = second;
+    }
+    if ((len & 1) == 0 && second == (len - 2) / 2) {
+        second = 2 * (second + 1);
+        first[hole] = first[second - 1];
+        hole = second - 1;
+    }
+    push_heap_(first, hole, top, value);
+}
+
+// std::__partial_sort(first, last, last) == make_heap + sort_heap
+ORBX_SORT_HD void heap_sort_(item_t* first, int len)
+{
+    if (len >= 2) {
+        int parent = (len - 2) / 2;
+        while (true) {
+            item_t v = first[parent];
+            adjust_heap_(first, parent, len, v);
+            if (parent == 0) break;
+            parent--;
+        }
+    }
+    int last = len;
+    while (last > 1) {
+        --last;
+        item_t v = first[last];
+        first[last] = first[0];
+        adjust_heap_(first, 0, last, v);
+    }
+}
+
+ORBX_SORT_HD void move_median_to_first_(item_t* result, item_t* a, item_t* b, item_t* c)
+{
+    if (lt(*a, *b)) {
+        if (lt(*b, *c)) swp(result, b);
+        else if (lt(*a, *c)) swp(result, c);
+        else swp(result, a);
+    } else if (lt(*a, *c)) swp(result, a);
+    else if (lt(*b, *c)) swp(result, c);
+    else swp(result, b);
+}
+
+ORBX_SORT_HD int unguarded_partition_(item_t* base, int first, int last, int pivot)
+{
+    while (true) {
+        while (lt(base[first], base[pivot])) ++first;
+        --last;
+        while (lt(base[pivot], base[last])) --last;
+        if (!(first < last)) return first;
+        swp(base + first, base + last);
+        ++first;
+    }
+}
+
+ORBX_SORT_HD void unguarded_linear_insert_(item_t* base, int last)
+{
+    item_t val = base[last];
+    int next = last - 1;
+    while (lt(val, base[next])) {
+        base[last] = base[next];
+        last = next;
+        --next;
+    }
+    base[last] = val;
+}
+
+ORBX_SORT_HD void insertion_sort_(item_t* base, int first, int last)
+{
+    if (first == last) return;
+    for (int i = first + 1; i != last; ++i) {
+        if (lt(base[i], base[first])) {
+            item_t val = base[i];
+            for (int j = i; j > first; --j) base[j] = base[j - 1];
+            base[first] = val;
+        } else {
+            unguarded_linear_insert_(base, i);
+        }
+    }
+}
+
+// std::sort(base, base + n, comp) with comp = "high 32 bits less-than".
+ORBX_SORT_HD void sort_replay(item_t* base, int n)
+{
+    if (n <= 0) return;
+    // __introsort_loop with an explicit stack (the recursion is on the right part, the loop on the left part)
+    int lg = 0;
+    for (int t = n; t > 1; t >>= 1) ++lg;
+    struct Frame { int first, last, depth; };
+    Frame stack[72];
+    int sp = 0;
+    stack[sp++] = Frame{0, n, 2 * lg};
+    while (sp > 0) {
+        Frame f = stack[--sp];
+        int first = f.first, last = f.last, depth = f.depth;
+        while (last - first > 16) {
+            if (depth == 0) {
+                heap_sort_(base + first, last - first);
+                break;
+            }
+            --depth;
+            const int mid = first + (last - first) / 2;
+            move_median_to_first_(base + first, base + first + 1, base + mid, base + last - 1);
+            const int cut = unguarded_partition_(base, first + 1, last, first);
+            // recursion: __introsort_loop(cut, last, depth) runs BEFORE the loop continues on [first, cut); the two
+            // ranges are disjoint so the order of processing does not change the result.
+            if (sp < 72) stack[sp++] = Frame{cut, last, depth};
+            last = cut;
+        }
+    }
+    // __final_insertion_sort
+    if (n > 16) {
+        insertion_sort_(base, 0, 16);
+        for (int i = 16; i != n; ++i) unguarded_linear_insert_(base, i);
+    } else {
+        insertion_sort_(base, 0, n);
+    }
+}
+
+}  // namespace orbx_sort

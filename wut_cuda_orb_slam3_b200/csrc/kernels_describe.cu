@@ -1,0 +1,275 @@
+// kernels_describe.cu — blur, orientation, rBRIEF descriptors and output packing.
+//
+//  * blur_kernel:        cv::GaussianBlur(level, 7x7, sigma 2, BORDER_REFLECT_101)   (reference src/ORBextractor.cc:1270-1273)
+//                        separable fixed point, kernel [18,34,48,56,48,34,18]/256 per axis, (v + 2^15) >> 16.
+//                        Reads the *bordered* pyramid level: its 19-px border already holds the reflect-101 values, so
+//                        the 3-px filter halo needs no index arithmetic at all.
+//  * orient_describe_kernel: IC_Angle (summation pattern src/OpenCL/Kernel/Angle.cl:24-53, umax src/ORBextractor.cc:455-467,
+//                        cv::fastAtan2) on the un-blurred level + computeOrbDescriptor (src/ORBextractor.cc:105-149) on the
+//                        blurred level; one warp per keypoint, lane = descriptor byte.
+//  * pack_kernel:        operator() output packing (src/ORBextractor.cc:1283-1306): scale, lapping-area split.
+#include <float.h>
+
+#include "orbx_internal.cuh"
+
+namespace orbx {
+
+namespace {
+
+__device__ __align__(16) const int8_t d_pattern[1024] = {
+#include "brief_pattern.inc"
+};
+
+__constant__ int c_umax[16] = {15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9, 8, 6, 3};
+
+constexpr int BT_W = 128, BT_H = 32;          // blur tile
+constexpr int BIN_P = 136;                    // input tile pitch (bytes): x0-4 .. x0+132
+constexpr int BIN_R = BT_H + 6;
+
+// cv::fastAtan2 (OpenCV mathfuncs_core atan_f32): float32, no FMA contraction.
+__device__ __forceinline__ float fast_atan2_dev(float y, float x)
+{
+    const float scale = (float)(180.0 / 3.14159265358979323846);
+    const float p1 = 0.9997878412794807f * scale, p3 = -0.3258083974640975f * scale;
+    const float p5 = 0.1555786518463281f * scale, p7 = -0.04432655554792128f * scale;
+    const float ax = fabsf(x), ay = fabsf(y);
+    float a, c, c2;
+    if (ax >= ay) {
+        c = __fdiv_rn(ay, __fadd_rn(ax, (float)DBL_EPSILON));
+        c2 = __fmul_rn(c, c);
+        a = __fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(p7, c2), p5), c2), p3), c2), p1), c);
+    } else {
+        c = __fdiv_rn(ax, __fadd_rn(ay, (float)DBL_EPSILON));
+        c2 = __fmul_rn(c, c);
+        a = __fsub_rn(90.f, __fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(p7, c2), p5), c2), p3), c2), p1), c));
+    }
+    if (x < 0) a = __fsub_rn(180.f, a);
+    if (y < 0) a = __fsub_rn(360.f, a);
+    return a;
+}
+
+}  // namespace
+
+// grid = (tiles over all levels, n_frames); tile table lookup by level prefix (computed on the fly).
+__global__ void __launch_bounds__(256) blur_kernel(const __grid_constant__ FrameGeom fg, Workspace ws)
+{
+    __shared__ __align__(16) uint8_t in[BIN_R * BIN_P];
+    __shared__ uint16_t hb[BIN_R * BT_W];
+    const int tid = threadIdx.x;
+    const int frame = blockIdx.y;
+    // locate (level, tile)
+    int t = blockIdx.x, level = 0, tx_n = 0;
+#pragma unroll 1
+    for (int l = 0; l < fg.nlevels; ++l) {
+        tx_n = (fg.L[l].w + BT_W - 1) / BT_W;
+        const int nt = tx_n * ((fg.L[l].h + BT_H - 1) / BT_H);
+        if (t < nt) { level = l; break; }
+        t -= nt;
+    }
+    const LevelGeom& g = fg.L[level];
+    const int ty0 = (t / tx_n) * BT_H, tx0 = (t % tx_n) * BT_W;
+    const uint8_t* base = ws.pyr + g.pyr_off + (size_t)frame * g.pyr_frame_stride;   // bordered buffer origin
+    // input tile: buffer rows (ty0 - 3 + 19) .., buffer byte columns (tx0 - 4 + 32) ..  (4-byte aligned)
+    const int brow0 = ty0 - 3 + kEdge, bcol0 = tx0 - 4 + kXPad;
+    for (int i = tid; i < BIN_R * (BIN_P / 4); i += 256) {
+        const int r = i / (BIN_P / 4), w = i - r * (BIN_P / 4);
+        const int br = brow0 + r, bc = bcol0 + 4 * w;
+        uint32_t v = 0;
+        if (br < g.rows_alloc && bc + 4 <= g.pitch) v = __ldg(reinterpret_cast<const uint32_t*>(base + (size_t)br * g.pitch + bc));
+        reinterpret_cast<uint32_t*>(in)[r * (BIN_P / 4) + w] = v;
+    }
+    __syncthreads();
+    // horizontal pass: hb[r][x] = sum_k K[k] * in[r][x + 1 + k]   (x = 0..127 <-> image column tx0 + x)
+    {
+        const int x = tid & (BT_W - 1);
+        for (int r = tid >> 7; r < BIN_R; r += 2) {
+            const uint8_t* p = in + r * BIN_P + x + 1;
+            const int s = 18 * (p[0] + p[6]) + 34 * (p[1] + p[5]) + 48 * (p[2] + p[4]) + 56 * p[3];
+            hb[r * BT_W + x] = (uint16_t)s;
+        }
+    }
+    __syncthreads();
+    // vertical pass: thread = column x, 16 consecutive rows, sliding 7-register window
+    {
+        const int x = tid & (BT_W - 1);
+        const int r0 = (tid >> 7) * 16;
+        if (tx0 + x < g.w) {
+            uint8_t* out = ws.blur + g.blur_off + (size_t)frame * g.blur_frame_stride + (size_t)tx0 + x;
+            uint32_t w0 = hb[(r0 + 0) * BT_W + x], w1 = hb[(r0 + 1) * BT_W + x], w2 = hb[(r0 + 2) * BT_W + x],
+                     w3 = hb[(r0 + 3) * BT_W + x], w4 = hb[(r0 + 4) * BT_W + x], w5 = hb[(r0 + 5) * BT_W + x];
+#pragma unroll
+            for (int r = 0; r < 16; ++r) {
+                const uint32_t w6 = hb[(r0 + r + 6) * BT_W + x];
+                const uint32_t s = 18u * (w0 + w6) + 34u * (w1 + w5) + 48u * (w2 + w4) + 56u * w3;
+                const int y = ty0 + r0 + r;
+                if (y < g.h) out[(size_t)y * g.bpitch] = (uint8_t)((s + 32768u) >> 16);
+                w0 = w1; w1 = w2; w2 = w3; w3 = w4; w4 = w5; w5 = w6;
+            }
+        }
+    }
+}
+
+// grid = (ceil(kp_slots / 8), n_frames), 8 warps per CTA, one warp per keypoint slot.
+__global__ void __launch_bounds__(256) orient_describe_kernel(const __grid_constant__ FrameGeom fg, Workspace ws)
+{
+    const int lane = threadIdx.x & 31;
+    const int slot = blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int frame = blockIdx.y;
+    if (slot >= fg.kp_slots) return;
+    int level = 0;
+#pragma unroll 1
+    for (int l = 1; l < fg.nlevels; ++l)
+        if (slot >= fg.L[l].kp_base) level = l;
+    const LevelGeom& g = fg.L[level];
+    const int i = slot - g.kp_base;
+    if (i >= ws.lvl_n[(size_t)frame * fg.nlevels + level]) return;
+    const uint32_t key = ws.lvl_kp[(size_t)frame * fg.kp_slots + slot];
+    const int x = (int)(key & 0xfff) + kWinBorder, y = (int)((key >> 12) & 0xfff) + kWinBorder;
+
+    // ---- IC_Angle on the un-blurred level: lane <-> column u = lane - 15 ----
+    const uint8_t* img = level_interior((const uint8_t*)ws.pyr, g, frame) + (size_t)y * g.pitch + x;
+    int m10 = 0, m01 = 0;
+    {
+        const int u = lane - kHalfPatch;
+        if (lane < 31) {
+            const int au = u < 0 ? -u : u;
+#pragma unroll
+            for (int v = -kHalfPatch; v <= kHalfPatch; ++v) {
+                const int av = v < 0 ? -v : v;
+                if (au <= c_umax[av]) {
+                    const int val = __ldg(img + v * g.pitch + u);
+                    m10 += u * val;
+                    m01 += v * val;
+                }
+            }
+        }
+#pragma unroll
+        for (int d = 16; d >= 1; d >>= 1) {
+            m10 += __shfl_xor_sync(0xffffffffu, m10, d);
+            m01 += __shfl_xor_sync(0xffffffffu, m01, d);
+        }
+    }
+    const float angle = fast_atan2_dev((float)m01, (float)m10);
+
+    // ---- rBRIEF on the blurred level: lane <-> descriptor byte ----
+    const float factorPI = (float)(3.14159265358979323846 / 180.f);
+    const float arad = __fmul_rn(angle, factorPI);
+    const float a = (float)cos((double)arad), b = (float)sin((double)arad);
+    const uint8_t* center = ws.blur + g.blur_off + (size_t)frame * g.blur_frame_stride + (size_t)y * g.bpitch + x;
+    const int step = g.bpitch;
+    const uint4* pat4 = reinterpret_cast<const uint4*>(d_pattern) + lane * 2;
+    uint32_t val = 0;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const uint4 q = pat4[h];
+        const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {     // one test per 32-bit word: (x0, y0, x1, y1) int8
+            const float x0 = (float)(int8_t)(w[k] & 0xff), y0 = (float)(int8_t)((w[k] >> 8) & 0xff);
+            const float x1 = (float)(int8_t)((w[k] >> 16) & 0xff), y1 = (float)(int8_t)(w[k] >> 24);
+            const int iy0 = __float2int_rn(__fadd_rn(__fmul_rn(x0, b), __fmul_rn(y0, a)));
+            const int ix0 = __float2int_rn(__fsub_rn(__fmul_rn(x0, a), __fmul_rn(y0, b)));
+            const int iy1 = __float2int_rn(__fadd_rn(__fmul_rn(x1, b), __fmul_rn(y1, a)));
+            const int ix1 = __float2int_rn(__fsub_rn(__fmul_rn(x1, a), __fmul_rn(y1, b)));
+            const int t0 = __ldg(center + iy0 * step + ix0), t1 = __ldg(center + iy1 * step + ix1);
+            val |= (uint32_t)(t0 < t1) << (h * 4 + k);
+        }
+    }
+    ws.lvl_desc[((size_t)frame * fg.kp_slots + slot) * 32 + lane] = (uint8_t)val;
+    if (lane == 0) ws.lvl_angle[(size_t)frame * fg.kp_slots + slot] = angle;
+}
+
+// grid = n_frames, 256 threads: src/ORBextractor.cc:1283-1306.
+__global__ void __launch_bounds__(256) pack_kernel(const __grid_constant__ FrameGeom fg, Workspace ws, int lap0, int lap1,
+                                                   orbx_keypoint* __restrict__ kps, uint8_t* __restrict__ desc, int capacity,
+                                                   int* __restrict__ n_out, int* __restrict__ n_mono)
+{
+    __shared__ int lvl_off[kMaxLevels + 1];
+    __shared__ int warp_cnt[8];
+    __shared__ int carry;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int frame = blockIdx.x;
+    if (tid == 0) {
+        int o = 0;
+        for (int l = 0; l < fg.nlevels; ++l) { lvl_off[l] = o; o += ws.lvl_n[(size_t)frame * fg.nlevels + l]; }
+        lvl_off[fg.nlevels] = o;
+        carry = 0;
+    }
+    __syncthreads();
+    const int nkp = lvl_off[fg.nlevels];
+    if (nkp > capacity) {
+        if (tid == 0) { n_out[frame] = nkp; n_mono[frame] = -1; }
+        return;
+    }
+    orbx_keypoint* okp = kps + (size_t)frame * capacity;
+    uint8_t* odesc = desc + (size_t)frame * capacity * 32;
+    const float flap0 = (float)lap0, flap1 = (float)lap1;
+    for (int base = 0; base < nkp; base += 256) {
+        const int t = base + tid;
+        bool valid = t < nkp, stereo = false;
+        orbx_keypoint kp;
+        int slot = 0;
+        if (valid) {
+            int level = 0;
+            for (int l = 1; l < fg.nlevels; ++l)
+                if (t >= lvl_off[l]) level = l;
+            const LevelGeom& g = fg.L[level];
+            slot = g.kp_base + (t - lvl_off[level]);
+            const uint32_t key = ws.lvl_kp[(size_t)frame * fg.kp_slots + slot];
+            float px = (float)((int)(key & 0xfff) + kWinBorder), py = (float)((int)((key >> 12) & 0xfff) + kWinBorder);
+            if (level != 0) { px = __fmul_rn(px, g.scale); py = __fmul_rn(py, g.scale); }
+            kp.x = px; kp.y = py; kp.size = g.kp_size;
+            kp.angle = ws.lvl_angle[(size_t)frame * fg.kp_slots + slot];
+            kp.response = (float)(key >> 24);
+            kp.octave = level; kp.class_id = -1;
+            stereo = px >= flap0 && px <= flap1;
+        }
+        const uint32_t mS = __ballot_sync(0xffffffffu, valid && stereo);
+        const uint32_t mV = __ballot_sync(0xffffffffu, valid);
+        if (lane == 0) warp_cnt[warp] = __popc(mS);
+        __syncthreads();
+        int before = carry;            // stereo keypoints before this chunk
+        for (int w = 0; w < warp; ++w) before += warp_cnt[w];
+        const int sBefore = before + __popc(mS & ((1u << lane) - 1));
+        if (valid) {
+            const int dst = stereo ? (nkp - 1 - sBefore) : (t - sBefore);
+            okp[dst] = kp;
+            const uint4* s = reinterpret_cast<const uint4*>(ws.lvl_desc + ((size_t)frame * fg.kp_slots + slot) * 32);
+            uint4* d = reinterpret_cast<uint4*>(odesc + (size_t)dst * 32);
+            d[0] = s[0]; d[1] = s[1];
+        }
+        __syncthreads();
+        if (tid == 0) { int c = carry; for (int w = 0; w < 8; ++w) c += warp_cnt[w]; carry = c; }
+        __syncthreads();
+        (void)mV;
+    }
+    if (tid == 0) { n_out[frame] = nkp; n_mono[frame] = nkp - carry; }
+}
+
+cudaError_t launch_blur(const FrameGeom& fg, const Workspace& ws, int n_frames, cudaStream_t st)
+{
+    int tiles = 0;
+    for (int l = 0; l < fg.nlevels; ++l) tiles += ((fg.L[l].w + BT_W - 1) / BT_W) * ((fg.L[l].h + BT_H - 1) / BT_H);
+    dim3 grid(tiles, n_frames);
+    blur_kernel<<<grid, 256, 0, st>>>(fg, ws);
+    count_launch();
+    return cudaGetLastError();
+}
+
+cudaError_t launch_orient_describe(const FrameGeom& fg, const Workspace& ws, int n_frames, cudaStream_t st)
+{
+    dim3 grid((fg.kp_slots + 7) / 8, n_frames);
+    orient_describe_kernel<<<grid, 256, 0, st>>>(fg, ws);
+    count_launch();
+    return cudaGetLastError();
+}
+
+cudaError_t launch_pack(const FrameGeom& fg, const Workspace& ws, int n_frames, int lap0, int lap1, orbx_keypoint* d_kps,
+                        uint8_t* d_desc, int capacity, int* d_n_out, int* d_n_mono, cudaStream_t st)
+{
+    pack_kernel<<<n_frames, 256, 0, st>>>(fg, ws, lap0, lap1, d_kps, d_desc, capacity, d_n_out, d_n_mono);
+    count_launch();
+    return cudaGetLastError();
+}
+
+}  // namespace orbx

@@ -1,0 +1,410 @@
+// kernels_match.cu — Hamming matching on the integer pipe (LOP3 + POPC), never tensor cores.
+//
+//  * knn2_kernel:        brute-force 2-NN (cv::BFMatcher(NORM_HAMMING).knnMatch(k=2), reference src/Frame.cc:1174; same
+//                        (d1,i1,d2) as the strict-'<' best/second scans of src/ORBmatcher1.cc:283-300 and
+//                        src/ORBmatcher2.cc:84-118).  DescriptorDistance (src/ORBmatcher3.cc:637-653) = 8 x (XOR, POPC).
+//  * knn2_merge_kernel:  lexicographic (distance, index) merge of per-chunk / per-shard candidates.
+//  * stereo kernels:     Frame::ComputeStereoMatches (src/Frame.cc:841-1011).
+//  * popc_bench_kernel:  POPC issue-rate microbenchmark (roofline denominator for the matcher).
+#include <limits.h>
+
+#include "orbx_internal.cuh"
+#include "synth.h"
+
+namespace orbx {
+
+namespace {
+
+constexpr int KNN_THREADS = 128;
+constexpr int KNN_QT = 4;                       // queries per thread
+constexpr int KNN_QTILE = KNN_THREADS * KNN_QT; // queries per CTA
+constexpr int KNN_DTILE = 256;                  // database rows staged per shared-memory tile (8 KB)
+
+__device__ __forceinline__ void top2_update(int dist, int idx, int& d1, int& i1, int& d2, int& i2)
+{
+    if (dist < d2) {
+        if (dist < d1) { d2 = d1; i2 = i1; d1 = dist; i1 = idx; }
+        else { d2 = dist; i2 = idx; }
+    }
+}
+
+// lexicographic (d, i) insert used by the merges; idx < 0 = missing
+__device__ __forceinline__ void top2_merge(int dist, int idx, int& d1, int& i1, int& d2, int& i2)
+{
+    if (idx < 0) return;
+    const bool lt1 = dist < d1 || (dist == d1 && (i1 < 0 || idx < i1));
+    if (lt1) { d2 = d1; i2 = i1; d1 = dist; i1 = idx; return; }
+    const bool lt2 = dist < d2 || (dist == d2 && (i2 < 0 || idx < i2));
+    if (lt2) { d2 = dist; i2 = idx; }
+}
+
+}  // namespace
+
+// grid = (query tiles, db chunks).  Each thread owns KNN_QT queries in registers; the CTA streams its database chunk
+// through shared memory (every lane reads the same row -> broadcast LDS.128) and keeps (d1,i1,d2,i2) per query.
+__global__ void __launch_bounds__(KNN_THREADS) knn2_kernel(const uint32_t* __restrict__ q, int nq,
+                                                          const uint4* __restrict__ db, long long ndb, int index_base,
+                                                          long long rows_per_chunk, int32_t* __restrict__ out_idx,
+                                                          int32_t* __restrict__ out_dist)
+{
+    __shared__ uint4 tile[2][KNN_DTILE * 2];
+    const int tid = threadIdx.x;
+    const int q0 = blockIdx.x * KNN_QTILE;
+    const long long r_begin = (long long)blockIdx.y * rows_per_chunk;
+    long long r_end = r_begin + rows_per_chunk;
+    if (r_end > ndb) r_end = ndb;
+
+    uint32_t qw[KNN_QT][8];
+    int d1[KNN_QT], i1[KNN_QT], d2[KNN_QT], i2[KNN_QT];
+#pragma unroll
+    for (int j = 0; j < KNN_QT; ++j) {
+        const int qi = q0 + j * KNN_THREADS + tid;
+        const uint4* p = reinterpret_cast<const uint4*>(q + (size_t)(qi < nq ? qi : 0) * 8);
+        const uint4 a = __ldg(p), b = __ldg(p + 1);
+        qw[j][0] = a.x; qw[j][1] = a.y; qw[j][2] = a.z; qw[j][3] = a.w;
+        qw[j][4] = b.x; qw[j][5] = b.y; qw[j][6] = b.z; qw[j][7] = b.w;
+        d1[j] = INT_MAX; d2[j] = INT_MAX; i1[j] = -1; i2[j] = -1;
+    }
+
+    // software pipeline: prefetch tile t+1 into registers while computing tile t
+    const long long ntiles = (r_end - r_begin + KNN_DTILE - 1) / KNN_DTILE;
+    uint4 pre[4];
+    auto fetch = [&](long long t) {
+        const long long base = r_begin + t * KNN_DTILE;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int e = k * KNN_THREADS + tid;                 // uint4 index inside the tile (2 per row)
+            const long long row = base + (e >> 1);
+            pre[k] = row < r_end ? __ldg(db + row * 2 + (e & 1)) : make_uint4(0, 0, 0, 0);
+        }
+    };
+    auto stash = [&](int buf) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) tile[buf][k * KNN_THREADS + tid] = pre[k];
+    };
+    if (ntiles > 0) { fetch(0); stash(0); }
+    __syncthreads();
+    for (long long t = 0; t < ntiles; ++t) {
+        const int buf = (int)(t & 1);
+        if (t + 1 < ntiles) fetch(t + 1);
+        const long long base = r_begin + t * KNN_DTILE;
+        const int rows = (int)((r_end - base) < KNN_DTILE ? (r_end - base) : KNN_DTILE);
+#pragma unroll 2
+        for (int r = 0; r < rows; ++r) {
+            const uint4 a = tile[buf][2 * r], b = tile[buf][2 * r + 1];
+            const int gi = index_base + (int)(base + r);
+#pragma unroll
+            for (int j = 0; j < KNN_QT; ++j) {
+                const int dist = __popc(qw[j][0] ^ a.x) + __popc(qw[j][1] ^ a.y) + __popc(qw[j][2] ^ a.z) +
+                                 __popc(qw[j][3] ^ a.w) + __popc(qw[j][4] ^ b.x) + __popc(qw[j][5] ^ b.y) +
+                                 __popc(qw[j][6] ^ b.z) + __popc(qw[j][7] ^ b.w);
+                top2_update(dist, gi, d1[j], i1[j], d2[j], i2[j]);
+            }
+        }
+        if (t + 1 < ntiles) stash(buf ^ 1);
+        __syncthreads();
+    }
+#pragma unroll
+    for (int j = 0; j < KNN_QT; ++j) {
+        const int qi = q0 + j * KNN_THREADS + tid;
+        if (qi < nq) {
+            const size_t o = ((size_t)blockIdx.y * nq + qi) * 2;
+            out_idx[o] = i1[j]; out_idx[o + 1] = i2[j];
+            out_dist[o] = d1[j]; out_dist[o + 1] = d2[j];
+        }
+    }
+}
+
+__global__ void knn2_merge_kernel(const int32_t* __restrict__ idx_sh, const int32_t* __restrict__ dist_sh, int n_shards,
+                                  int nq, int32_t* __restrict__ idx, int32_t* __restrict__ dist)
+{
+    const int qi = blockIdx.x * blockDim.x + threadIdx.x;
+    if (qi >= nq) return;
+    int d1 = INT_MAX, d2 = INT_MAX, i1 = -1, i2 = -1;
+    for (int s = 0; s < n_shards; ++s) {
+        const size_t o = ((size_t)s * nq + qi) * 2;
+        top2_merge(dist_sh[o], idx_sh[o], d1, i1, d2, i2);
+        top2_merge(dist_sh[o + 1], idx_sh[o + 1], d1, i1, d2, i2);
+    }
+    idx[2 * (size_t)qi] = i1; idx[2 * (size_t)qi + 1] = i2;
+    dist[2 * (size_t)qi] = d1; dist[2 * (size_t)qi + 1] = d2;
+}
+
+static uint8_t* g_knn_partial[64] = {nullptr};
+static size_t g_knn_partial_bytes[64] = {0};
+
+cudaError_t launch_knn2(const uint8_t* d_q, int nq, const uint8_t* d_db, long long ndb, int index_base, int32_t* d_idx,
+                        int32_t* d_dist, cudaStream_t st)
+{
+    if (nq <= 0) return cudaSuccess;
+    const int qtiles = (nq + KNN_QTILE - 1) / KNN_QTILE;
+    // chunk the database so that the grid has a few thousand CTAs but every chunk is long enough to amortise the
+    // query load / result store
+    int chunks = 1;
+    if (ndb > 0) {
+        const long long target_ctas = 148LL * 16;
+        long long want = (target_ctas + qtiles - 1) / qtiles;
+        const long long max_chunks = (ndb + 4095) / 4096;
+        if (want > max_chunks) want = max_chunks;
+        if (want < 1) want = 1;
+        if (want > 1024) want = 1024;
+        chunks = (int)want;
+    }
+    long long rows_per_chunk = ndb > 0 ? (ndb + chunks - 1) / chunks : 1;
+    rows_per_chunk = (rows_per_chunk + KNN_DTILE - 1) / KNN_DTILE * KNN_DTILE;
+    chunks = ndb > 0 ? (int)((ndb + rows_per_chunk - 1) / rows_per_chunk) : 1;
+    int32_t* p_idx = d_idx;
+    int32_t* p_dist = d_dist;
+    if (chunks > 1) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        dev &= 63;
+        const size_t need = (size_t)chunks * nq * 2 * sizeof(int32_t) * 2;
+        if (g_knn_partial_bytes[dev] < need) {
+            if (g_knn_partial[dev]) cudaFree(g_knn_partial[dev]);
+            g_knn_partial[dev] = nullptr; g_knn_partial_bytes[dev] = 0;
+            cudaError_t e = cudaMalloc(&g_knn_partial[dev], need);
+            if (e != cudaSuccess) return e;
+            g_knn_partial_bytes[dev] = need;
+        }
+        p_idx = reinterpret_cast<int32_t*>(g_knn_partial[dev]);
+        p_dist = p_idx + (size_t)chunks * nq * 2;
+    }
+    dim3 grid(qtiles, chunks);
+    knn2_kernel<<<grid, KNN_THREADS, 0, st>>>(reinterpret_cast<const uint32_t*>(d_q), nq,
+                                              reinterpret_cast<const uint4*>(d_db), ndb, index_base, rows_per_chunk, p_idx,
+                                              p_dist);
+    count_launch();
+    if (chunks > 1) {
+        knn2_merge_kernel<<<(nq + 255) / 256, 256, 0, st>>>(p_idx, p_dist, chunks, nq, d_idx, d_dist);
+        count_launch();
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t launch_knn2_merge(const int32_t* d_idx_sh, const int32_t* d_dist_sh, int n_shards, int nq, int32_t* d_idx,
+                              int32_t* d_dist, cudaStream_t st)
+{
+    if (nq <= 0) return cudaSuccess;
+    knn2_merge_kernel<<<(nq + 255) / 256, 256, 0, st>>>(d_idx_sh, d_dist_sh, n_shards, nq, d_idx, d_dist);
+    count_launch();
+    return cudaGetLastError();
+}
+
+// ---- POPC issue-rate microbenchmark: 8 independent dependent-chains per thread ------------------------------------
+__global__ void __launch_bounds__(256) popc_bench_kernel(unsigned long long* sink, int iters)
+{
+    uint32_t x[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) x[k] = (threadIdx.x * 2654435761u) ^ (blockIdx.x * 40503u + k * 0x9E3779B9u);
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) x[k] = __popc(x[k]) ^ (0xA5A5A5A5u << k);
+    }
+    uint32_t s = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s += x[k];
+    if (s == 0x12345678u) sink[0] = s;   // practically never; keeps the chain alive
+}
+
+cudaError_t launch_popc_bench(unsigned long long* d_sink, int iters, int blocks, cudaStream_t st)
+{
+    popc_bench_kernel<<<blocks, 256, 0, st>>>(d_sink, iters);
+    count_launch();
+    return cudaGetLastError();
+}
+
+// ---- stereo ---------------------------------------------------------------------------------------------------------
+namespace {
+
+__device__ __forceinline__ int hamming256(const uint32_t* a, const uint32_t* b)
+{
+    int d = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) d += __popc(a[k] ^ b[k]);
+    return d;
+}
+
+}  // namespace
+
+// one warp per left keypoint (src/Frame.cc:881-995)
+__global__ void __launch_bounds__(256) stereo_match_kernel(const __grid_constant__ FrameGeom fg, StereoArgs A)
+{
+    __shared__ int s_sad[8][12];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int iL = blockIdx.x * 8 + warp;
+    if (iL >= A.nL) return;
+    const int TH_HIGH = 100, TH_LOW = 50;
+    const int thOrbDist = (TH_HIGH + TH_LOW) / 2;
+    const orbx_keypoint kL = A.kpL[iL];
+    const int levelL = kL.octave;
+    const float vL = kL.y, uL = kL.x;
+    float out_u = -1.0f, out_d = -1.0f;
+    int out_sad = -1;
+    const float minD = 0.f, maxD = A.maxD;
+    const float minU = __fsub_rn(uL, maxD), maxU = __fsub_rn(uL, minD);
+    if (!(maxU < 0)) {
+        const int row = (int)vL;
+        uint32_t dl[8];
+        const uint32_t* pl = reinterpret_cast<const uint32_t*>(A.descL + (size_t)iL * 32);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) dl[k] = __ldg(pl + k);
+        // best = min over (dist, iR): the reference scans row buckets in ascending iR with strict '<'
+        unsigned best = 0xffffffffu;
+        for (int iR = lane; iR < A.nR; iR += 32) {
+            const orbx_keypoint kR = A.kpR[iR];
+            const float r = __fmul_rn(2.0f, fg.L[kR.octave].scale);
+            const int maxr = (int)ceilf(__fadd_rn(kR.y, r));
+            const int minr = (int)floorf(__fsub_rn(kR.y, r));
+            if (row < minr || row > maxr) continue;
+            if (kR.octave < levelL - 1 || kR.octave > levelL + 1) continue;
+            if (kR.x >= minU && kR.x <= maxU) {
+                const int dist = hamming256(dl, reinterpret_cast<const uint32_t*>(A.descR + (size_t)iR * 32));
+                if (dist < TH_HIGH) best = min(best, ((unsigned)dist << 20) | (unsigned)iR);
+            }
+        }
+#pragma unroll
+        for (int d = 16; d >= 1; d >>= 1) best = min(best, __shfl_xor_sync(0xffffffffu, best, d));
+        const int bestDist = best == 0xffffffffu ? TH_HIGH : (int)(best >> 20);
+        if (bestDist < thOrbDist) {
+            const int bestIdxR = (int)(best & 0xfffffu);
+            const float uR0 = A.kpR[bestIdxR].x;
+            const LevelGeom& g = fg.L[levelL];
+            const float sf = g.inv_scale;
+            const float scaleduL = roundf(__fmul_rn(kL.x, sf));
+            const float scaledvL = roundf(__fmul_rn(kL.y, sf));
+            const float scaleduR0 = roundf(__fmul_rn(uR0, sf));
+            const int w = 5, L = 5;
+            const float iniu = scaleduR0 + L - w;
+            const float endu = scaleduR0 + L + w + 1;
+            if (!(iniu < 0 || endu >= g.w)) {
+                const uint8_t* IL = level_interior(A.pyrL, g, A.frameL);
+                const uint8_t* IR = level_interior(A.pyrR, g, A.frameR);
+                if (lane < 11) s_sad[warp][lane] = 0;
+                __syncwarp();
+                const int cu = (int)scaleduL, cv = (int)scaledvL, cr = (int)scaleduR0;
+                for (int task = lane; task < 121; task += 32) {
+                    const int inc = task / 11 - L, dy = task % 11 - w;
+                    const uint8_t* pl2 = IL + (ptrdiff_t)(cv + dy) * g.pitch + (cu - w);
+                    const uint8_t* pr2 = IR + (ptrdiff_t)(cv + dy) * g.pitch + (cr + inc - w);
+                    int acc = 0;
+#pragma unroll
+                    for (int dx = 0; dx < 11; ++dx) acc += abs((int)__ldg(pl2 + dx) - (int)__ldg(pr2 + dx));
+                    atomicAdd(&s_sad[warp][inc + L], acc);
+                }
+                __syncwarp();
+                int bestS = INT_MAX, bestinc = 0;
+                for (int k = 0; k < 11; ++k) {
+                    const float dist = (float)s_sad[warp][k];
+                    if (dist < (float)bestS) { bestS = (int)dist; bestinc = k - L; }
+                }
+                if (!(bestinc == -L || bestinc == L)) {
+                    const float dist1 = (float)s_sad[warp][L + bestinc - 1];
+                    const float dist2 = (float)s_sad[warp][L + bestinc];
+                    const float dist3 = (float)s_sad[warp][L + bestinc + 1];
+                    const float deltaR = __fdiv_rn(__fsub_rn(dist1, dist3),
+                                                   __fmul_rn(2.0f, __fsub_rn(__fadd_rn(dist1, dist3), __fmul_rn(2.0f, dist2))));
+                    if (!(deltaR < -1 || deltaR > 1)) {
+                        float bestuR = __fmul_rn(g.scale, __fadd_rn(__fadd_rn(scaleduR0, (float)bestinc), deltaR));
+                        float disparity = __fsub_rn(uL, bestuR);
+                        if (disparity >= minD && disparity < maxD) {
+                            if (disparity <= 0) { disparity = 0.01f; bestuR = (float)((double)uL - 0.01); }
+                            out_d = __fdiv_rn(A.bf, disparity);
+                            out_u = bestuR;
+                            out_sad = bestS;
+                        }
+                    }
+                }
+            }
+        }
+    }
+    if (lane == 0) { A.uRight[iL] = out_u; A.depth[iL] = out_d; A.sad[iL] = out_sad; }
+}
+
+// single CTA: median filter of src/Frame.cc:997-1010
+__global__ void __launch_bounds__(1024) stereo_median_kernel(StereoArgs A)
+{
+    __shared__ int s_n, s_median;
+    const int tid = threadIdx.x;
+    if (tid == 0) { s_n = 0; s_median = -1; }
+    __syncthreads();
+    int cnt = 0;
+    for (int i = tid; i < A.nL; i += 1024) cnt += A.sad[i] >= 0;
+    atomicAdd(&s_n, cnt);
+    __syncthreads();
+    const int n = s_n;
+    if (n == 0) return;
+    const int target = n / 2;
+    // rank of element i in the sorted (sad, iL) list
+    for (int i = tid; i < A.nL; i += 1024) {
+        const int si = A.sad[i];
+        if (si < 0) continue;
+        int rank = 0;
+        for (int j = 0; j < A.nL; ++j) {
+            const int sj = A.sad[j];
+            if (sj < 0) continue;
+            rank += (sj < si) || (sj == si && j < i);
+        }
+        if (rank == target) s_median = si;
+    }
+    __syncthreads();
+    const float median = (float)s_median;
+    const float thDist = 1.5f * 1.4f * median;
+    for (int i = tid; i < A.nL; i += 1024) {
+        const int si = A.sad[i];
+        if (si >= 0 && !((float)si < thDist)) { A.uRight[i] = -1.f; A.depth[i] = -1.f; }
+    }
+}
+
+cudaError_t launch_stereo(const FrameGeom& fg, const StereoArgs& a, cudaStream_t st)
+{
+    if (a.nL <= 0) return cudaSuccess;
+    stereo_match_kernel<<<(a.nL + 7) / 8, 256, 0, st>>>(fg, a);
+    count_launch();
+    stereo_median_kernel<<<1, 1024, 0, st>>>(a);
+    count_launch();
+    return cudaGetLastError();
+}
+
+// ---- synthetic inputs ---------------------------------------------------------------------------------------------------
+__global__ void synth_images_kernel(uint32_t seed0, int view, int cols, int rows, int max_disp, uint8_t* dst, size_t pitch,
+                                    size_t frame_stride)
+{
+    const int x4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    const int y = blockIdx.y, f = blockIdx.z;
+    if (x4 >= cols) return;
+    uint8_t* row = dst + (size_t)f * frame_stride + (size_t)y * pitch;
+    for (int j = 0; j < 4 && x4 + j < cols; ++j) row[x4 + j] = orbx_synth::image_pixel(seed0 + (uint32_t)f, view, x4 + j, y, max_disp);
+}
+
+cudaError_t launch_synth_images(uint32_t seed0, int view, int n_frames, int cols, int rows, int max_disp, uint8_t* d_dst,
+                                size_t pitch, size_t frame_stride, cudaStream_t st)
+{
+    dim3 grid(((cols + 3) / 4 + 127) / 128, rows, n_frames);
+    synth_images_kernel<<<grid, 128, 0, st>>>(seed0, view, cols, rows, max_disp, d_dst, pitch, frame_stride);
+    count_launch();
+    return cudaGetLastError();
+}
+
+__global__ void synth_desc_kernel(uint32_t seed, int is_query, long long first_row, long long n_rows, long long ndb,
+                                  int plant_every, uint32_t* dst)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // word index
+    if (i >= n_rows * 8) return;
+    const uint32_t row = (uint32_t)(first_row + (i >> 3)), w = (uint32_t)(i & 7);
+    dst[i] = is_query ? orbx_synth::query_word(seed, row, w, (uint32_t)ndb, (uint32_t)plant_every)
+                      : orbx_synth::desc_word(seed, row, w);
+}
+
+cudaError_t launch_synth_desc(uint32_t seed, int is_query, long long first_row, long long n_rows, long long ndb,
+                              int plant_every, uint8_t* d_dst, cudaStream_t st)
+{
+    if (n_rows <= 0) return cudaSuccess;
+    const long long words = n_rows * 8;
+    synth_desc_kernel<<<(unsigned)((words + 255) / 256), 256, 0, st>>>(seed, is_query, first_row, n_rows, ndb, plant_every,
+                                                                       reinterpret_cast<uint32_t*>(d_dst));
+    count_launch();
+    return cudaGetLastError();
+}
+
+}  // namespace orbx

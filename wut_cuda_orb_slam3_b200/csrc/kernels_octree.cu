@@ -1,0 +1,466 @@
+// kernels_octree.cu — ORBextractor::DistributeOctTree (reference src/ORBextractor.cc:584-774, DivideNode 515-567,
+// compareNodes 569-582) as a deterministic array algorithm: one CTA per (frame, level).
+//
+// Reformulation (bit-exact, see DESIGN.md "Octree"):
+//  * A key's path through the quadtree depends only on geometry: root = (int)(x / hX), then at every depth the
+//    quadrant given by x < UL.x + ceil(w/2), y < UL.y + ceil(h/2).  Every key gets a path code (root, 2 bits per depth,
+//    n1=0,n2=1,n3=2,n4=3).  One STABLE LSD radix sort by path code makes every node of every depth a contiguous
+//    segment whose keys keep their original (cell-major, y, x) order — exactly what DivideNode's stable 4-way
+//    partition produces — and the four children of a node are its four sub-segments, found by binary search.
+//  * The std::list is an array in list order.  A sweep that splits a set of nodes processed in the order p=0..nS-1
+//    turns the list into [children(p=nS-1) n4..n1, ..., children(p=0) n4..n1, untouched nodes in old order]
+//    (every split push_front()s its non-empty children n1..n4 and erases the parent).  Positions come from prefix sums.
+//  * Phase 1 (src 635-693) splits every node with >1 key in list order.  Phase 2 (699-752) sorts the expandable
+//    nodes with std::sort(compareNodes) — replayed exactly (introsort_replay.h) because ties are broken by the
+//    algorithm's internal permutation — and splits from the back until size >= N.
+//  * Retain (756-771): first key with maximal response per node, in list order.
+#include "introsort_replay.h"
+#include "orbx_internal.cuh"
+
+namespace orbx {
+
+namespace {
+
+constexpr int T = 256;                     // threads per CTA
+constexpr int kHistWords = 16 * T + (16 * T) / 32;
+
+struct Smem {
+    // carved from dynamic shared memory; M = node capacity
+    uint32_t* hist;        // [kHistWords]
+    int* warp_tmp;         // [64]
+    uint32_t* nbeg[2];     // node segment begin           [M] x2 (ping-pong)
+    uint32_t* ncnt[2];     // node key count
+    uint32_t* nx[2];       // ULx | URx << 16
+    uint32_t* ndep[2];     // depth
+    uint32_t* cc;          // [4*M] child counts of processed node p: cc[4*p+k]
+    int* sa;               // [M] scan scratch a
+    int* sb;               // [M] scan scratch b
+    int* sc;               // [M] scan scratch c
+    int* sd;               // [M] scratch d
+    int* procpos;          // [M] list position of the p-th processed node
+    orbx_sort::item_t* vec;   // [M] expandable nodes, creation order: (cnt<<13 | ULx) << 32 | list position
+    orbx_sort::item_t* vec2;  // [M]
+};
+
+// Exclusive prefix sum of a[0..n) in place (int), returns the total.  All T threads must call.
+__device__ int block_exclusive_scan(int* a, int n, int* warp_tmp)
+{
+    __shared__ int carry;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) carry = 0;
+    __syncthreads();
+    for (int base = 0; base < n; base += T) {
+        const int i = base + tid;
+        const int v = i < n ? a[i] : 0;
+        int incl = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += t;
+        }
+        if (lane == 31) warp_tmp[warp] = incl;
+        __syncthreads();
+        int woff = 0;
+        for (int w = 0; w < warp; ++w) woff += warp_tmp[w];
+        const int c = carry;
+        if (i < n) a[i] = c + woff + incl - v;
+        __syncthreads();
+        if (tid == T - 1) carry = c + woff + incl;
+        __syncthreads();
+    }
+    return carry;
+}
+
+// Path code of a key (window-relative x, y).
+__device__ __forceinline__ uint32_t path_code(int x, int y, const LevelGeom& g, int winH)
+{
+    const int r = (int)__fdiv_rn((float)x, g.hX);                      // vpIniNodes[kp.pt.x / hX]   (src 613)
+    int ulx = (int)__fmul_rn(g.hX, (float)r), urx = (int)__fmul_rn(g.hX, (float)(r + 1));   // src 602-603
+    int uly = 0, bry = winH;
+    uint32_t code = (uint32_t)r;
+    for (int d = 0; d < g.depth; ++d) {
+        const int mx = ulx + ((urx - ulx + 1) >> 1);                   // UL.x + ceil((UR.x-UL.x)/2)   (src 517)
+        const int my = uly + ((bry - uly + 1) >> 1);
+        const uint32_t qx = x >= mx, qy = y >= my;                     // src 546-557
+        code = (code << 2) | qx | (qy << 1);
+        if (qx) ulx = mx; else urx = mx;
+        if (qy) uly = my; else bry = my;
+    }
+    return code;
+}
+
+// first index in [lo, hi) with (codes[i] >> shift) >= v
+__device__ __forceinline__ uint32_t lower_bound_code(const uint32_t* codes, uint32_t lo, uint32_t hi, int shift, uint32_t v)
+{
+    while (lo < hi) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if ((codes[mid] >> shift) < v) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
+}  // namespace
+
+size_t octree_smem_bytes(int M)
+{
+    size_t b = 0;
+    b += sizeof(uint32_t) * kHistWords;
+    b += sizeof(int) * 64;
+    b += sizeof(uint32_t) * (size_t)M * 8;      // node arrays x2
+    b += sizeof(uint32_t) * (size_t)M * 4;      // cc
+    b += sizeof(int) * (size_t)M * 5;           // sa, sb, sc, sd, procpos
+    b += 8;                                     // alignment slack
+    b += sizeof(orbx_sort::item_t) * (size_t)M * 2;
+    return b;
+}
+
+// grid = (nlevels, n_frames); dynamic smem sized for the largest level's node capacity.
+__global__ void __launch_bounds__(T) octree_kernel(const __grid_constant__ FrameGeom fg, Workspace ws, int M,
+                                                   int* __restrict__ err_flag)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ int s_nL, s_nS, s_total;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int level = blockIdx.x, frame = blockIdx.y;
+    const LevelGeom& g = fg.L[level];
+    const int N = g.nfeat;
+    const int winW = g.w - 2 * kWinBorder, winH = g.h - 2 * kWinBorder;
+
+    Smem S;
+    {
+        unsigned char* p = smem_raw;
+        S.hist = (uint32_t*)p; p += sizeof(uint32_t) * kHistWords;
+        S.warp_tmp = (int*)p; p += sizeof(int) * 64;
+        for (int b = 0; b < 2; ++b) {
+            S.nbeg[b] = (uint32_t*)p; p += 4 * (size_t)M;
+            S.ncnt[b] = (uint32_t*)p; p += 4 * (size_t)M;
+            S.nx[b] = (uint32_t*)p; p += 4 * (size_t)M;
+            S.ndep[b] = (uint32_t*)p; p += 4 * (size_t)M;
+        }
+        S.cc = (uint32_t*)p; p += 16 * (size_t)M;
+        S.sa = (int*)p; p += 4 * (size_t)M;
+        S.sb = (int*)p; p += 4 * (size_t)M;
+        S.sc = (int*)p; p += 4 * (size_t)M;
+        S.sd = (int*)p; p += 4 * (size_t)M;
+        S.procpos = (int*)p; p += 4 * (size_t)M;
+        p = (unsigned char*)(((uintptr_t)p + 7) & ~(uintptr_t)7);
+        S.vec = (orbx_sort::item_t*)p; p += 8 * (size_t)M;
+        S.vec2 = (orbx_sort::item_t*)p;
+    }
+
+    int* out_n = ws.lvl_n + (size_t)frame * fg.nlevels + level;
+    int* out_ncand = ws.lvl_ncand + (size_t)frame * fg.nlevels + level;
+    uint32_t* out_kp = ws.lvl_kp + (size_t)frame * fg.kp_slots + g.kp_base;
+
+    const int ncells = g.nCols * g.nRows;
+    if (ncells <= 0 || g.nIni <= 0 || winW <= 0 || winH <= 0) {
+        if (tid == 0) { *out_n = 0; *out_ncand = 0; }
+        return;
+    }
+
+    // ---- 0. gather the level's candidates in cell-major order, compute path codes ------------------------------
+    uint32_t* scratch = ws.oct + (size_t)frame * fg.oct_frame_stride + g.oct_off;
+    const int nmax = g.cand_max;
+    uint32_t* keys[2] = {scratch, scratch + nmax};
+    uint32_t* codes[2] = {scratch + 2 * (size_t)nmax, scratch + 3 * (size_t)nmax};
+    int* cell_off = (int*)(scratch + 4 * (size_t)nmax);                     // [ncells]
+    const int* cell_count = ws.cell_count + (size_t)frame * fg.total_cells + g.cell_base;
+    for (int c = tid; c < ncells; c += T) cell_off[c] = cell_count[c];
+    __syncthreads();
+    const int n = block_exclusive_scan(cell_off, ncells, S.warp_tmp);
+    if (tid == 0) *out_ncand = n;
+    if (n == 0) {
+        if (tid == 0) *out_n = 0;
+        return;
+    }
+    {
+        const uint32_t* cand = ws.cand + (size_t)frame * fg.cand_frame_stride + g.cand_off;
+        for (int c = warp; c < ncells; c += T / 32) {
+            const int cnt = cell_count[c], o = cell_off[c];
+            const uint32_t* src = cand + (size_t)c * g.cell_cap;
+            for (int i = lane; i < cnt; i += 32) {
+                const uint32_t k = src[i];
+                keys[0][o + i] = k;
+                codes[0][o + i] = path_code((int)(k & 0xfff), (int)((k >> 12) & 0xfff), g, winH);
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- 1. stable LSD radix sort of (code, key) by code, 4 bits per pass ---------------------------------------
+    int cur = 0;
+    {
+        const int nbits = 2 * g.depth + g.root_bits;
+        const int ipt = (n + T - 1) / T;
+        const int i0 = min(tid * ipt, n), i1 = min(i0 + ipt, n);
+        for (int shift = 0; shift < nbits; shift += 4) {
+            for (int i = tid; i < kHistWords; i += T) S.hist[i] = 0;
+            __syncthreads();
+            const uint32_t* cin = codes[cur];
+            for (int i = i0; i < i1; ++i) {
+                const int d = (cin[i] >> shift) & 15;
+                const int idx = d * T + tid;
+                S.hist[idx + (idx >> 5)]++;
+            }
+            __syncthreads();
+            // exclusive scan of the 16*T counters in (digit-major, thread-minor) order: padded raking
+            {
+                int sum = 0;
+                const int b = tid * 16;
+#pragma unroll
+                for (int k = 0; k < 16; ++k) sum += S.hist[b + k + ((b + k) >> 5)];
+                int incl = sum;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const int t = __shfl_up_sync(0xffffffffu, incl, d);
+                    if (lane >= d) incl += t;
+                }
+                if (lane == 31) S.warp_tmp[warp] = incl;
+                __syncthreads();
+                int woff = 0;
+                for (int w = 0; w < warp; ++w) woff += S.warp_tmp[w];
+                int run = woff + incl - sum;
+#pragma unroll
+                for (int k = 0; k < 16; ++k) {
+                    const int a = b + k + ((b + k) >> 5);
+                    const int v = S.hist[a];
+                    S.hist[a] = run;
+                    run += v;
+                }
+            }
+            __syncthreads();
+            const uint32_t* kin = keys[cur];
+            uint32_t* cout_ = codes[cur ^ 1];
+            uint32_t* kout = keys[cur ^ 1];
+            for (int i = i0; i < i1; ++i) {
+                const uint32_t c = cin[i];
+                const int d = (c >> shift) & 15;
+                const int idx = d * T + tid;
+                const int pos = S.hist[idx + (idx >> 5)]++;
+                cout_[pos] = c;
+                kout[pos] = kin[i];
+            }
+            cur ^= 1;
+            __syncthreads();
+        }
+    }
+    const uint32_t* K = keys[cur];
+    const uint32_t* C = codes[cur];
+
+    // ---- 2. root nodes (src 589-626) --------------------------------------------------------------------------------
+    int a = 0;   // active node buffer
+    {
+        const int rshift = 2 * g.depth;
+        if (tid < g.nIni) {
+            const uint32_t lo = lower_bound_code(C, 0, n, rshift, tid), hi = lower_bound_code(C, 0, n, rshift, tid + 1);
+            S.sa[tid] = hi > lo ? 1 : 0;
+            S.cc[4 * tid] = lo; S.cc[4 * tid + 1] = hi - lo;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            int m = 0;
+            for (int r = 0; r < g.nIni; ++r)
+                if (S.sa[r]) {
+                    S.nbeg[a][m] = S.cc[4 * r]; S.ncnt[a][m] = S.cc[4 * r + 1];
+                    const int ulx = (int)__fmul_rn(g.hX, (float)r), urx = (int)__fmul_rn(g.hX, (float)(r + 1));
+                    S.nx[a][m] = (uint32_t)ulx | ((uint32_t)urx << 16);
+                    S.ndep[a][m] = 0;
+                    ++m;
+                }
+            s_nL = m;
+        }
+        __syncthreads();
+    }
+
+    // Computes the children of the node at list position `pos` into cc[4*p..]; returns (#non-empty) | (#expandable << 8).
+    auto split_counts = [&](int p, int pos) -> int {
+        const uint32_t beg = S.nbeg[a][pos], cnt = S.ncnt[a][pos];
+        const int dep = (int)S.ndep[a][pos];
+        int ne = 0, nx = 0;
+        if (dep >= g.depth) {           // cannot happen for distinct pixels (depth is sized for it); flag, keep the node whole
+            atomicExch(err_flag, 1);
+            S.cc[4 * p] = cnt; S.cc[4 * p + 1] = S.cc[4 * p + 2] = S.cc[4 * p + 3] = 0;
+            return 1 | ((cnt > 1 ? 1 : 0) << 8);
+        }
+        const int shift = 2 * (g.depth - 1 - dep);
+        const uint32_t prefix = (C[beg] >> shift) & ~3u;
+        const uint32_t e = beg + cnt;
+        const uint32_t b1 = lower_bound_code(C, beg, e, shift, prefix | 1u);
+        const uint32_t b2 = lower_bound_code(C, b1, e, shift, prefix | 2u);
+        const uint32_t b3 = lower_bound_code(C, b2, e, shift, prefix | 3u);
+        const uint32_t c0 = b1 - beg, c1 = b2 - b1, c2 = b3 - b2, c3 = e - b3;
+        S.cc[4 * p] = c0; S.cc[4 * p + 1] = c1; S.cc[4 * p + 2] = c2; S.cc[4 * p + 3] = c3;
+        ne = (c0 > 0) + (c1 > 0) + (c2 > 0) + (c3 > 0);
+        nx = (c0 > 1) + (c1 > 1) + (c2 > 1) + (c3 > 1);
+        return ne | (nx << 8);
+    };
+
+    // Applies the splits of processed nodes p = 0..nS-1 (list positions procpos[p], child counts in cc, sa[p] = #non-empty,
+    // sb[p] = #expandable), builds the new list in buffer a^1 and the new expandable vector in `vout`.
+    // Returns new list size via s_nL and the new vector length via s_total.
+    auto apply_splits = [&](int nL, int nS, orbx_sort::item_t* vout) {
+        const int b = a ^ 1;
+        // keep flags: sc[pos] = 1 for untouched nodes
+        for (int i = tid; i < nL; i += T) S.sc[i] = 1;
+        __syncthreads();
+        for (int p = tid; p < nS; p += T) S.sc[S.procpos[p]] = 0;
+        __syncthreads();
+        const int nKeep = block_exclusive_scan(S.sc, nL, S.warp_tmp);          // sc[pos] = rank among kept (valid where kept)
+        // we still need to know which were kept: recompute from procpos by marking with -1-rank
+        for (int p = tid; p < nS; p += T) S.sc[S.procpos[p]] = -1;
+        __syncthreads();
+        // per-p child bookkeeping: stash ne/nx because the scans overwrite sa/sb
+        int* packed = S.sd;
+        for (int p = tid; p < nS; p += T) packed[p] = S.sa[p] | (S.sb[p] << 8);
+        __syncthreads();
+        const int Stot = block_exclusive_scan(S.sa, nS, S.warp_tmp);           // sa[p] = sum_{p'<p} ne
+        const int Etot = block_exclusive_scan(S.sb, nS, S.warp_tmp);           // sb[p] = sum_{p'<p} nx
+        for (int p = tid; p < nS; p += T) {
+            const int pos = S.procpos[p];
+            const int ne = packed[p] & 0xff;
+            const uint32_t beg = S.nbeg[a][pos];
+            const uint32_t x = S.nx[a][pos];
+            const int ulx = (int)(x & 0xffff), urx = (int)(x >> 16);
+            const int mx = ulx + ((urx - ulx + 1) >> 1);
+            const uint32_t dep = S.ndep[a][pos] + 1;
+            const uint32_t c0 = S.cc[4 * p], c1 = S.cc[4 * p + 1], c2 = S.cc[4 * p + 2], c3 = S.cc[4 * p + 3];
+            const uint32_t cb[4] = {beg, beg + c0, beg + c0 + c1, beg + c0 + c1 + c2};
+            const uint32_t cn[4] = {c0, c1, c2, c3};
+            const uint32_t cx[4] = {(uint32_t)ulx | ((uint32_t)mx << 16), (uint32_t)mx | ((uint32_t)urx << 16),
+                                    (uint32_t)ulx | ((uint32_t)mx << 16), (uint32_t)mx | ((uint32_t)urx << 16)};
+            // group start: groups of later-processed nodes come first
+            const int gstart = Stot - (S.sa[p] + ne);
+            int slot = gstart, vslot = S.sb[p];
+            int posk[4];
+#pragma unroll
+            for (int k = 3; k >= 0; --k) {            // list order inside the group: n4, n3, n2, n1
+                posk[k] = -1;
+                if (cn[k] > 0) {
+                    S.nbeg[b][slot] = cb[k]; S.ncnt[b][slot] = cn[k]; S.nx[b][slot] = cx[k]; S.ndep[b][slot] = dep;
+                    posk[k] = slot++;
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k)               // creation order of vSizeAndPointerToNode: n1..n4 with > 1 key
+                if (cn[k] > 1)
+                    vout[vslot++] = orbx_sort::make_item(((orbx_sort::item_t)cn[k] << 13) | (cx[k] & 0xffff), (uint32_t)posk[k]);
+        }
+        for (int i = tid; i < nL; i += T) {
+            const int r = S.sc[i];
+            if (r >= 0) {
+                const int slot = Stot + r;
+                S.nbeg[b][slot] = S.nbeg[a][i]; S.ncnt[b][slot] = S.ncnt[a][i]; S.nx[b][slot] = S.nx[a][i];
+                S.ndep[b][slot] = S.ndep[a][i];
+            }
+        }
+        __syncthreads();
+        if (tid == 0) { s_nL = Stot + nKeep; s_total = Etot; }
+        __syncthreads();
+        a = b;
+    };
+
+    // ---- 3. main loop (src 635-753) ---------------------------------------------------------------------------------
+    bool finish = false;
+    while (!finish) {
+        int nL = s_nL;
+        const int prevSize = nL;
+        // phase-1 sweep: every node with more than one key, in list order
+        for (int i = tid; i < nL; i += T) S.sc[i] = S.ncnt[a][i] > 1 ? 1 : 0;
+        __syncthreads();
+        const int nS = block_exclusive_scan(S.sc, nL, S.warp_tmp);
+        for (int i = tid; i < nL; i += T)
+            if (S.ncnt[a][i] > 1) S.procpos[S.sc[i]] = i;
+        __syncthreads();
+        for (int p = tid; p < nS; p += T) {
+            const int r = split_counts(p, S.procpos[p]);
+            S.sa[p] = r & 0xff; S.sb[p] = r >> 8;
+        }
+        __syncthreads();
+        apply_splits(nL, nS, S.vec);
+        nL = s_nL;
+        int nToExpand = s_total;
+        if (nL >= N || nL == prevSize) {
+            finish = true;
+        } else if (nL + nToExpand * 3 > N) {
+            // phase 2
+            orbx_sort::item_t* vprev = S.vec;
+            orbx_sort::item_t* vnext = S.vec2;
+            while (!finish) {
+                const int prev2 = nL;
+                const int m = nToExpand;
+                if (tid == 0) orbx_sort::sort_replay(vprev, m);            // std::sort(compareNodes)  (src 709)
+                __syncthreads();
+                // processing order p = 0..m-1 walks the sorted vector from the back (src 710)
+                for (int p = tid; p < m; p += T) {
+                    const int pos = (int)orbx_sort::payload(vprev[m - 1 - p]);
+                    S.procpos[p] = pos;
+                    const int r = split_counts(p, pos);
+                    S.sa[p] = r & 0xff; S.sb[p] = r >> 8;
+                    S.sc[p] = (r & 0xff) - 1;                               // list growth of this split
+                }
+                __syncthreads();
+                // cut-off: stop right after the first split that makes size >= N (src 745-746)
+                block_exclusive_scan(S.sc, m, S.warp_tmp);                  // sc[p] = growth before p
+                if (tid == 0) s_nS = m;
+                __syncthreads();
+                for (int p = tid; p < m; p += T) {
+                    const int after = prev2 + S.sc[p] + (S.sa[p] - 1);
+                    const int before = prev2 + S.sc[p];
+                    if (after >= N && before < N) s_nS = p + 1;
+                }
+                __syncthreads();
+                const int nS2 = s_nS;
+                apply_splits(prev2, nS2, vnext);
+                nL = s_nL;
+                nToExpand = s_total;
+                orbx_sort::item_t* t = vprev; vprev = vnext; vnext = t;
+                if (nL >= N || nL == prev2) finish = true;
+            }
+        }
+    }
+
+    // ---- 4. retain the best key per node, in list order (src 756-771) ------------------------------------------------
+    const int nL = s_nL;
+    for (int i = warp; i < nL; i += T / 32) {
+        const uint32_t beg = S.nbeg[a][i], cnt = S.ncnt[a][i];
+        uint32_t best = 0;   // (score << 24) | (0xffffff - rel)  -> max = highest score, earliest key
+        for (uint32_t j = lane; j < cnt; j += 32) {
+            const uint32_t k = K[beg + j];
+            const uint32_t v = (k & 0xff000000u) | (0xffffffu - j);
+            best = max(best, v);
+        }
+#pragma unroll
+        for (int d = 16; d >= 1; d >>= 1) best = max(best, __shfl_xor_sync(0xffffffffu, best, d));
+        if (lane == 0) out_kp[i] = K[beg + (0xffffffu - (best & 0xffffffu))];
+    }
+    if (tid == 0) *out_n = nL;
+}
+
+cudaError_t octree_prepare()
+{
+    return cudaFuncSetAttribute(octree_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+}
+
+static int* g_err_flag[64] = {nullptr};
+
+cudaError_t launch_octree(const FrameGeom& fg, const Workspace& ws, int n_frames, cudaStream_t st)
+{
+    int M = 0;
+    for (int l = 0; l < fg.nlevels; ++l) M = M > fg.L[l].kp_cap ? M : fg.L[l].kp_cap;
+    const size_t smem = octree_smem_bytes(M);
+    if (smem > 200 * 1024) return cudaErrorInvalidConfiguration;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!g_err_flag[dev & 63]) {
+        cudaError_t e = cudaMalloc(&g_err_flag[dev & 63], sizeof(int));
+        if (e != cudaSuccess) return e;
+        cudaMemset(g_err_flag[dev & 63], 0, sizeof(int));
+    }
+    dim3 grid(fg.nlevels, n_frames);
+    octree_kernel<<<grid, T, smem, st>>>(fg, ws, M, g_err_flag[dev & 63]);
+    count_launch();
+    return cudaGetLastError();
+}
+
+}  // namespace orbx

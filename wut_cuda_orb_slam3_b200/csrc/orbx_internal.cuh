@@ -1,0 +1,122 @@
+// orbx_internal.cuh — shared definitions between the host API (api.cu) and the sm_100a kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/orbx.h"
+
+namespace orbx {
+
+constexpr int kEdge = ORBX_EDGE_THRESHOLD;   // 19
+constexpr int kXPad = 32;                     // left pad of a pyramid row: interior pixel 0 is 16-byte aligned
+constexpr int kWinBorder = 16;                // EDGE_THRESHOLD - 3: FAST window origin (src/ORBextractor.cc:960-962)
+constexpr int kMaxLevels = ORBX_MAX_LEVELS;
+constexpr int kMaxCellDim = 70;               // wCell/hCell < 70 whenever the grid has >= 1 cell
+constexpr int kMaxDim = 4128;                 // packed 12-bit window coordinates
+constexpr int kHalfPatch = 15;
+
+// Geometry of one pyramid level for the current image shape (host-computed, passed to kernels by value).
+struct LevelGeom {
+    int w, h;                 // interior size
+    int pitch;                // bytes per row of the bordered buffer (multiple of 16)
+    int rows_alloc;           // h + 2*19
+    unsigned long long pyr_off;       // byte offset of this level's slab inside the pyramid allocation
+    unsigned long long pyr_frame_stride;
+    int bpitch;               // blurred level pitch
+    unsigned long long blur_off, blur_frame_stride;
+    // FAST cell grid (src/ORBextractor.cc:873-886)
+    int nCols, nRows, wCell, hCell;
+    int cell_base;            // first global cell id of this level (cells of all levels are numbered consecutively)
+    int cell_cap;             // staging slots per cell = ceil(wCell/2)*ceil(hCell/2)
+    unsigned long long cand_off;      // u32 offset of this level's staging slab inside one frame's staging area
+    int cand_max;             // nCols*nRows*cell_cap
+    unsigned long long oct_off;       // u32 offset of this level's octree scratch inside one frame's scratch area
+    // octree
+    int nfeat;                // mnFeaturesPerLevel[level]
+    int nIni;                 // round(width/height)
+    float hX;                 // width / nIni
+    int depth;                // quadtree depth needed to separate distinct pixels
+    int root_bits;
+    int kp_base;              // first slot of this level in the per-frame level-keypoint arrays
+    int kp_cap;               // nfeat + 4
+    // resize tables (device pointers): entry = {src offset, a0 | a1<<16}
+    const uint2* xtab;        // [w + 2*19 + pad] indexed by bordered column
+    const uint2* ytab;        // [h + 2*19] indexed by bordered row
+    int area2x;               // 1 if this level is an exact 2x decimation (OpenCV INTER_AREA fast path)
+    float scale;              // mvScaleFactor[level]
+    float inv_scale;          // mvInvScaleFactor[level]
+    float kp_size;            // (float)(int)(31*scale)
+};
+
+struct FrameGeom {
+    int nlevels;
+    int rows, cols;
+    int total_cells;          // per frame
+    int kp_slots;             // per frame = sum kp_cap
+    unsigned long long cand_frame_stride;  // u32 per frame
+    unsigned long long oct_frame_stride;   // u32 per frame
+    int iniTh, minTh;
+    LevelGeom L[kMaxLevels];
+};
+
+// Device workspace pointers of one extractor (one "slot").
+struct Workspace {
+    uint8_t* pyr;             // bordered pyramid, [level][frame][rows_alloc][pitch]
+    uint8_t* blur;            // blurred levels
+    uint32_t* cand;           // per-cell candidate staging (packed x | y<<12 | score<<24, window-relative)
+    int* cell_count;          // [frame][total_cells]
+    uint32_t* oct;            // octree scratch
+    uint32_t* lvl_kp;         // [frame][kp_slots] packed retained keypoints (window-relative)
+    int* lvl_n;               // [frame][nlevels]
+    float* lvl_angle;         // [frame][kp_slots]
+    uint8_t* lvl_desc;        // [frame][kp_slots][32]
+    int* lvl_ncand;           // [frame][nlevels] number of FAST candidates (probe)
+};
+
+inline __host__ __device__ uint8_t* level_interior(uint8_t* pyr, const LevelGeom& g, int frame)
+{
+    return pyr + g.pyr_off + (unsigned long long)frame * g.pyr_frame_stride + (unsigned long long)kEdge * g.pitch + kXPad;
+}
+inline __host__ __device__ const uint8_t* level_interior(const uint8_t* pyr, const LevelGeom& g, int frame)
+{
+    return pyr + g.pyr_off + (unsigned long long)frame * g.pyr_frame_stride + (unsigned long long)kEdge * g.pitch + kXPad;
+}
+
+// ---- launchers (defined in the kernel translation units) ---------------------------------------------------
+void count_launch(int n = 1);
+
+cudaError_t launch_pyramid(const FrameGeom& fg, const Workspace& ws, const uint8_t* d_images, size_t frame_stride,
+                           size_t pitch, int n_frames, cudaStream_t st);
+cudaError_t launch_fast(const FrameGeom& fg, const Workspace& ws, int n_frames, cudaStream_t st);
+cudaError_t launch_blur(const FrameGeom& fg, const Workspace& ws, int n_frames, cudaStream_t st);
+cudaError_t launch_octree(const FrameGeom& fg, const Workspace& ws, int n_frames, cudaStream_t st);
+cudaError_t launch_orient_describe(const FrameGeom& fg, const Workspace& ws, int n_frames, cudaStream_t st);
+cudaError_t launch_pack(const FrameGeom& fg, const Workspace& ws, int n_frames, int lap0, int lap1,
+                        orbx_keypoint* d_kps, uint8_t* d_desc, int capacity, int* d_n_out, int* d_n_mono,
+                        cudaStream_t st);
+size_t octree_smem_bytes(int nfeat);
+cudaError_t octree_prepare();   // opt in to large dynamic shared memory
+
+cudaError_t launch_knn2(const uint8_t* d_q, int nq, const uint8_t* d_db, long long ndb, int index_base, int32_t* d_idx,
+                        int32_t* d_dist, cudaStream_t st);
+cudaError_t launch_knn2_merge(const int32_t* d_idx_sh, const int32_t* d_dist_sh, int n_shards, int nq, int32_t* d_idx,
+                              int32_t* d_dist, cudaStream_t st);
+cudaError_t launch_popc_bench(unsigned long long* d_sink, int iters, int blocks, cudaStream_t st);
+
+struct StereoArgs {
+    const uint8_t* pyrL; const uint8_t* pyrR;       // pyramid allocations (same geometry)
+    int frameL, frameR;
+    const orbx_keypoint* kpL; const uint8_t* descL; int nL;
+    const orbx_keypoint* kpR; const uint8_t* descR; int nR;
+    float bf, maxD;
+    float* uRight; float* depth;                    // [nL]
+    int* sad;                                       // [nL] scratch: SAD of accepted matches, -1 otherwise
+};
+cudaError_t launch_stereo(const FrameGeom& fg, const StereoArgs& a, cudaStream_t st);
+
+cudaError_t launch_synth_images(uint32_t seed0, int view, int n_frames, int cols, int rows, int max_disp, uint8_t* d_dst,
+                                size_t pitch, size_t frame_stride, cudaStream_t st);
+cudaError_t launch_synth_desc(uint32_t seed, int is_query, long long first_row, long long n_rows, long long ndb,
+                              int plant_every, uint8_t* d_dst, cudaStream_t st);
+
+}  // namespace orbx
