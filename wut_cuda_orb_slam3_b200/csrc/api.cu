@@ -203,7 +203,7 @@ static int configure(orbx_extractor* ex, int rows, int cols)
         g.cand_max = g.nCols * g.nRows * g.cell_cap;
         cand_off += (unsigned long long)g.cand_max;
         g.oct_off = oct_off;
-        oct_off += 4ull * g.cand_max + (unsigned long long)(g.nCols * g.nRows) + 16;
+        oct_off += 5ull * g.cand_max + (unsigned long long)(g.nCols * g.nRows) + 16;
         // octree
         g.nfeat = ex->tab.nfeat[l];
         g.nIni = (width > 0 && height > 0) ? (int)round(width / height) : 0;   // src 589
@@ -658,7 +658,7 @@ int orbx_distribute_octree(int device, const int* xs, const int* ys, const int* 
         if (2 * g.depth + g.root_bits > 32) return fail(ORBX_ERR_UNSUPPORTED, "path code too long");
     }
     g.kp_base = 0; g.kp_cap = std::max(nFeatures + 4, 4 * g.nIni + 1);
-    fg.kp_slots = g.kp_cap; fg.cand_frame_stride = g.cand_max; fg.oct_frame_stride = 4ull * g.cand_max + 32;
+    fg.kp_slots = g.kp_cap; fg.cand_frame_stride = g.cand_max; fg.oct_frame_stride = 5ull * g.cand_max + 32;
     if (octree_smem_bytes(g.kp_cap) > 200 * 1024) return fail(ORBX_ERR_UNSUPPORTED, "nFeatures too large");
     CU(octree_prepare());
     std::vector<uint32_t> packed(std::max(n, 1));

@@ -4,9 +4,10 @@
 // Reformulation (bit-exact, see DESIGN.md "Octree"):
 //  * A key's path through the quadtree depends only on geometry: root = (int)(x / hX), then at every depth the
 //    quadrant given by x < UL.x + ceil(w/2), y < UL.y + ceil(h/2).  Every key gets a path code (root, 2 bits per depth,
-//    n1=0,n2=1,n3=2,n4=3).  One STABLE LSD radix sort by path code makes every node of every depth a contiguous
-//    segment whose keys keep their original (cell-major, y, x) order — exactly what DivideNode's stable 4-way
-//    partition produces — and the four children of a node are its four sub-segments, found by binary search.
+//    n1=0,n2=1,n3=2,n4=3).  One LSD radix sort of (path code, original index) makes every node of every depth a
+//    contiguous segment and the four children of a node its four sub-segments, found by binary search.  DivideNode's
+//    stable partition keeps a node's keys in original (cell-major, y, x) order; that order only matters for the
+//    "first key with maximal response" rule, which is evaluated on the carried original indices.
 //  * The std::list is an array in list order.  A sweep that splits a set of nodes processed in the order p=0..nS-1
 //    turns the list into [children(p=nS-1) n4..n1, ..., children(p=0) n4..n1, untouched nodes in old order]
 //    (every split push_front()s its non-empty children n1..n4 and erases the parent).  Positions come from prefix sums.
@@ -68,7 +69,9 @@ __device__ int block_exclusive_scan(int* a, int n, int* warp_tmp)
         if (tid == T - 1) carry = c + woff + incl;
         __syncthreads();
     }
-    return carry;
+    const int total = carry;
+    __syncthreads();            // nobody may re-enter (and reset carry) before everyone has read the total
+    return total;
 }
 
 // Path code of a key (window-relative x, y).
@@ -162,9 +165,11 @@ __global__ void __launch_bounds__(T) octree_kernel(const __grid_constant__ Frame
     // ---- 0. gather the level's candidates in cell-major order, compute path codes ------------------------------
     uint32_t* scratch = ws.oct + (size_t)frame * fg.oct_frame_stride + g.oct_off;
     const int nmax = g.cand_max;
-    uint32_t* keys[2] = {scratch, scratch + nmax};
-    uint32_t* codes[2] = {scratch + 2 * (size_t)nmax, scratch + 3 * (size_t)nmax};
-    int* cell_off = (int*)(scratch + 4 * (size_t)nmax);                     // [ncells]
+    // keys0 = packed candidates in original (cell-major, y, x) order; the sort permutes (code, original index) pairs
+    uint32_t* keys0 = scratch;
+    uint32_t* keys[2] = {scratch + nmax, scratch + 2 * (size_t)nmax};       // original indices, ping-pong
+    uint32_t* codes[2] = {scratch + 3 * (size_t)nmax, scratch + 4 * (size_t)nmax};
+    int* cell_off = (int*)(scratch + 5 * (size_t)nmax);                     // [ncells]
     const int* cell_count = ws.cell_count + (size_t)frame * fg.total_cells + g.cell_base;
     for (int c = tid; c < ncells; c += T) cell_off[c] = cell_count[c];
     __syncthreads();
@@ -181,7 +186,8 @@ __global__ void __launch_bounds__(T) octree_kernel(const __grid_constant__ Frame
             const uint32_t* src = cand + (size_t)c * g.cell_cap;
             for (int i = lane; i < cnt; i += 32) {
                 const uint32_t k = src[i];
-                keys[0][o + i] = k;
+                keys0[o + i] = k;
+                keys[0][o + i] = (uint32_t)(o + i);
                 codes[0][o + i] = path_code((int)(k & 0xfff), (int)((k >> 12) & 0xfff), g, winH);
             }
         }
@@ -424,15 +430,17 @@ __global__ void __launch_bounds__(T) octree_kernel(const __grid_constant__ Frame
     const int nL = s_nL;
     for (int i = warp; i < nL; i += T / 32) {
         const uint32_t beg = S.nbeg[a][i], cnt = S.ncnt[a][i];
-        uint32_t best = 0;   // (score << 24) | (0xffffff - rel)  -> max = highest score, earliest key
+        // The segment is ordered by sub-path, not by original position, so "first key with maximal response" (src 758-768)
+        // = max score, then min ORIGINAL index: (score << 24) | (0xffffff - original index).
+        uint32_t best = 0;
         for (uint32_t j = lane; j < cnt; j += 32) {
-            const uint32_t k = K[beg + j];
-            const uint32_t v = (k & 0xff000000u) | (0xffffffu - j);
+            const uint32_t oi = K[beg + j];
+            const uint32_t v = (keys0[oi] & 0xff000000u) | (0xffffffu - oi);
             best = max(best, v);
         }
 #pragma unroll
         for (int d = 16; d >= 1; d >>= 1) best = max(best, __shfl_xor_sync(0xffffffffu, best, d));
-        if (lane == 0) out_kp[i] = K[beg + (0xffffffu - (best & 0xffffffu))];
+        if (lane == 0) out_kp[i] = keys0[0xffffffu - (best & 0xffffffu)];
     }
     if (tid == 0) *out_n = nL;
 }
