@@ -162,6 +162,13 @@ int orbx_stereo_match(orbx_extractor* exL, int frameL, orbx_extractor* exR, int 
 
 /* ---- measurement helpers ----------------------------------------------------------------------------------- */
 
+/* Per-stage device timing: between begin and end every extraction on `ex` records CUDA events around its stages on the
+ * launching stream; end() waits for them and returns the summed milliseconds of the 6 stages
+ * {pyramid, fast, blur, octree, orient+describe, pack} and the number of chunks timed. */
+#define ORBX_NUM_STAGES 6
+int orbx_profile_begin(orbx_extractor* ex);
+int orbx_profile_end(orbx_extractor* ex, float* stage_ms, int* n_chunks);
+
 /* POPC.b32 issue-rate microbenchmark on `device`: returns popc instructions (per 32-bit lane) per second. */
 int orbx_measure_popc_peak(int device, double* popc_per_second);
 /* Number of kernel launches issued by this library on the calling process since load (for bench gpu_launches). */

@@ -148,10 +148,20 @@ void fast9(const uint8_t* img, int w, int h, size_t step, int threshold, bool nm
 {
     out.clear();
     if (w < 7 || h < 7) return;
-    std::vector<uint8_t> sc((size_t)w * h, 0);
+    static thread_local std::vector<uint8_t> sc;
+    sc.assign((size_t)w * h, 0);
+    const ptrdiff_t st = (ptrdiff_t)step;
     for (int y = 3; y < h - 3; ++y)
         for (int x = 3; x < w - 3; ++x) {
-            int s = fast_score(img + (size_t)y * step + x, step);
+            // Cheap exact rejection (speed only; OpenCV does the same kind of early-out): a 9-arc always contains two
+            // adjacent compass points of the circle, so a corner at `threshold` needs two adjacent ones beyond it.
+            const uint8_t* p = img + (size_t)y * step + x;
+            const int v = p[0], t = threshold;
+            const int d0 = v - p[3 * st], d4 = v - p[3], d8 = v - p[-3 * st], d12 = v - p[-3];
+            const bool b = ((d0 > t) | (d8 > t)) & ((d4 > t) | (d12 > t));
+            const bool k = ((d0 < -t) | (d8 < -t)) & ((d4 < -t) | (d12 < -t));
+            if (!(b | k)) continue;
+            int s = fast_score(p, step);
             if (s >= threshold) sc[(size_t)y * w + x] = (uint8_t)s;   // OpenCV stores (uchar)score
         }
     // A pixel with score >= threshold but threshold == 0 and score == 0 would be stored as 0 and lost
@@ -175,19 +185,34 @@ void fast9(const uint8_t* img, int w, int h, size_t step, int threshold, bool nm
 void gaussian_blur7(const uint8_t* src, int w, int h, size_t sstep, uint8_t* dst, size_t dstep)
 {
     static const int k[7] = {18, 34, 48, 56, 48, 34, 18};
-    std::vector<uint16_t> hbuf((size_t)w * h);
-    for (int y = 0; y < h; ++y)
-        for (int x = 0; x < w; ++x) {
-            int s = 0;
-            for (int t = -3; t <= 3; ++t) s += k[t + 3] * src[(size_t)y * sstep + reflect101(x + t, w)];
-            hbuf[(size_t)y * w + x] = (uint16_t)s;
-        }
-    for (int y = 0; y < h; ++y)
+    // reflect-101 padded copy (3 px) so that the two passes are plain loops
+    const int pw = w + 6, ph = h + 6;
+    static thread_local std::vector<uint8_t> pad;
+    static thread_local std::vector<uint16_t> hbuf;
+    pad.resize((size_t)pw * ph);
+    hbuf.resize((size_t)w * ph);
+    for (int y = 0; y < ph; ++y) {
+        const uint8_t* srow = src + (size_t)reflect101(y - 3, h) * sstep;
+        uint8_t* prow = &pad[(size_t)y * pw];
+        for (int x = 0; x < 3; ++x) prow[x] = srow[reflect101(x - 3, w)];
+        memcpy(prow + 3, srow, w);
+        for (int x = 0; x < 3; ++x) prow[w + 3 + x] = srow[reflect101(w + x, w)];
+    }
+    for (int y = 0; y < ph; ++y) {
+        const uint8_t* p = &pad[(size_t)y * pw];
+        uint16_t* hrow = &hbuf[(size_t)y * w];
+        for (int x = 0; x < w; ++x)
+            hrow[x] = (uint16_t)(k[0] * (p[x] + p[x + 6]) + k[1] * (p[x + 1] + p[x + 5]) + k[2] * (p[x + 2] + p[x + 4]) + k[3] * p[x + 3]);
+    }
+    for (int y = 0; y < h; ++y) {
+        const uint16_t* r0 = &hbuf[(size_t)y * w];
+        uint8_t* drow = dst + (size_t)y * dstep;
         for (int x = 0; x < w; ++x) {
             uint32_t s = 0;
-            for (int t = -3; t <= 3; ++t) s += (uint32_t)k[t + 3] * hbuf[(size_t)reflect101(y + t, h) * w + x];
-            dst[(size_t)y * dstep + x] = (uint8_t)((s + 32768u) >> 16);
+            for (int t = 0; t < 7; ++t) s += (uint32_t)k[t] * r0[(size_t)t * w + x];
+            drow[x] = (uint8_t)((s + 32768u) >> 16);
         }
+    }
 }
 
 // cv::fastAtan2(y, x) — imported at src/ORBextractor.cc:85 (the CPU IC_Angle that called it was deleted

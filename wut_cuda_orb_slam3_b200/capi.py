@@ -55,6 +55,8 @@ SIGNATURES = {
     "orbx_knn2_merge_device": (_i, [_i, _vp, _vp, _i, _i, _vp, _vp, _vp]),
     "orbx_ratio_test": (_i, [_vp, _i, _f, _i, _i, _vp]),
     "orbx_stereo_match": (_i, [_vp, _i, _vp, _i, _vp, _vp, _i, _vp, _vp, _i, _f, _f, _vp, _vp]),
+    "orbx_profile_begin": (_i, [_vp]),
+    "orbx_profile_end": (_i, [_vp, _vp, _vp]),
     "orbx_measure_popc_peak": (_i, [_i, C.POINTER(C.c_double)]),
     "orbx_launch_count": (_i64, []),
     "orbx_synth_image_host": (None, [_u32, _i, _i, _i, _i, _vp, _sz]),

@@ -110,6 +110,10 @@ struct orbx_extractor {
     Slot slots[kSlots];
     int last_frames = 0;           // frames of the last call that are probe-able (slot 0)
     int max_kp = 0;
+    // per-stage CUDA-event timing (orbx_profile_begin / orbx_profile_end)
+    bool profiling = false;
+    std::vector<cudaEvent_t> ev_pool;   // kStages+1 events per profiled chunk
+    size_t ev_used = 0;
 };
 
 namespace orbx {
@@ -338,17 +342,39 @@ static int ensure_host_staging(Slot& s, size_t in_bytes, int frames, int capacit
 }
 
 // The whole per-chunk pipeline on one stream.
+static const int kStages = 6;   // pyramid, fast, blur, octree, orient+describe, pack
+
+static int prof_mark(orbx_extractor* ex, cudaStream_t st)
+{
+    if (!ex->profiling) return ORBX_OK;
+    if (ex->ev_used == ex->ev_pool.size()) {
+        cudaEvent_t e;
+        CU(cudaEventCreate(&e));
+        ex->ev_pool.push_back(e);
+    }
+    CU(cudaEventRecord(ex->ev_pool[ex->ev_used++], st));
+    return ORBX_OK;
+}
+
 static int run_chunk(orbx_extractor* ex, Slot& s, const uint8_t* d_images, size_t frame_stride, size_t pitch, int frames,
                      int lap0, int lap1, orbx_keypoint* d_kps, uint8_t* d_desc, int capacity, int* d_n, int* d_nm,
                      cudaStream_t st)
 {
     const FrameGeom& fg = ex->fg;
+    int rc;
+    if ((rc = prof_mark(ex, st))) return rc;
     CU(launch_pyramid(fg, s.ws, d_images, frame_stride, pitch, frames, st));
+    if ((rc = prof_mark(ex, st))) return rc;
     CU(launch_fast(fg, s.ws, frames, st));
+    if ((rc = prof_mark(ex, st))) return rc;
     CU(launch_blur(fg, s.ws, frames, st));
+    if ((rc = prof_mark(ex, st))) return rc;
     CU(launch_octree(fg, s.ws, frames, st));
+    if ((rc = prof_mark(ex, st))) return rc;
     CU(launch_orient_describe(fg, s.ws, frames, st));
+    if ((rc = prof_mark(ex, st))) return rc;
     CU(launch_pack(fg, s.ws, frames, lap0, lap1, d_kps, d_desc, capacity, d_n, d_nm, st));
+    if ((rc = prof_mark(ex, st))) return rc;
     return ORBX_OK;
 }
 
@@ -424,6 +450,7 @@ void orbx_destroy(orbx_extractor* ex)
         if (ex->slots[i].stream) cudaStreamDestroy(ex->slots[i].stream);
     }
     if (ex->d_tables) cudaFree(ex->d_tables);
+    for (cudaEvent_t e : ex->ev_pool) cudaEventDestroy(e);
     delete ex;
 }
 
@@ -542,6 +569,33 @@ int orbx_extract(orbx_extractor* ex, const uint8_t* image, int rows, int cols, s
     const uint8_t* imgs[1] = {image};
     if (!image) return fail(ORBX_ERR_EMPTY_IMAGE, "empty image");
     return orbx_extract_batch(ex, imgs, 1, rows, cols, step, lap0, lap1, keypoints, descriptors, capacity, n_out, n_mono);
+}
+
+// ---- per-stage timing with CUDA events on the launching stream ---------------------------------------------------------
+int orbx_profile_begin(orbx_extractor* ex)
+{
+    if (!ex) return fail(ORBX_ERR_INVALID_ARG, "extractor is NULL");
+    ex->profiling = true;
+    ex->ev_used = 0;
+    return ORBX_OK;
+}
+
+int orbx_profile_end(orbx_extractor* ex, float* stage_ms, int* n_chunks)
+{
+    if (!ex || !stage_ms) return fail(ORBX_ERR_INVALID_ARG, "bad arguments");
+    ex->profiling = false;
+    for (int k = 0; k < kStages; ++k) stage_ms[k] = 0.f;
+    const size_t per = kStages + 1, chunks = ex->ev_used / per;
+    if (chunks > 0) CU(cudaEventSynchronize(ex->ev_pool[ex->ev_used - 1]));
+    for (size_t c = 0; c < chunks; ++c)
+        for (int k = 0; k < kStages; ++k) {
+            float ms = 0.f;
+            CU(cudaEventElapsedTime(&ms, ex->ev_pool[c * per + k], ex->ev_pool[c * per + k + 1]));
+            stage_ms[k] += ms;
+        }
+    if (n_chunks) *n_chunks = (int)chunks;
+    ex->ev_used = 0;
+    return ORBX_OK;
 }
 
 // ---- probes ---------------------------------------------------------------------------------------------------------

@@ -116,6 +116,18 @@ class ORBextractor:
     def sync(self):
         check(lib().orbx_sync(self._h))
 
+    STAGES = ("pyramid", "fast", "blur", "octree", "orient_describe", "pack")
+
+    def profile_begin(self):
+        check(lib().orbx_profile_begin(self._h))
+
+    def profile_end(self):
+        """Returns ({stage: summed milliseconds}, n_chunks) measured with CUDA events on the launching stream."""
+        ms = np.zeros(len(self.STAGES), np.float32)
+        n = C.c_int(0)
+        check(lib().orbx_profile_end(self._h, ptr(ms), C.byref(n)))
+        return dict(zip(self.STAGES, ms.tolist())), n.value
+
     # ---- mvImagePyramid (include/ORBextractor.h:92) and stage probes -----------------------------------------
     @property
     def mvImagePyramid(self):
