@@ -256,6 +256,16 @@ static int configure(orbx_extractor* ex, int rows, int cols)
     fg.cand_frame_stride = cand_off + 16;
     fg.oct_frame_stride = oct_off + 16;
     ex->max_kp = kp_base;
+    // cell table (FAST kernel: global cell id -> level | cell row << 4 | cell column << 16), stored after the resize tables
+    const size_t cell_tab_off = tables.size();
+    {
+        std::vector<uint32_t> flat;
+        for (int l = 0; l < ex->nlevels; ++l)
+            for (int i = 0; i < fg.L[l].nRows; ++i)
+                for (int j = 0; j < fg.L[l].nCols; ++j) flat.push_back((uint32_t)l | ((uint32_t)i << 4) | ((uint32_t)j << 16));
+        if (flat.size() & 1) flat.push_back(0);
+        for (size_t k = 0; k < flat.size(); k += 2) tables.push_back(make_uint2(flat[k], flat[k + 1]));
+    }
     if (!tables.empty()) {
         CU(cudaMalloc((void**)&ex->d_tables, tables.size() * sizeof(uint2)));
         CU(cudaMemcpy(ex->d_tables, tables.data(), tables.size() * sizeof(uint2), cudaMemcpyHostToDevice));
@@ -263,6 +273,7 @@ static int configure(orbx_extractor* ex, int rows, int cols)
             fg.L[l].xtab = ex->d_tables + xtab_off[l];
             fg.L[l].ytab = ex->d_tables + ytab_off[l];
         }
+        fg.cell_tab = reinterpret_cast<const uint32_t*>(ex->d_tables + cell_tab_off);
     }
     const size_t smem = octree_smem_bytes([&] { int M = 0; for (int l = 0; l < fg.nlevels; ++l) M = std::max(M, fg.L[l].kp_cap); return M; }());
     if (smem > 200 * 1024) return fail(ORBX_ERR_UNSUPPORTED, "nfeatures too large for the octree kernel (%zu B shared memory)", smem);

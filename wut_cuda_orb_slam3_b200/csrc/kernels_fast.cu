@@ -23,23 +23,50 @@ constexpr int kRoiPitch = 80;                   // >= 3 (misalignment) + 70 + 6,
 constexpr int kRoiRows = 76;                    // >= 70 + 6
 constexpr int kPlane = kRoiRows * kRoiPitch;    // ROI plane and score plane share one geometry
 constexpr int kMaxEval = kMaxCellDim * kMaxCellDim;
+constexpr int kListCap = kMaxEval + 4 * 32;     // four warp-private regions, each rounded up to 32
 constexpr int kBitWords = (kPlane + 31) / 32;   // survivor bitmaps are indexed by plane position
 
-// FAST score of the pixel at `c` (shared memory, row pitch kRoiPitch): max over the 16 arcs of 9 contiguous circle
-// pixels of min(v - ring) / min(ring - v), minus 1.  Both signs are carried in one register as s16x2
-// (low = v - ring "centre brighter", high = ring - v) so one VIMNMX.S16x2 serves both.
+// Shared-memory accessors on explicit 32-bit shared addresses.  (nvcc re-derives the shared-window base — S2UR
+// SR_CgaCtaId + ULEA — at every use inside divergent regions when it goes through C++ pointers; the first version of this
+// kernel spent ~15 % of its issue slots on that.)  Offsets are compile-time immediates folded into the instruction.
+#define ORBX_LDS_U8(dst, addr, off) asm volatile("ld.shared.u8 %0, [%1+" #off "];" : "=r"(dst) : "r"(addr))
+__device__ __forceinline__ uint32_t lds_u8(uint32_t a) { uint32_t v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ uint32_t lds_u16(uint32_t a) { uint32_t v; asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ uint32_t lds_u32(uint32_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ void sts_u8(uint32_t a, uint32_t v) { asm volatile("st.shared.u8 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ void sts_u16(uint32_t a, uint32_t v) { asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ void sts_u32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ void sts_zero16(uint32_t a) { asm volatile("st.shared.v4.u32 [%0], {%1, %1, %1, %1};" ::"r"(a), "r"(0u) : "memory"); }
+__device__ __forceinline__ void atom_or(uint32_t a, uint32_t v) { asm volatile("red.shared.or.b32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+
+// FAST score of the pixel whose plane address is `c`: max over the 16 arcs of 9 contiguous circle pixels of
+// min(v - ring) / min(ring - v), minus 1.  Both signs are carried in one register as s16x2 (low = v - ring "centre
+// brighter", high = ring - v) so one VIMNMX.S16x2 serves both.
 //   packing:  A = (v+1, 1-v),  ~(r, -r) = r*0xFFFF - 1  ->  P = A + ~(r,-r) per half = (v - r, r - v)
 //   windows:  prefix/suffix minima inside the two half-circles, window k = min(suffix(k), prefix(k+8))
-__device__ __forceinline__ int fast_score(const uint8_t* c)
+__device__ __forceinline__ int fast_score(uint32_t c)
 {
-    constexpr int rp = kRoiPitch;
-    const uint32_t v = c[0];
+    // base moved to the top-left of the 7x7 neighbourhood so that every offset is a non-negative immediate
+    const uint32_t b = c - 3 * kRoiPitch - 3;
+    uint32_t v, r[16];
+    ORBX_LDS_U8(v, b, 243);       // (3,3)
+    ORBX_LDS_U8(r[0], b, 483);    // ( 0, 3): row 6, col 3
+    ORBX_LDS_U8(r[1], b, 484);    // ( 1, 3)
+    ORBX_LDS_U8(r[2], b, 405);    // ( 2, 2): row 5, col 5
+    ORBX_LDS_U8(r[3], b, 326);    // ( 3, 1): row 4, col 6
+    ORBX_LDS_U8(r[4], b, 246);    // ( 3, 0)
+    ORBX_LDS_U8(r[5], b, 166);    // ( 3,-1): row 2, col 6
+    ORBX_LDS_U8(r[6], b, 85);     // ( 2,-2): row 1, col 5
+    ORBX_LDS_U8(r[7], b, 4);      // ( 1,-3): row 0, col 4
+    ORBX_LDS_U8(r[8], b, 3);      // ( 0,-3)
+    ORBX_LDS_U8(r[9], b, 2);      // (-1,-3)
+    ORBX_LDS_U8(r[10], b, 81);    // (-2,-2): row 1, col 1
+    ORBX_LDS_U8(r[11], b, 160);   // (-3,-1): row 2, col 0
+    ORBX_LDS_U8(r[12], b, 240);   // (-3, 0)
+    ORBX_LDS_U8(r[13], b, 320);   // (-3, 1)
+    ORBX_LDS_U8(r[14], b, 401);   // (-2, 2): row 5, col 1
+    ORBX_LDS_U8(r[15], b, 482);   // (-1, 3): row 6, col 2
     const uint32_t A = v * 0xFFFF0001u + 0x00010001u;
-    uint32_t r[16];
-    r[0] = c[3 * rp];       r[1] = c[3 * rp + 1];   r[2] = c[2 * rp + 2];   r[3] = c[rp + 3];
-    r[4] = c[3];            r[5] = c[-rp + 3];      r[6] = c[-2 * rp + 2];  r[7] = c[-3 * rp + 1];
-    r[8] = c[-3 * rp];      r[9] = c[-3 * rp - 1];  r[10] = c[-2 * rp - 2]; r[11] = c[-rp - 3];
-    r[12] = c[-3];          r[13] = c[rp - 3];      r[14] = c[2 * rp - 2];  r[15] = c[3 * rp - 1];
     uint32_t P[16], pf[16], sf[16];
 #pragma unroll
     for (int k = 0; k < 16; ++k) P[k] = __vadd2(A, r[k] * 0xFFFFu + 0xFFFFFFFFu);
@@ -61,9 +88,10 @@ __device__ __forceinline__ int fast_score(const uint8_t* c)
     for (int s = 8; s >= 1; s >>= 1)
 #pragma unroll
         for (int k = 0; k < s; ++k) w[k] = __vmaxs2(w[k], w[k + s]);
-    const int a = (int)(short)(w[0] & 0xffff), b = (int)(short)(w[0] >> 16);
-    return max(a, b) - 1;
+    const int a = (int)(short)(w[0] & 0xffff), bb = (int)(short)(w[0] >> 16);
+    return max(a, bb) - 1;
 }
+static_assert(kRoiPitch == 80, "fast_score() hard-codes the 7x7 offsets for an 80-byte pitch");
 
 }  // namespace
 
@@ -71,22 +99,19 @@ __global__ void __launch_bounds__(128) fast_cells_kernel(const __grid_constant__
 {
     __shared__ __align__(16) uint8_t roi[kPlane];
     __shared__ __align__(16) uint8_t sc[kPlane];
-    __shared__ uint16_t list[kMaxEval];
+    __shared__ __align__(4) uint16_t list[kListCap];
     __shared__ uint32_t selA[kBitWords], selH[kBitWords];
     __shared__ int off[kBitWords];
-    __shared__ int n_list, total;
+    __shared__ int wcnt[4], total;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int frame = blockIdx.y;
-    int cell = blockIdx.x;
-    int level = 0;
-#pragma unroll 1
-    for (int l = 1; l < fg.nlevels; ++l)
-        if (cell >= fg.L[l].cell_base) level = l;
+    // cell -> (level, cell row, cell column) from a small table (built by the host with the geometry)
+    const uint32_t ct = __ldg(fg.cell_tab + blockIdx.x);
+    const int level = ct & 15, ci = (ct >> 4) & 0xfff, cj = ct >> 16;
     const LevelGeom& g = fg.L[level];
-    cell -= g.cell_base;
-    const int ci = cell / g.nCols, cj = cell - ci * g.nCols;   // cell row, cell column
-    int* count_out = ws.cell_count + (size_t)frame * fg.total_cells + g.cell_base + cell;
+    const int cell = (int)blockIdx.x - g.cell_base;
+    int* count_out = ws.cell_count + (size_t)frame * fg.total_cells + blockIdx.x;
 
     const int maxBX = g.w - kWinBorder, maxBY = g.h - kWinBorder;
     const int iniX = kWinBorder + cj * g.wCell, iniY = kWinBorder + ci * g.hCell;
@@ -98,80 +123,92 @@ __global__ void __launch_bounds__(128) fast_cells_kernel(const __grid_constant__
         return;
     }
     const int minTh = max(fg.minTh, 1), iniTh = fg.iniTh;
+    const uint32_t roi_s = (uint32_t)__cvta_generic_to_shared(roi), sc_s = (uint32_t)__cvta_generic_to_shared(sc);
+    const uint32_t list_s = (uint32_t)__cvta_generic_to_shared(list);
+    const uint32_t selA_s = (uint32_t)__cvta_generic_to_shared(selA), selH_s = (uint32_t)__cvta_generic_to_shared(selH);
 
     // 1. ROI -> shared memory with aligned 32-bit loads (the row misalignment m is the same for every row because the
     //    pitch is a multiple of 16); zero the score plane and the survivor bitmaps
     const uint8_t* src = level_interior((const uint8_t*)ws.pyr, g, frame) + (size_t)iniY * g.pitch + iniX;
     const int m = (int)((uintptr_t)src & 3);
-    const int nwords = (m + rw + 3) >> 2;                       // <= 20
     {
-        const uint32_t* src4 = reinterpret_cast<const uint32_t*>(src - m);
+        const int nwords = (m + rw + 3) >> 2;                   // <= 20
+        const uint32_t* src4 = reinterpret_cast<const uint32_t*>(src - m) + lane;
         const int wpitch = g.pitch >> 2;
-        for (int y = warp; y < rh; y += 4)
-            if (lane < nwords) reinterpret_cast<uint32_t*>(roi)[y * (kRoiPitch / 4) + lane] = __ldg(src4 + (size_t)y * wpitch + lane);
+        if (lane < nwords)
+            for (int y = warp; y < rh; y += 4) sts_u32(roi_s + y * kRoiPitch + lane * 4, __ldg(src4 + (size_t)y * wpitch));
         const int nz = (rh * kRoiPitch + 15) >> 4;
-        for (int i = tid; i < nz; i += 128) reinterpret_cast<uint4*>(sc)[i] = make_uint4(0, 0, 0, 0);
-        for (int i = tid; i < kBitWords; i += 128) { selA[i] = 0; selH[i] = 0; }
-        if (tid == 0) n_list = 0;
+        for (int i = tid; i < nz; i += 128) sts_zero16(sc_s + i * 16);
+        for (int i = tid; i < kBitWords; i += 128) { sts_u32(selA_s + i * 4, 0); sts_u32(selH_s + i * 4, 0); }
     }
     __syncthreads();
 
     // 2. pre-test on the 8 even circle points: every 9-arc contains one point of each opposite pair, so a corner needs
-    //    max_p min(r_a, r_b) < v - t  (bright) or  min_p max(r_a, r_b) > v + t  (dark).  Survivors are compacted so the
-    //    expensive arc test runs on dense warps.
+    //    max_p min(r_a, r_b) < v - t  (bright) or  min_p max(r_a, r_b) > v + t  (dark).  Each warp owns a contiguous
+    //    quarter of the pixels and compacts its survivors (plane positions) into its own region of `list`: no atomics.
     const int npix = ew * eh;
-    const int npad = (npix + 31) & ~31;
+    const int Q = (((npix + 3) >> 2) + 31) & ~31;               // pixels per warp, multiple of 32
     {
-        const int sdy = 128 / ew, sdx = 128 - sdy * ew;
-        int ey = tid / ew, ex = tid - ey * ew;
-        for (int e = tid; e < npad; e += 128) {
+        const int e0 = warp * Q + lane;
+        const int eend = min(e0 - lane + Q, npix);              // warp-uniform end of this warp's range
+        const float inv_ew = 1.0f / (float)ew;
+        int ey = (int)(((float)e0 + 0.5f) * inv_ew);
+        int ex = e0 - ey * ew;
+        const int sdy = (int)(32.5f * inv_ew), sdx = 32 - sdy * ew;
+        uint32_t wl = list_s + (uint32_t)(warp * Q) * 2;        // write cursor of this warp (bytes)
+        for (int e = e0; e - lane < eend; e += 32) {
             bool pass = false;
             const int pos = (ey + 3) * kRoiPitch + m + ex + 3;
-            if (e < npix) {
-                const uint8_t* c = roi + pos;
-                constexpr int rp = kRoiPitch;
-                const int v = c[0];
-                const int r0 = c[3 * rp], r8 = c[-3 * rp], r4 = c[3], r12 = c[-3];
-                const int r2 = c[2 * rp + 2], r10 = c[-2 * rp - 2], r6 = c[-2 * rp + 2], r14 = c[2 * rp - 2];
+            if (e < eend) {
+                const uint32_t b = roi_s + pos - 3 * kRoiPitch - 3;
+                uint32_t v, r0, r2, r4, r6, r8, r10, r12, r14;
+                ORBX_LDS_U8(v, b, 243);
+                ORBX_LDS_U8(r0, b, 483);  ORBX_LDS_U8(r8, b, 3);
+                ORBX_LDS_U8(r4, b, 246);  ORBX_LDS_U8(r12, b, 240);
+                ORBX_LDS_U8(r2, b, 405);  ORBX_LDS_U8(r10, b, 81);
+                ORBX_LDS_U8(r6, b, 85);   ORBX_LDS_U8(r14, b, 401);
                 const int M1 = max(max(min(r0, r8), min(r4, r12)), max(min(r2, r10), min(r6, r14)));
                 const int M2 = min(min(max(r0, r8), max(r4, r12)), min(max(r2, r10), max(r6, r14)));
-                pass = (M1 < v - minTh) | (M2 > v + minTh);
+                pass = (M1 < (int)v - minTh) | (M2 > (int)v + minTh);
             }
             const uint32_t mk = __ballot_sync(0xffffffffu, pass);
-            if (mk) {
-                int base = 0;
-                if (lane == 0) base = atomicAdd(&n_list, __popc(mk));
-                base = __shfl_sync(0xffffffffu, base, 0);
-                if (pass) list[base + __popc(mk & ((1u << lane) - 1))] = (uint16_t)pos;
-            }
+            if (pass) sts_u16(wl + 2 * __popc(mk & ((1u << lane) - 1)), (uint32_t)pos);
+            wl += 2 * __popc(mk);
             ex += sdx; ey += sdy;
             if (ex >= ew) { ex -= ew; ++ey; }
         }
+        if (lane == 0) wcnt[warp] = (int)((wl - list_s) >> 1) - warp * Q;
     }
     __syncthreads();
 
+    // flat index over the four warp regions -> list slot
+    const int c0 = wcnt[0], c1 = c0 + wcnt[1], c2 = c1 + wcnt[2], nl = c2 + wcnt[3];
+    auto slot = [&](int i) { return i < c0 ? i : (i < c1 ? Q + i - c0 : (i < c2 ? 2 * Q + i - c1 : 3 * Q + i - c2)); };
+
     // 3. full arc score on the compacted list (order inside the list is irrelevant)
-    const int nl = n_list;
     for (int i = tid; i < nl; i += 128) {
-        const int pos = list[i];
-        const int s = fast_score(roi + pos);
-        if (s >= minTh) sc[pos] = (uint8_t)s;
+        const uint32_t pos = lds_u16(list_s + 2 * slot(i));
+        const int s = fast_score(roi_s + pos);
+        if (s >= minTh) sts_u8(sc_s + pos, (uint32_t)s);
     }
     __syncthreads();
 
     // 4. 3x3 strict NMS inside the cell (pixels outside the evaluated region hold score 0 = cv::FAST's zeroed buffer);
     //    survivors set their bit in position-indexed bitmaps
     for (int i = tid; i < nl; i += 128) {
-        const int pos = list[i];
-        const uint8_t* p = sc + pos;
-        const int s = p[0];
+        const uint32_t pos = lds_u16(list_s + 2 * slot(i));
+        const uint32_t b = sc_s + pos - kRoiPitch - 1;
+        uint32_t s;
+        ORBX_LDS_U8(s, b, 81);
         if (s > 0) {
-            constexpr int sp = kRoiPitch;
-            const bool keep = s > p[-1] && s > p[1] && s > p[-sp - 1] && s > p[-sp] && s > p[-sp + 1] && s > p[sp - 1] &&
-                              s > p[sp] && s > p[sp + 1];
-            if (keep) {
-                atomicOr(&selA[pos >> 5], 1u << (pos & 31));
-                if (s >= iniTh) atomicOr(&selH[pos >> 5], 1u << (pos & 31));
+            uint32_t n0, n1, n2, n3, n4, n5, n6, n7;
+            ORBX_LDS_U8(n0, b, 0);   ORBX_LDS_U8(n1, b, 1);   ORBX_LDS_U8(n2, b, 2);
+            ORBX_LDS_U8(n3, b, 80);  ORBX_LDS_U8(n4, b, 82);
+            ORBX_LDS_U8(n5, b, 160); ORBX_LDS_U8(n6, b, 161); ORBX_LDS_U8(n7, b, 162);
+            const uint32_t mx = max(max(max(n0, n1), max(n2, n3)), max(max(n4, n5), max(n6, n7)));
+            if (s > mx) {
+                atom_or(selA_s + (pos >> 5) * 4, 1u << (pos & 31));
+                if ((int)s >= iniTh) atom_or(selH_s + (pos >> 5) * 4, 1u << (pos & 31));
             }
         }
     }

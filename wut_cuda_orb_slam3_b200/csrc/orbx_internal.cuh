@@ -56,6 +56,7 @@ struct FrameGeom {
     unsigned long long cand_frame_stride;  // u32 per frame
     unsigned long long oct_frame_stride;   // u32 per frame
     int iniTh, minTh;
+    const uint32_t* cell_tab;  // [total_cells] level | cell_row << 4 | cell_col << 16   (device)
     LevelGeom L[kMaxLevels];
 };
 
