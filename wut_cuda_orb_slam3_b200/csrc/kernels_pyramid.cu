@@ -10,6 +10,8 @@
 // Data layout: every level is a bordered buffer [rows+38][pitch] per frame, interior pixel (0,0) at byte
 // 19*pitch + 32 (16-byte aligned), frames strided by pyr_frame_stride, levels by pyr_off.  Each thread produces one
 // aligned 32-bit word (4 pixels) of a bordered row, so stores are fully coalesced 128-byte lines per warp.
+#include <limits.h>
+
 #include "orbx_internal.cuh"
 
 namespace orbx {
@@ -86,6 +88,178 @@ __global__ void __launch_bounds__(128) pyr_resize_kernel(const __grid_constant__
     reinterpret_cast<uint32_t*>(dst)[word] = out;
 }
 
+// ---- tiled kernels (the production path; the per-word kernels above are the generic fallback) -----------------------
+// Reflect-101 border written by the tile that owns the mirrored interior pixels (tile = x0..x0+tw, y0..y0+th of the
+// interior, pixels in shared memory `t` with pitch TP): horizontal bands are copied as whole 16-byte row segments,
+// vertical bands (<= 19 columns) with byte stores; corners ride along with the vertical bands.
+template <int TP>
+__device__ __forceinline__ void write_border_mirrors(uint8_t* D, int pitch, int w, int h, int x0, int y0, int tw, int th,
+                                                     const uint8_t* t, int tid, int nthreads)
+{
+    const bool top = y0 <= kEdge, bottom = y0 + th >= h - 1 - kEdge;
+    // horizontal bands: row y (1..19) -> row -y ; row y (h-20..h-2) -> row 2(h-1)-y ; 16-byte segments
+    if (top || bottom) {
+        const int nv = (tw + 15) >> 4;
+        for (int i = tid; i < th * nv; i += nthreads) {
+            const int ty = i / nv, v = i - ty * nv;
+            const int y = y0 + ty;
+            int ym = INT_MIN;
+            if (y >= 1 && y <= kEdge) ym = -y;
+            else if (y >= h - 1 - kEdge && y <= h - 2) ym = 2 * (h - 1) - y;
+            if (ym == INT_MIN) continue;
+            uint8_t* dst = D + (ptrdiff_t)ym * pitch + x0 + v * 16;
+            if (v * 16 + 16 <= tw) *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(t + ty * TP + v * 16);
+            else for (int b = v * 16; b < tw; ++b) dst[b - v * 16] = t[ty * TP + b];
+            // a level lower than 40 rows can have a row in both bands
+            if (y >= 1 && y <= kEdge && y >= h - 1 - kEdge && y <= h - 2) {
+                uint8_t* d2 = D + (ptrdiff_t)(2 * (h - 1) - y) * pitch + x0 + v * 16;
+                for (int b = v * 16; b < min(tw, v * 16 + 16); ++b) d2[b - v * 16] = t[ty * TP + b];
+            }
+        }
+    }
+    // vertical bands: columns 1..19 -> -x, columns w-20..w-2 -> 2(w-1)-x, for every row of the tile and its row mirrors
+    const int lx0 = max(x0, 1), lx1 = min(x0 + tw - 1, kEdge);                 // left band columns inside this tile
+    const int rx0 = max(x0, w - 1 - kEdge), rx1 = min(x0 + tw - 1, w - 2);     // right band columns inside this tile
+    const int nl = max(lx1 - lx0 + 1, 0), nr = max(rx1 - rx0 + 1, 0);
+    const int nb = nl + nr;
+    if (nb == 0) return;
+    for (int i = tid; i < th * nb; i += nthreads) {
+        const int ty = i / nb, k = i - ty * nb;
+        const int x = k < nl ? lx0 + k : rx0 + (k - nl);
+        const int y = y0 + ty;
+        const uint8_t val = t[ty * TP + (x - x0)];
+        int ys[3], ny = 1;
+        ys[0] = y;
+        if (y >= 1 && y <= kEdge) ys[ny++] = -y;
+        if (y >= h - 1 - kEdge && y <= h - 2) ys[ny++] = 2 * (h - 1) - y;
+        for (int a = 0; a < ny; ++a) {
+            if (x >= 1 && x <= kEdge) D[(ptrdiff_t)ys[a] * pitch - x] = val;
+            if (x >= w - 1 - kEdge && x <= w - 2) D[(ptrdiff_t)ys[a] * pitch + 2 * (w - 1) - x] = val;
+        }
+    }
+}
+
+// Level 0, fast path (16-byte aligned input rows): copy 128x16 tiles with 16-byte loads/stores + border mirrors.
+constexpr int PT_W = 128, PT_H = 16, PT_THREADS = 256;
+
+__global__ void __launch_bounds__(PT_THREADS) pyr_level0_tiled_kernel(const __grid_constant__ FrameGeom fg, Workspace ws,
+                                                                     const uint8_t* __restrict__ images, size_t frame_stride, size_t in_pitch)
+{
+    __shared__ __align__(16) uint8_t t[PT_H * PT_W];
+    const LevelGeom& g = fg.L[0];
+    const int tid = threadIdx.x;
+    const int x0 = blockIdx.x * PT_W, y0 = blockIdx.y * PT_H, frame = blockIdx.z;
+    const int tw = min(PT_W, g.w - x0), th = min(PT_H, g.h - y0);
+    const uint8_t* S = images + (size_t)frame * frame_stride;
+    uint8_t* D = level_interior(ws.pyr, g, frame);
+    if (tid < PT_H * (PT_W / 16)) {
+        const int ty = tid >> 3, v = tid & 7;
+        if (ty < th && v * 16 < tw) {
+            const uint8_t* sp = S + (size_t)(y0 + ty) * in_pitch + x0 + v * 16;
+            uint8_t* dp = D + (size_t)(y0 + ty) * g.pitch + x0 + v * 16;
+            if (v * 16 + 16 <= tw) {
+                const uint4 q = __ldg(reinterpret_cast<const uint4*>(sp));
+                *reinterpret_cast<uint4*>(t + ty * PT_W + v * 16) = q;
+                *reinterpret_cast<uint4*>(dp) = q;
+            } else {
+                for (int b = 0; b < tw - v * 16; ++b) { const uint8_t c = __ldg(sp + b); t[ty * PT_W + v * 16 + b] = c; dp[b] = c; }
+            }
+        }
+    }
+    const bool edge = x0 <= kEdge || x0 + tw >= g.w - kEdge - 1 || y0 <= kEdge || y0 + th >= g.h - kEdge - 1;
+    if (!edge) return;
+    __syncthreads();
+    write_border_mirrors<PT_W>(D, g.pitch, g.w, g.h, x0, y0, tw, th, t, tid, PT_THREADS);
+}
+
+// Level l >= 1: one CTA produces a 128x16 tile of the level interior.  The source footprint (<= 34 rows x 304 bytes for
+// scale <= 2) is staged in shared memory with 16-byte loads, the horizontal fixed-point pass runs once per source row
+// into an int32 plane, the vertical pass combines two rows per output row (4 pixels per thread, 128-bit shared loads),
+// and the finished tile is written with 16-byte stores.
+constexpr int PT_SR = 2 * PT_H + 2;            // source rows
+constexpr int PT_SP = 2 * PT_W + 48;           // source pitch (bytes), multiple of 16
+
+__global__ void __launch_bounds__(PT_THREADS) pyr_resize_tiled_kernel(const __grid_constant__ FrameGeom fg, Workspace ws, int level)
+{
+    __shared__ __align__(16) uint8_t src[PT_SR * PT_SP];
+    __shared__ __align__(16) int hbuf[PT_SR * PT_W];
+    __shared__ __align__(16) uint8_t outt[PT_H * PT_W];
+    __shared__ uint2 ytl[PT_H];
+
+    const LevelGeom& g = fg.L[level];
+    const LevelGeom& p = fg.L[level - 1];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int x0 = blockIdx.x * PT_W, y0 = blockIdx.y * PT_H, frame = blockIdx.z;
+    const int tw = min(PT_W, g.w - x0), th = min(PT_H, g.h - y0);
+    const int tx = tid & (PT_W - 1);
+
+    // tables are indexed by bordered coordinates: interior x -> entry x + 19
+    const uint2 xt = __ldg(g.xtab + kEdge + x0 + min(tx, tw - 1));
+    if (tid < PT_H) ytl[tid] = __ldg(g.ytab + kEdge + y0 + min(tid, th - 1));
+    const uint2 xfirst = __ldg(g.xtab + kEdge + x0), xlast = __ldg(g.xtab + kEdge + x0 + tw - 1);
+    const uint2 yfirst = __ldg(g.ytab + kEdge + y0), ylast = __ldg(g.ytab + kEdge + y0 + th - 1);
+    const int sxmin = (int)(xfirst.x & 0xffff), sxmax = (int)(xlast.x >> 16);
+    const int symin = (int)(yfirst.x & 0xffff), symax = (int)(ylast.x >> 16);
+    const int cbase = sxmin & ~15;
+    const int nvec = ((sxmax - cbase) >> 4) + 1;            // 16-byte vectors per source row (<= 19)
+    const int nrows = symax - symin + 1;
+
+    const uint8_t* P = level_interior((const uint8_t*)ws.pyr, p, frame) + (size_t)symin * p.pitch + cbase;
+    if (lane < nvec)
+        for (int r = warp; r < nrows; r += PT_THREADS / 32)
+            *reinterpret_cast<uint4*>(src + r * PT_SP + lane * 16) = __ldg(reinterpret_cast<const uint4*>(P + (size_t)r * p.pitch) + lane);
+    __syncthreads();
+
+    // horizontal pass: thread = output column, every other source row
+    {
+        const int c0 = (int)(xt.x & 0xffff) - cbase, c1 = (int)(xt.x >> 16) - cbase;
+        const int a0 = (int)(xt.y & 0xffff), a1 = (int)(xt.y >> 16);
+        const uint8_t* s0 = src + c0;
+        const uint8_t* s1 = src + c1;
+        int* hb = hbuf + tx;
+        for (int r = tid >> 7; r < nrows; r += PT_THREADS / PT_W)
+            hb[r * PT_W] = (int)s0[r * PT_SP] * a0 + (int)s1[r * PT_SP] * a1;
+    }
+    __syncthreads();
+
+    // vertical pass: thread = 4 consecutive columns x 2 rows -> one 32-bit word per row of the output tile
+    {
+        const int xq = (tid & 31) * 4;
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            const int ty = (tid >> 5) + 8 * k;
+            const uint2 yt = ytl[ty];
+            const int4 r0 = *reinterpret_cast<const int4*>(hbuf + ((int)(yt.x & 0xffff) - symin) * PT_W + xq);
+            const int4 r1 = *reinterpret_cast<const int4*>(hbuf + ((int)(yt.x >> 16) - symin) * PT_W + xq);
+            const int b0 = (int)(yt.y & 0xffff), b1 = (int)(yt.y >> 16);
+            uint32_t o;
+            if (g.area2x) {
+                o = (uint32_t)((r0.x + r1.x + 2) >> 2) | ((uint32_t)((r0.y + r1.y + 2) >> 2) << 8) |
+                    ((uint32_t)((r0.z + r1.z + 2) >> 2) << 16) | ((uint32_t)((r0.w + r1.w + 2) >> 2) << 24);
+            } else {
+                auto f = [&](int a, int b) { return (uint32_t)((((b0 * (a >> 4)) >> 16) + ((b1 * (b >> 4)) >> 16) + 2) >> 2) & 0xffu; };
+                o = f(r0.x, r1.x) | (f(r0.y, r1.y) << 8) | (f(r0.z, r1.z) << 16) | (f(r0.w, r1.w) << 24);
+            }
+            *reinterpret_cast<uint32_t*>(outt + ty * PT_W + xq) = o;
+        }
+    }
+    __syncthreads();
+
+    // interior: 16-byte stores (interior rows are 16-byte aligned and x0 is a multiple of 128)
+    uint8_t* D = level_interior(ws.pyr, g, frame);
+    if (tid < PT_H * (PT_W / 16)) {
+        const int ty = tid >> 3, v = tid & 7;
+        if (ty < th && v * 16 < tw) {
+            uint8_t* dst = D + (size_t)(y0 + ty) * g.pitch + x0 + v * 16;
+            if (v * 16 + 16 <= tw) *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(outt + ty * PT_W + v * 16);
+            else for (int b = v * 16; b < tw; ++b) dst[b - v * 16] = outt[ty * PT_W + b];
+        }
+    }
+    const bool edge = x0 <= kEdge || x0 + tw >= g.w - kEdge - 1 || y0 <= kEdge || y0 + th >= g.h - kEdge - 1;
+    if (!edge) return;
+    write_border_mirrors<PT_W>(D, g.pitch, g.w, g.h, x0, y0, tw, th, outt, tid, PT_THREADS);
+}
+
 cudaError_t launch_pyramid(const FrameGeom& fg, const Workspace& ws, const uint8_t* d_images, size_t frame_stride,
                            size_t pitch, int n_frames, cudaStream_t st)
 {
@@ -93,8 +267,19 @@ cudaError_t launch_pyramid(const FrameGeom& fg, const Workspace& ws, const uint8
         const LevelGeom& g = fg.L[l];
         const int words = g.pitch / 4;
         dim3 grid((words + 127) / 128, g.rows_alloc, n_frames);
-        if (l == 0) pyr_level0_kernel<<<grid, 128, 0, st>>>(fg, ws, d_images, frame_stride, pitch);
-        else pyr_resize_kernel<<<grid, 128, 0, st>>>(fg, ws, l);
+        dim3 tgrid((g.w + PT_W - 1) / PT_W, (g.h + PT_H - 1) / PT_H, n_frames);
+        const bool big = g.w >= 2 * kEdge + 2 && g.h >= 2 * kEdge + 2;      // border band narrower than the level
+        if (l == 0) {
+            const bool aligned = ((uintptr_t)d_images & 15) == 0 && (frame_stride & 15) == 0 && (pitch & 15) == 0;
+            if (big && aligned) pyr_level0_tiled_kernel<<<tgrid, PT_THREADS, 0, st>>>(fg, ws, d_images, frame_stride, pitch);
+            else pyr_level0_kernel<<<grid, 128, 0, st>>>(fg, ws, d_images, frame_stride, pitch);
+        } else {
+            const LevelGeom& p = fg.L[l - 1];
+            // the tiled kernel needs a source footprint of at most 2x the tile
+            const bool tiled = big && (long long)p.w <= 2LL * g.w && (long long)p.h <= 2LL * g.h;
+            if (tiled) pyr_resize_tiled_kernel<<<tgrid, PT_THREADS, 0, st>>>(fg, ws, l);
+            else pyr_resize_kernel<<<grid, 128, 0, st>>>(fg, ws, l);
+        }
         count_launch();
     }
     return cudaGetLastError();
