@@ -23,7 +23,7 @@ __device__ __align__(16) const int8_t d_pattern[1024] = {
 __constant__ int c_umax[16] = {15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9, 8, 6, 3};
 
 constexpr int BT_W = 128, BT_H = 32;          // blur tile
-constexpr int BIN_P = 136;                    // input tile pitch (bytes): x0-4 .. x0+132
+constexpr int BIN_P = 160;                    // input tile pitch (bytes): image columns x0-16 .. x0+143 (16-byte aligned)
 constexpr int BIN_R = BT_H + 6;
 
 // cv::fastAtan2 (OpenCV mathfuncs_core atan_f32): float32, no FMA contraction.
@@ -50,11 +50,14 @@ __device__ __forceinline__ float fast_atan2_dev(float y, float x)
 
 }  // namespace
 
-// grid = (tiles over all levels, n_frames); tile table lookup by level prefix (computed on the fly).
+// grid = (tiles over all levels, n_frames).  Separable fixed-point 7x7: the horizontal pass is two IDP.4A (dp4a) per
+// pixel on byte windows realigned with funnel shifts (kernel bytes 18,34,48,56 | 48,34,18,0), the vertical pass a
+// sliding 32-bit window using the kernel's symmetry; the tile leaves through shared memory as 16-byte stores.
 __global__ void __launch_bounds__(256) blur_kernel(const __grid_constant__ FrameGeom fg, Workspace ws)
 {
     __shared__ __align__(16) uint8_t in[BIN_R * BIN_P];
-    __shared__ uint16_t hb[BIN_R * BT_W];
+    __shared__ __align__(16) uint32_t hb[BIN_R * BT_W];
+    __shared__ __align__(16) uint8_t outt[BT_H * BT_W];
     const int tid = threadIdx.x;
     const int frame = blockIdx.y;
     // locate (level, tile)
@@ -67,44 +70,55 @@ __global__ void __launch_bounds__(256) blur_kernel(const __grid_constant__ Frame
         t -= nt;
     }
     const LevelGeom& g = fg.L[level];
-    const int ty0 = (t / tx_n) * BT_H, tx0 = (t % tx_n) * BT_W;
+    const int tyi = t / tx_n;
+    const int ty0 = tyi * BT_H, tx0 = (t - tyi * tx_n) * BT_W;
     const uint8_t* base = ws.pyr + g.pyr_off + (size_t)frame * g.pyr_frame_stride;   // bordered buffer origin
-    // input tile: buffer rows (ty0 - 3 + 19) .., buffer byte columns (tx0 - 4 + 32) ..  (4-byte aligned)
-    const int brow0 = ty0 - 3 + kEdge, bcol0 = tx0 - 4 + kXPad;
-    for (int i = tid; i < BIN_R * (BIN_P / 4); i += 256) {
-        const int r = i / (BIN_P / 4), w = i - r * (BIN_P / 4);
-        const int br = brow0 + r, bc = bcol0 + 4 * w;
-        uint32_t v = 0;
-        if (br < g.rows_alloc && bc + 4 <= g.pitch) v = __ldg(reinterpret_cast<const uint32_t*>(base + (size_t)br * g.pitch + bc));
-        reinterpret_cast<uint32_t*>(in)[r * (BIN_P / 4) + w] = v;
+    // input tile: buffer rows (ty0 - 3 + 19) .., buffer byte columns (tx0 - 16 + 32) .. : 16-byte aligned
+    const int brow0 = ty0 - 3 + kEdge, bcol0 = tx0 - 16 + kXPad;
+    for (int i = tid; i < BIN_R * (BIN_P / 16); i += 256) {
+        const int r = i / (BIN_P / 16), v = i - r * (BIN_P / 16);
+        const int br = brow0 + r, bc = bcol0 + 16 * v;
+        uint4 q = make_uint4(0, 0, 0, 0);
+        if (br < g.rows_alloc && bc + 16 <= g.pitch) q = __ldg(reinterpret_cast<const uint4*>(base + (size_t)br * g.pitch + bc));
+        reinterpret_cast<uint4*>(in)[i] = q;
     }
     __syncthreads();
-    // horizontal pass: hb[r][x] = sum_k K[k] * in[r][x + 1 + k]   (x = 0..127 <-> image column tx0 + x)
+    // horizontal pass: task = (row, group of 4 columns); output x = 4q + j reads tile columns 4q+13+j .. 4q+19+j
+    for (int i = tid; i < BIN_R * (BT_W / 4); i += 256) {
+        const int r = i >> 5, q = i & 31;
+        const uint32_t* wp = reinterpret_cast<const uint32_t*>(in + r * BIN_P) + q + 3;
+        const uint32_t w0 = wp[0], w1 = wp[1], w2 = wp[2];
+        const uint32_t KA = 0x38302212u, KB = 0x00122230u;
+        uint4 h;
+        h.x = __dp4a(__funnelshift_r(w0, w1, 8), KA, __dp4a(__funnelshift_r(w1, w2, 8), KB, 0u));
+        h.y = __dp4a(__funnelshift_r(w0, w1, 16), KA, __dp4a(__funnelshift_r(w1, w2, 16), KB, 0u));
+        h.z = __dp4a(__funnelshift_r(w0, w1, 24), KA, __dp4a(__funnelshift_r(w1, w2, 24), KB, 0u));
+        h.w = __dp4a(w1, KA, __dp4a(w2, KB, 0u));
+        *reinterpret_cast<uint4*>(hb + r * BT_W + 4 * q) = h;
+    }
+    __syncthreads();
+    // vertical pass: thread = 2 adjacent columns x 8 rows, sliding window
     {
-        const int x = tid & (BT_W - 1);
-        for (int r = tid >> 7; r < BIN_R; r += 2) {
-            const uint8_t* p = in + r * BIN_P + x + 1;
-            const int s = 18 * (p[0] + p[6]) + 34 * (p[1] + p[5]) + 48 * (p[2] + p[4]) + 56 * p[3];
-            hb[r * BT_W + x] = (uint16_t)s;
+        const int cp = (tid & 63) * 2, r0 = (tid >> 6) * 8;
+        uint2 w[14];
+#pragma unroll
+        for (int k = 0; k < 14; ++k) w[k] = *reinterpret_cast<const uint2*>(hb + (r0 + k) * BT_W + cp);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const uint32_t s0 = 18u * (w[i].x + w[i + 6].x) + 34u * (w[i + 1].x + w[i + 5].x) + 48u * (w[i + 2].x + w[i + 4].x) + 56u * w[i + 3].x;
+            const uint32_t s1 = 18u * (w[i].y + w[i + 6].y) + 34u * (w[i + 1].y + w[i + 5].y) + 48u * (w[i + 2].y + w[i + 4].y) + 56u * w[i + 3].y;
+            const uint32_t o = ((s0 + 32768u) >> 16) | (((s1 + 32768u) >> 16) << 8);
+            *reinterpret_cast<uint16_t*>(outt + (r0 + i) * BT_W + cp) = (uint16_t)o;
         }
     }
     __syncthreads();
-    // vertical pass: thread = column x, 16 consecutive rows, sliding 7-register window
+    // 16-byte stores (the blurred level's pitch is a multiple of 16, so the last vector of a row may spill into padding)
     {
-        const int x = tid & (BT_W - 1);
-        const int r0 = (tid >> 7) * 16;
-        if (tx0 + x < g.w) {
-            uint8_t* out = ws.blur + g.blur_off + (size_t)frame * g.blur_frame_stride + (size_t)tx0 + x;
-            uint32_t w0 = hb[(r0 + 0) * BT_W + x], w1 = hb[(r0 + 1) * BT_W + x], w2 = hb[(r0 + 2) * BT_W + x],
-                     w3 = hb[(r0 + 3) * BT_W + x], w4 = hb[(r0 + 4) * BT_W + x], w5 = hb[(r0 + 5) * BT_W + x];
-#pragma unroll
-            for (int r = 0; r < 16; ++r) {
-                const uint32_t w6 = hb[(r0 + r + 6) * BT_W + x];
-                const uint32_t s = 18u * (w0 + w6) + 34u * (w1 + w5) + 48u * (w2 + w4) + 56u * w3;
-                const int y = ty0 + r0 + r;
-                if (y < g.h) out[(size_t)y * g.bpitch] = (uint8_t)((s + 32768u) >> 16);
-                w0 = w1; w1 = w2; w2 = w3; w3 = w4; w4 = w5; w5 = w6;
-            }
+        const int r = tid >> 3, v = tid & 7;
+        const int y = ty0 + r, x = tx0 + 16 * v;
+        if (y < g.h && x < g.w) {
+            uint8_t* out = ws.blur + g.blur_off + (size_t)frame * g.blur_frame_stride + (size_t)y * g.bpitch + x;
+            *reinterpret_cast<uint4*>(out) = *reinterpret_cast<const uint4*>(outt + r * BT_W + 16 * v);
         }
     }
 }
