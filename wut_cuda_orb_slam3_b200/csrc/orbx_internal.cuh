@@ -72,6 +72,8 @@ struct Workspace {
     float* lvl_angle;         // [frame][kp_slots]
     uint8_t* lvl_desc;        // [frame][kp_slots][32]
     int* lvl_ncand;           // [frame][nlevels] number of FAST candidates (probe)
+    long long* dbg;           // optional octree phase timing (nullptr in production)
+    int dbg_level;
 };
 
 inline __host__ __device__ uint8_t* level_interior(uint8_t* pyr, const LevelGeom& g, int frame)
@@ -95,7 +97,7 @@ cudaError_t launch_orient_describe(const FrameGeom& fg, const Workspace& ws, int
 cudaError_t launch_pack(const FrameGeom& fg, const Workspace& ws, int n_frames, int lap0, int lap1,
                         orbx_keypoint* d_kps, uint8_t* d_desc, int capacity, int* d_n_out, int* d_n_mono,
                         cudaStream_t st);
-size_t octree_smem_bytes(int nfeat);
+size_t octree_smem_bytes(int node_capacity, int threads = 256);
 cudaError_t octree_prepare();   // opt in to large dynamic shared memory
 
 cudaError_t launch_knn2(const uint8_t* d_q, int nq, const uint8_t* d_db, long long ndb, int index_base, int32_t* d_idx,
