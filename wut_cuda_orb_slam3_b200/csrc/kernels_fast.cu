@@ -135,11 +135,24 @@ __global__ void __launch_bounds__(128) fast_cells_kernel(const __grid_constant__
         const int nwords = (m + rw + 3) >> 2;                   // <= 20
         const uint32_t* src4 = reinterpret_cast<const uint32_t*>(src - m) + lane;
         const int wpitch = g.pitch >> 2;
-        if (lane < nwords)
-            for (int y = warp; y < rh; y += 4) sts_u32(roi_s + y * kRoiPitch + lane * 4, __ldg(src4 + (size_t)y * wpitch));
+        // all global loads of this lane are issued before the first shared store (the stores are volatile asm, which would
+        // otherwise serialise ~10 dependent L2 round trips at the start of every CTA)
+        constexpr int kRowsPerWarp = (kRoiRows + 3) / 4;
+        uint32_t tmp[kRowsPerWarp];
+        const bool ld = lane < nwords;
+#pragma unroll
+        for (int k = 0; k < kRowsPerWarp; ++k) {
+            const int y = warp + 4 * k;
+            tmp[k] = (ld && y < rh) ? __ldg(src4 + (size_t)y * wpitch) : 0u;
+        }
         const int nz = (rh * kRoiPitch + 15) >> 4;
         for (int i = tid; i < nz; i += 128) sts_zero16(sc_s + i * 16);
         for (int i = tid; i < kBitWords; i += 128) { sts_u32(selA_s + i * 4, 0); sts_u32(selH_s + i * 4, 0); }
+#pragma unroll
+        for (int k = 0; k < kRowsPerWarp; ++k) {
+            const int y = warp + 4 * k;
+            if (ld && y < rh) sts_u32(roi_s + y * kRoiPitch + lane * 4, tmp[k]);
+        }
     }
     __syncthreads();
 
@@ -150,32 +163,32 @@ __global__ void __launch_bounds__(128) fast_cells_kernel(const __grid_constant__
     const int Q = (((npix + 3) >> 2) + 31) & ~31;               // pixels per warp, multiple of 32
     {
         const int e0 = warp * Q + lane;
-        const int eend = min(e0 - lane + Q, npix);              // warp-uniform end of this warp's range
+        const int eend = min(warp * Q + Q, npix);               // warp-uniform end of this warp's range
         const float inv_ew = 1.0f / (float)ew;
         int ey = (int)(((float)e0 + 0.5f) * inv_ew);
         int ex = e0 - ey * ew;
-        const int sdy = (int)(32.5f * inv_ew), sdx = 32 - sdy * ew;
+        int pos = (ey + 3) * kRoiPitch + m + ex + 3;
+        const int wrapfix = kRoiPitch - ew;
+        const int safe = 3 * kRoiPitch + m + 3;                  // first evaluated pixel: a valid address for idle lanes
         uint32_t wl = list_s + (uint32_t)(warp * Q) * 2;        // write cursor of this warp (bytes)
-        for (int e = e0; e - lane < eend; e += 32) {
-            bool pass = false;
-            const int pos = (ey + 3) * kRoiPitch + m + ex + 3;
-            if (e < eend) {
-                const uint32_t b = roi_s + pos - 3 * kRoiPitch - 3;
-                uint32_t v, r0, r2, r4, r6, r8, r10, r12, r14;
-                ORBX_LDS_U8(v, b, 243);
-                ORBX_LDS_U8(r0, b, 483);  ORBX_LDS_U8(r8, b, 3);
-                ORBX_LDS_U8(r4, b, 246);  ORBX_LDS_U8(r12, b, 240);
-                ORBX_LDS_U8(r2, b, 405);  ORBX_LDS_U8(r10, b, 81);
-                ORBX_LDS_U8(r6, b, 85);   ORBX_LDS_U8(r14, b, 401);
-                const int M1 = max(max(min(r0, r8), min(r4, r12)), max(min(r2, r10), min(r6, r14)));
-                const int M2 = min(min(max(r0, r8), max(r4, r12)), min(max(r2, r10), max(r6, r14)));
-                pass = (M1 < (int)v - minTh) | (M2 > (int)v + minTh);
-            }
+        const int vlo = minTh, vhi = minTh;
+        for (int base = warp * Q; base < eend; base += 32) {
+            const bool valid = base + lane < eend;
+            const uint32_t b = roi_s + (valid ? pos : safe) - 3 * kRoiPitch - 3;
+            uint32_t v, r0, r2, r4, r6, r8, r10, r12, r14;
+            ORBX_LDS_U8(v, b, 243);
+            ORBX_LDS_U8(r0, b, 483);  ORBX_LDS_U8(r8, b, 3);
+            ORBX_LDS_U8(r4, b, 246);  ORBX_LDS_U8(r12, b, 240);
+            ORBX_LDS_U8(r2, b, 405);  ORBX_LDS_U8(r10, b, 81);
+            ORBX_LDS_U8(r6, b, 85);   ORBX_LDS_U8(r14, b, 401);
+            const int M1 = max(max(min(r0, r8), min(r4, r12)), max(min(r2, r10), min(r6, r14)));
+            const int M2 = min(min(max(r0, r8), max(r4, r12)), min(max(r2, r10), max(r6, r14)));
+            const bool pass = valid & ((M1 < (int)v - vlo) | (M2 > (int)v + vhi));
             const uint32_t mk = __ballot_sync(0xffffffffu, pass);
             if (pass) sts_u16(wl + 2 * __popc(mk & ((1u << lane) - 1)), (uint32_t)pos);
             wl += 2 * __popc(mk);
-            ex += sdx; ey += sdy;
-            if (ex >= ew) { ex -= ew; ++ey; }
+            ex += 32; pos += 32;
+            while (ex >= ew) { ex -= ew; pos += wrapfix; }
         }
         if (lane == 0) wcnt[warp] = (int)((wl - list_s) >> 1) - warp * Q;
     }
