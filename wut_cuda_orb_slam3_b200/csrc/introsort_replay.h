@@ -89,12 +89,38 @@ ORBX_SORT_HD void move_median_to_first_(item_t* result, item_t* a, item_t* b, it
     else swp(result, b);
 }
 
-ORBX_SORT_HD int unguarded_partition_(item_t* base, int first, int last, int pivot)
+// The scans below look 4 elements ahead: the probes of one step are independent loads, so a single GPU lane is not
+// serialised on one shared-memory round trip per comparison.  `n` bounds the speculative reads; decisions are taken in
+// exactly the order of the libstdc++ loops.
+ORBX_SORT_HD int unguarded_partition_(item_t* base, int n, int first, int last, int pivot)
 {
+    const item_t pv = base[pivot];
     while (true) {
-        while (lt(base[first], base[pivot])) ++first;
+        while (true) {                                        // while (comp(first, pivot)) ++first;
+            const item_t a0 = base[first], a1 = base[first + 1 < n ? first + 1 : n - 1],
+                         a2 = base[first + 2 < n ? first + 2 : n - 1], a3 = base[first + 3 < n ? first + 3 : n - 1];
+            if (!lt(a0, pv)) break;
+            ++first;
+            if (!lt(a1, pv)) break;
+            ++first;
+            if (!lt(a2, pv)) break;
+            ++first;
+            if (!lt(a3, pv)) break;
+            ++first;
+        }
         --last;
-        while (lt(base[pivot], base[last])) --last;
+        while (true) {                                        // while (comp(pivot, last)) --last;
+            const item_t a0 = base[last], a1 = base[last - 1 > 0 ? last - 1 : 0], a2 = base[last - 2 > 0 ? last - 2 : 0],
+                         a3 = base[last - 3 > 0 ? last - 3 : 0];
+            if (!lt(pv, a0)) break;
+            --last;
+            if (!lt(pv, a1)) break;
+            --last;
+            if (!lt(pv, a2)) break;
+            --last;
+            if (!lt(pv, a3)) break;
+            --last;
+        }
         if (!(first < last)) return first;
         swp(base + first, base + last);
         ++first;
@@ -103,12 +129,20 @@ ORBX_SORT_HD int unguarded_partition_(item_t* base, int first, int last, int piv
 
 ORBX_SORT_HD void unguarded_linear_insert_(item_t* base, int last)
 {
-    item_t val = base[last];
+    const item_t val = base[last];
     int next = last - 1;
-    while (lt(val, base[next])) {
-        base[last] = base[next];
-        last = next;
-        --next;
+    while (true) {
+        // positions <= next are never written by the shifts of this step, so they can be read ahead
+        const item_t a0 = base[next > 0 ? next : 0], a1 = base[next - 1 > 0 ? next - 1 : 0], a2 = base[next - 2 > 0 ? next - 2 : 0],
+                     a3 = base[next - 3 > 0 ? next - 3 : 0];
+        if (!lt(val, a0)) break;
+        base[last] = a0; last = next; --next;
+        if (!lt(val, a1)) break;
+        base[last] = a1; last = next; --next;
+        if (!lt(val, a2)) break;
+        base[last] = a2; last = next; --next;
+        if (!lt(val, a3)) break;
+        base[last] = a3; last = next; --next;
     }
     base[last] = val;
 }
@@ -149,7 +183,7 @@ ORBX_SORT_HD void sort_replay(item_t* base, int n)
             --depth;
             const int mid = first + (last - first) / 2;
             move_median_to_first_(base + first, base + first + 1, base + mid, base + last - 1);
-            const int cut = unguarded_partition_(base, first + 1, last, first);
+            const int cut = unguarded_partition_(base, n, first + 1, last, first);
             // recursion: __introsort_loop(cut, last, depth) runs BEFORE the loop continues on [first, cut); the two
             // ranges are disjoint so the order of processing does not change the result.
             if (sp < 72) stack[sp++] = Frame{cut, last, depth};

@@ -29,6 +29,7 @@ struct Smem {
     // carved from dynamic shared memory; M = node capacity
     uint32_t* hist;        // [kHistWords]
     int* warp_tmp;         // [64]
+    int* sort_stk;         // [3*72]
     uint32_t* nbeg[2];     // node segment begin           [M] x2 (ping-pong)
     uint32_t* ncnt[2];     // node key count
     uint32_t* nx[2];       // ULx | URx << 16
@@ -109,7 +110,7 @@ size_t octree_smem_bytes(int M, int T)
 {
     size_t b = 0;
     b += sizeof(uint32_t) * (16 * T + (16 * T) / 32);
-    b += sizeof(int) * 64;
+    b += sizeof(int) * (64 + 224);
     b += sizeof(uint32_t) * (size_t)M * 8;      // node arrays x2
     b += sizeof(uint32_t) * (size_t)M * 4;      // cc
     b += sizeof(int) * (size_t)M * 5;           // sa, sb, sc, sd, procpos
@@ -142,6 +143,7 @@ __global__ void __launch_bounds__(T) octree_kernel(const __grid_constant__ Frame
         unsigned char* p = smem_raw;
         S.hist = (uint32_t*)p; p += sizeof(uint32_t) * kHistWords;
         S.warp_tmp = (int*)p; p += sizeof(int) * 64;
+        S.sort_stk = (int*)p; p += sizeof(int) * 224;
         for (int b = 0; b < 2; ++b) {
             S.nbeg[b] = (uint32_t*)p; p += 4 * (size_t)M;
             S.ncnt[b] = (uint32_t*)p; p += 4 * (size_t)M;
@@ -187,15 +189,33 @@ __global__ void __launch_bounds__(T) octree_kernel(const __grid_constant__ Frame
         return;
     }
     {
-        const uint32_t* cand = ws.cand + (size_t)frame * fg.cand_frame_stride + g.cand_off;
-        for (int c = warp; c < ncells; c += T / 32) {
-            const int cnt = cell_count[c], o = cell_off[c];
-            const uint32_t* src = cand + (size_t)c * g.cell_cap;
-            for (int i = lane; i < cnt; i += 32) {
-                const uint32_t k = src[i];
-                keys0[o + i] = k;
-                keys[0][o + i] = (uint32_t)(o + i);
-                codes[0][o + i] = path_code((int)(k & 0xfff), (int)((k >> 12) & 0xfff), g, winH);
+        // warp = 4 cells per iteration so that the dependent global loads (offset -> candidates) of several cells overlap;
+        // payload = original index | score << 24 (the retain step needs only the payload)
+        const uint32_t* __restrict__ cand = ws.cand + (size_t)frame * fg.cand_frame_stride + g.cand_off;
+        for (int c0 = warp * 4; c0 < ncells; c0 += (T / 32) * 4) {
+            int cnt[4], o[4];
+            uint32_t k[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int c = c0 + u;
+                cnt[u] = c < ncells ? cell_count[c] : 0;
+                o[u] = c < ncells ? cell_off[c] : 0;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) k[u] = lane < cnt[u] ? cand[(size_t)(c0 + u) * g.cell_cap + lane] : 0u;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (lane < cnt[u]) {
+                    keys0[o[u] + lane] = k[u];
+                    keys[0][o[u] + lane] = (uint32_t)(o[u] + lane) | (k[u] & 0xff000000u);
+                    codes[0][o[u] + lane] = path_code((int)(k[u] & 0xfff), (int)((k[u] >> 12) & 0xfff), g, winH);
+                }
+                for (int i = lane + 32; i < cnt[u]; i += 32) {           // cells with more than 32 candidates (rare)
+                    const uint32_t kk = cand[(size_t)(c0 + u) * g.cell_cap + i];
+                    keys0[o[u] + i] = kk;
+                    keys[0][o[u] + i] = (uint32_t)(o[u] + i) | (kk & 0xff000000u);
+                    codes[0][o[u] + i] = path_code((int)(kk & 0xfff), (int)((kk >> 12) & 0xfff), g, winH);
+                }
             }
         }
     }
@@ -211,11 +231,17 @@ __global__ void __launch_bounds__(T) octree_kernel(const __grid_constant__ Frame
         for (int shift = 0; shift < nbits; shift += 4) {
             for (int i = tid; i < kHistWords; i += T) S.hist[i] = 0;
             __syncthreads();
-            const uint32_t* cin = codes[cur];
-            for (int i = i0; i < i1; ++i) {
-                const int d = (cin[i] >> shift) & 15;
-                const int idx = d * T + tid;
-                S.hist[idx + (idx >> 5)]++;
+            const uint32_t* __restrict__ cin = codes[cur];
+            for (int i = i0; i < i1; i += 8) {                  // batches of 8 independent loads
+                uint32_t c8[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) c8[j] = i + j < i1 ? cin[i + j] : 0u;
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    if (i + j < i1) {
+                        const int idx = (int)((c8[j] >> shift) & 15) * T + tid;
+                        S.hist[idx + (idx >> 5)]++;
+                    }
             }
             __syncthreads();
             // exclusive scan of the 16*T counters in (digit-major, thread-minor) order: padded raking
@@ -244,16 +270,21 @@ __global__ void __launch_bounds__(T) octree_kernel(const __grid_constant__ Frame
                 }
             }
             __syncthreads();
-            const uint32_t* kin = keys[cur];
-            uint32_t* cout_ = codes[cur ^ 1];
-            uint32_t* kout = keys[cur ^ 1];
-            for (int i = i0; i < i1; ++i) {
-                const uint32_t c = cin[i];
-                const int d = (c >> shift) & 15;
-                const int idx = d * T + tid;
-                const int pos = S.hist[idx + (idx >> 5)]++;
-                cout_[pos] = c;
-                kout[pos] = kin[i];
+            const uint32_t* __restrict__ kin = keys[cur];
+            uint32_t* __restrict__ cout_ = codes[cur ^ 1];
+            uint32_t* __restrict__ kout = keys[cur ^ 1];
+            for (int i = i0; i < i1; i += 8) {
+                uint32_t c8[8], k8[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) { c8[j] = i + j < i1 ? cin[i + j] : 0u; k8[j] = i + j < i1 ? kin[i + j] : 0u; }
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    if (i + j < i1) {
+                        const int idx = (int)((c8[j] >> shift) & 15) * T + tid;
+                        const int pos = S.hist[idx + (idx >> 5)]++;
+                        cout_[pos] = c8[j];
+                        kout[pos] = k8[j];
+                    }
             }
             cur ^= 1;
             __syncthreads();
@@ -301,9 +332,16 @@ __global__ void __launch_bounds__(T) octree_kernel(const __grid_constant__ Frame
         const int shift = 2 * (g.depth - 1 - dep);
         const uint32_t prefix = (C[beg] >> shift) & ~3u;
         const uint32_t e = beg + cnt;
-        const uint32_t b1 = lower_bound_code(C, beg, e, shift, prefix | 1u);
-        const uint32_t b2 = lower_bound_code(C, b1, e, shift, prefix | 2u);
-        const uint32_t b3 = lower_bound_code(C, b2, e, shift, prefix | 3u);
+        // three lower bounds in lock-step: the probes of one step are independent loads (chain length log2(cnt), not 3x)
+        uint32_t lo1 = beg, hi1 = e, lo2 = beg, hi2 = e, lo3 = beg, hi3 = e;
+        while (lo1 < hi1 || lo2 < hi2 || lo3 < hi3) {
+            const uint32_t m1 = (lo1 + hi1) >> 1, m2 = (lo2 + hi2) >> 1, m3 = (lo3 + hi3) >> 1;
+            const uint32_t v1 = C[min(m1, e - 1)] >> shift, v2 = C[min(m2, e - 1)] >> shift, v3 = C[min(m3, e - 1)] >> shift;
+            if (lo1 < hi1) { if (v1 < (prefix | 1u)) lo1 = m1 + 1; else hi1 = m1; }
+            if (lo2 < hi2) { if (v2 < (prefix | 2u)) lo2 = m2 + 1; else hi2 = m2; }
+            if (lo3 < hi3) { if (v3 < (prefix | 3u)) lo3 = m3 + 1; else hi3 = m3; }
+        }
+        const uint32_t b1 = lo1, b2 = lo2, b3 = lo3;
         const uint32_t c0 = b1 - beg, c1 = b2 - b1, c2 = b3 - b2, c3 = e - b3;
         S.cc[4 * p] = c0; S.cc[4 * p + 1] = c1; S.cc[4 * p + 2] = c2; S.cc[4 * p + 3] = c3;
         ne = (c0 > 0) + (c1 > 0) + (c2 > 0) + (c3 > 0);
@@ -449,9 +487,8 @@ __global__ void __launch_bounds__(T) octree_kernel(const __grid_constant__ Frame
         // = max score, then min ORIGINAL index: (score << 24) | (0xffffff - original index).
         uint32_t best = 0;
         for (uint32_t j = lane; j < cnt; j += 32) {
-            const uint32_t oi = K[beg + j];
-            const uint32_t v = (keys0[oi] & 0xff000000u) | (0xffffffu - oi);
-            best = max(best, v);
+            const uint32_t pl = K[beg + j];                      // original index | score << 24
+            best = max(best, (pl & 0xff000000u) | (0xffffffu - (pl & 0xffffffu)));
         }
 #pragma unroll
         for (int d = 16; d >= 1; d >>= 1) best = max(best, __shfl_xor_sync(0xffffffffu, best, d));
