@@ -168,7 +168,9 @@ __global__ void __launch_bounds__(256) orient_describe_kernel(const __grid_const
     // ---- rBRIEF on the blurred level: lane <-> descriptor byte ----
     const float factorPI = (float)(3.14159265358979323846 / 180.f);
     const float arad = __fmul_rn(angle, factorPI);
-    const float a = (float)cos((double)arad), b = (float)sin((double)arad);
+    double sd, cd;
+    sincos((double)arad, &sd, &cd);                 // same values as sin()/cos(), one argument reduction
+    const float a = (float)cd, b = (float)sd;
     const uint8_t* center = ws.blur + g.blur_off + (size_t)frame * g.blur_frame_stride + (size_t)y * g.bpitch + x;
     const int step = g.bpitch;
     const uint4* pat4 = reinterpret_cast<const uint4*>(d_pattern) + lane * 2;
