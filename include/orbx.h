@@ -152,6 +152,15 @@ int orbx_knn2_merge_device(int device, const int32_t* d_idx_shards, const int32_
  * (d1 < d2 * ratio, no gate).  accept[i] = 0/1. */
 int orbx_ratio_test(const int32_t* dist, int nq, float ratio, int th_low, int mode, uint8_t* accept);
 
+/* Rotation-consistency filter applied to accepted matches by SearchByBoW / SearchByProjection (src/ORBmatcher1.cc:344-356
+ * histogram of round((angleA-angleB [+360]) * (1/HISTO_LENGTH)) over HISTO_LENGTH=30 bins, src/ORBmatcher1.cc:408-427 removal,
+ * ComputeThreeMaxima src/ORBmatcher3.cc:592-633): keep[i] = 1 iff match i falls in one of the (up to) three dominant bins. Host. */
+int orbx_rotation_consistency(const float* angle_a, const float* angle_b, int n, uint8_t* keep);
+
+/* MapPoint::ComputeDistinctiveDescriptors (src/MapPoint.cc:329-401): N x N Hamming distances, per-row median at index
+ * (int)(0.5*(N-1)) of the sorted row, first row with the least median.  Host (N is a handful of observations). */
+int orbx_distinctive_descriptor(const uint8_t* descriptors, int n, int* best_idx);
+
 /* void Frame::ComputeStereoMatches() — src/Frame.cc:841-1011.  Uses the un-blurred pyramids of frame `frameL` /
  * `frameR` of the LAST calls on exL / exR (which must live on the same device; they may be the same handle) and
  * HOST keypoints/descriptors as returned by orbx_extract.  bf = mbf; maxD = mbf/mb is explicit because the

@@ -899,6 +899,60 @@ int orbo_stereo_match(const orbo_keypoint* kpL, const uint8_t* descL, int nL, co
     return kept;
 }
 
+// Rotation histogram + ComputeThreeMaxima — src/ORBmatcher1.cc:236-238, 344-356, 408-427; src/ORBmatcher3.cc:592-633.
+void orbo_rotation_consistency(const float* angle_a, const float* angle_b, int n, uint8_t* keep)
+{
+    const int HISTO_LENGTH = 30;
+    std::vector<int> rotHist[HISTO_LENGTH];
+    const float factor = 1.0f / HISTO_LENGTH;
+    for (int i = 0; i < n; ++i) {
+        float rot = angle_a[i] - angle_b[i];
+        if (rot < 0.0) rot += 360.0f;
+        int bin = (int)round(rot * factor);
+        if (bin == HISTO_LENGTH) bin = 0;
+        rotHist[bin].push_back(i);
+    }
+    int ind1 = -1, ind2 = -1, ind3 = -1;
+    {
+        int max1 = 0, max2 = 0, max3 = 0;
+        for (int i = 0; i < HISTO_LENGTH; i++) {
+            const int s = (int)rotHist[i].size();
+            if (s > max1) { max3 = max2; max2 = max1; max1 = s; ind3 = ind2; ind2 = ind1; ind1 = i; }
+            else if (s > max2) { max3 = max2; max2 = s; ind3 = ind2; ind2 = i; }
+            else if (s > max3) { max3 = s; ind3 = i; }
+        }
+        if (max2 < 0.1f * (float)max1) { ind2 = -1; ind3 = -1; }
+        else if (max3 < 0.1f * (float)max1) { ind3 = -1; }
+    }
+    for (int i = 0; i < n; ++i) keep[i] = 1;
+    for (int i = 0; i < HISTO_LENGTH; i++) {
+        if (i == ind1 || i == ind2 || i == ind3) continue;
+        for (size_t j = 0; j < rotHist[i].size(); j++) keep[rotHist[i][j]] = 0;
+    }
+}
+
+// MapPoint::ComputeDistinctiveDescriptors — src/MapPoint.cc:368-395.
+int orbo_distinctive_descriptor(const uint8_t* desc, int N)
+{
+    std::vector<std::vector<float>> Distances(N, std::vector<float>(N, 0.f));
+    for (int i = 0; i < N; i++) {
+        Distances[i][i] = 0;
+        for (int j = i + 1; j < N; j++) {
+            int distij = descriptor_distance(desc + (size_t)i * 32, desc + (size_t)j * 32);
+            Distances[i][j] = (float)distij;
+            Distances[j][i] = (float)distij;
+        }
+    }
+    int BestMedian = INT_MAX, BestIdx = 0;
+    for (int i = 0; i < N; i++) {
+        std::vector<int> vDists(Distances[i].begin(), Distances[i].end());
+        std::sort(vDists.begin(), vDists.end());
+        int median = vDists[(size_t)(0.5 * (N - 1))];
+        if (median < BestMedian) { BestMedian = median; BestIdx = i; }
+    }
+    return BestIdx;
+}
+
 // std::sort with a comparator that looks only at the bits above bit 24 (the GPU octree's replay of libstdc++'s
 // introsort is checked against this, tests/test_introsort.py).
 void orbo_std_sort_hi40(unsigned long long* items, int n)

@@ -58,8 +58,20 @@ class Oracle:
         L.orbo_knn2.argtypes = [_vp, C.c_int, _vp, C.c_int, _vp, _vp, C.c_int]
         L.orbo_ratio_accept.argtypes = [C.c_int, C.c_int, C.c_float, C.c_int]
         L.orbo_std_sort_hi40.argtypes = [_vp, C.c_int]
+        L.orbo_rotation_consistency.argtypes = [_vp, _vp, C.c_int, _vp]
+        L.orbo_distinctive_descriptor.argtypes = [_vp, C.c_int]
         L.orbo_stereo_match.argtypes = [_vp, _vp, C.c_int, _vp, _vp, C.c_int, _vp, _vp, _vp, _vp, C.c_int, _vp, _vp,
                                         C.c_float, C.c_float, _vp, _vp]
+
+    def rotation_consistency(self, a, b):
+        a = np.ascontiguousarray(a, np.float32); b = np.ascontiguousarray(b, np.float32)
+        keep = np.zeros(len(a), np.uint8)
+        self.lib.orbo_rotation_consistency(_ptr(a), _ptr(b), len(a), _ptr(keep))
+        return keep.astype(bool)
+
+    def distinctive_descriptor(self, desc):
+        desc = np.ascontiguousarray(desc, np.uint8)
+        return self.lib.orbo_distinctive_descriptor(_ptr(desc), len(desc))
 
     def std_sort_hi40(self, items):
         items = np.ascontiguousarray(items, np.uint64).copy()

@@ -88,3 +88,22 @@ def test_synth_generator_is_deterministic_and_textured():
     assert d.shape == (100, 32) and q.shape == (100, 32)
     bits = np.unpackbits(d).mean()
     assert 0.45 < bits < 0.55
+
+
+def test_rotation_consistency_matches_oracle(oracle):
+    rng = np.random.default_rng(1)
+    for n in (0, 1, 5, 200, 3000):
+        a = rng.uniform(0, 360, n).astype(np.float32)
+        b = (a - rng.choice([0.0, 30.0, 61.0, 200.0], n, p=[0.6, 0.25, 0.1, 0.05]) + rng.normal(0, 3, n)).astype(np.float32) % np.float32(360)
+        keep = orbx.rotation_consistency(a, b)
+        assert np.array_equal(keep, oracle.rotation_consistency(a, b))
+        if n >= 200:
+            assert keep.any() and not keep.all()
+
+
+def test_distinctive_descriptor_matches_oracle(oracle):
+    rng = np.random.default_rng(2)
+    for n in (1, 2, 3, 8, 25):
+        base = rng.integers(0, 256, 32, dtype=np.uint8)
+        d = np.stack([base ^ np.packbits(rng.random(256) < p) for p in rng.uniform(0.0, 0.2, n)])
+        assert orbx.distinctive_descriptor(d) == oracle.distinctive_descriptor(d)

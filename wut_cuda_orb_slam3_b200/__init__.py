@@ -7,7 +7,7 @@ the built library raises (no CPU fallback).
 from . import capi, synth  # noqa: F401
 from .capi import KP_DTYPE, OrbxError, lib  # noqa: F401
 from .extractor import ORBextractor, compute_tables, distribute_octree  # noqa: F401
-from .matcher import (ORBmatcher, compute_stereo_matches, knn2_device, knn2_merge_device,  # noqa: F401
-                      measure_popc_peak)
+from .matcher import (ORBmatcher, compute_stereo_matches, distinctive_descriptor, knn2_device,  # noqa: F401
+                      knn2_merge_device, measure_popc_peak, rotation_consistency)
 
 lib()  # fail loudly at import time if the CUDA extension is missing

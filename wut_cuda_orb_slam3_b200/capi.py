@@ -54,6 +54,8 @@ SIGNATURES = {
     "orbx_knn2_device": (_i, [_i, _vp, _i, _vp, _i64, C.c_int32, _vp, _vp, _vp]),
     "orbx_knn2_merge_device": (_i, [_i, _vp, _vp, _i, _i, _vp, _vp, _vp]),
     "orbx_ratio_test": (_i, [_vp, _i, _f, _i, _i, _vp]),
+    "orbx_rotation_consistency": (_i, [_vp, _vp, _i, _vp]),
+    "orbx_distinctive_descriptor": (_i, [_vp, _i, _vp]),
     "orbx_stereo_match": (_i, [_vp, _i, _vp, _i, _vp, _vp, _i, _vp, _vp, _i, _f, _f, _vp, _vp]),
     "orbx_profile_begin": (_i, [_vp]),
     "orbx_profile_end": (_i, [_vp, _vp, _vp]),

@@ -3,7 +3,9 @@
 // One orbx_extractor == one ORB_SLAM3::ORBextractor instance (reference include/ORBextractor.h:52-120): parameters,
 // scale tables, a private CUDA stream and a device workspace sized for the current image shape.  There is no CPU
 // fallback anywhere in this file: without a CUDA device every compute entry point returns ORBX_ERR_NO_DEVICE.
+#include <algorithm>
 #include <atomic>
+#include <climits>
 #include <cfloat>
 #include <cmath>
 #include <cstdarg>
@@ -827,6 +829,56 @@ int orbx_ratio_test(const int32_t* dist, int nq, float ratio, int th_low, int mo
         else ok = (float)d1 < (float)d2 * (double)ratio;                            // src/Frame.cc:1181
         accept[i] = ok ? 1 : 0;
     }
+    return ORBX_OK;
+}
+
+int orbx_rotation_consistency(const float* angle_a, const float* angle_b, int n, uint8_t* keep)
+{
+    if (n < 0 || (n > 0 && (!angle_a || !angle_b || !keep))) return fail(ORBX_ERR_INVALID_ARG, "bad arguments");
+    const int HISTO_LENGTH = 30;
+    const float factor = 1.0f / HISTO_LENGTH;                 // src/ORBmatcher1.cc:238 (sic: bins are 30 degrees wide)
+    std::vector<int> bin(n);
+    int count[HISTO_LENGTH] = {0};
+    for (int i = 0; i < n; ++i) {
+        float rot = angle_a[i] - angle_b[i];
+        if (rot < 0.0) rot += 360.0f;
+        int b = (int)round(rot * factor);
+        if (b == HISTO_LENGTH) b = 0;
+        if (b < 0 || b >= HISTO_LENGTH) return fail(ORBX_ERR_INVALID_ARG, "angle %d out of range (reference asserts)", i);
+        bin[i] = b;
+        count[b]++;
+    }
+    int max1 = 0, max2 = 0, max3 = 0, ind1 = -1, ind2 = -1, ind3 = -1;      // ComputeThreeMaxima
+    for (int i = 0; i < HISTO_LENGTH; i++) {
+        const int s = count[i];
+        if (s > max1) { max3 = max2; max2 = max1; max1 = s; ind3 = ind2; ind2 = ind1; ind1 = i; }
+        else if (s > max2) { max3 = max2; max2 = s; ind3 = ind2; ind2 = i; }
+        else if (s > max3) { max3 = s; ind3 = i; }
+    }
+    if (max2 < 0.1f * (float)max1) { ind2 = -1; ind3 = -1; }
+    else if (max3 < 0.1f * (float)max1) { ind3 = -1; }
+    for (int i = 0; i < n; ++i) keep[i] = (bin[i] == ind1 || bin[i] == ind2 || bin[i] == ind3) ? 1 : 0;
+    return ORBX_OK;
+}
+
+int orbx_distinctive_descriptor(const uint8_t* descriptors, int n, int* best_idx)
+{
+    if (n <= 0 || !descriptors || !best_idx) return fail(ORBX_ERR_INVALID_ARG, "bad arguments");
+    std::vector<int> dist((size_t)n * n, 0);
+    for (int i = 0; i < n; ++i)
+        for (int j = i + 1; j < n; ++j) {
+            const int d = orbx_descriptor_distance(descriptors + (size_t)i * 32, descriptors + (size_t)j * 32);
+            dist[(size_t)i * n + j] = d; dist[(size_t)j * n + i] = d;
+        }
+    int bestMedian = INT_MAX, bestIdx = 0;
+    std::vector<int> row(n);
+    for (int i = 0; i < n; ++i) {
+        std::copy(dist.begin() + (size_t)i * n, dist.begin() + (size_t)(i + 1) * n, row.begin());
+        std::sort(row.begin(), row.end());
+        const int median = row[(size_t)(0.5 * (n - 1))];
+        if (median < bestMedian) { bestMedian = median; bestIdx = i; }
+    }
+    *best_idx = bestIdx;
     return ORBX_OK;
 }
 

@@ -39,6 +39,22 @@ class ORBmatcher:
         return acc.astype(bool)
 
 
+def rotation_consistency(angle_a, angle_b):
+    """The 30-bin rotation histogram + ComputeThreeMaxima filter of SearchByBoW (src/ORBmatcher1.cc:344-427): bool keep[n]."""
+    a = np.ascontiguousarray(angle_a, np.float32); b = np.ascontiguousarray(angle_b, np.float32)
+    keep = np.zeros(len(a), np.uint8)
+    check(lib().orbx_rotation_consistency(ptr(a), ptr(b), len(a), ptr(keep)))
+    return keep.astype(bool)
+
+
+def distinctive_descriptor(descriptors):
+    """MapPoint::ComputeDistinctiveDescriptors (src/MapPoint.cc:329-401): index of the least-median-distance descriptor."""
+    d = np.ascontiguousarray(descriptors, np.uint8).reshape(-1, 32)
+    best = C.c_int(0)
+    check(lib().orbx_distinctive_descriptor(ptr(d), len(d), C.byref(best)))
+    return best.value
+
+
 def knn2_device(d_q, nq, d_db, ndb, d_idx, d_dist, index_base=0, device=0, stream=None):
     check(lib().orbx_knn2_device(device, ptr(d_q), nq, ptr(d_db), ndb, index_base, ptr(d_idx), ptr(d_dist), ptr(stream) if stream else None))
 
