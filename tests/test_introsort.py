@@ -54,3 +54,16 @@ def test_octree_like_keys(oracle):
         ulx = (rng.integers(0, 8, n) * 45).astype(np.uint64)
         items = make((cnt << np.uint64(13)) | ulx)
         assert np.array_equal(replay(items), oracle.std_sort_hi40(items))
+
+
+def test_32bit_rank_items_give_the_same_permutation(oracle):
+    """The kernel sorts (dense rank << 16 | creation index) when there are <= 512 nodes; same permutation as the 64-bit items."""
+    rng = np.random.default_rng(7)
+    for n in (1, 2, 17, 40, 118, 300, 512):
+        for nkeys in (1, 3, 20, 10 ** 6):
+            keys = rng.integers(0, nkeys, n).astype(np.uint64)
+            ref = oracle.std_sort_hi40(make(keys))
+            rank = np.array([(keys < k).sum() for k in keys], np.uint32)
+            items = np.ascontiguousarray((rank << np.uint32(16)) | np.arange(n, dtype=np.uint32))
+            lib().orbx_debug_sort_replay32(ptr(items), n)
+            assert np.array_equal(items & np.uint32(0xffff), (ref & np.uint64(0xffffff)).astype(np.uint32)), (n, nkeys)

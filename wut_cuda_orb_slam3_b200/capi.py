@@ -91,6 +91,8 @@ def lib():
             fn.argtypes = args
         L.orbx_debug_sort_replay.restype = None
         L.orbx_debug_sort_replay.argtypes = [_vp, _i]
+        L.orbx_debug_sort_replay32.restype = None
+        L.orbx_debug_sort_replay32.argtypes = [_vp, _i]
         _lib = L
     return _lib
 

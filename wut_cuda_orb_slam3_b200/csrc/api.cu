@@ -1025,5 +1025,6 @@ int orbx_debug_octree_timing(orbx_extractor* ex, const uint8_t* image, int rows,
 
 // Test hook: the std::sort replay used by the octree kernel, on the host (tests/test_introsort.py).
 void orbx_debug_sort_replay(unsigned long long* items, int n) { orbx_sort::sort_replay(items, n); }
+void orbx_debug_sort_replay32(uint32_t* items, int n) { orbx_sort::sort_replay(items, n); }
 
 }  // extern "C"

@@ -20,15 +20,16 @@
 
 namespace orbx_sort {
 
-typedef unsigned long long item_t;
-
 constexpr int kPayloadBits = 24;
-ORBX_SORT_HD item_t make_item(item_t key, uint32_t payload) { return (key << kPayloadBits) | (payload & 0xffffffu); }
-ORBX_SORT_HD uint32_t payload(item_t v) { return (uint32_t)(v & 0xffffffu); }
-ORBX_SORT_HD bool lt(item_t a, item_t b) { return (a >> kPayloadBits) < (b >> kPayloadBits); }
-ORBX_SORT_HD void swp(item_t* a, item_t* b) { item_t t = *a; *a = *b; *b = t; }
+ORBX_SORT_HD unsigned long long make_item(unsigned long long key, uint32_t payload) { return (key << kPayloadBits) | (payload & 0xffffffu); }
+ORBX_SORT_HD uint32_t payload(unsigned long long v) { return (uint32_t)(v & 0xffffffu); }
+// 64-bit items: compared by the bits above the 24-bit payload
+ORBX_SORT_HD bool lt(unsigned long long a, unsigned long long b) { return (a >> kPayloadBits) < (b >> kPayloadBits); }
+// 32-bit items: rank << 16 | payload, compared by rank only:  rank(a) < rank(b)  <=>  (a | 0xffff) < b
+ORBX_SORT_HD bool lt(uint32_t a, uint32_t b) { return (a | 0xffffu) < b; }
+template <typename item_t> ORBX_SORT_HD void swp(item_t* a, item_t* b) { item_t t = *a; *a = *b; *b = t; }
 
-ORBX_SORT_HD void push_heap_(item_t* first, int hole, int top, item_t value)
+template <typename item_t> ORBX_SORT_HD void push_heap_(item_t* first, int hole, int top, item_t value)
 {
     int parent = (hole - 1) / 2;
     while (hole > top && lt(first[parent], value)) {
@@ -39,7 +40,7 @@ ORBX_SORT_HD void push_heap_(item_t* first, int hole, int top, item_t value)
     first[hole] = value;
 }
 
-ORBX_SORT_HD void adjust_heap_(item_t* first, int hole, int len, item_t value)
+template <typename item_t> ORBX_SORT_HD void adjust_heap_(item_t* first, int hole, int len, item_t value)
 {
     const int top = hole;
     int second = hole;
@@ -58,7 +59,7 @@ ORBX_SORT_HD void adjust_heap_(item_t* first, int hole, int len, item_t value)
 }
 
 // std::__partial_sort(first, last, last) == make_heap + sort_heap
-ORBX_SORT_HD void heap_sort_(item_t* first, int len)
+template <typename item_t> ORBX_SORT_HD void heap_sort_(item_t* first, int len)
 {
     if (len >= 2) {
         int parent = (len - 2) / 2;
@@ -78,7 +79,7 @@ ORBX_SORT_HD void heap_sort_(item_t* first, int len)
     }
 }
 
-ORBX_SORT_HD void move_median_to_first_(item_t* result, item_t* a, item_t* b, item_t* c)
+template <typename item_t> ORBX_SORT_HD void move_median_to_first_(item_t* result, item_t* a, item_t* b, item_t* c)
 {
     if (lt(*a, *b)) {
         if (lt(*b, *c)) swp(result, b);
@@ -92,7 +93,7 @@ ORBX_SORT_HD void move_median_to_first_(item_t* result, item_t* a, item_t* b, it
 // The scans below look 4 elements ahead: the probes of one step are independent loads, so a single GPU lane is not
 // serialised on one shared-memory round trip per comparison.  `n` bounds the speculative reads; decisions are taken in
 // exactly the order of the libstdc++ loops.
-ORBX_SORT_HD int unguarded_partition_(item_t* base, int n, int first, int last, int pivot)
+template <typename item_t> ORBX_SORT_HD int unguarded_partition_(item_t* base, int n, int first, int last, int pivot)
 {
     const item_t pv = base[pivot];
     while (true) {
@@ -127,7 +128,7 @@ ORBX_SORT_HD int unguarded_partition_(item_t* base, int n, int first, int last, 
     }
 }
 
-ORBX_SORT_HD void unguarded_linear_insert_(item_t* base, int last)
+template <typename item_t> ORBX_SORT_HD void unguarded_linear_insert_(item_t* base, int last)
 {
     const item_t val = base[last];
     int next = last - 1;
@@ -147,7 +148,7 @@ ORBX_SORT_HD void unguarded_linear_insert_(item_t* base, int last)
     base[last] = val;
 }
 
-ORBX_SORT_HD void insertion_sort_(item_t* base, int first, int last)
+template <typename item_t> ORBX_SORT_HD void insertion_sort_(item_t* base, int first, int last)
 {
     if (first == last) return;
     for (int i = first + 1; i != last; ++i) {
@@ -162,7 +163,7 @@ ORBX_SORT_HD void insertion_sort_(item_t* base, int first, int last)
 }
 
 // std::sort(base, base + n, comp) with comp = "high 32 bits less-than".
-ORBX_SORT_HD void sort_replay(item_t* base, int n)
+template <typename item_t> ORBX_SORT_HD void sort_replay(item_t* base, int n)
 {
     if (n <= 0) return;
     // __introsort_loop with an explicit stack (the recursion is on the right part, the loop on the left part)

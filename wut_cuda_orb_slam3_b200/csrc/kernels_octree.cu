@@ -15,6 +15,8 @@
 //    nodes with std::sort(compareNodes) — replayed exactly (introsort_replay.h) because ties are broken by the
 //    algorithm's internal permutation — and splits from the back until size >= N.
 //  * Retain (756-771): first key with maximal response per node, in list order.
+#include <stdlib.h>
+
 #include "introsort_replay.h"
 #include "orbx_internal.cuh"
 
@@ -22,7 +24,7 @@ namespace orbx {
 
 namespace {
 
-constexpr int kMaxT = 512;                 // largest CTA size the kernel is instantiated with
+constexpr int kMaxT = 1024;                 // largest CTA size the kernel is instantiated with
 constexpr int kHistWordsMax = 16 * kMaxT + (16 * kMaxT) / 32;
 
 struct Smem {
@@ -40,8 +42,8 @@ struct Smem {
     int* sc;               // [M] scan scratch c
     int* sd;               // [M] scratch d
     int* procpos;          // [M] list position of the p-th processed node
-    orbx_sort::item_t* vec;   // [M] expandable nodes, creation order: (cnt<<13 | ULx) << 32 | list position
-    orbx_sort::item_t* vec2;  // [M]
+    unsigned long long* vec;   // [M] expandable nodes, creation order: (cnt<<13 | ULx) << 32 | list position
+    unsigned long long* vec2;  // [M]
 };
 
 // Exclusive prefix sum of a[0..n) in place (int), returns the total.  All T threads must call.
@@ -115,7 +117,7 @@ size_t octree_smem_bytes(int M, int T)
     b += sizeof(uint32_t) * (size_t)M * 4;      // cc
     b += sizeof(int) * (size_t)M * 5;           // sa, sb, sc, sd, procpos
     b += 8;                                     // alignment slack
-    b += sizeof(orbx_sort::item_t) * (size_t)M * 2;
+    b += sizeof(unsigned long long) * (size_t)M * 2;
     return b;
 }
 
@@ -157,8 +159,8 @@ __global__ void __launch_bounds__(T) octree_kernel(const __grid_constant__ Frame
         S.sd = (int*)p; p += 4 * (size_t)M;
         S.procpos = (int*)p; p += 4 * (size_t)M;
         p = (unsigned char*)(((uintptr_t)p + 7) & ~(uintptr_t)7);
-        S.vec = (orbx_sort::item_t*)p; p += 8 * (size_t)M;
-        S.vec2 = (orbx_sort::item_t*)p;
+        S.vec = (unsigned long long*)p; p += 8 * (size_t)M;
+        S.vec2 = (unsigned long long*)p;
     }
 
     int* out_n = ws.lvl_n + (size_t)frame * fg.nlevels + level;
@@ -352,7 +354,7 @@ __global__ void __launch_bounds__(T) octree_kernel(const __grid_constant__ Frame
     // Applies the splits of processed nodes p = 0..nS-1 (list positions procpos[p], child counts in cc, sa[p] = #non-empty,
     // sb[p] = #expandable), builds the new list in buffer a^1 and the new expandable vector in `vout`.
     // Returns new list size via s_nL and the new vector length via s_total.
-    auto apply_splits = [&](int nL, int nS, orbx_sort::item_t* vout) {
+    auto apply_splits = [&](int nL, int nS, unsigned long long* vout) {
         const int b = a ^ 1;
         // keep flags: sc[pos] = 1 for untouched nodes
         for (int i = tid; i < nL; i += T) S.sc[i] = 1;
@@ -397,7 +399,7 @@ __global__ void __launch_bounds__(T) octree_kernel(const __grid_constant__ Frame
 #pragma unroll
             for (int k = 0; k < 4; ++k)               // creation order of vSizeAndPointerToNode: n1..n4 with > 1 key
                 if (cn[k] > 1)
-                    vout[vslot++] = orbx_sort::make_item(((orbx_sort::item_t)cn[k] << 13) | (cx[k] & 0xffff), (uint32_t)posk[k]);
+                    vout[vslot++] = orbx_sort::make_item(((unsigned long long)cn[k] << 13) | (cx[k] & 0xffff), (uint32_t)posk[k]);
         }
         for (int i = tid; i < nL; i += T) {
             const int r = S.sc[i];
@@ -440,18 +442,33 @@ __global__ void __launch_bounds__(T) octree_kernel(const __grid_constant__ Frame
             finish = true;
         } else if (nL + nToExpand * 3 > N) {
             // phase 2
-            orbx_sort::item_t* vprev = S.vec;
-            orbx_sort::item_t* vnext = S.vec2;
+            unsigned long long* vprev = S.vec;
+            unsigned long long* vnext = S.vec2;
             while (!finish) {
                 const int prev2 = nL;
                 const int m = nToExpand;
                 if (dbg) { dbg[8] += 1; if (m > dbg[10]) dbg[10] = m; }
-                if (tid == 0) orbx_sort::sort_replay(vprev, m);            // std::sort(compareNodes)  (src 709)
+                // std::sort(compareNodes) (src 709).  For the usual few hundred nodes the replay runs on 32-bit items
+                // (dense rank of (count, UL.x) << 16 | creation index): one shared-memory word per move/compare.
+                const bool small = m <= 512;
+                uint32_t* s32 = reinterpret_cast<uint32_t*>(S.sd);
+                if (small) {
+                    for (int i = tid; i < m; i += T) {
+                        const unsigned long long ki = vprev[i] >> orbx_sort::kPayloadBits;
+                        int rank = 0;
+                        for (int j = 0; j < m; ++j) rank += (vprev[j] >> orbx_sort::kPayloadBits) < ki;
+                        s32[i] = ((uint32_t)rank << 16) | (uint32_t)i;
+                    }
+                    __syncthreads();
+                    if (tid == 0) orbx_sort::sort_replay(s32, m);
+                } else {
+                    if (tid == 0) orbx_sort::sort_replay(vprev, m);
+                }
                 __syncthreads();
                 OCT_MARK(4);
                 // processing order p = 0..m-1 walks the sorted vector from the back (src 710)
                 for (int p = tid; p < m; p += T) {
-                    const int pos = (int)orbx_sort::payload(vprev[m - 1 - p]);
+                    const int pos = (int)orbx_sort::payload(small ? vprev[s32[m - 1 - p] & 0xffffu] : vprev[m - 1 - p]);
                     S.procpos[p] = pos;
                     const int r = split_counts(p, pos);
                     S.sa[p] = r & 0xff; S.sb[p] = r >> 8;
@@ -472,7 +489,7 @@ __global__ void __launch_bounds__(T) octree_kernel(const __grid_constant__ Frame
                 apply_splits(prev2, nS2, vnext);
                 nL = s_nL;
                 nToExpand = s_total;
-                orbx_sort::item_t* t = vprev; vprev = vnext; vnext = t;
+                unsigned long long* t = vprev; vprev = vnext; vnext = t;
                 if (nL >= N || nL == prev2) finish = true;
                 OCT_MARK(5);
             }
@@ -504,7 +521,9 @@ cudaError_t octree_prepare()
 {
     cudaError_t e = cudaFuncSetAttribute(octree_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(octree_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    e = cudaFuncSetAttribute(octree_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(octree_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
 }
 
 static int* g_err_flag[64] = {nullptr};
@@ -513,8 +532,11 @@ cudaError_t launch_octree(const FrameGeom& fg, const Workspace& ws, int n_frames
 {
     int M = 0;
     for (int l = 0; l < fg.nlevels; ++l) M = M > fg.L[l].kp_cap ? M : fg.L[l].kp_cap;
-    const int T = 256;   // measured: 128- and 512-thread CTAs are both ~30 % slower on 512-frame batches
-    (void)n_frames;
+    // Batches: 256-thread CTAs (measured: 128- and 512-thread CTAs are both ~30 % slower on 512-frame batches).
+    // A few frames: the level-0 CTA is the critical path of the whole extraction, so give it more lanes.
+    static const int t_override = getenv("ORBX_OCTREE_THREADS") ? atoi(getenv("ORBX_OCTREE_THREADS")) : 0;
+    int T = n_frames >= 8 ? 256 : 1024;
+    if (t_override == 256 || t_override == 512 || t_override == 1024) T = t_override;
     const size_t smem = octree_smem_bytes(M, T);
     if (smem > 200 * 1024) return cudaErrorInvalidConfiguration;
     int dev = 0;
@@ -527,7 +549,8 @@ cudaError_t launch_octree(const FrameGeom& fg, const Workspace& ws, int n_frames
     dim3 grid(fg.nlevels, n_frames);
     // The kernel is latency-bound (sequential sort replay, dependent binary searches): big batches run more, smaller CTAs
     // per SM to overlap those chains; a single frame gets the larger CTA for the shortest critical path.
-    if (T == 512) octree_kernel<512><<<grid, 512, smem, st>>>(fg, ws, M, g_err_flag[dev & 63]);
+    if (T == 1024) octree_kernel<1024><<<grid, 1024, smem, st>>>(fg, ws, M, g_err_flag[dev & 63]);
+    else if (T == 512) octree_kernel<512><<<grid, 512, smem, st>>>(fg, ws, M, g_err_flag[dev & 63]);
     else octree_kernel<256><<<grid, 256, smem, st>>>(fg, ws, M, g_err_flag[dev & 63]);
     count_launch();
     return cudaGetLastError();
