@@ -20,12 +20,56 @@ constexpr int KNN_QT = 4;                       // queries per thread
 constexpr int KNN_QTILE = KNN_THREADS * KNN_QT; // queries per CTA
 constexpr int KNN_DTILE = 256;                  // database rows staged per shared-memory tile (8 KB)
 
+// Out of line on purpose: after the first few thousand rows an update is rare, so the hot loop should pay one compare and
+// one (not-taken) branch per distance — inlined, the compiler if-converts this into six ALU-pipe instructions per compare,
+// and the ALU pipe is the bound of the matcher.
+__device__ __noinline__ int4 top2_insert(int dist, int idx, int4 s)      // s = (d1, i1, d2, i2), by value: stays in registers
+{
+    if (dist < s.x) return make_int4(dist, idx, s.x, s.y);
+    return make_int4(s.x, s.y, dist, idx);
+}
 __device__ __forceinline__ void top2_update(int dist, int idx, int& d1, int& i1, int& d2, int& i2)
 {
     if (dist < d2) {
-        if (dist < d1) { d2 = d1; i2 = i1; d1 = dist; i1 = idx; }
-        else { d2 = dist; i2 = idx; }
+        const int4 r = top2_insert(dist, idx, make_int4(d1, i1, d2, i2));
+        d1 = r.x; i1 = r.y; d2 = r.z; i2 = r.w;
     }
+}
+
+// 256-bit Hamming distance with a carry-save front end.  POPC issues at 16 lanes/clk/SM (a quarter of LOP3), so the plain
+// 8 x (XOR, POPC) form is POPC-bound at 0.5 clk per compare per SM.  Three full-adder layers (each 2 LOP3) compress the
+// eight XOR words to four population counts of weight 1,1,2,4:
+//     (c1,s1)=CSA(x0,x1,x2) (c2,s2)=CSA(x3,x4,x5) (c3,s3)=CSA(s1,s2,x6) (d1,t1)=CSA(c1,c2,c3)
+//     dist = popc(s3) + popc(x7) + 2*popc(t1) + 4*popc(d1)
+// 16 LOP3 + 4 POPC per compare balances the ALU pipe (0.27 clk) against the POPC pipe (0.25 clk).
+__device__ __forceinline__ uint32_t lop3_xor3(uint32_t a, uint32_t b, uint32_t c)
+{
+    uint32_t d;
+    asm("lop3.b32 %0, %1, %2, %3, 0x96;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+__device__ __forceinline__ uint32_t lop3_maj(uint32_t a, uint32_t b, uint32_t c)
+{
+    uint32_t d;
+    asm("lop3.b32 %0, %1, %2, %3, 0xE8;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+__device__ __forceinline__ void csa(uint32_t a, uint32_t b, uint32_t c, uint32_t& carry, uint32_t& sum)
+{
+    sum = lop3_xor3(a, b, c);
+    carry = lop3_maj(a, b, c);
+}
+
+__device__ __forceinline__ int hamming256_csa(const uint32_t (&q)[8], const uint4& a, const uint4& b)
+{
+    const uint32_t x0 = q[0] ^ a.x, x1 = q[1] ^ a.y, x2 = q[2] ^ a.z, x3 = q[3] ^ a.w;
+    const uint32_t x4 = q[4] ^ b.x, x5 = q[5] ^ b.y, x6 = q[6] ^ b.z, x7 = q[7] ^ b.w;
+    uint32_t c1, s1, c2, s2, c3, s3, d1, t1;
+    csa(x0, x1, x2, c1, s1);
+    csa(x3, x4, x5, c2, s2);
+    csa(s1, s2, x6, c3, s3);
+    csa(c1, c2, c3, d1, t1);
+    return __popc(s3) + __popc(x7) + 2 * __popc(t1) + 4 * __popc(d1);
 }
 
 // lexicographic (d, i) insert used by the merges; idx < 0 = missing
@@ -95,9 +139,7 @@ __global__ void __launch_bounds__(KNN_THREADS) knn2_kernel(const uint32_t* __res
             const int gi = index_base + (int)(base + r);
 #pragma unroll
             for (int j = 0; j < KNN_QT; ++j) {
-                const int dist = __popc(qw[j][0] ^ a.x) + __popc(qw[j][1] ^ a.y) + __popc(qw[j][2] ^ a.z) +
-                                 __popc(qw[j][3] ^ a.w) + __popc(qw[j][4] ^ b.x) + __popc(qw[j][5] ^ b.y) +
-                                 __popc(qw[j][6] ^ b.z) + __popc(qw[j][7] ^ b.w);
+                const int dist = hamming256_csa(qw[j], a, b);
                 top2_update(dist, gi, d1[j], i1[j], d2[j], i2[j]);
             }
         }
