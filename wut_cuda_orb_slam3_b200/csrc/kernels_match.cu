@@ -16,7 +16,7 @@ namespace orbx {
 namespace {
 
 constexpr int KNN_THREADS = 128;
-constexpr int KNN_QT = 4;                       // queries per thread
+constexpr int KNN_QT = 4;                       // queries per thread (8 was measured 11 % slower: 145 registers)
 constexpr int KNN_QTILE = KNN_THREADS * KNN_QT; // queries per CTA
 constexpr int KNN_DTILE = 256;                  // database rows staged per shared-memory tile (8 KB)
 
