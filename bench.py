@@ -378,8 +378,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=512, help="frames per GPU per step")
-    ap.add_argument("--e2e-batch", type=int, default=256)
-    ap.add_argument("--e2e-chunk", type=int, default=32)
+    ap.add_argument("--e2e-batch", type=int, default=512)
+    ap.add_argument("--e2e-chunk", type=int, default=64)
     ap.add_argument("--no-knn2", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--knn-nq", type=int, default=NQ)
