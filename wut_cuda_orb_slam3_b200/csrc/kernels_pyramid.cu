@@ -140,19 +140,20 @@ __device__ __forceinline__ void write_border_mirrors(uint8_t* D, int pitch, int 
 }
 
 // Level 0, fast path (16-byte aligned input rows): copy 128x16 tiles with 16-byte loads/stores + border mirrors.
-constexpr int PT_W = 128, PT_H = 16, PT_THREADS = 256;
+constexpr int PT_W = 128, PT_THREADS = 256;
+constexpr int L0_H = 32;                     // level-0 copy tile height
 
 __global__ void __launch_bounds__(PT_THREADS) pyr_level0_tiled_kernel(const __grid_constant__ FrameGeom fg, Workspace ws,
                                                                      const uint8_t* __restrict__ images, size_t frame_stride, size_t in_pitch)
 {
-    __shared__ __align__(16) uint8_t t[PT_H * PT_W];
+    __shared__ __align__(16) uint8_t t[L0_H * PT_W];
     const LevelGeom& g = fg.L[0];
     const int tid = threadIdx.x;
-    const int x0 = blockIdx.x * PT_W, y0 = blockIdx.y * PT_H, frame = blockIdx.z;
-    const int tw = min(PT_W, g.w - x0), th = min(PT_H, g.h - y0);
+    const int x0 = blockIdx.x * PT_W, y0 = blockIdx.y * L0_H, frame = blockIdx.z;
+    const int tw = min(PT_W, g.w - x0), th = min(L0_H, g.h - y0);
     const uint8_t* S = images + (size_t)frame * frame_stride;
     uint8_t* D = level_interior(ws.pyr, g, frame);
-    if (tid < PT_H * (PT_W / 16)) {
+    if (tid < L0_H * (PT_W / 16)) {
         const int ty = tid >> 3, v = tid & 7;
         if (ty < th && v * 16 < tw) {
             const uint8_t* sp = S + (size_t)(y0 + ty) * in_pitch + x0 + v * 16;
@@ -172,13 +173,11 @@ __global__ void __launch_bounds__(PT_THREADS) pyr_level0_tiled_kernel(const __gr
     write_border_mirrors<PT_W>(D, g.pitch, g.w, g.h, x0, y0, tw, th, t, tid, PT_THREADS);
 }
 
-// Level l >= 1: one CTA produces a 128x16 tile of the level interior.  The source footprint (<= 34 rows x 304 bytes for
-// scale <= 2) is staged in shared memory with 16-byte loads, the horizontal fixed-point pass runs once per source row
+// Level l >= 1: one CTA produces a 128 x PT_H tile of the level interior (32 rows for scale <= 1.5, 16 rows up to 2).  The
+// source footprint is staged in shared memory with 16-byte loads, the horizontal fixed-point pass runs once per source row
 // into an int32 plane, the vertical pass combines two rows per output row (4 pixels per thread, 128-bit shared loads),
 // and the finished tile is written with 16-byte stores.
-constexpr int PT_SR = 2 * PT_H + 2;            // source rows
-constexpr int PT_SP = 2 * PT_W + 48;           // source pitch (bytes), multiple of 16
-
+template <int PT_H, int PT_SR, int PT_SP>      // tile rows, source rows, source pitch (bytes, multiple of 16)
 __global__ void __launch_bounds__(PT_THREADS) pyr_resize_tiled_kernel(const __grid_constant__ FrameGeom fg, Workspace ws, int level)
 {
     __shared__ __align__(16) uint8_t src[PT_SR * PT_SP];
@@ -222,11 +221,11 @@ __global__ void __launch_bounds__(PT_THREADS) pyr_resize_tiled_kernel(const __gr
     }
     __syncthreads();
 
-    // vertical pass: thread = 4 consecutive columns x 2 rows -> one 32-bit word per row of the output tile
+    // vertical pass: thread = 4 consecutive columns x PT_H/8 rows -> one 32-bit word per row of the output tile
     {
         const int xq = (tid & 31) * 4;
 #pragma unroll
-        for (int k = 0; k < 2; ++k) {
+        for (int k = 0; k < PT_H / 8; ++k) {
             const int ty = (tid >> 5) + 8 * k;
             const uint2 yt = ytl[ty];
             const int4 r0 = *reinterpret_cast<const int4*>(hbuf + ((int)(yt.x & 0xffff) - symin) * PT_W + xq);
@@ -247,8 +246,8 @@ __global__ void __launch_bounds__(PT_THREADS) pyr_resize_tiled_kernel(const __gr
 
     // interior: 16-byte stores (interior rows are 16-byte aligned and x0 is a multiple of 128)
     uint8_t* D = level_interior(ws.pyr, g, frame);
-    if (tid < PT_H * (PT_W / 16)) {
-        const int ty = tid >> 3, v = tid & 7;
+    for (int i = tid; i < PT_H * (PT_W / 16); i += PT_THREADS) {
+        const int ty = i >> 3, v = i & 7;
         if (ty < th && v * 16 < tw) {
             uint8_t* dst = D + (size_t)(y0 + ty) * g.pitch + x0 + v * 16;
             if (v * 16 + 16 <= tw) *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(outt + ty * PT_W + v * 16);
@@ -267,18 +266,26 @@ cudaError_t launch_pyramid(const FrameGeom& fg, const Workspace& ws, const uint8
         const LevelGeom& g = fg.L[l];
         const int words = g.pitch / 4;
         dim3 grid((words + 127) / 128, g.rows_alloc, n_frames);
-        dim3 tgrid((g.w + PT_W - 1) / PT_W, (g.h + PT_H - 1) / PT_H, n_frames);
         const bool big = g.w >= 2 * kEdge + 2 && g.h >= 2 * kEdge + 2;      // border band narrower than the level
         if (l == 0) {
             const bool aligned = ((uintptr_t)d_images & 15) == 0 && (frame_stride & 15) == 0 && (pitch & 15) == 0;
+            dim3 tgrid((g.w + PT_W - 1) / PT_W, (g.h + L0_H - 1) / L0_H, n_frames);
             if (big && aligned) pyr_level0_tiled_kernel<<<tgrid, PT_THREADS, 0, st>>>(fg, ws, d_images, frame_stride, pitch);
             else pyr_level0_kernel<<<grid, 128, 0, st>>>(fg, ws, d_images, frame_stride, pitch);
         } else {
             const LevelGeom& p = fg.L[l - 1];
-            // the tiled kernel needs a source footprint of at most 2x the tile
-            const bool tiled = big && (long long)p.w <= 2LL * g.w && (long long)p.h <= 2LL * g.h;
-            if (tiled) pyr_resize_tiled_kernel<<<tgrid, PT_THREADS, 0, st>>>(fg, ws, l);
-            else pyr_resize_kernel<<<grid, 128, 0, st>>>(fg, ws, l);
+            // source footprint of a tile must fit the staged window: scale <= 1.5 -> 128x32 tiles, <= 2 -> 128x16 tiles
+            const bool s15 = 2LL * p.w <= 3LL * g.w && 2LL * p.h <= 3LL * g.h;
+            const bool s20 = (long long)p.w <= 2LL * g.w && (long long)p.h <= 2LL * g.h;
+            if (big && s15) {
+                dim3 tgrid((g.w + PT_W - 1) / PT_W, (g.h + 31) / 32, n_frames);
+                pyr_resize_tiled_kernel<32, 52, 224><<<tgrid, PT_THREADS, 0, st>>>(fg, ws, l);
+            } else if (big && s20) {
+                dim3 tgrid((g.w + PT_W - 1) / PT_W, (g.h + 15) / 16, n_frames);
+                pyr_resize_tiled_kernel<16, 34, 304><<<tgrid, PT_THREADS, 0, st>>>(fg, ws, l);
+            } else {
+                pyr_resize_kernel<<<grid, 128, 0, st>>>(fg, ws, l);
+            }
         }
         count_launch();
     }
