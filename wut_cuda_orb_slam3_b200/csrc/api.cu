@@ -10,6 +10,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -83,6 +84,24 @@ static void make_tables(Tables& t, int nfeatures, float scaleFactorF, int nlevel
         nDesired *= factor;
     }
     t.nfeat[nlevels - 1] = std::max(nfeatures - sum, 0);
+}
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time dependency on libcuda)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn get_encode_tiled()
+{
+    static EncodeTiledFn fn = [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) {
+            cudaGetLastError();
+            p = nullptr;
+        }
+        return (EncodeTiledFn)p;
+    }();
+    return fn;
 }
 
 struct Slot {
@@ -253,6 +272,23 @@ static int configure(orbx_extractor* ex, int rows, int cols)
             for (int br = 0; br < g.h + 2 * kEdge; ++br) tables.push_back(entry(reflect101(br - kEdge, g.h), scale_y, p.h));
         }
     }
+    // TMA box of level l when it is the SOURCE of level l+1 (128x32 output tiles): the largest source window any tile needs
+    for (int l = 0; l + 1 < ex->nlevels; ++l) {
+        const LevelGeom& d = fg.L[l + 1];
+        const uint2* xt = tables.data() + xtab_off[l + 1];
+        const uint2* yt = tables.data() + ytab_off[l + 1];
+        int bw = 0, bh = 0;
+        for (int x0 = 0; x0 < d.w; x0 += 128) {
+            const int x1 = std::min(x0 + 128, d.w) - 1;
+            bw = std::max(bw, (int)(xt[kEdge + x1].x >> 16) - ((int)(xt[kEdge + x0].x & 0xffff) & ~15) + 1);   // box starts 16-byte aligned
+        }
+        for (int y0 = 0; y0 < d.h; y0 += 32) {
+            const int y1 = std::min(y0 + 32, d.h) - 1;
+            bh = std::max(bh, (int)(yt[kEdge + y1].x >> 16) - (int)(yt[kEdge + y0].x & 0xffff) + 1);
+        }
+        fg.L[l].tma_box_w = (int)align_up((size_t)bw, 16);
+        fg.L[l].tma_box_h = bh;
+    }
     fg.total_cells = cell_base;
     fg.kp_slots = kp_base;
     fg.cand_frame_stride = cand_off + 16;
@@ -309,6 +345,36 @@ static int ensure_slot(orbx_extractor* ex, Slot& s, int frames)
     if ((rc = dev_alloc(s, &s.ws.lvl_ncand, (size_t)fg.nlevels * frames))) return rc;
     if ((rc = dev_alloc(s, &s.ws.lvl_angle, (size_t)fg.kp_slots * frames))) return rc;
     if ((rc = dev_alloc(s, &s.ws.lvl_desc, (size_t)fg.kp_slots * frames * 32))) return rc;
+    // TMA descriptors of the bordered pyramid levels (3-D: byte column, row, frame)
+    s.ws.tmap_resize = nullptr; s.ws.tmap_blur = nullptr;
+    if (EncodeTiledFn enc = get_encode_tiled()) {
+        std::vector<CUtensorMap> maps(2 * kMaxLevels);
+        bool ok_resize = true, ok_blur = true;
+        for (int l = 0; l < fg.nlevels; ++l) {
+            const LevelGeom& g = fg.L[l];
+            const cuuint64_t dims[3] = {(cuuint64_t)g.pitch, (cuuint64_t)g.rows_alloc, (cuuint64_t)frames};
+            const cuuint64_t strides[2] = {(cuuint64_t)g.pitch, (cuuint64_t)g.pyr_frame_stride};
+            const cuuint32_t estr[3] = {1, 1, 1};
+            void* base = s.ws.pyr + g.pyr_off;
+            if (l + 1 < fg.nlevels) {
+                const bool fits = g.tma_box_w > 0 && g.tma_box_w <= 224 && g.tma_box_h > 0 && g.tma_box_h <= 52;
+                const cuuint32_t box[3] = {(cuuint32_t)std::max(g.tma_box_w, 16), (cuuint32_t)std::max(g.tma_box_h, 1), 1};
+                if (!fits || enc(&maps[l], CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                 CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+                    ok_resize = false;
+            }
+            const cuuint32_t bbox[3] = {160, 38, 1};
+            if (enc(&maps[kMaxLevels + l], CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, base, dims, strides, bbox, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+                ok_blur = false;
+        }
+        CUtensorMap* d_maps = nullptr;
+        if ((rc = dev_alloc(s, &d_maps, maps.size()))) return rc;
+        CU(cudaMemcpy(d_maps, maps.data(), maps.size() * sizeof(CUtensorMap), cudaMemcpyHostToDevice));
+        static const bool no_tma = getenv("ORBX_NO_TMA") != nullptr;      // A/B switch for measurements
+        if (ok_resize && !no_tma) s.ws.tmap_resize = d_maps;
+        if (ok_blur && !no_tma) s.ws.tmap_blur = d_maps + kMaxLevels;
+    }
     CU(cudaMemsetAsync(s.ws.pyr, 0, pyr + 256, s.stream));
     CU(cudaMemsetAsync(s.ws.lvl_n, 0, sizeof(int) * (size_t)fg.nlevels * frames, s.stream));
     CU(cudaStreamSynchronize(s.stream));

@@ -55,7 +55,7 @@ __device__ __forceinline__ float fast_atan2_dev(float y, float x)
 // sliding 32-bit window using the kernel's symmetry; the tile leaves through shared memory as 16-byte stores.
 __global__ void __launch_bounds__(256) blur_kernel(const __grid_constant__ FrameGeom fg, Workspace ws)
 {
-    __shared__ __align__(16) uint8_t in[BIN_R * BIN_P];
+    __shared__ __align__(128) uint8_t in[BIN_R * BIN_P];
     __shared__ __align__(16) uint32_t hb[BIN_R * BT_W];
     __shared__ __align__(16) uint8_t outt[BT_H * BT_W];
     const int tid = threadIdx.x;
@@ -75,14 +75,26 @@ __global__ void __launch_bounds__(256) blur_kernel(const __grid_constant__ Frame
     const uint8_t* base = ws.pyr + g.pyr_off + (size_t)frame * g.pyr_frame_stride;   // bordered buffer origin
     // input tile: buffer rows (ty0 - 3 + 19) .., buffer byte columns (tx0 - 16 + 32) .. : 16-byte aligned
     const int brow0 = ty0 - 3 + kEdge, bcol0 = tx0 - 16 + kXPad;
-    for (int i = tid; i < BIN_R * (BIN_P / 16); i += 256) {
-        const int r = i / (BIN_P / 16), v = i - r * (BIN_P / 16);
-        const int br = brow0 + r, bc = bcol0 + 16 * v;
-        uint4 q = make_uint4(0, 0, 0, 0);
-        if (br < g.rows_alloc && bc + 16 <= g.pitch) q = __ldg(reinterpret_cast<const uint4*>(base + (size_t)br * g.pitch + bc));
-        reinterpret_cast<uint4*>(in)[i] = q;
+    if (ws.tmap_blur) {
+        // TMA: 160 x 38 box of the bordered level (out-of-range rows/columns are zero-filled by the copy engine)
+        __shared__ __align__(8) uint64_t bar;
+        if (tid == 0) mbar_init(&bar, 1);
+        __syncthreads();
+        if (tid == 0) {
+            mbar_expect_tx(&bar, BIN_R * BIN_P);
+            tma_load_3d(in, ws.tmap_blur + level, &bar, bcol0, brow0, frame);
+        }
+        mbar_wait(&bar, 0);
+    } else {
+        for (int i = tid; i < BIN_R * (BIN_P / 16); i += 256) {
+            const int r = i / (BIN_P / 16), v = i - r * (BIN_P / 16);
+            const int br = brow0 + r, bc = bcol0 + 16 * v;
+            uint4 q = make_uint4(0, 0, 0, 0);
+            if (br < g.rows_alloc && bc + 16 <= g.pitch) q = __ldg(reinterpret_cast<const uint4*>(base + (size_t)br * g.pitch + bc));
+            reinterpret_cast<uint4*>(in)[i] = q;
+        }
+        __syncthreads();
     }
-    __syncthreads();
     // horizontal pass: task = (row, group of 4 columns); output x = 4q + j reads tile columns 4q+13+j .. 4q+19+j
     for (int i = tid; i < BIN_R * (BT_W / 4); i += 256) {
         const int r = i >> 5, q = i & 31;

@@ -180,7 +180,7 @@ __global__ void __launch_bounds__(PT_THREADS) pyr_level0_tiled_kernel(const __gr
 template <int PT_H, int PT_SR, int PT_SP>      // tile rows, source rows, source pitch (bytes, multiple of 16)
 __global__ void __launch_bounds__(PT_THREADS) pyr_resize_tiled_kernel(const __grid_constant__ FrameGeom fg, Workspace ws, int level)
 {
-    __shared__ __align__(16) uint8_t src[PT_SR * PT_SP];
+    __shared__ __align__(128) uint8_t src[PT_SR * PT_SP];
     __shared__ __align__(16) int hbuf[PT_SR * PT_W];
     __shared__ __align__(16) uint8_t outt[PT_H * PT_W];
     __shared__ uint2 ytl[PT_H];
@@ -199,15 +199,31 @@ __global__ void __launch_bounds__(PT_THREADS) pyr_resize_tiled_kernel(const __gr
     const uint2 yfirst = __ldg(g.ytab + kEdge + y0), ylast = __ldg(g.ytab + kEdge + y0 + th - 1);
     const int sxmin = (int)(xfirst.x & 0xffff), sxmax = (int)(xlast.x >> 16);
     const int symin = (int)(yfirst.x & 0xffff), symax = (int)(ylast.x >> 16);
-    const int cbase = sxmin & ~15;
-    const int nvec = ((sxmax - cbase) >> 4) + 1;            // 16-byte vectors per source row (<= 19)
     const int nrows = symax - symin + 1;
-
-    const uint8_t* P = level_interior((const uint8_t*)ws.pyr, p, frame) + (size_t)symin * p.pitch + cbase;
-    if (lane < nvec)
-        for (int r = warp; r < nrows; r += PT_THREADS / 32)
-            *reinterpret_cast<uint4*>(src + r * PT_SP + lane * 16) = __ldg(reinterpret_cast<const uint4*>(P + (size_t)r * p.pitch) + lane);
-    __syncthreads();
+    int cbase, spitch;                                       // first staged source column, staged row pitch (bytes)
+    if (PT_H == 32 && ws.tmap_resize) {
+        // TMA: one elected thread issues a 3-D tiled bulk copy of the source window (box sized for this level's scale on
+        // the host); completion is signalled on an mbarrier, nobody spends instructions on the copy.
+        __shared__ __align__(8) uint64_t bar;
+        cbase = sxmin & ~15;                                 // TMA needs a 16-byte aligned box start for 1-byte elements
+        spitch = p.tma_box_w;
+        if (tid == 0) mbar_init(&bar, 1);
+        __syncthreads();
+        if (tid == 0) {
+            mbar_expect_tx(&bar, (uint32_t)(p.tma_box_w * p.tma_box_h));
+            tma_load_3d(src, ws.tmap_resize + (level - 1), &bar, kXPad + cbase, kEdge + symin, frame);
+        }
+        mbar_wait(&bar, 0);
+    } else {
+        cbase = sxmin & ~15;
+        spitch = PT_SP;
+        const int nvec = ((sxmax - cbase) >> 4) + 1;        // 16-byte vectors per source row
+        const uint8_t* P = level_interior((const uint8_t*)ws.pyr, p, frame) + (size_t)symin * p.pitch + cbase;
+        if (lane < nvec)
+            for (int r = warp; r < nrows; r += PT_THREADS / 32)
+                *reinterpret_cast<uint4*>(src + r * PT_SP + lane * 16) = __ldg(reinterpret_cast<const uint4*>(P + (size_t)r * p.pitch) + lane);
+        __syncthreads();
+    }
 
     // horizontal pass: thread = output column, every other source row
     {
@@ -217,7 +233,7 @@ __global__ void __launch_bounds__(PT_THREADS) pyr_resize_tiled_kernel(const __gr
         const uint8_t* s1 = src + c1;
         int* hb = hbuf + tx;
         for (int r = tid >> 7; r < nrows; r += PT_THREADS / PT_W)
-            hb[r * PT_W] = (int)s0[r * PT_SP] * a0 + (int)s1[r * PT_SP] * a1;
+            hb[r * PT_W] = (int)s0[r * spitch] * a0 + (int)s1[r * spitch] * a1;
     }
     __syncthreads();
 

@@ -1,5 +1,6 @@
 // orbx_internal.cuh — shared definitions between the host API (api.cu) and the sm_100a kernels.
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -46,6 +47,7 @@ struct LevelGeom {
     float scale;              // mvScaleFactor[level]
     float inv_scale;          // mvInvScaleFactor[level]
     float kp_size;            // (float)(int)(31*scale)
+    int tma_box_w, tma_box_h; // box of THIS level's resize-source descriptor (when it is the source of level+1)
 };
 
 struct FrameGeom {
@@ -73,6 +75,8 @@ struct Workspace {
     uint8_t* lvl_desc;        // [frame][kp_slots][32]
     int* lvl_ncand;           // [frame][nlevels] number of FAST candidates (probe)
     long long* dbg;           // optional octree phase timing (nullptr in production)
+    const CUtensorMap* tmap_resize;   // [nlevels] TMA descriptors of the pyramid levels, box = resize source window (or nullptr)
+    const CUtensorMap* tmap_blur;     // [nlevels] TMA descriptors of the pyramid levels, box = blur input tile (or nullptr)
     int dbg_level;
 };
 
@@ -84,6 +88,35 @@ inline __host__ __device__ const uint8_t* level_interior(const uint8_t* pyr, con
 {
     return pyr + g.pyr_off + (unsigned long long)frame * g.pyr_frame_stride + (unsigned long long)kEdge * g.pitch + kXPad;
 }
+
+// ---- TMA / mbarrier helpers (sm_90+ PTX; SASS: UTMALDG, SYNCS) ----------------------------------------------------------
+#if defined(__CUDACC__)
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
+{
+    const uint32_t a = (uint32_t)__cvta_generic_to_shared(bar);
+    uint32_t ok;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(a), "r"(parity) : "memory");
+    } while (!ok);
+}
+// 3-D tiled load: coordinates (byte column, row, frame) of the bordered level buffer; out-of-range elements are zero-filled
+__device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int x, int y, int z)
+{
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                 ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(map), "r"(x), "r"(y), "r"(z),
+                 "r"((uint32_t)__cvta_generic_to_shared(bar)) : "memory");
+}
+#endif
 
 // ---- launchers (defined in the kernel translation units) ---------------------------------------------------
 void count_launch(int n = 1);
