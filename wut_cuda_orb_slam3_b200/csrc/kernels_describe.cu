@@ -153,21 +153,27 @@ __global__ void __launch_bounds__(256) orient_describe_kernel(const __grid_const
     const int x = (int)(key & 0xfff) + kWinBorder, y = (int)((key >> 12) & 0xfff) + kWinBorder;
 
     // ---- IC_Angle on the un-blurred level: lane <-> column u = lane - 15 ----
-    const uint8_t* img = level_interior((const uint8_t*)ws.pyr, g, frame) + (size_t)y * g.pitch + x;
     int m10 = 0, m01 = 0;
     {
         const int u = lane - kHalfPatch;
         if (lane < 31) {
             const int au = u < 0 ? -u : u;
+            // walking row pointer (one 64-bit add per row) instead of re-deriving base + v*pitch + u for every load;
+            // m10 = u * (sum of the column) needs a single multiply at the end
+            const uint8_t* row = level_interior((const uint8_t*)ws.pyr, g, frame) + (ptrdiff_t)(y - kHalfPatch) * g.pitch + (x + u);
+            const ptrdiff_t pitch = g.pitch;
+            int sum = 0;
 #pragma unroll
             for (int v = -kHalfPatch; v <= kHalfPatch; ++v) {
                 const int av = v < 0 ? -v : v;
                 if (au <= c_umax[av]) {
-                    const int val = __ldg(img + v * g.pitch + u);
-                    m10 += u * val;
+                    const int val = __ldg(row);
+                    sum += val;
                     m01 += v * val;
                 }
+                row += pitch;
             }
+            m10 = u * sum;
         }
 #pragma unroll
         for (int d = 16; d >= 1; d >>= 1) {
