@@ -127,7 +127,7 @@ struct orbx_extractor {
     uint2* d_tables = nullptr;     // resize tables
     size_t per_frame_pyr = 0, per_frame_blur = 0;
     int max_batch = 0;
-    static const int kSlots = 3;
+    static const int kSlots = 6;
     Slot slots[kSlots];
     int last_frames = 0;           // frames of the last call that are probe-able (slot 0)
     int max_kp = 0;
