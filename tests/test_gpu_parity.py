@@ -35,8 +35,9 @@ def compare_full(oracle, ex, oex, img, lapping):
     dang = np.minimum(dang, 360.0 - dang)
     assert dang.max(initial=0.0) <= ANGLE_TOL_DEG
     same = (desc == desc_o).all(axis=1)
-    assert same.mean() >= DESC_IDENTICAL_MIN, same.mean()
-    return kps, desc, float(same.mean()), float(dang.max(initial=0.0))
+    frac = float(same.mean()) if len(same) else 1.0
+    assert frac >= DESC_IDENTICAL_MIN, frac
+    return kps, desc, frac, float(dang.max(initial=0.0))
 
 
 @pytest.mark.parametrize("cols,rows,nfeatures,seed", CONFIGS)
@@ -87,6 +88,18 @@ def test_other_parameters(oracle):
         ex = orbx.ORBextractor(nf, sf, nl, ini, mn)
         oex = oracle.extractor(nf, sf, nl, ini, mn)
         compare_full(oracle, ex, oex, img, (0, 0))
+
+
+@pytest.mark.parametrize("cols,rows,nfeatures,nlevels", [(1920, 1080, 3000, 8), (480, 752, 1000, 8), (97, 83, 200, 8), (64, 64, 100, 5),
+                                                         (2048, 1536, 4000, 10)])
+def test_unusual_shapes(oracle, cols, rows, nfeatures, nlevels):
+    """Full-HD and larger, portrait (nIni = 1), and images so small that the deep levels have no FAST window at all."""
+    img = synth.image(55, cols, rows)
+    ex = orbx.ORBextractor(nfeatures, 1.2, nlevels, 20, 7)
+    oex = oracle.extractor(nfeatures, 1.2, nlevels, 20, 7)
+    compare_full(oracle, ex, oex, img, (0, 0))
+    for level in range(nlevels):
+        assert np.array_equal(ex.pyramid_level(level, with_border=True), oex.pyramid_level(level, with_border=True)), level
 
 
 def test_flat_and_noise_images(oracle):
