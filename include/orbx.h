@@ -169,6 +169,87 @@ int orbx_stereo_match(orbx_extractor* exL, int frameL, orbx_extractor* exR, int 
                       const uint8_t* descL, int nL, const orbx_keypoint* kpR, const uint8_t* descR, int nR, float bf,
                       float maxD, float* uRight, float* depth);
 
+/* ---- bag-of-words transform and vocabulary-guided matching -------------------- */
+
+/* DBoW2::TemplatedVocabulary<FORB::TDescriptor, FORB> (Thirdparty/DBoW2/DBoW2/TemplatedVocabulary.h): a k-ary tree of
+ * 256-bit node descriptors.  Nodes are numbered as in m_nodes (0 = root, children in creation order = ascending id,
+ * TemplatedVocabulary.h:1340-1398 loadFromTextFile); leaves carry a word id and a weight.  The handle owns a device copy. */
+typedef struct orbx_vocabulary orbx_vocabulary;
+typedef enum orbx_weighting { ORBX_TF_IDF = 0, ORBX_TF = 1, ORBX_IDF = 2, ORBX_BINARY = 3 } orbx_weighting;     /* BowVector.h:27-33 */
+typedef enum orbx_scoring { ORBX_L1_NORM = 0, ORBX_L2_NORM = 1, ORBX_CHI_SQUARE = 2, ORBX_KL = 3, ORBX_BHATTACHARYYA = 4,
+                            ORBX_DOT_PRODUCT = 5 } orbx_scoring;                                              /* BowVector.h:43-51 */
+/* (the scoring type selects how orbx_compute_bow normalises; orbx_bow_score implements L1_NORM, the ORBvoc.txt setting) */
+/* parent[0] = -1; descriptors [n_nodes][32]; weights [n_nodes] (leaf weight = idf, TemplatedVocabulary.h:1393);
+ * a node is a leaf iff it has no children; word ids are assigned to leaves in ascending node id (TemplatedVocabulary.h:1388-1392). */
+int orbx_vocab_create(int device, int n_nodes, const int32_t* parent, const uint8_t* descriptors, const double* weights, int k,
+                      int L, int scoring, int weighting, orbx_vocabulary** out);
+/* TemplatedVocabulary::loadFromTextFile (TemplatedVocabulary.h:1340-1398; the ORBvoc.txt format: "k L scoring weighting",
+ * then per node "parent is_leaf b0 .. b31 weight"). */
+int orbx_vocab_load_text(int device, const char* path, orbx_vocabulary** out);
+void orbx_vocab_destroy(orbx_vocabulary* voc);
+int orbx_vocab_info(const orbx_vocabulary* voc, int* n_nodes, int* n_words, int* k, int* L);
+
+/* transform(feature, word_id, weight, &nid, levelsup) for every feature (TemplatedVocabulary.h:1217-1259): greedy descent,
+ * the child with the least Hamming distance wins, ties -> the first child; node_id = the node met at level L - levelsup
+ * (0 = root when L - levelsup <= 0).  HOST arrays of n entries; any output may be NULL.  Runs on the GPU. */
+int orbx_bow_transform(const orbx_vocabulary* voc, const uint8_t* descriptors, int n, int levelsup, uint32_t* word_id,
+                       double* weight, uint32_t* node_id);
+/* Frame::ComputeBoW / KeyFrame::ComputeBoW (src/Frame.cc:768-775): transform(features, BowVector, FeatureVector, levelsup)
+ * (TemplatedVocabulary.h:1126-1204, BowVector.cpp:34-90, FeatureVector.cpp:32-46).
+ *   BowVector    -> bow_ids[*n_bow] ascending, bow_vals[*n_bow] (weighted + normalised exactly as the std::map code does);
+ *   FeatureVector -> CSR: fv_nodes[*n_fv] ascending node ids, fv_offsets[*n_fv + 1], fv_indices[n] (feature ids ascending per node).
+ * bow_* need capacity n, fv_nodes n, fv_offsets n + 1, fv_indices n. */
+int orbx_compute_bow(const orbx_vocabulary* voc, const uint8_t* descriptors, int n, int levelsup, uint32_t* bow_ids,
+                     double* bow_vals, int* n_bow, uint32_t* fv_nodes, int32_t* fv_offsets, uint32_t* fv_indices, int* n_fv);
+/* DBoW2 score between two BowVectors for the vocabulary's scoring type (ScoringObject.cpp; L1: 1 - 0.5*sum|a-b| computed as
+ * sum(|a-b| - |a| - |b|) over common words, ScoringObject.cpp:24-62).  Host. */
+int orbx_bow_score(const orbx_vocabulary* voc, const uint32_t* ids_a, const double* vals_a, int na, const uint32_t* ids_b,
+                   const double* vals_b, int nb, double* score);
+
+/* A DBoW2::FeatureVector (std::map<NodeId, std::vector<unsigned>>, FeatureVector.h:23-25) in CSR form, node ids ascending. */
+typedef struct orbx_feature_vector {
+    int n_nodes;
+    const uint32_t* node_ids;    /* [n_nodes] */
+    const int32_t* offsets;      /* [n_nodes + 1] */
+    const uint32_t* indices;     /* [offsets[n_nodes]] feature indices */
+} orbx_feature_vector;
+
+/* int ORBmatcher::SearchByBoW(KeyFrame* pKF, Frame& F, vector<MapPoint*>& vpMapPointMatches) — src/ORBmatcher1.cc:225-427
+ * (mode 0) and SearchByBoW(KeyFrame* pKF1, KeyFrame* pKF2, vector<MapPoint*>& vpMatches12) — src/ORBmatcher2.cc:36-171 (mode 1).
+ * A = the key frame whose features drive the outer loop (pKF / pKF1), B = the searched set (F / pKF2).
+ *   valid_a[i] != 0  <=> feature i of A has a usable map point (non-NULL, !isBad(); mode 1 also folds the NLeft test of :77-79)
+ *   valid_b[j] != 0  <=> mode 1 only: pKF2's map point j is usable (:95-103); ignored (may be NULL) in mode 0
+ *   nleft_b          = F.Nleft (-1 for anything but a two-fisheye rig): mode 0 keeps separate best/second for j < Nleft and
+ *                      j >= Nleft and accepts the right one without a ratio test (the reference's '|| true', :381)
+ * Features of B already matched are skipped by later features of A inside the same vocabulary node (:289, :98): that
+ * sequential dependence is honoured (one warp walks a node's A-list in order; lanes scan the B-list).
+ * Outputs: mode 0: match_b[nB] = index of the A feature whose map point was assigned to B's feature j (vpMapPointMatches),
+ *          mode 1: match_a[nA] = index of the B feature matched to A's feature i (vpMatches12), -1 = none; the other array
+ *          (may be NULL) receives the inverse map.  *n_matches = the reference's return value (after the rotation filter). */
+int orbx_search_by_bow(int device, int mode, const uint8_t* desc_a, const float* angle_a, const uint8_t* valid_a, int n_a,
+                       const orbx_feature_vector* fv_a, const uint8_t* desc_b, const float* angle_b, const uint8_t* valid_b,
+                       int n_b, const orbx_feature_vector* fv_b, int nleft_b, float nn_ratio, int check_orientation,
+                       int32_t* match_a, int32_t* match_b, int* n_matches);
+
+/* int ORBmatcher::SearchForTriangulation(pKF1, pKF2, vMatchedPairs, bOnlyStereo, bCoarse) — src/ORBmatcher2.cc:173-471, the
+ * single-camera (pinhole, !mpCamera2) path.  Per feature of KF1 without a map point: scan the features of KF2 in the same
+ * vocabulary node, keep the candidate of least distance <= TH_LOW (a later candidate of EQUAL distance replaces the
+ * earlier one, :289) that passes the epipole-distance gate (:299-307) and Pinhole::epipolarConstrain
+ * (src/CameraModels/Pinhole.cpp:107-129) unless coarse.  vbMatched2 is never set by the reference, so queries are independent.
+ *   kp_a / kp_b      = mvKeysUn (pt, octave, angle are read)
+ *   free_a / free_b  != 0 <=> the feature has no map point yet (:246-252, :273-277)
+ *   stereo_a / stereo_b != 0 <=> mvuRight[i] >= 0 (:254, :279)
+ *   F12[9]           = row-major K1^-T [t12]x R12 K2^-1 computed by the caller exactly as Pinhole.cpp:109-112 does
+ *   ep[2]            = projection of KF1's camera centre into KF2 (:186-189); scale_b / sigma2_b = mvScaleFactors and mvLevelSigma2
+ *                      of KF2, n_levels entries (Pinhole::epipolarConstrain ignores its sigmaLevel argument, KF1's sigma)
+ * Output: match_a[nA] = index in B or -1 (vMatches12 after the rotation filter); *n_matches = the return value. */
+int orbx_search_for_triangulation(int device, const orbx_keypoint* kp_a, const uint8_t* desc_a, const uint8_t* free_a,
+                                  const uint8_t* stereo_a, int n_a, const orbx_feature_vector* fv_a, const orbx_keypoint* kp_b,
+                                  const uint8_t* desc_b, const uint8_t* free_b, const uint8_t* stereo_b, int n_b,
+                                  const orbx_feature_vector* fv_b, const float* F12, const float* ep, const float* scale_b,
+                                  const float* sigma2_b, int n_levels, int only_stereo, int coarse, int check_orientation,
+                                  int32_t* match_a, int* n_matches);
+
 /* ---- measurement helpers ----------------------------------------------------------------------------------- */
 
 /* Per-stage device timing: between begin and end every extraction on `ex` records CUDA events around its stages on the

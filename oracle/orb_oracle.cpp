@@ -961,3 +961,430 @@ void orbo_std_sort_hi40(unsigned long long* items, int n)
 }
 
 }  // extern "C"
+
+// =====================================================================================================================
+// Bag of words (DBoW2) and the vocabulary-guided searches.  DBoW2 is vendored in the reference tree
+// (Thirdparty/DBoW2) but needs OpenCV + boost::serialization headers to compile, which this image lacks, so it is
+// restated here like the rest; the std::map containers are the same ones DBoW2 derives from (BowVector.h:56-57,
+// FeatureVector.h:23-25), so iteration and floating-point summation order are identical by construction.
+// =====================================================================================================================
+#include <map>
+
+namespace {
+
+// TemplatedVocabulary<FORB::TDescriptor, FORB>::Node — Thirdparty/DBoW2/DBoW2/TemplatedVocabulary.h:182-218
+struct VocNode {
+    int id = 0, parent = 0;
+    double weight = 0;
+    std::vector<int> children;
+    uint8_t descriptor[32] = {0};
+    int word_id = -1;
+    bool isLeaf() const { return children.empty(); }
+};
+struct Vocabulary {
+    int k = 0, L = 0, scoring = 0, weighting = 0;
+    std::vector<VocNode> nodes;
+    int n_words = 0;
+};
+
+// FORB::distance — Thirdparty/DBoW2/DBoW2/FORB.cpp:81-101
+int forb_distance(const uint8_t* a, const uint8_t* b)
+{
+    int32_t pa[8], pb[8];
+    memcpy(pa, a, 32); memcpy(pb, b, 32);
+    int dist = 0;
+    for (int i = 0; i < 8; i++) {
+        unsigned int v = pa[i] ^ pb[i];
+        v = v - ((v >> 1) & 0x55555555);
+        v = (v & 0x33333333) + ((v >> 2) & 0x33333333);
+        dist += (((v + (v >> 4)) & 0xF0F0F0F) * 0x1010101) >> 24;
+    }
+    return dist;
+}
+
+// transform(feature, word_id, weight, nid, levelsup) — TemplatedVocabulary.h:1217-1259
+void voc_transform_one(const Vocabulary& V, const uint8_t* feature, unsigned& word_id, double& weight, unsigned* nid, int levelsup)
+{
+    std::vector<int> nodes;
+    const int nid_level = V.L - levelsup;
+    if (nid_level <= 0 && nid != nullptr) *nid = 0;   // root
+    int final_id = 0;
+    int current_level = 0;
+    do {
+        ++current_level;
+        nodes = V.nodes[final_id].children;
+        final_id = nodes[0];
+        double best_d = forb_distance(feature, V.nodes[final_id].descriptor);
+        for (size_t n = 1; n < nodes.size(); ++n) {
+            const int id = nodes[n];
+            const double d = forb_distance(feature, V.nodes[id].descriptor);
+            if (d < best_d) { best_d = d; final_id = id; }
+        }
+        if (nid != nullptr && current_level == nid_level) *nid = final_id;
+    } while (!V.nodes[final_id].isLeaf());
+    word_id = V.nodes[final_id].word_id;
+    weight = V.nodes[final_id].weight;
+}
+
+// DBoW2::FeatureVector in CSR form (node ids ascending)
+struct FeatVec {
+    std::map<unsigned, std::vector<unsigned>> m;
+    FeatVec(int n_nodes, const uint32_t* node_ids, const int32_t* offsets, const uint32_t* indices)
+    {
+        for (int i = 0; i < n_nodes; ++i) m[node_ids[i]] = std::vector<unsigned>(indices + offsets[i], indices + offsets[i + 1]);
+    }
+};
+
+const int TH_LOW = 50;          // src/ORBmatcher1.cc:37
+const int HISTO_LENGTH = 30;    // src/ORBmatcher1.cc:39
+
+// ORBmatcher::ComputeThreeMaxima — src/ORBmatcher3.cc:592-633
+void compute_three_maxima(std::vector<int>* histo, const int L, int& ind1, int& ind2, int& ind3)
+{
+    int max1 = 0, max2 = 0, max3 = 0;
+    for (int i = 0; i < L; i++) {
+        const int s = (int)histo[i].size();
+        if (s > max1) { max3 = max2; max2 = max1; max1 = s; ind3 = ind2; ind2 = ind1; ind1 = i; }
+        else if (s > max2) { max3 = max2; max2 = s; ind3 = ind2; ind2 = i; }
+        else if (s > max3) { max3 = s; ind3 = i; }
+    }
+    if (max2 < 0.1f * (float)max1) { ind2 = -1; ind3 = -1; }
+    else if (max3 < 0.1f * (float)max1) { ind3 = -1; }
+}
+
+}  // namespace
+
+extern "C" {
+
+void* orbo_vocab_create(int n_nodes, const int32_t* parent, const uint8_t* descriptors, const double* weights, int k, int L,
+                        int scoring, int weighting)
+{
+    // node numbering, children order and word ids as built by loadFromTextFile — TemplatedVocabulary.h:1378-1418
+    Vocabulary* V = new Vocabulary;
+    V->k = k; V->L = L; V->scoring = scoring; V->weighting = weighting;
+    V->nodes.resize(n_nodes);
+    for (int nid = 1; nid < n_nodes; ++nid) {
+        V->nodes[nid].id = nid;
+        V->nodes[nid].parent = parent[nid];
+        V->nodes[parent[nid]].children.push_back(nid);
+        memcpy(V->nodes[nid].descriptor, descriptors + (size_t)nid * 32, 32);
+        V->nodes[nid].weight = weights[nid];
+    }
+    for (int nid = 1; nid < n_nodes; ++nid)
+        if (V->nodes[nid].isLeaf()) V->nodes[nid].word_id = V->n_words++;
+    return V;
+}
+void orbo_vocab_destroy(void* v) { delete (Vocabulary*)v; }
+
+void orbo_bow_transform(void* v, const uint8_t* desc, int n, int levelsup, uint32_t* word_id, double* weight, uint32_t* node_id)
+{
+    const Vocabulary& V = *(Vocabulary*)v;
+    for (int i = 0; i < n; ++i) {
+        unsigned id = 0, nid = 0; double w = 0;
+        voc_transform_one(V, desc + (size_t)i * 32, id, w, &nid, levelsup);
+        word_id[i] = id; weight[i] = w; node_id[i] = nid;
+    }
+}
+
+// transform(features, BowVector, FeatureVector, levelsup) — TemplatedVocabulary.h:1126-1204; BowVector.cpp:34-86;
+// FeatureVector.cpp:32-46.  Called by Frame::ComputeBoW with levelsup = 4 (src/Frame.cc:768-775).
+void orbo_compute_bow(void* v, const uint8_t* desc, int n, int levelsup, uint32_t* bow_ids, double* bow_vals, int* n_bow,
+                      uint32_t* fv_nodes, int32_t* fv_offsets, uint32_t* fv_indices, int* n_fv)
+{
+    const Vocabulary& V = *(Vocabulary*)v;
+    std::map<unsigned, double> bow;
+    std::map<unsigned, std::vector<unsigned>> fv;
+    const bool must = V.scoring != 5;                 // every scoring class but DotProduct normalises (ScoringObject.h:73-89)
+    const bool l2 = V.scoring == 1;
+    if (V.weighting == 1 || V.weighting == 0) {       // TF || TF_IDF
+        unsigned i_feature = 0;
+        for (int f = 0; f < n; ++f, ++i_feature) {
+            unsigned id, nid = 0; double w;
+            voc_transform_one(V, desc + (size_t)f * 32, id, w, &nid, levelsup);
+            if (w > 0) {
+                auto vit = bow.lower_bound(id);       // BowVector::addWeight
+                if (vit != bow.end() && !(bow.key_comp()(id, vit->first))) vit->second += w;
+                else bow.insert(vit, std::map<unsigned, double>::value_type(id, w));
+                auto fit = fv.lower_bound(nid);       // FeatureVector::addFeature
+                if (fit != fv.end() && fit->first == nid) fit->second.push_back(i_feature);
+                else { fit = fv.insert(fit, std::map<unsigned, std::vector<unsigned>>::value_type(nid, std::vector<unsigned>())); fit->second.push_back(i_feature); }
+            }
+        }
+        if (!bow.empty() && !must) {
+            const double nd = bow.size();
+            for (auto vit = bow.begin(); vit != bow.end(); vit++) vit->second /= nd;
+        }
+    } else {                                          // IDF || BINARY
+        unsigned i_feature = 0;
+        for (int f = 0; f < n; ++f, ++i_feature) {
+            unsigned id, nid = 0; double w;
+            voc_transform_one(V, desc + (size_t)f * 32, id, w, &nid, levelsup);
+            if (w > 0) {
+                auto vit = bow.lower_bound(id);       // BowVector::addIfNotExist
+                if (vit == bow.end() || (bow.key_comp()(id, vit->first))) bow.insert(vit, std::map<unsigned, double>::value_type(id, w));
+                auto fit = fv.lower_bound(nid);
+                if (fit != fv.end() && fit->first == nid) fit->second.push_back(i_feature);
+                else { fit = fv.insert(fit, std::map<unsigned, std::vector<unsigned>>::value_type(nid, std::vector<unsigned>())); fit->second.push_back(i_feature); }
+            }
+        }
+    }
+    if (must) {                                       // BowVector::normalize
+        double norm = 0.0;
+        if (!l2) { for (auto it = bow.begin(); it != bow.end(); ++it) norm += fabs(it->second); }
+        else { for (auto it = bow.begin(); it != bow.end(); ++it) norm += it->second * it->second; norm = sqrt(norm); }
+        if (norm > 0.0) for (auto it = bow.begin(); it != bow.end(); ++it) it->second /= norm;
+    }
+    int nb = 0;
+    for (auto& kv : bow) { bow_ids[nb] = kv.first; bow_vals[nb] = kv.second; ++nb; }
+    *n_bow = nb;
+    int nf = 0, off = 0;
+    fv_offsets[0] = 0;
+    for (auto& kv : fv) { fv_nodes[nf] = kv.first; for (unsigned i : kv.second) fv_indices[off++] = i; fv_offsets[++nf] = off; }
+    *n_fv = nf;
+}
+
+// L1Scoring::score — Thirdparty/DBoW2/DBoW2/ScoringObject.cpp:24-65
+double orbo_bow_score_l1(const uint32_t* ids_a, const double* vals_a, int na, const uint32_t* ids_b, const double* vals_b, int nb)
+{
+    std::map<unsigned, double> v1, v2;
+    for (int i = 0; i < na; ++i) v1[ids_a[i]] = vals_a[i];
+    for (int i = 0; i < nb; ++i) v2[ids_b[i]] = vals_b[i];
+    auto v1_it = v1.begin(), v2_it = v2.begin();
+    double score = 0;
+    while (v1_it != v1.end() && v2_it != v2.end()) {
+        const double& vi = v1_it->second;
+        const double& wi = v2_it->second;
+        if (v1_it->first == v2_it->first) { score += fabs(vi - wi) - fabs(vi) - fabs(wi); ++v1_it; ++v2_it; }
+        else if (v1_it->first < v2_it->first) v1_it = v1.lower_bound(v2_it->first);
+        else v2_it = v2.lower_bound(v1_it->first);
+    }
+    score = -score / 2.0;
+    return score;
+}
+
+// ORBmatcher::SearchByBoW(KeyFrame* pKF, Frame& F, vector<MapPoint*>& vpMapPointMatches) — src/ORBmatcher1.cc:225-427.
+// valid_kf[i] = pMP && !pMP->isBad(); match_f[j] = index of the KF feature whose MapPoint ends up in vpMapPointMatches[j].
+int orbo_search_by_bow_kf_frame(const uint8_t* desc_kf, const float* angle_kf, const uint8_t* valid_kf, int n_kf, int fvk_n,
+                                const uint32_t* fvk_nodes, const int32_t* fvk_off, const uint32_t* fvk_idx, const uint8_t* desc_f,
+                                const float* angle_f, int n_f, int fvf_n, const uint32_t* fvf_nodes, const int32_t* fvf_off,
+                                const uint32_t* fvf_idx, int Nleft, float mfNNratio, int mbCheckOrientation, int32_t* match_f)
+{
+    (void)n_kf;
+    FeatVec vFeatVecKF(fvk_n, fvk_nodes, fvk_off, fvk_idx), FFeatVec(fvf_n, fvf_nodes, fvf_off, fvf_idx);
+    std::vector<int> vpMapPointMatches(n_f, -1);
+    int nmatches = 0;
+    std::vector<int> rotHist[HISTO_LENGTH];
+    const float factor = 1.0f / HISTO_LENGTH;
+    auto KFit = vFeatVecKF.m.begin(), Fit = FFeatVec.m.begin();
+    const auto KFend = vFeatVecKF.m.end(), Fend = FFeatVec.m.end();
+    while (KFit != KFend && Fit != Fend) {
+        if (KFit->first == Fit->first) {
+            const std::vector<unsigned> vIndicesKF = KFit->second, vIndicesF = Fit->second;
+            for (size_t iKF = 0; iKF < vIndicesKF.size(); iKF++) {
+                const unsigned realIdxKF = vIndicesKF[iKF];
+                if (!valid_kf[realIdxKF]) continue;
+                const uint8_t* dKF = desc_kf + (size_t)realIdxKF * 32;
+                int bestDist1 = 256, bestIdxF = -1, bestDist2 = 256;
+                int bestDist1R = 256, bestIdxFR = -1, bestDist2R = 256;
+                for (size_t iF = 0; iF < vIndicesF.size(); iF++) {
+                    const unsigned realIdxF = vIndicesF[iF];
+                    if (vpMapPointMatches[realIdxF] >= 0) continue;
+                    const int dist = descriptor_distance(dKF, desc_f + (size_t)realIdxF * 32);
+                    if (Nleft == -1) {
+                        if (dist < bestDist1) { bestDist2 = bestDist1; bestDist1 = dist; bestIdxF = realIdxF; }
+                        else if (dist < bestDist2) bestDist2 = dist;
+                    } else {
+                        if ((int)realIdxF < Nleft && dist < bestDist1) { bestDist2 = bestDist1; bestDist1 = dist; bestIdxF = realIdxF; }
+                        else if ((int)realIdxF < Nleft && dist < bestDist2) bestDist2 = dist;
+                        if ((int)realIdxF >= Nleft && dist < bestDist1R) { bestDist2R = bestDist1R; bestDist1R = dist; bestIdxFR = realIdxF; }
+                        else if ((int)realIdxF >= Nleft && dist < bestDist2R) bestDist2R = dist;
+                    }
+                }
+                if (bestDist1 <= TH_LOW) {
+                    if (static_cast<float>(bestDist1) < mfNNratio * static_cast<float>(bestDist2)) {
+                        vpMapPointMatches[bestIdxF] = realIdxKF;
+                        if (mbCheckOrientation) {
+                            float rot = angle_kf[realIdxKF] - angle_f[bestIdxF];
+                            if (rot < 0.0) rot += 360.0f;
+                            int bin = round(rot * factor);
+                            if (bin == HISTO_LENGTH) bin = 0;
+                            rotHist[bin].push_back(bestIdxF);
+                        }
+                        nmatches++;
+                    }
+                    if (bestDist1R <= TH_LOW) {
+                        if (static_cast<float>(bestDist1R) < mfNNratio * static_cast<float>(bestDist2R) || true) {
+                            vpMapPointMatches[bestIdxFR] = realIdxKF;
+                            if (mbCheckOrientation) {
+                                float rot = angle_kf[realIdxKF] - angle_f[bestIdxFR];
+                                if (rot < 0.0) rot += 360.0f;
+                                int bin = round(rot * factor);
+                                if (bin == HISTO_LENGTH) bin = 0;
+                                rotHist[bin].push_back(bestIdxFR);
+                            }
+                            nmatches++;
+                        }
+                    }
+                }
+            }
+            KFit++; Fit++;
+        } else if (KFit->first < Fit->first) KFit = vFeatVecKF.m.lower_bound(Fit->first);
+        else Fit = FFeatVec.m.lower_bound(KFit->first);
+    }
+    if (mbCheckOrientation) {
+        int ind1 = -1, ind2 = -1, ind3 = -1;
+        compute_three_maxima(rotHist, HISTO_LENGTH, ind1, ind2, ind3);
+        for (int i = 0; i < HISTO_LENGTH; i++) {
+            if (i == ind1 || i == ind2 || i == ind3) continue;
+            for (size_t j = 0, jend = rotHist[i].size(); j < jend; j++) { vpMapPointMatches[rotHist[i][j]] = -1; nmatches--; }
+        }
+    }
+    for (int j = 0; j < n_f; ++j) match_f[j] = vpMapPointMatches[j];
+    return nmatches;
+}
+
+// ORBmatcher::SearchByBoW(KeyFrame* pKF1, KeyFrame* pKF2, vector<MapPoint*>& vpMatches12) — src/ORBmatcher2.cc:36-171.
+// valid1[i] / valid2[j] = map point present and not bad (and index < mvKeysUn.size() when NLeft != -1);
+// match12[i] = index of the KF2 feature whose MapPoint ends up in vpMatches12[i].
+int orbo_search_by_bow_kf_kf(const uint8_t* desc1, const float* angle1, const uint8_t* valid1, int n1, int fv1_n,
+                             const uint32_t* fv1_nodes, const int32_t* fv1_off, const uint32_t* fv1_idx, const uint8_t* desc2,
+                             const float* angle2, const uint8_t* valid2, int n2, int fv2_n, const uint32_t* fv2_nodes,
+                             const int32_t* fv2_off, const uint32_t* fv2_idx, float mfNNratio, int mbCheckOrientation, int32_t* match12)
+{
+    FeatVec vFeatVec1(fv1_n, fv1_nodes, fv1_off, fv1_idx), vFeatVec2(fv2_n, fv2_nodes, fv2_off, fv2_idx);
+    std::vector<int> vpMatches12(n1, -1);
+    std::vector<bool> vbMatched2(n2, false);
+    std::vector<int> rotHist[HISTO_LENGTH];
+    const float factor = 1.0f / HISTO_LENGTH;
+    int nmatches = 0;
+    auto f1it = vFeatVec1.m.begin(), f2it = vFeatVec2.m.begin();
+    const auto f1end = vFeatVec1.m.end(), f2end = vFeatVec2.m.end();
+    while (f1it != f1end && f2it != f2end) {
+        if (f1it->first == f2it->first) {
+            for (size_t i1 = 0, iend1 = f1it->second.size(); i1 < iend1; i1++) {
+                const size_t idx1 = f1it->second[i1];
+                if (!valid1[idx1]) continue;
+                const uint8_t* d1 = desc1 + idx1 * 32;
+                int bestDist1 = 256, bestIdx2 = -1, bestDist2 = 256;
+                for (size_t i2 = 0, iend2 = f2it->second.size(); i2 < iend2; i2++) {
+                    const size_t idx2 = f2it->second[i2];
+                    if (vbMatched2[idx2] || !valid2[idx2]) continue;
+                    const int dist = descriptor_distance(d1, desc2 + idx2 * 32);
+                    if (dist < bestDist1) { bestDist2 = bestDist1; bestDist1 = dist; bestIdx2 = (int)idx2; }
+                    else if (dist < bestDist2) bestDist2 = dist;
+                }
+                if (bestDist1 < TH_LOW) {
+                    if (static_cast<float>(bestDist1) < mfNNratio * static_cast<float>(bestDist2)) {
+                        vpMatches12[idx1] = bestIdx2;
+                        vbMatched2[bestIdx2] = true;
+                        if (mbCheckOrientation) {
+                            float rot = angle1[idx1] - angle2[bestIdx2];
+                            if (rot < 0.0) rot += 360.0f;
+                            int bin = round(rot * factor);
+                            if (bin == HISTO_LENGTH) bin = 0;
+                            rotHist[bin].push_back((int)idx1);
+                        }
+                        nmatches++;
+                    }
+                }
+            }
+            f1it++; f2it++;
+        } else if (f1it->first < f2it->first) f1it = vFeatVec1.m.lower_bound(f2it->first);
+        else f2it = vFeatVec2.m.lower_bound(f1it->first);
+    }
+    if (mbCheckOrientation) {
+        int ind1 = -1, ind2 = -1, ind3 = -1;
+        compute_three_maxima(rotHist, HISTO_LENGTH, ind1, ind2, ind3);
+        for (int i = 0; i < HISTO_LENGTH; i++) {
+            if (i == ind1 || i == ind2 || i == ind3) continue;
+            for (size_t j = 0, jend = rotHist[i].size(); j < jend; j++) { vpMatches12[rotHist[i][j]] = -1; nmatches--; }
+        }
+    }
+    for (int i = 0; i < n1; ++i) match12[i] = vpMatches12[i];
+    return nmatches;
+}
+
+// ORBmatcher::SearchForTriangulation — src/ORBmatcher2.cc:173-471, single pinhole camera (!mpCamera2 on both key frames);
+// Pinhole::epipolarConstrain — src/CameraModels/Pinhole.cpp:107-129 with F12 = K1^-T [t12]x R12 K2^-1 supplied by the caller.
+int orbo_search_for_triangulation(const KeyPoint* kp1s, const uint8_t* desc1, const uint8_t* free1, const uint8_t* stereo1, int n1,
+                                  int fv1_n, const uint32_t* fv1_nodes, const int32_t* fv1_off, const uint32_t* fv1_idx,
+                                  const KeyPoint* kp2s, const uint8_t* desc2, const uint8_t* free2, const uint8_t* stereo2, int n2,
+                                  int fv2_n, const uint32_t* fv2_nodes, const int32_t* fv2_off, const uint32_t* fv2_idx,
+                                  const float* F12, const float* ep, const float* mvScaleFactors2, const float* mvLevelSigma2_2,
+                                  int bOnlyStereo, int bCoarse, int mbCheckOrientation, int32_t* match12)
+{
+    FeatVec vFeatVec1(fv1_n, fv1_nodes, fv1_off, fv1_idx), vFeatVec2(fv2_n, fv2_nodes, fv2_off, fv2_idx);
+    int nmatches = 0;
+    std::vector<bool> vbMatched2(n2, false);
+    std::vector<int> vMatches12(n1, -1);
+    std::vector<int> rotHist[HISTO_LENGTH];
+    const float factor = 1.0f / HISTO_LENGTH;
+    auto Fm = [&](int r, int c) { return F12[r * 3 + c]; };
+    auto f1it = vFeatVec1.m.begin(), f2it = vFeatVec2.m.begin();
+    const auto f1end = vFeatVec1.m.end(), f2end = vFeatVec2.m.end();
+    while (f1it != f1end && f2it != f2end) {
+        if (f1it->first == f2it->first) {
+            for (size_t i1 = 0, iend1 = f1it->second.size(); i1 < iend1; i1++) {
+                const size_t idx1 = f1it->second[i1];
+                if (!free1[idx1]) continue;                       // already a MapPoint
+                const bool bStereo1 = stereo1[idx1] != 0;
+                if (bOnlyStereo) if (!bStereo1) continue;
+                const KeyPoint& kp1 = kp1s[idx1];
+                const uint8_t* d1 = desc1 + idx1 * 32;
+                int bestDist = TH_LOW, bestIdx2 = -1;
+                for (size_t i2 = 0, iend2 = f2it->second.size(); i2 < iend2; i2++) {
+                    const size_t idx2 = f2it->second[i2];
+                    if (vbMatched2[idx2] || !free2[idx2]) continue;
+                    const bool bStereo2 = stereo2[idx2] != 0;
+                    if (bOnlyStereo) if (!bStereo2) continue;
+                    const int dist = descriptor_distance(d1, desc2 + idx2 * 32);
+                    if (dist > TH_LOW || dist > bestDist) continue;
+                    const KeyPoint& kp2 = kp2s[idx2];
+                    if (!bStereo1 && !bStereo2) {
+                        const float distex = ep[0] - kp2.x;
+                        const float distey = ep[1] - kp2.y;
+                        if (distex * distex + distey * distey < 100 * mvScaleFactors2[kp2.octave]) continue;
+                    }
+                    bool ok = bCoarse != 0;
+                    if (!ok) {
+                        const float unc = mvLevelSigma2_2[kp2.octave];
+                        const float a = kp1.x * Fm(0, 0) + kp1.y * Fm(1, 0) + Fm(2, 0);
+                        const float b = kp1.x * Fm(0, 1) + kp1.y * Fm(1, 1) + Fm(2, 1);
+                        const float c = kp1.x * Fm(0, 2) + kp1.y * Fm(1, 2) + Fm(2, 2);
+                        const float num = a * kp2.x + b * kp2.y + c;
+                        const float den = a * a + b * b;
+                        if (den == 0) ok = false;
+                        else { const float dsqr = num * num / den; ok = dsqr < 3.84 * unc; }
+                    }
+                    if (ok) { bestIdx2 = (int)idx2; bestDist = dist; }
+                }
+                if (bestIdx2 >= 0) {
+                    const KeyPoint& kp2 = kp2s[bestIdx2];
+                    vMatches12[idx1] = bestIdx2;
+                    nmatches++;
+                    if (mbCheckOrientation) {
+                        float rot = kp1.angle - kp2.angle;
+                        if (rot < 0.0) rot += 360.0f;
+                        int bin = round(rot * factor);
+                        if (bin == HISTO_LENGTH) bin = 0;
+                        rotHist[bin].push_back((int)idx1);
+                    }
+                }
+            }
+            f1it++; f2it++;
+        } else if (f1it->first < f2it->first) f1it = vFeatVec1.m.lower_bound(f2it->first);
+        else f2it = vFeatVec2.m.lower_bound(f1it->first);
+    }
+    if (mbCheckOrientation) {
+        int ind1 = -1, ind2 = -1, ind3 = -1;
+        compute_three_maxima(rotHist, HISTO_LENGTH, ind1, ind2, ind3);
+        for (int i = 0; i < HISTO_LENGTH; i++) {
+            if (i == ind1 || i == ind2 || i == ind3) continue;
+            for (size_t j = 0, jend = rotHist[i].size(); j < jend; j++) { vMatches12[rotHist[i][j]] = -1; nmatches--; }
+        }
+    }
+    for (int i = 0; i < n1; ++i) match12[i] = vMatches12[i];
+    return nmatches;
+}
+
+}  // extern "C"

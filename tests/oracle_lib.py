@@ -150,6 +150,59 @@ class Oracle:
     def ratio_accept(self, d1, d2, ratio, th_low):
         return bool(self.lib.orbo_ratio_accept(int(d1), int(d2), float(ratio), int(th_low)))
 
+    # ---- bag of words / vocabulary-guided searches ----------------------------------------------
+    def vocabulary(self, parent, descriptors, weights, k, L, scoring=0, weighting=0):
+        return OracleVocabulary(self, parent, descriptors, weights, k, L, scoring, weighting)
+
+    def bow_score_l1(self, a, b):
+        ia = np.ascontiguousarray(a[0], np.uint32); va = np.ascontiguousarray(a[1], np.float64)
+        ib = np.ascontiguousarray(b[0], np.uint32); vb = np.ascontiguousarray(b[1], np.float64)
+        self.lib.orbo_bow_score_l1.restype = C.c_double
+        return self.lib.orbo_bow_score_l1(_ptr(ia), _ptr(va), len(ia), _ptr(ib), _ptr(vb), len(ib))
+
+    @staticmethod
+    def _fv(fv):
+        n, o, i = (np.ascontiguousarray(fv[0], np.uint32), np.ascontiguousarray(fv[1], np.int32), np.ascontiguousarray(fv[2], np.uint32))
+        return n, o, i
+
+    def search_by_bow_kf_frame(self, desc_kf, angle_kf, valid_kf, fv_kf, desc_f, angle_f, fv_f, nleft=-1, nnratio=0.6, check_ori=True):
+        dk = np.ascontiguousarray(desc_kf, np.uint8); df = np.ascontiguousarray(desc_f, np.uint8)
+        ak = np.ascontiguousarray(angle_kf, np.float32); af = np.ascontiguousarray(angle_f, np.float32)
+        vk = np.ascontiguousarray(valid_kf, np.uint8)
+        kn, ko, ki = self._fv(fv_kf); fn, fo, fi = self._fv(fv_f)
+        out = np.full(len(df), -1, np.int32)
+        nm = self.lib.orbo_search_by_bow_kf_frame(_ptr(dk), _ptr(ak), _ptr(vk), len(dk), len(kn), _ptr(kn), _ptr(ko), _ptr(ki), _ptr(df),
+                                                  _ptr(af), len(df), len(fn), _ptr(fn), _ptr(fo), _ptr(fi), int(nleft),
+                                                  C.c_float(nnratio), int(check_ori), _ptr(out))
+        return out, nm
+
+    def search_by_bow_kf_kf(self, d1, a1, v1, fv1, d2, a2, v2, fv2, nnratio=0.6, check_ori=True):
+        d1 = np.ascontiguousarray(d1, np.uint8); d2 = np.ascontiguousarray(d2, np.uint8)
+        a1 = np.ascontiguousarray(a1, np.float32); a2 = np.ascontiguousarray(a2, np.float32)
+        v1 = np.ascontiguousarray(v1, np.uint8); v2 = np.ascontiguousarray(v2, np.uint8)
+        n1, o1, i1 = self._fv(fv1); n2, o2, i2 = self._fv(fv2)
+        out = np.full(len(d1), -1, np.int32)
+        nm = self.lib.orbo_search_by_bow_kf_kf(_ptr(d1), _ptr(a1), _ptr(v1), len(d1), len(n1), _ptr(n1), _ptr(o1), _ptr(i1), _ptr(d2),
+                                               _ptr(a2), _ptr(v2), len(d2), len(n2), _ptr(n2), _ptr(o2), _ptr(i2), C.c_float(nnratio),
+                                               int(check_ori), _ptr(out))
+        return out, nm
+
+    def search_for_triangulation(self, kp1, d1, free1, st1, fv1, kp2, d2, free2, st2, fv2, F12, ep, scale2, sigma2_2, only_stereo=False,
+                                 coarse=False, check_ori=True):
+        kp1 = np.ascontiguousarray(kp1, KP_DTYPE); kp2 = np.ascontiguousarray(kp2, KP_DTYPE)
+        d1 = np.ascontiguousarray(d1, np.uint8); d2 = np.ascontiguousarray(d2, np.uint8)
+        free1 = np.ascontiguousarray(free1, np.uint8); free2 = np.ascontiguousarray(free2, np.uint8)
+        st1 = np.ascontiguousarray(st1, np.uint8); st2 = np.ascontiguousarray(st2, np.uint8)
+        n1, o1, i1 = self._fv(fv1); n2, o2, i2 = self._fv(fv2)
+        F = np.ascontiguousarray(F12, np.float32).reshape(9); e = np.ascontiguousarray(ep, np.float32)
+        sc = np.ascontiguousarray(scale2, np.float32); sg = np.ascontiguousarray(sigma2_2, np.float32)
+        out = np.full(len(d1), -1, np.int32)
+        nm = self.lib.orbo_search_for_triangulation(_ptr(kp1), _ptr(d1), _ptr(free1), _ptr(st1), len(d1), len(n1), _ptr(n1), _ptr(o1),
+                                                    _ptr(i1), _ptr(kp2), _ptr(d2), _ptr(free2), _ptr(st2), len(d2), len(n2), _ptr(n2),
+                                                    _ptr(o2), _ptr(i2), _ptr(F), _ptr(e), _ptr(sc), _ptr(sg), int(only_stereo), int(coarse),
+                                                    int(check_ori), _ptr(out))
+        return out, nm
+
     # ---- extractor --------------------------------------------------------------------------
     def extractor(self, nfeatures=1000, scale_factor=1.2, nlevels=8, ini_th=20, min_th=7):
         return OracleExtractor(self, nfeatures, scale_factor, nlevels, ini_th, min_th)
@@ -179,6 +232,38 @@ class Oracle:
         kept = self.lib.orbo_stereo_match(_ptr(kpL), _ptr(descL), len(kpL), _ptr(kpR), _ptr(descR), len(kpR), PL, PR, steps,
                                           widths, n_rows, _ptr(scale), _ptr(inv), float(mbf), float(max_d), _ptr(u), _ptr(d))
         return u, d, kept
+
+
+class OracleVocabulary:
+    def __init__(self, o, parent, descriptors, weights, k, L, scoring, weighting):
+        self.o = o
+        parent = np.ascontiguousarray(parent, np.int32); descriptors = np.ascontiguousarray(descriptors, np.uint8)
+        weights = np.ascontiguousarray(weights, np.float64)
+        o.lib.orbo_vocab_create.restype = _vp
+        self.h = _vp(o.lib.orbo_vocab_create(len(parent), _ptr(parent), _ptr(descriptors), _ptr(weights), k, L, scoring, weighting))
+
+    def __del__(self):
+        try:
+            self.o.lib.orbo_vocab_destroy(self.h)
+        except Exception:
+            pass
+
+    def transform_features(self, desc, levelsup=4):
+        d = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32)
+        n = len(d)
+        word = np.zeros(n, np.uint32); weight = np.zeros(n, np.float64); node = np.zeros(n, np.uint32)
+        self.o.lib.orbo_bow_transform(self.h, _ptr(d), n, levelsup, _ptr(word), _ptr(weight), _ptr(node))
+        return word, weight, node
+
+    def transform(self, desc, levelsup=4):
+        d = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32)
+        n = len(d)
+        ids = np.zeros(max(n, 1), np.uint32); vals = np.zeros(max(n, 1), np.float64)
+        nodes = np.zeros(max(n, 1), np.uint32); offs = np.zeros(n + 1, np.int32); idx = np.zeros(max(n, 1), np.uint32)
+        nb = C.c_int(0); nf = C.c_int(0)
+        self.o.lib.orbo_compute_bow(self.h, _ptr(d), n, levelsup, _ptr(ids), _ptr(vals), C.byref(nb), _ptr(nodes), _ptr(offs), _ptr(idx),
+                                    C.byref(nf))
+        return (ids[:nb.value].copy(), vals[:nb.value].copy()), (nodes[:nf.value].copy(), offs[:nf.value + 1].copy(), idx[:offs[nf.value]].copy())
 
 
 class OracleExtractor:

@@ -6,6 +6,7 @@ the built library raises (no CPU fallback).
 """
 from . import capi, synth  # noqa: F401
 from .capi import KP_DTYPE, OrbxError, lib  # noqa: F401
+from .bow import FeatureVector, ORBVocabulary, search_by_bow, search_for_triangulation  # noqa: F401
 from .extractor import ORBextractor, compute_tables, distribute_octree  # noqa: F401
 from .matcher import (ORBmatcher, compute_stereo_matches, distinctive_descriptor, knn2_device,  # noqa: F401
                       knn2_merge_device, measure_popc_peak, rotation_consistency)

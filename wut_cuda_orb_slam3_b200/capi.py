@@ -57,6 +57,16 @@ SIGNATURES = {
     "orbx_rotation_consistency": (_i, [_vp, _vp, _i, _vp]),
     "orbx_distinctive_descriptor": (_i, [_vp, _i, _vp]),
     "orbx_stereo_match": (_i, [_vp, _i, _vp, _i, _vp, _vp, _i, _vp, _vp, _i, _f, _f, _vp, _vp]),
+    "orbx_vocab_create": (_i, [_i, _i, _vp, _vp, _vp, _i, _i, _i, _i, C.POINTER(_vp)]),
+    "orbx_vocab_load_text": (_i, [_i, C.c_char_p, C.POINTER(_vp)]),
+    "orbx_vocab_destroy": (None, [_vp]),
+    "orbx_vocab_info": (_i, [_vp, _vp, _vp, _vp, _vp]),
+    "orbx_bow_transform": (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp]),
+    "orbx_compute_bow": (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "orbx_bow_score": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _i, C.POINTER(C.c_double)]),
+    "orbx_search_by_bow": (_i, [_i, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _i, _vp, _i, _f, _i, _vp, _vp, _vp]),
+    "orbx_search_for_triangulation": (_i, [_i, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _i, _i,
+                                           _i, _i, _vp, _vp]),
     "orbx_profile_begin": (_i, [_vp]),
     "orbx_profile_end": (_i, [_vp, _vp, _vp]),
     "orbx_measure_popc_peak": (_i, [_i, C.POINTER(C.c_double)]),
@@ -66,6 +76,11 @@ SIGNATURES = {
     "orbx_synth_descriptors_host": (None, [_u32, _i, _i64, _i64, _i64, _i, _vp]),
     "orbx_synth_descriptors_device": (_i, [_i, _u32, _i, _i64, _i64, _i64, _i, _vp, _vp]),
 }
+
+
+class FeatureVectorC(C.Structure):
+    """orbx_feature_vector (include/orbx.h): a DBoW2::FeatureVector in CSR form."""
+    _fields_ = [("n_nodes", C.c_int), ("node_ids", _vp), ("offsets", _vp), ("indices", _vp)]
 
 
 class OrbxError(RuntimeError):

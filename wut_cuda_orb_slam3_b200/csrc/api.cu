@@ -28,7 +28,7 @@ static std::atomic<long long> g_launches{0};
 
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
-static int fail(int code, const char* fmt, ...)
+int fail(int code, const char* fmt, ...)
 {
     char buf[512];
     va_list ap;
@@ -114,6 +114,32 @@ struct Slot {
     std::vector<void*> allocs;
 };
 
+int rotation_bin(float angle_a, float angle_b)
+{
+    const int HISTO_LENGTH = 30;
+    const float factor = 1.0f / HISTO_LENGTH;                 // src/ORBmatcher1.cc:238 (sic: bins are 30 degrees wide)
+    float rot = angle_a - angle_b;
+    if (rot < 0.0) rot += 360.0f;
+    int b = (int)round(rot * factor);
+    if (b == HISTO_LENGTH) b = 0;
+    return (b < 0 || b >= HISTO_LENGTH) ? -1 : b;
+}
+
+void three_maxima(const int* count, int L, int& ind1, int& ind2, int& ind3)
+{
+    int max1 = 0, max2 = 0, max3 = 0;
+    ind1 = ind2 = ind3 = -1;
+    for (int i = 0; i < L; i++) {
+        const int s = count[i];
+        if (s > max1) { max3 = max2; max2 = max1; max1 = s; ind3 = ind2; ind2 = ind1; ind1 = i; }
+        else if (s > max2) { max3 = max2; max2 = s; ind3 = ind2; ind2 = i; }
+        else if (s > max3) { max3 = s; ind3 = i; }
+    }
+    if (max2 < 0.1f * (float)max1) { ind2 = -1; ind3 = -1; }
+    else if (max3 < 0.1f * (float)max1) { ind3 = -1; }
+}
+
+
 }  // namespace orbx
 
 using namespace orbx;
@@ -139,7 +165,7 @@ struct orbx_extractor {
 
 namespace orbx {
 
-static int set_device(int device)
+int set_device(int device)
 {
     int n = 0;
     if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0) {
@@ -902,27 +928,16 @@ int orbx_rotation_consistency(const float* angle_a, const float* angle_b, int n,
 {
     if (n < 0 || (n > 0 && (!angle_a || !angle_b || !keep))) return fail(ORBX_ERR_INVALID_ARG, "bad arguments");
     const int HISTO_LENGTH = 30;
-    const float factor = 1.0f / HISTO_LENGTH;                 // src/ORBmatcher1.cc:238 (sic: bins are 30 degrees wide)
     std::vector<int> bin(n);
     int count[HISTO_LENGTH] = {0};
     for (int i = 0; i < n; ++i) {
-        float rot = angle_a[i] - angle_b[i];
-        if (rot < 0.0) rot += 360.0f;
-        int b = (int)round(rot * factor);
-        if (b == HISTO_LENGTH) b = 0;
-        if (b < 0 || b >= HISTO_LENGTH) return fail(ORBX_ERR_INVALID_ARG, "angle %d out of range (reference asserts)", i);
+        const int b = rotation_bin(angle_a[i], angle_b[i]);
+        if (b < 0) return fail(ORBX_ERR_INVALID_ARG, "angle %d out of range (reference asserts)", i);
         bin[i] = b;
         count[b]++;
     }
-    int max1 = 0, max2 = 0, max3 = 0, ind1 = -1, ind2 = -1, ind3 = -1;      // ComputeThreeMaxima
-    for (int i = 0; i < HISTO_LENGTH; i++) {
-        const int s = count[i];
-        if (s > max1) { max3 = max2; max2 = max1; max1 = s; ind3 = ind2; ind2 = ind1; ind1 = i; }
-        else if (s > max2) { max3 = max2; max2 = s; ind3 = ind2; ind2 = i; }
-        else if (s > max3) { max3 = s; ind3 = i; }
-    }
-    if (max2 < 0.1f * (float)max1) { ind2 = -1; ind3 = -1; }
-    else if (max3 < 0.1f * (float)max1) { ind3 = -1; }
+    int ind1, ind2, ind3;
+    three_maxima(count, HISTO_LENGTH, ind1, ind2, ind3);
     for (int i = 0; i < n; ++i) keep[i] = (bin[i] == ind1 || bin[i] == ind2 || bin[i] == ind3) ? 1 : 0;
     return ORBX_OK;
 }

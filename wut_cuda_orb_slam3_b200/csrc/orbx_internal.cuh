@@ -150,6 +150,52 @@ struct StereoArgs {
 };
 cudaError_t launch_stereo(const FrameGeom& fg, const StereoArgs& a, cudaStream_t st);
 
+// ---- bag-of-words / vocabulary-guided matching (kernels_bow.cu, api_bow.cu) ---------------------------------------------
+struct VocabDev {
+    const int* child_begin;      // [n_nodes] first child slot of a node
+    const int* child_count;      // [n_nodes] 0 for leaves
+    const int* child_id;         // [n_nodes - 1] node id of a child slot (children of a node are contiguous slots)
+    const uint8_t* cdesc;        // [n_nodes - 1][32] descriptor of a child slot
+    const int* word_of_node;     // [n_nodes] word id of a leaf, -1 otherwise
+    const double* weight;        // [n_nodes]
+};
+cudaError_t launch_bow_descend(const VocabDev& v, const uint8_t* d_desc, int n, int nid_level, uint32_t* d_word, double* d_weight,
+                               uint32_t* d_node, cudaStream_t st);
+
+struct BowSearchArgs {
+    int mode;                    // 0: KF -> Frame (src/ORBmatcher1.cc:225-427), 1: KF -> KF (src/ORBmatcher2.cc:36-171)
+    int n_pairs;
+    const int4* pairs;           // per common node: (a_begin, a_end, b_begin, b_end) into idx_a / idx_b
+    const uint32_t* idx_a; const uint32_t* idx_b;
+    const uint8_t* desc_a; const uint8_t* desc_b;
+    const uint8_t* valid_a; const uint8_t* valid_b;
+    int nleft_b;
+    float nn_ratio;
+    int* match_b;                // [nB] init -1: A index matched to B's feature (also the "already matched" state)
+    int* match_a;                // [nA] init -1 (may be null)
+    int* match_a_right;          // [nA] init -1 (mode 0 with nleft_b >= 0; may be null)
+};
+cudaError_t launch_search_by_bow(const BowSearchArgs& a, cudaStream_t st);
+
+struct TriSearchArgs {
+    int n_jobs;
+    const int4* jobs;            // (iA, b_begin, b_end, 0)
+    const uint32_t* idx_b;
+    const orbx_keypoint* kp_a; const orbx_keypoint* kp_b;
+    const uint8_t* desc_a; const uint8_t* desc_b;
+    const uint8_t* stereo_a; const uint8_t* stereo_b; const uint8_t* free_b;
+    float F12[9]; float ep[2]; float scale_b[kMaxLevels]; float sigma2_b[kMaxLevels];
+    int only_stereo, coarse;
+    int* match_a;                // [nA] init -1
+};
+cudaError_t launch_search_triangulation(const TriSearchArgs& a, cudaStream_t st);
+
+// host helpers shared by api.cu / api_bow.cu
+int fail(int code, const char* fmt, ...);
+int set_device(int device);
+void three_maxima(const int* count, int L, int& ind1, int& ind2, int& ind3);   // ORBmatcher::ComputeThreeMaxima (src/ORBmatcher3.cc:592-633)
+int rotation_bin(float angle_a, float angle_b);                                 // src/ORBmatcher1.cc:344-351; -1 if out of range
+
 cudaError_t launch_synth_images(uint32_t seed0, int view, int n_frames, int cols, int rows, int max_disp, uint8_t* d_dst,
                                 size_t pitch, size_t frame_stride, cudaStream_t st);
 cudaError_t launch_synth_desc(uint32_t seed, int is_query, long long first_row, long long n_rows, long long ndb,
