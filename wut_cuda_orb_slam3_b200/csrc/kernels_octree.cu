@@ -110,15 +110,15 @@ __device__ __forceinline__ uint32_t lower_bound_code(const uint32_t* codes, uint
 
 size_t octree_smem_bytes(int M, int T)
 {
+    // the radix-sort histogram is dead once the sort is done: it shares its bytes with the node / scan arrays of the tree phases
+    const size_t hist = sizeof(uint32_t) * (16 * T + (16 * T) / 32);
     size_t b = 0;
-    b += sizeof(uint32_t) * (16 * T + (16 * T) / 32);
-    b += sizeof(int) * (64 + 224);
     b += sizeof(uint32_t) * (size_t)M * 8;      // node arrays x2
     b += sizeof(uint32_t) * (size_t)M * 4;      // cc
     b += sizeof(int) * (size_t)M * 5;           // sa, sb, sc, sd, procpos
     b += 8;                                     // alignment slack
     b += sizeof(unsigned long long) * (size_t)M * 2;
-    return b;
+    return sizeof(int) * (64 + 224) + (b > hist ? b : hist);
 }
 
 // grid = (nlevels, n_frames); dynamic smem sized for the largest level's node capacity.
@@ -143,9 +143,9 @@ __global__ void __launch_bounds__(T) octree_kernel(const __grid_constant__ Frame
     Smem S;
     {
         unsigned char* p = smem_raw;
-        S.hist = (uint32_t*)p; p += sizeof(uint32_t) * kHistWords;
         S.warp_tmp = (int*)p; p += sizeof(int) * 64;
         S.sort_stk = (int*)p; p += sizeof(int) * 224;
+        S.hist = (uint32_t*)p;          // aliases the arrays below: used by the radix sort only, which ends with a barrier
         for (int b = 0; b < 2; ++b) {
             S.nbeg[b] = (uint32_t*)p; p += 4 * (size_t)M;
             S.ncnt[b] = (uint32_t*)p; p += 4 * (size_t)M;
@@ -521,6 +521,8 @@ cudaError_t octree_prepare()
 {
     cudaError_t e = cudaFuncSetAttribute(octree_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(octree_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(octree_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (e != cudaSuccess) return e;
     return cudaFuncSetAttribute(octree_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
@@ -536,7 +538,7 @@ cudaError_t launch_octree(const FrameGeom& fg, const Workspace& ws, int n_frames
     // A few frames: the level-0 CTA is the critical path of the whole extraction, so give it more lanes.
     static const int t_override = getenv("ORBX_OCTREE_THREADS") ? atoi(getenv("ORBX_OCTREE_THREADS")) : 0;
     int T = n_frames >= 8 ? 256 : 1024;
-    if (t_override == 256 || t_override == 512 || t_override == 1024) T = t_override;
+    if (t_override == 128 || t_override == 256 || t_override == 512 || t_override == 1024) T = t_override;
     const size_t smem = octree_smem_bytes(M, T);
     if (smem > 200 * 1024) return cudaErrorInvalidConfiguration;
     int dev = 0;
@@ -549,7 +551,8 @@ cudaError_t launch_octree(const FrameGeom& fg, const Workspace& ws, int n_frames
     dim3 grid(fg.nlevels, n_frames);
     // The kernel is latency-bound (sequential sort replay, dependent binary searches): big batches run more, smaller CTAs
     // per SM to overlap those chains; a single frame gets the larger CTA for the shortest critical path.
-    if (T == 1024) octree_kernel<1024><<<grid, 1024, smem, st>>>(fg, ws, M, g_err_flag[dev & 63]);
+    if (T == 128) octree_kernel<128><<<grid, 128, smem, st>>>(fg, ws, M, g_err_flag[dev & 63]);
+    else if (T == 1024) octree_kernel<1024><<<grid, 1024, smem, st>>>(fg, ws, M, g_err_flag[dev & 63]);
     else if (T == 512) octree_kernel<512><<<grid, 512, smem, st>>>(fg, ws, M, g_err_flag[dev & 63]);
     else octree_kernel<256><<<grid, 256, smem, st>>>(fg, ws, M, g_err_flag[dev & 63]);
     count_launch();
