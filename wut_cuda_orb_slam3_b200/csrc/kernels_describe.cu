@@ -10,17 +10,21 @@
 //  * pack_kernel:        operator() output packing (src/ORBextractor.cc:1283-1306): scale, lapping-area split.
 #include <float.h>
 
+#include <mutex>
+
 #include "orbx_internal.cuh"
 
 namespace orbx {
 
 namespace {
 
-__device__ __align__(16) const int8_t d_pattern[1024] = {
-#include "brief_pattern.inc"
-};
-
 __constant__ int c_umax[16] = {15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9, 8, 6, 3};
+
+// Filled once per device by launch_orient_describe():
+//   d_pattern_f[k][lane] = (x0, y0, x1, y1) of test 8*lane + k as floats (coalesced 16-byte loads, no int->float conversions)
+//   d_mom_mask[|v|][j]   = byte mask of the patch-row words j = 0..7 (columns u = -15 + 4j .. -12 + 4j): 0xff where |u| <= umax[|v|]
+__device__ float4 d_pattern_f[8][32];
+__device__ uint4 d_mom_mask[16][2];
 
 constexpr int BT_W = 128, BT_H = 32;          // blur tile
 constexpr int BIN_P = 160;                    // input tile pitch (bytes): image columns x0-16 .. x0+143 (16-byte aligned)
@@ -152,28 +156,35 @@ __global__ void __launch_bounds__(256) orient_describe_kernel(const __grid_const
     const uint32_t key = ws.lvl_kp[(size_t)frame * fg.kp_slots + slot];
     const int x = (int)(key & 0xfff) + kWinBorder, y = (int)((key >> 12) & 0xfff) + kWinBorder;
 
-    // ---- IC_Angle on the un-blurred level: lane <-> column u = lane - 15 ----
+    // ---- IC_Angle on the un-blurred level: lane <-> patch row v = lane - 15 ----
+    // The row's 31 bytes arrive as 9 aligned 32-bit words, realigned with funnel shifts (the misalignment is the same for
+    // every row: the pitch is a multiple of 16), masked to the disc |u| <= umax[|v|] and summed with dp4a:
+    //   m10 = sum_u u * I(u, v) = dp4a(bytes, (u0, u0+1, u0+2, u0+3)),   m01 = v * sum_u I(u, v) = v * dp4a(bytes, (1,1,1,1)).
     int m10 = 0, m01 = 0;
     {
-        const int u = lane - kHalfPatch;
+        const int v = lane - kHalfPatch;
         if (lane < 31) {
-            const int au = u < 0 ? -u : u;
-            // walking row pointer (one 64-bit add per row) instead of re-deriving base + v*pitch + u for every load;
-            // m10 = u * (sum of the column) needs a single multiply at the end
-            const uint8_t* row = level_interior((const uint8_t*)ws.pyr, g, frame) + (ptrdiff_t)(y - kHalfPatch) * g.pitch + (x + u);
-            const ptrdiff_t pitch = g.pitch;
+            const uint8_t* rowp = level_interior((const uint8_t*)ws.pyr, g, frame) + (ptrdiff_t)(y + v) * g.pitch + (x - kHalfPatch);
+            const int mis = (int)((uintptr_t)rowp & 3);
+            const uint32_t* rw = reinterpret_cast<const uint32_t*>(rowp - mis);
+            uint32_t w[9];
+#pragma unroll
+            for (int j = 0; j < 9; ++j) w[j] = __ldg(rw + j);
+            const int av = v < 0 ? -v : v;
+            const uint4 ma = d_mom_mask[av][0], mb = d_mom_mask[av][1];
+            const uint32_t mk[8] = {ma.x, ma.y, ma.z, ma.w, mb.x, mb.y, mb.z, mb.w};
+            const int sh = 8 * mis;
             int sum = 0;
 #pragma unroll
-            for (int v = -kHalfPatch; v <= kHalfPatch; ++v) {
-                const int av = v < 0 ? -v : v;
-                if (au <= c_umax[av]) {
-                    const int val = __ldg(row);
-                    sum += val;
-                    m01 += v * val;
-                }
-                row += pitch;
+            for (int j = 0; j < 8; ++j) {
+                const uint32_t px = __funnelshift_r(w[j], w[j + 1], sh) & mk[j];
+                const int u0 = -kHalfPatch + 4 * j;
+                const uint32_t wt = (uint32_t)(u0 & 0xff) | ((uint32_t)((u0 + 1) & 0xff) << 8) | ((uint32_t)((u0 + 2) & 0xff) << 16) |
+                                    ((uint32_t)((u0 + 3) & 0xff) << 24);
+                asm("dp4a.u32.s32 %0, %1, %2, %0;" : "+r"(m10) : "r"(px), "r"(wt));
+                sum = (int)__dp4a(px, 0x01010101u, (uint32_t)sum);
             }
-            m10 = u * sum;
+            m01 = v * sum;
         }
 #pragma unroll
         for (int d = 16; d >= 1; d >>= 1) {
@@ -191,23 +202,20 @@ __global__ void __launch_bounds__(256) orient_describe_kernel(const __grid_const
     const float a = (float)cd, b = (float)sd;
     const uint8_t* center = ws.blur + g.blur_off + (size_t)frame * g.blur_frame_stride + (size_t)y * g.bpitch + x;
     const int step = g.bpitch;
-    const uint4* pat4 = reinterpret_cast<const uint4*>(d_pattern) + lane * 2;
+    // cvRound (round half to even) without the conversion unit: adding 1.5 * 2^23 leaves the rounded integer in the low
+    // mantissa bits (|value| <= 19 here), so int = bits - 0x4B400000
+    const float kMagic = 12582912.0f;
+    const int kMagicBits = 0x4B400000;
     uint32_t val = 0;
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
-        const uint4 q = pat4[h];
-        const uint32_t w[4] = {q.x, q.y, q.z, q.w};
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {     // one test per 32-bit word: (x0, y0, x1, y1) int8
-            const float x0 = (float)(int8_t)(w[k] & 0xff), y0 = (float)(int8_t)((w[k] >> 8) & 0xff);
-            const float x1 = (float)(int8_t)((w[k] >> 16) & 0xff), y1 = (float)(int8_t)(w[k] >> 24);
-            const int iy0 = __float2int_rn(__fadd_rn(__fmul_rn(x0, b), __fmul_rn(y0, a)));
-            const int ix0 = __float2int_rn(__fsub_rn(__fmul_rn(x0, a), __fmul_rn(y0, b)));
-            const int iy1 = __float2int_rn(__fadd_rn(__fmul_rn(x1, b), __fmul_rn(y1, a)));
-            const int ix1 = __float2int_rn(__fsub_rn(__fmul_rn(x1, a), __fmul_rn(y1, b)));
-            const int t0 = __ldg(center + iy0 * step + ix0), t1 = __ldg(center + iy1 * step + ix1);
-            val |= (uint32_t)(t0 < t1) << (h * 4 + k);
-        }
+    for (int k = 0; k < 8; ++k) {
+        const float4 q = d_pattern_f[k][lane];          // (x0, y0, x1, y1) of test 8 * lane + k
+        const int iy0 = __float_as_int(__fadd_rn(__fadd_rn(__fmul_rn(q.x, b), __fmul_rn(q.y, a)), kMagic)) - kMagicBits;
+        const int ix0 = __float_as_int(__fadd_rn(__fsub_rn(__fmul_rn(q.x, a), __fmul_rn(q.y, b)), kMagic)) - kMagicBits;
+        const int iy1 = __float_as_int(__fadd_rn(__fadd_rn(__fmul_rn(q.z, b), __fmul_rn(q.w, a)), kMagic)) - kMagicBits;
+        const int ix1 = __float_as_int(__fadd_rn(__fsub_rn(__fmul_rn(q.z, a), __fmul_rn(q.w, b)), kMagic)) - kMagicBits;
+        const int t0 = __ldg(center + iy0 * step + ix0), t1 = __ldg(center + iy1 * step + ix1);
+        val |= (uint32_t)(t0 < t1) << k;
     }
     ws.lvl_desc[((size_t)frame * fg.kp_slots + slot) * 32 + lane] = (uint8_t)val;
     if (lane == 0) ws.lvl_angle[(size_t)frame * fg.kp_slots + slot] = angle;
@@ -290,8 +298,45 @@ cudaError_t launch_blur(const FrameGeom& fg, const Workspace& ws, int n_frames, 
     return cudaGetLastError();
 }
 
+static cudaError_t fill_describe_tables()
+{
+    static const int8_t pat[1024] = {
+#include "brief_pattern.inc"
+    };
+    static const int umax[16] = {15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9, 8, 6, 3};
+    float4 pf[8][32];
+    for (int lane = 0; lane < 32; ++lane)
+        for (int k = 0; k < 8; ++k) {
+            const int8_t* t = pat + 4 * (8 * lane + k);
+            pf[k][lane] = make_float4((float)t[0], (float)t[1], (float)t[2], (float)t[3]);
+        }
+    uint32_t mask[16][8];
+    for (int av = 0; av < 16; ++av)
+        for (int j = 0; j < 8; ++j) {
+            uint32_t m = 0;
+            for (int bb = 0; bb < 4; ++bb) {
+                const int u = -15 + 4 * j + bb;
+                if ((u < 0 ? -u : u) <= umax[av]) m |= 0xffu << (8 * bb);
+            }
+            mask[av][j] = m;
+        }
+    cudaError_t e = cudaMemcpyToSymbol(d_pattern_f, pf, sizeof pf);
+    if (e != cudaSuccess) return e;
+    return cudaMemcpyToSymbol(d_mom_mask, mask, sizeof mask);
+}
+
 cudaError_t launch_orient_describe(const FrameGeom& fg, const Workspace& ws, int n_frames, cudaStream_t st)
 {
+    static bool filled[64] = {false};      // per device (the tables are __device__ symbols, one copy per context)
+    static std::mutex mu;                  // the left / right extractors launch from two host threads
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> lock(mu);
+    if (!filled[dev & 63]) {
+        cudaError_t e = fill_describe_tables();          // synchronous copy: ordered before every later launch
+        if (e != cudaSuccess) return e;
+        filled[dev & 63] = true;
+    }
     dim3 grid((fg.kp_slots + 7) / 8, n_frames);
     orient_describe_kernel<<<grid, 256, 0, st>>>(fg, ws);
     count_launch();
