@@ -108,6 +108,9 @@ def lib():
         L.orbx_debug_sort_replay.argtypes = [_vp, _i]
         L.orbx_debug_sort_replay32.restype = None
         L.orbx_debug_sort_replay32.argtypes = [_vp, _i]
+        for nm in ("orbx_debug_sort_replay_ranges", "orbx_debug_sort_replay_ranges32"):
+            getattr(L, nm).restype = None
+            getattr(L, nm).argtypes = [_vp, _i]
         _lib = L
     return _lib
 

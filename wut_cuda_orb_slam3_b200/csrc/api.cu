@@ -636,16 +636,41 @@ int orbx_extract_batch(orbx_extractor* ex, const uint8_t* const* images, int n_f
     if (rc) return rc;
     if ((rc = configure(ex, rows, cols))) return rc;
     const int chunk = ex->max_batch > 0 ? std::min(ex->max_batch, n_frames) : std::min(n_frames, 64);
-    const int nchunks = (n_frames + chunk - 1) / chunk;
+    // Chunk schedule: the first host->device copy cannot overlap any compute, so the pipeline ramps up with a quarter and a
+    // half chunk before it settles on full chunks (shorter un-overlapped prologue; the tail is whatever remains).
+    std::vector<std::pair<int, int>> sched;          // (first frame, frames)
+    int max_chunk = chunk;
+    {
+        int f0 = 0;
+        const char* env = getenv("ORBX_BATCH_SCHED");            // measurement override: "64,192,256" (last entry repeats)
+        if (env && *env) {
+            std::vector<int> sizes;
+            for (const char* p = env; *p;) { sizes.push_back(std::max(atoi(p), 1)); while (*p && *p != ',') ++p; if (*p == ',') ++p; }
+            for (size_t i = 0; f0 < n_frames; ++i) {
+                const int nf = std::min(sizes[std::min(i, sizes.size() - 1)], n_frames - f0);
+                sched.emplace_back(f0, nf); f0 += nf; max_chunk = std::max(max_chunk, nf);
+            }
+        } else {
+            const int ramp[2] = {std::max(chunk / 4, 1), std::max(chunk / 2, 1)};
+            for (int r = 0; r < 2 && n_frames - f0 > 2 * chunk; ++r) { sched.emplace_back(f0, ramp[r]); f0 += ramp[r]; }
+            while (f0 < n_frames) { const int nf = std::min(chunk, n_frames - f0); sched.emplace_back(f0, nf); f0 += nf; }
+        }
+    }
+    const int nchunks = (int)sched.size();
     const int nslots = std::min(nchunks, (int)orbx_extractor::kSlots);
-    if ((rc = ensure_capacity(ex, chunk, nslots))) return rc;
+    if ((rc = ensure_capacity(ex, max_chunk, nslots))) return rc;
     const size_t dpitch = (size_t)cols;
     const size_t dframe = dpitch * rows;
     for (int i = 0; i < nslots; ++i)
-        if ((rc = ensure_host_staging(ex->slots[i], dframe * chunk, chunk, capacity))) return rc;
+        if ((rc = ensure_host_staging(ex->slots[i], dframe * max_chunk, max_chunk, capacity))) return rc;
+    // ORBX_TRACE_BATCH=1: per-chunk timeline (H2D start/end, compute end, D2H end; ms since the first H2D) on stderr
+    static const bool trace = getenv("ORBX_TRACE_BATCH") != nullptr;
+    std::vector<cudaEvent_t> tev;
+    auto mark = [&](cudaStream_t st) { if (trace) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, st); tev.push_back(e); } };
     for (int c = 0; c < nchunks; ++c) {
         Slot& s = ex->slots[c % nslots];
-        const int f0 = c * chunk, nf = std::min(chunk, n_frames - f0);
+        const int f0 = sched[c].first, nf = sched[c].second;
+        mark(s.stream);
         // stream order makes reuse of the slot's staging safe: the previous D2H on this stream precedes these H2D copies
         bool contiguous = step == (size_t)cols;
         for (int f = 1; f < nf && contiguous; ++f) contiguous = images[f0 + f] == images[f0 + f - 1] + dframe;
@@ -655,14 +680,25 @@ int orbx_extract_batch(orbx_extractor* ex, const uint8_t* const* images, int n_f
             for (int f = 0; f < nf; ++f)
                 CU(cudaMemcpy2DAsync(s.d_in + (size_t)f * dframe, dpitch, images[f0 + f], step, cols, rows, cudaMemcpyHostToDevice, s.stream));
         }
+        mark(s.stream);
         if ((rc = run_chunk(ex, s, s.d_in, dframe, dpitch, nf, lap0, lap1, s.d_kps, s.d_desc, capacity, s.d_n, s.d_nm, s.stream))) return rc;
+        mark(s.stream);
         CU(cudaMemcpyAsync(keypoints + (size_t)f0 * capacity, s.d_kps, sizeof(orbx_keypoint) * (size_t)nf * capacity, cudaMemcpyDeviceToHost, s.stream));
         CU(cudaMemcpyAsync(descriptors + (size_t)f0 * capacity * 32, s.d_desc, (size_t)nf * capacity * 32, cudaMemcpyDeviceToHost, s.stream));
         CU(cudaMemcpyAsync(n_out + f0, s.d_n, sizeof(int) * nf, cudaMemcpyDeviceToHost, s.stream));
         CU(cudaMemcpyAsync(n_mono + f0, s.d_nm, sizeof(int) * nf, cudaMemcpyDeviceToHost, s.stream));
+        mark(s.stream);
         if (c % nslots == 0) ex->last_frames = nf;
     }
     for (int i = 0; i < nslots; ++i) CU(cudaStreamSynchronize(ex->slots[i].stream));
+    if (trace) {
+        for (int c = 0; c < nchunks; ++c) {
+            float t[4];
+            for (int k = 0; k < 4; ++k) cudaEventElapsedTime(&t[k], tev[0], tev[4 * c + k]);
+            fprintf(stderr, "[orbx] chunk %2d frames %3d: h2d %.3f-%.3f compute-end %.3f d2h-end %.3f ms\n", c, sched[c].second, t[0], t[1], t[2], t[3]);
+        }
+        for (cudaEvent_t e : tev) cudaEventDestroy(e);
+    }
     for (int f = 0; f < n_frames; ++f)
         if (n_out[f] > capacity) return fail(ORBX_ERR_CAPACITY, "frame %d has %d keypoints, capacity %d", f, n_out[f], capacity);
     return ORBX_OK;
@@ -1107,5 +1143,19 @@ int orbx_debug_octree_timing(orbx_extractor* ex, const uint8_t* image, int rows,
 // Test hook: the std::sort replay used by the octree kernel, on the host (tests/test_introsort.py).
 void orbx_debug_sort_replay(unsigned long long* items, int n) { orbx_sort::sort_replay(items, n); }
 void orbx_debug_sort_replay32(uint32_t* items, int n) { orbx_sort::sort_replay(items, n); }
+// host simulation of the range-parallel schedule the octree kernel runs (n < 4352: at most 256 ranges longer than 16)
+void orbx_debug_sort_replay_ranges(unsigned long long* items, int n)
+{
+    if (n <= 0 || n >= 4352) { orbx_sort::sort_replay(items, n); return; }
+    std::vector<uint32_t> blk(n);
+    std::vector<unsigned long long> tmp(n);
+    orbx_sort::sort_replay_ranges_host(items, n, blk.data(), tmp.data());
+}
+void orbx_debug_sort_replay_ranges32(uint32_t* items, int n)
+{
+    if (n <= 0 || n >= 4352) { orbx_sort::sort_replay(items, n); return; }
+    std::vector<uint32_t> blk(n), tmp(n);
+    orbx_sort::sort_replay_ranges_host(items, n, blk.data(), tmp.data());
+}
 
 }  // extern "C"

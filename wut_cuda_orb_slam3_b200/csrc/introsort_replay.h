@@ -200,4 +200,78 @@ template <typename item_t> ORBX_SORT_HD void sort_replay(item_t* base, int n)
     }
 }
 
+// ---- range-parallel formulation ----------------------------------------------------------------------------------------
+// The introsort loop recurses on disjoint ranges, so the partition steps of one recursion level are independent: every
+// range longer than 16 is partitioned by its own lane (the partition itself stays the exact sequential Hoare scan), the
+// children go to the next round.  __final_insertion_sort is a STABLE sort of each leftover block of <= 16 elements: after
+// the partitions every element left of a block compares <= and every element right of it >=, so an insertion never leaves
+// its block (a guarded insertion into block 0 equals an unguarded one that stops at index 0), and a stable sort of a block
+// is unique — it is evaluated by rank counting, one lane per element.  Ranges whose depth budget is exhausted are
+// heap-sorted by their lane and left alone (the insertion pass finds them already ordered).
+// Same permutation as sort_replay() / std::sort; ~2n dependent steps instead of ~n log n.
+struct Range { int first, last, depth; };
+
+// One introsort step on r (last - first > 16).  Returns the number of children written to out (0: heap-sorted).
+template <typename item_t> ORBX_SORT_HD int range_step(item_t* base, int n, Range r, Range out[2])
+{
+    if (r.depth == 0) {
+        heap_sort_(base + r.first, r.last - r.first);
+        return 0;
+    }
+    const int depth = r.depth - 1;
+    const int mid = r.first + (r.last - r.first) / 2;
+    move_median_to_first_(base + r.first, base + r.first + 1, base + mid, base + r.last - 1);
+    const int cut = unguarded_partition_(base, n, r.first + 1, r.last, r.first);
+    out[0] = Range{r.first, cut, depth};
+    out[1] = Range{cut, r.last, depth};
+    return 2;
+}
+
+// Position of element i after the stable sort of its block [f, l).
+template <typename item_t> ORBX_SORT_HD int block_stable_pos(const item_t* base, int f, int l, int i)
+{
+    const item_t e = base[i];
+    int rank = 0;
+    for (int j = f; j < l; ++j) rank += (lt(base[j], e) || (j < i && !lt(e, base[j]))) ? 1 : 0;
+    return f + rank;
+}
+
+ORBX_SORT_HD int initial_depth(int n)
+{
+    int lg = 0;
+    for (int t = n; t > 1; t >>= 1) ++lg;
+    return 2 * lg;
+}
+
+// Host-side sequential simulation of the range-parallel schedule (rounds of independent range steps, then the block-wise
+// stable placement): the device version in kernels_octree.cu runs the same steps with one lane per range / element.
+// blk[n]: packed block bounds (f | l << 16) per element; tmp[n]: output buffer.  n < 65536.
+template <typename item_t> inline void sort_replay_ranges_host(item_t* base, int n, uint32_t* blk, item_t* tmp)
+{
+    if (n <= 0) return;
+    Range cur[256], nxt[256];          // ranges longer than 16 elements: at most n / 17 of them
+    int nc = 0, nn = 0;
+    auto settle = [&](Range r, bool sorted) {
+        for (int i = r.first; i < r.last; ++i) blk[i] = sorted ? ((uint32_t)i | ((uint32_t)(i + 1) << 16)) : ((uint32_t)r.first | ((uint32_t)r.last << 16));
+    };
+    Range all{0, n, initial_depth(n)};
+    if (n > 16) cur[nc++] = all; else settle(all, false);
+    while (nc > 0) {
+        nn = 0;
+        for (int q = 0; q < nc; ++q) {
+            Range out[2];
+            const int k = range_step(base, n, cur[q], out);
+            if (k == 0) settle(cur[q], true);
+            for (int c = 0; c < k; ++c) {
+                if (out[c].last - out[c].first > 16) nxt[nn++] = out[c];
+                else settle(out[c], false);
+            }
+        }
+        for (int q = 0; q < nn; ++q) cur[q] = nxt[q];
+        nc = nn;
+    }
+    for (int i = 0; i < n; ++i) tmp[block_stable_pos(base, (int)(blk[i] & 0xffffu), (int)(blk[i] >> 16), i)] = base[i];
+    for (int i = 0; i < n; ++i) base[i] = tmp[i];
+}
+
 }  // namespace orbx_sort

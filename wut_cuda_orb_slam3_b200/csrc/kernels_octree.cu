@@ -78,6 +78,61 @@ __device__ int block_exclusive_scan(int* a, int n, int* warp_tmp)
     return total;
 }
 
+// std::sort replay, range-parallel (introsort_replay.h): all T threads call.  base[m] = 32-bit items in shared memory,
+// blk[m] / tmp[m] = shared scratch, q = 224 ints of shared scratch (three round counters + two queues of <= 32 ranges: a
+// range in a queue is longer than 16 elements and m <= 512).  Range r of a round is handled by lane r / NW of warp r % NW, so
+// that the longest partitions of a round run in different warps.  One barrier per round: the counters rotate (the one read
+// in round k is cleared in round k + 1 and refilled in round k + 2).
+template <int T>
+__device__ void sort_replay_parallel(uint32_t* base, int m, uint32_t* blk, uint32_t* tmp, int* q)
+{
+    constexpr int NW = T / 32;
+    const int tid = threadIdx.x;
+    int* cnt = q;
+    int* Q[2] = {q + 8, q + 8 + 96};
+    if (m <= 16) {
+        for (int i = tid; i < m; i += T) blk[i] = (uint32_t)m << 16;
+    } else if (tid == 0) {
+        Q[0][0] = 0; Q[0][1] = m; Q[0][2] = orbx_sort::initial_depth(m);
+    }
+    if (tid == 0) { cnt[0] = m > 16 ? 1 : 0; cnt[1] = 0; cnt[2] = 0; }
+    __syncthreads();
+    for (int round = 0;; ++round) {
+        const int c = cnt[round % 3];
+        if (c == 0) break;                                   // uniform
+        if (tid == 0) cnt[(round + 2) % 3] = 0;
+        int* nxt_cnt = cnt + (round + 1) % 3;
+        const int* qi = Q[round & 1];
+        int* qo = Q[(round + 1) & 1];
+        const int r = (tid >> 5) + (tid & 31) * NW;
+        if (r < c) {
+            const orbx_sort::Range rg{qi[3 * r], qi[3 * r + 1], qi[3 * r + 2]};
+            orbx_sort::Range out[2];
+            const int k = orbx_sort::range_step(base, m, rg, out);
+            if (k == 0)
+                for (int i = rg.first; i < rg.last; ++i) blk[i] = (uint32_t)i | ((uint32_t)(i + 1) << 16);   // heap-sorted: final
+            for (int ch = 0; ch < k; ++ch) {
+                if (out[ch].last - out[ch].first > 16) {
+                    const int slot = atomicAdd(nxt_cnt, 1);
+                    qo[3 * slot] = out[ch].first; qo[3 * slot + 1] = out[ch].last; qo[3 * slot + 2] = out[ch].depth;
+                } else {
+                    const uint32_t b = (uint32_t)out[ch].first | ((uint32_t)out[ch].last << 16);
+                    for (int i = out[ch].first; i < out[ch].last; ++i) blk[i] = b;
+                }
+            }
+        }
+        __syncthreads();
+    }
+    // __final_insertion_sort == stable sort of every leftover block: rank counting, one lane per element
+    for (int i = tid; i < m; i += T) {
+        const uint32_t b = blk[i];
+        tmp[orbx_sort::block_stable_pos(base, (int)(b & 0xffffu), (int)(b >> 16), i)] = base[i];
+    }
+    __syncthreads();
+    for (int i = tid; i < m; i += T) base[i] = tmp[i];
+    __syncthreads();
+}
+
 // Path code of a key (window-relative x, y).
 __device__ __forceinline__ uint32_t path_code(int x, int y, const LevelGeom& g, int winH)
 {
@@ -123,7 +178,7 @@ size_t octree_smem_bytes(int M, int T)
 
 // grid = (nlevels, n_frames); dynamic smem sized for the largest level's node capacity.
 template <int T>
-__global__ void __launch_bounds__(T) octree_kernel(const __grid_constant__ FrameGeom fg, Workspace ws, int M,
+__global__ void __launch_bounds__(T, 1024 / T) octree_kernel(const __grid_constant__ FrameGeom fg, Workspace ws, int M,
                                                    int* __restrict__ err_flag)
 {
     constexpr int kHistWords = 16 * T + (16 * T) / 32;
@@ -460,7 +515,7 @@ __global__ void __launch_bounds__(T) octree_kernel(const __grid_constant__ Frame
                         s32[i] = ((uint32_t)rank << 16) | (uint32_t)i;
                     }
                     __syncthreads();
-                    if (tid == 0) orbx_sort::sort_replay(s32, m);
+                    sort_replay_parallel<T>(s32, m, reinterpret_cast<uint32_t*>(S.sa), reinterpret_cast<uint32_t*>(S.sb), S.sort_stk);
                 } else {
                     if (tid == 0) orbx_sort::sort_replay(vprev, m);
                 }
