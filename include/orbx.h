@@ -95,6 +95,17 @@ int orbx_max_keypoints(const orbx_extractor* ex);
 int orbx_extract(orbx_extractor* ex, const uint8_t* image, int rows, int cols, size_t step, int lap0, int lap1,
                  orbx_keypoint* keypoints, uint8_t* descriptors, int capacity, int* n_out, int* n_mono);
 
+/* Image prep of Tracking::GrabImageStereo / GrabImageMonocular / GrabImageRGBD (src/Tracking2.cc:289-316, 347-361, 392-406):
+ * cv::cvtColor(im, im, COLOR_{RGB,BGR,RGBA,BGRA}2GRAY) chosen by the channel count and mbRGB, fused in front of operator():
+ * `image` is a HOST rows x cols image of `channels` (3 or 4) interleaved 8-bit channels, `rgb` != 0 means channel 0 is red
+ * (mbRGB).  8U arithmetic of OpenCV: (R*9798 + G*19235 + B*3735 + 2^14) >> 15.  The grey image is level 0 of the pyramid
+ * (orbx_get_pyramid_level) — the reference keeps it as mImGray. */
+int orbx_extract_color(orbx_extractor* ex, const uint8_t* image, int rows, int cols, size_t step, int channels, int rgb, int lap0,
+                       int lap1, orbx_keypoint* keypoints, uint8_t* descriptors, int capacity, int* n_out, int* n_mono);
+/* The conversion alone on device-resident frames (frame f at d_src + f*src_frame_stride, src_pitch bytes per row). */
+int orbx_cvt_gray_device(int device, const uint8_t* d_src, size_t src_pitch, size_t src_frame_stride, int channels, int rgb,
+                         int n_frames, int rows, int cols, uint8_t* d_dst, size_t dst_pitch, size_t dst_frame_stride, void* stream);
+
 /* Batched operator(): n_frames HOST images of identical shape (images[i] -> rows x cols, `step` bytes per row).
  * Outputs are [n_frames][capacity] slabs; n_out / n_mono are [n_frames].  Host<->device copies are pipelined
  * against compute when the host buffers are page-locked. */

@@ -1388,3 +1388,16 @@ int orbo_search_for_triangulation(const KeyPoint* kp1s, const uint8_t* desc1, co
 }
 
 }  // extern "C"
+
+// cv::cvtColor(src, dst, COLOR_{RGB,BGR,RGBA,BGRA}2GRAY) as called by Tracking::GrabImage* (src/Tracking2.cc:289-316, 347-361,
+// 392-406).  OpenCV 8U arithmetic (un-vendored dependency; pinned bit-exact against cv2 4.13 in tests/test_oracle_cv2.py):
+// gray = (R*9798 + G*19235 + B*3735 + (1 << 14)) >> 15.
+extern "C" void orbo_cvt_gray(const uint8_t* src, int rows, int cols, size_t step, int channels, int rgb, uint8_t* dst, size_t dstep)
+{
+    const int ri = rgb ? 0 : 2, bi = rgb ? 2 : 0;
+    for (int y = 0; y < rows; ++y)
+        for (int x = 0; x < cols; ++x) {
+            const uint8_t* p = src + (size_t)y * step + (size_t)x * channels;
+            dst[(size_t)y * dstep + x] = (uint8_t)((p[ri] * 9798 + p[1] * 19235 + p[bi] * 3735 + (1 << 14)) >> 15);
+        }
+}

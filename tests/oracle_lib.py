@@ -150,6 +150,14 @@ class Oracle:
     def ratio_accept(self, d1, d2, ratio, th_low):
         return bool(self.lib.orbo_ratio_accept(int(d1), int(d2), float(ratio), int(th_low)))
 
+    def cvt_gray(self, img, rgb=True):
+        img = np.ascontiguousarray(img, np.uint8)
+        rows, cols, ch = img.shape
+        out = np.zeros((rows, cols), np.uint8)
+        self.lib.orbo_cvt_gray.argtypes = [_vp, C.c_int, C.c_int, _sz, C.c_int, C.c_int, _vp, _sz]
+        self.lib.orbo_cvt_gray(_ptr(img), rows, cols, img.strides[0], ch, int(rgb), _ptr(out), out.strides[0])
+        return out
+
     # ---- bag of words / vocabulary-guided searches ----------------------------------------------
     def vocabulary(self, parent, descriptors, weights, k, L, scoring=0, weighting=0):
         return OracleVocabulary(self, parent, descriptors, weights, k, L, scoring, weighting)

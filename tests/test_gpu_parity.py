@@ -234,3 +234,28 @@ def test_stereo_matches(oracle, cols, rows, nfeatures):
     ou, od, kept = oracle.stereo_match(oL, oR, okL, odL, okR, odR, bf, max_d)
     assert np.array_equal(u, ou) and np.array_equal(d, od)
     assert kept > 50 and (u >= 0).sum() == kept
+
+
+@pytest.mark.parametrize("ch,rgb", [(3, True), (3, False), (4, True), (4, False)])
+def test_color_input_cvt_gray(oracle, ch, rgb):
+    """Tracking::GrabImage* image prep (src/Tracking2.cc:289-316): cvtColor on the device in front of operator()."""
+    rng = np.random.default_rng(90 + ch)
+    for (cols, rows) in [(752, 480), (331, 277), (161, 123)]:
+        base = synth.image(70 + ch, cols, rows).astype(np.int32)
+        color = np.clip(base[..., None] + rng.integers(-40, 41, (rows, cols, ch)), 0, 255).astype(np.uint8)
+        gray = oracle.cvt_gray(color, rgb)
+        ex = orbx.ORBextractor(600, 1.2, 8, 20, 7)
+        nm, kps, desc = ex.extract_color(color, rgb)
+        assert np.array_equal(ex.pyramid_level(0), gray)                     # mImGray
+        ex2 = orbx.ORBextractor(600, 1.2, 8, 20, 7)
+        nm2, kps2, desc2 = ex2(gray)
+        assert nm == nm2 and np.array_equal(kps, kps2) and np.array_equal(desc, desc2)
+        oex = oracle.extractor(600, 1.2, 8, 20, 7)
+        kps_o, desc_o, nm_o = oex.extract(gray, (0, 0))
+        assert nm == nm_o and np.array_equal(kps["x"], kps_o["x"]) and np.array_equal(kps["y"], kps_o["y"])
+    # strided (non-contiguous rows) colour view
+    big = rng.integers(0, 256, (200, 300, ch), dtype=np.uint8)
+    view = big[10:150, 20:260]
+    ex = orbx.ORBextractor(300, 1.2, 8, 20, 7)
+    nm, kps, desc = ex.extract_color(view, rgb)
+    assert np.array_equal(ex.pyramid_level(0), oracle.cvt_gray(np.ascontiguousarray(view), rgb))

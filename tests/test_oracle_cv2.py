@@ -205,3 +205,17 @@ def test_ic_angle_against_numpy_moments(oracle):
             u = np.arange(-d, d + 1)
             m10 += int((u * row).sum()); m01 += int(v * row.sum())
         assert oracle.ic_angle(img, x, y) == cv2.fastAtan2(float(m01), float(m10))
+
+
+@pytest.mark.parametrize("code,ch,rgb", [(cv2.COLOR_RGB2GRAY, 3, True), (cv2.COLOR_BGR2GRAY, 3, False),
+                                         (cv2.COLOR_RGBA2GRAY, 4, True), (cv2.COLOR_BGRA2GRAY, 4, False)])
+def test_cvt_gray_bit_exact(oracle, code, ch, rgb):
+    """cv::cvtColor to grey as Tracking::GrabImage* calls it (reference src/Tracking2.cc:289-316)."""
+    rng = np.random.default_rng(5)
+    for (h, w) in [(480, 752), (37, 53), (1, 1), (3, 4)]:
+        img = rng.integers(0, 256, (h, w, ch), dtype=np.uint8)
+        assert np.array_equal(oracle.cvt_gray(img, rgb), cv2.cvtColor(img, code).reshape(h, w))
+    ramp = np.stack(np.meshgrid(np.arange(256), np.arange(256), indexing="ij"), -1).astype(np.uint8)   # every (c0, c1) pair
+    for c2 in (0, 1, 127, 255):
+        img = np.concatenate([ramp, np.full((256, 256, ch - 2), c2, np.uint8)], -1)
+        assert np.array_equal(oracle.cvt_gray(img, rgb), cv2.cvtColor(img, code))

@@ -41,6 +41,8 @@ SIGNATURES = {
     "orbx_level_size": (_i, [_vp, _i, _i, _i, _vp, _vp]),
     "orbx_max_keypoints": (_i, [_vp]),
     "orbx_extract": (_i, [_vp, _vp, _i, _i, _sz, _i, _i, _vp, _vp, _i, _vp, _vp]),
+    "orbx_extract_color": (_i, [_vp, _vp, _i, _i, _sz, _i, _i, _i, _i, _vp, _vp, _i, _vp, _vp]),
+    "orbx_cvt_gray_device": (_i, [_i, _vp, _sz, _sz, _i, _i, _i, _i, _i, _vp, _sz, _sz, _vp]),
     "orbx_extract_batch": (_i, [_vp, _vp, _i, _i, _i, _sz, _i, _i, _vp, _vp, _i, _vp, _vp]),
     "orbx_extract_batch_device": (_i, [_vp, _vp, _sz, _i, _i, _i, _sz, _i, _i, _vp, _vp, _i, _vp, _vp, _vp]),
     "orbx_sync": (_i, [_vp]),

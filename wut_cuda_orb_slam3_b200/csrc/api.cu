@@ -110,6 +110,7 @@ struct Slot {
     int cap_frames = 0;
     // staging for the host-buffer API
     uint8_t* d_in = nullptr; size_t d_in_bytes = 0;
+    uint8_t* d_color = nullptr; size_t d_color_bytes = 0;      // colour input of orbx_extract_color
     orbx_keypoint* d_kps = nullptr; uint8_t* d_desc = nullptr; int* d_n = nullptr; int* d_nm = nullptr; int out_cap = 0;
     std::vector<void*> allocs;
 };
@@ -183,7 +184,7 @@ static void free_slot(Slot& s)
     s.allocs.clear();
     s.ws = Workspace{};
     s.cap_frames = 0;
-    s.d_in = nullptr; s.d_in_bytes = 0; s.d_kps = nullptr; s.d_desc = nullptr; s.d_n = nullptr; s.d_nm = nullptr; s.out_cap = 0;
+    s.d_in = nullptr; s.d_in_bytes = 0; s.d_color = nullptr; s.d_color_bytes = 0; s.d_kps = nullptr; s.d_desc = nullptr; s.d_n = nullptr; s.d_nm = nullptr; s.out_cap = 0;
 }
 
 template <typename T>
@@ -710,6 +711,51 @@ int orbx_extract(orbx_extractor* ex, const uint8_t* image, int rows, int cols, s
     const uint8_t* imgs[1] = {image};
     if (!image) return fail(ORBX_ERR_EMPTY_IMAGE, "empty image");
     return orbx_extract_batch(ex, imgs, 1, rows, cols, step, lap0, lap1, keypoints, descriptors, capacity, n_out, n_mono);
+}
+
+int orbx_cvt_gray_device(int device, const uint8_t* d_src, size_t src_pitch, size_t src_frame_stride, int channels, int rgb,
+                         int n_frames, int rows, int cols, uint8_t* d_dst, size_t dst_pitch, size_t dst_frame_stride, void* stream)
+{
+    if (!d_src || !d_dst || n_frames <= 0 || rows <= 0 || cols <= 0 || (channels != 3 && channels != 4) ||
+        src_pitch < (size_t)cols * channels || dst_pitch < (size_t)cols)
+        return fail(ORBX_ERR_INVALID_ARG, "bad arguments");
+    int rc = set_device(device);
+    if (rc) return rc;
+    CU(launch_cvt_gray(d_src, src_pitch, src_frame_stride, channels, rgb, n_frames, rows, cols, d_dst, dst_pitch, dst_frame_stride,
+                       (cudaStream_t)stream));
+    return ORBX_OK;
+}
+
+int orbx_extract_color(orbx_extractor* ex, const uint8_t* image, int rows, int cols, size_t step, int channels, int rgb, int lap0,
+                       int lap1, orbx_keypoint* keypoints, uint8_t* descriptors, int capacity, int* n_out, int* n_mono)
+{
+    if (!ex) return fail(ORBX_ERR_INVALID_ARG, "extractor is NULL");
+    if (!image || rows <= 0 || cols <= 0) return fail(ORBX_ERR_EMPTY_IMAGE, "empty image");
+    if (channels == 1) return orbx_extract(ex, image, rows, cols, step, lap0, lap1, keypoints, descriptors, capacity, n_out, n_mono);
+    if ((channels != 3 && channels != 4) || step < (size_t)cols * channels) return fail(ORBX_ERR_INVALID_ARG, "channels must be 1, 3 or 4");
+    if (!keypoints || !descriptors || !n_out || !n_mono || capacity <= 0) return fail(ORBX_ERR_INVALID_ARG, "bad output buffers");
+    int rc = set_device(ex->device);
+    if (rc) return rc;
+    if ((rc = configure(ex, rows, cols))) return rc;
+    if ((rc = ensure_capacity(ex, 1, 1))) return rc;
+    Slot& s = ex->slots[0];
+    const size_t gpitch = (size_t)cols, cpitch = align_up((size_t)cols * channels, 16);
+    if ((rc = ensure_host_staging(s, gpitch * rows, 1, capacity))) return rc;
+    if (s.d_color_bytes < cpitch * rows) {
+        if ((rc = dev_alloc(s, &s.d_color, cpitch * rows))) return rc;
+        s.d_color_bytes = cpitch * rows;
+    }
+    CU(cudaMemcpy2DAsync(s.d_color, cpitch, image, step, (size_t)cols * channels, rows, cudaMemcpyHostToDevice, s.stream));
+    CU(launch_cvt_gray(s.d_color, cpitch, 0, channels, rgb, 1, rows, cols, s.d_in, gpitch, 0, s.stream));
+    if ((rc = run_chunk(ex, s, s.d_in, gpitch * rows, gpitch, 1, lap0, lap1, s.d_kps, s.d_desc, capacity, s.d_n, s.d_nm, s.stream))) return rc;
+    CU(cudaMemcpyAsync(keypoints, s.d_kps, sizeof(orbx_keypoint) * (size_t)capacity, cudaMemcpyDeviceToHost, s.stream));
+    CU(cudaMemcpyAsync(descriptors, s.d_desc, (size_t)capacity * 32, cudaMemcpyDeviceToHost, s.stream));
+    CU(cudaMemcpyAsync(n_out, s.d_n, sizeof(int), cudaMemcpyDeviceToHost, s.stream));
+    CU(cudaMemcpyAsync(n_mono, s.d_nm, sizeof(int), cudaMemcpyDeviceToHost, s.stream));
+    CU(cudaStreamSynchronize(s.stream));
+    ex->last_frames = 1;
+    if (*n_out > capacity) return fail(ORBX_ERR_CAPACITY, "%d keypoints, capacity %d", *n_out, capacity);
+    return ORBX_OK;
 }
 
 // ---- per-stage timing with CUDA events on the launching stream ---------------------------------------------------------

@@ -308,4 +308,54 @@ cudaError_t launch_pyramid(const FrameGeom& fg, const Workspace& ws, const uint8
     return cudaGetLastError();
 }
 
+// ---- image prep: cv::cvtColor(RGB/BGR/RGBA/BGRA -> GRAY) of Tracking::GrabImage* (reference src/Tracking2.cc:289-316) ---------
+// OpenCV 8U: gray = (R*9798 + G*19235 + B*3735 + 2^14) >> 15 (checked bit-exact against cv2 4.13 in tests/test_oracle_cv2.py).
+// One thread = 4 output pixels: 3 (or 4) aligned 32-bit loads, one 32-bit store.  grid = (ceil(cols/4/128), rows, frames).
+template <int CH>
+__global__ void __launch_bounds__(128) cvt_gray_kernel(const uint8_t* __restrict__ src, size_t src_pitch, size_t src_frame_stride, int swap_rb,
+                                                       int rows, int cols, uint8_t* __restrict__ dst, size_t dst_pitch, size_t dst_frame_stride)
+{
+    const int x4 = blockIdx.x * 128 + threadIdx.x, y = blockIdx.y, f = blockIdx.z;
+    const int x = 4 * x4;
+    if (x >= cols) return;
+    const uint8_t* sp = src + (size_t)f * src_frame_stride + (size_t)y * src_pitch + (size_t)x * CH;
+    uint8_t* dp = dst + (size_t)f * dst_frame_stride + (size_t)y * dst_pitch + x;
+    const int c0 = swap_rb ? 3735 : 9798, c2 = swap_rb ? 9798 : 3735;          // weight of channel 0 / channel 2
+    uint32_t px[4] = {0, 0, 0, 0};                                             // packed (ch0, ch1, ch2) per pixel
+    const bool vec = x + 4 <= cols && (((uintptr_t)sp | src_pitch | src_frame_stride) & 3) == 0;
+    if (vec) {
+        const uint32_t* w = reinterpret_cast<const uint32_t*>(sp);
+        if (CH == 4) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) px[i] = __ldg(w + i);
+        } else {
+            const uint32_t a = __ldg(w), b = __ldg(w + 1), c = __ldg(w + 2);      // a = p0.012 p1.0 | b = p1.12 p2.01 | c = p2.2 p3.012
+            px[0] = a; px[1] = __funnelshift_r(a, b, 24); px[2] = __funnelshift_r(b, c, 16); px[3] = c >> 8;
+        }
+    } else {
+        for (int i = 0; i < 4 && x + i < cols; ++i)
+            px[i] = (uint32_t)sp[i * CH] | ((uint32_t)sp[i * CH + 1] << 8) | ((uint32_t)sp[i * CH + 2] << 16);
+    }
+    uint32_t out = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const uint32_t v = (px[i] & 0xff) * c0 + ((px[i] >> 8) & 0xff) * 19235u + ((px[i] >> 16) & 0xff) * c2 + (1u << 14);
+        out |= (v >> 15) << (8 * i);
+    }
+    if (x + 4 <= cols && (((uintptr_t)dp) & 3) == 0) *reinterpret_cast<uint32_t*>(dp) = out;
+    else for (int i = 0; i < 4 && x + i < cols; ++i) dp[i] = (uint8_t)(out >> (8 * i));
+}
+
+cudaError_t launch_cvt_gray(const uint8_t* d_src, size_t src_pitch, size_t src_frame_stride, int channels, int rgb, int n_frames,
+                            int rows, int cols, uint8_t* d_dst, size_t dst_pitch, size_t dst_frame_stride, cudaStream_t st)
+{
+    if (n_frames <= 0 || rows <= 0 || cols <= 0) return cudaSuccess;
+    dim3 grid(((cols + 3) / 4 + 127) / 128, rows, n_frames);
+    // channel 0 is R for RGB / RGBA input (mbRGB, src/Tracking2.cc:292-296) and B for BGR / BGRA
+    if (channels == 3) cvt_gray_kernel<3><<<grid, 128, 0, st>>>(d_src, src_pitch, src_frame_stride, rgb ? 0 : 1, rows, cols, d_dst, dst_pitch, dst_frame_stride);
+    else cvt_gray_kernel<4><<<grid, 128, 0, st>>>(d_src, src_pitch, src_frame_stride, rgb ? 0 : 1, rows, cols, d_dst, dst_pitch, dst_frame_stride);
+    count_launch();
+    return cudaGetLastError();
+}
+
 }  // namespace orbx

@@ -77,6 +77,8 @@ class ORBextractor:
         monoIndex is -1 for an empty image, exactly like the reference."""
         if image is None or image.size == 0:
             return -1, np.zeros(0, KP_DTYPE), np.zeros((0, 32), np.uint8)
+        if image.ndim == 3:
+            return self.extract_color(image, True, vLappingArea)
         assert image.dtype == np.uint8 and image.ndim == 2, "CV_8UC1 expected (src/ORBextractor.cc:1235)"
         if image.strides[1] != 1:
             image = np.ascontiguousarray(image)
@@ -87,6 +89,22 @@ class ORBextractor:
         n, nm = C.c_int(0), C.c_int(0)
         check(lib().orbx_extract(self._h, ptr(image), rows, cols, image.strides[0], int(vLappingArea[0]), int(vLappingArea[1]),
                                  ptr(kps), ptr(desc), cap, C.byref(n), C.byref(nm)))
+        self._shape = (rows, cols)
+        return nm.value, kps[:n.value].copy(), desc[:n.value].copy()
+
+    def extract_color(self, image, rgb=True, vLappingArea=(0, 0)):
+        """Tracking::GrabImage* + operator(): HxWx3 / HxWx4 uint8 image, rgb = mbRGB (channel 0 is red); the cvtColor to grey
+        (src/Tracking2.cc:289-316) runs on the device in front of the pyramid."""
+        assert image.dtype == np.uint8 and image.ndim == 3 and image.shape[2] in (3, 4)
+        if image.strides[2] != 1 or image.strides[1] != image.shape[2]:
+            image = np.ascontiguousarray(image)
+        rows, cols, ch = image.shape
+        cap = self.max_keypoints()
+        kps = np.zeros(cap, KP_DTYPE)
+        desc = np.zeros((cap, 32), np.uint8)
+        n, nm = C.c_int(0), C.c_int(0)
+        check(lib().orbx_extract_color(self._h, ptr(image), rows, cols, image.strides[0], ch, int(bool(rgb)), int(vLappingArea[0]),
+                                       int(vLappingArea[1]), ptr(kps), ptr(desc), cap, C.byref(n), C.byref(nm)))
         self._shape = (rows, cols)
         return nm.value, kps[:n.value].copy(), desc[:n.value].copy()
 
