@@ -335,7 +335,7 @@ __device__ __forceinline__ int fast_score16(uint32_t c /* byte address of the ce
     return max(bright, dark) - 1;
 }
 
-constexpr int kWarpsPerCta = 4;
+constexpr int kWarpsPerCta = 1;
 constexpr int kMaxBmWordsPerLane = (kRoiRows * kRoiPitch / 32 + 31) / 32;   // 6: bitmap words a lane may own
 
 // per-warp shared-memory carve-up for a plane of `rows` x PA pixels and `list_cap` pre-test survivors
