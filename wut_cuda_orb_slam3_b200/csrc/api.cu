@@ -1179,8 +1179,19 @@ int orbx_debug_octree_timing(orbx_extractor* ex, const uint8_t* image, int rows,
     std::vector<uint8_t> desc((size_t)cap * 32);
     int n = 0, nm = 0;
     s.ws.dbg = d_dbg; s.ws.dbg_level = level;
+    // ORBX_DBG_REPLICAS=R (<= 64): time the CTA of frame 0 while R copies of the frame are in flight (phase times under load)
+    const int reps = getenv("ORBX_DBG_REPLICAS") ? std::min(std::max(atoi(getenv("ORBX_DBG_REPLICAS")), 1), 64) : 1;
+    if (reps > 1) {
+        std::vector<const uint8_t*> imgs(reps, image);
+        std::vector<orbx_keypoint> kb((size_t)cap * reps);
+        std::vector<uint8_t> db((size_t)cap * 32 * reps);
+        std::vector<int> nb(reps), nmb(reps);
+        if ((rc = ensure_capacity(ex, reps, 1))) return rc;
+        ex->slots[0].ws.dbg = d_dbg; ex->slots[0].ws.dbg_level = level;
+        rc = orbx_extract_batch(ex, imgs.data(), reps, rows, cols, step, 0, 0, kb.data(), db.data(), cap, nb.data(), nmb.data());
+    } else
     rc = orbx_extract(ex, image, rows, cols, step, 0, 0, kps.data(), desc.data(), cap, &n, &nm);
-    s.ws.dbg = nullptr;
+    ex->slots[0].ws.dbg = nullptr;
     if (!rc) cudaMemcpy(out16, d_dbg, 16 * sizeof(long long), cudaMemcpyDeviceToHost);
     cudaFree(d_dbg);
     return rc;

@@ -176,7 +176,7 @@ size_t octree_smem_bytes(int M, int T)
     return sizeof(int) * (64 + 224) + (b > hist ? b : hist);
 }
 
-// grid = (nlevels, n_frames); dynamic smem sized for the largest level's node capacity.
+// grid = (n_frames, nlevels); dynamic smem sized for the largest level's node capacity.
 template <int T>
 __global__ void __launch_bounds__(T, 1024 / T) octree_kernel(const __grid_constant__ FrameGeom fg, Workspace ws, int M,
                                                    int* __restrict__ err_flag)
@@ -186,7 +186,8 @@ __global__ void __launch_bounds__(T, 1024 / T) octree_kernel(const __grid_consta
     __shared__ int s_nL, s_nS, s_total;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int level = blockIdx.x, frame = blockIdx.y;
+    // level-major dispatch: the CTAs of level 0 (most candidates, longest) start first, the short deep levels pack the tail
+    const int frame = blockIdx.x, level = blockIdx.y;
     const LevelGeom& g = fg.L[level];
     const int N = g.nfeat;
     // optional phase timing of one CTA (orbx_debug_octree_timing): dbg[0..6] cycles, dbg[7..] counters
@@ -605,7 +606,7 @@ cudaError_t launch_octree(const FrameGeom& fg, const Workspace& ws, int n_frames
         if (e != cudaSuccess) return e;
         cudaMemset(g_err_flag[dev & 63], 0, sizeof(int));
     }
-    dim3 grid(fg.nlevels, n_frames);
+    dim3 grid(n_frames, fg.nlevels);
     // The kernel is latency-bound (sequential sort replay, dependent binary searches): big batches run more, smaller CTAs
     // per SM to overlap those chains; a single frame gets the larger CTA for the shortest critical path.
     if (T == 128) octree_kernel<128><<<grid, 128, smem, st>>>(fg, ws, M, g_err_flag[dev & 63]);
