@@ -139,7 +139,7 @@ def run_reference(args, rank, world):
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    per_step = max(32, 4 * threads)
+    per_step = 64 * threads                   # ~1.5 s of work per step on all host threads
     for _ in range(args.warmup):
         cpu_oracle_throughput(max(threads, 8), threads)
     t0 = time.perf_counter()
@@ -231,30 +231,41 @@ def run_ours(args, rank, world, local_rank):
     kp_mean = float(d_n.float().mean().item())
 
     # ---- end to end through the host-buffer C-ABI call (pinned host memory, H2D + D2H inside the timed region) ----------
-    Be = min(B, args.e2e_batch)
-    h_img = torch.empty((Be, ROWS, COLS), dtype=torch.uint8).pin_memory()
-    h_img.copy_(d_img[:Be])
-    h_kps = torch.empty((Be, cap, 7), dtype=torch.float32).pin_memory()
-    h_desc = torch.empty((Be, cap, 32), dtype=torch.uint8).pin_memory()
-    h_n = torch.empty(Be, dtype=torch.int32).pin_memory()
-    h_nm = torch.empty(Be, dtype=torch.int32).pin_memory()
-    ex2 = orbx.ORBextractor(NFEAT, SCALE, NLEVELS, INI_TH, MIN_TH, device=local_rank, max_cols=COLS, max_rows=ROWS, max_batch=args.e2e_chunk)
-    ptrs = (C.c_void_p * Be)(*[h_img.data_ptr() + f * ROWS * COLS for f in range(Be)])
+    def run_e2e(Be, chunk):
+        """frames/s through orbx_extract_batch: Be frames per call from pinned host memory (frames repeat modulo B), results
+        back in pinned host memory; H2D + compute + D2H all inside the timed region."""
+        h_img = torch.empty((Be, ROWS, COLS), dtype=torch.uint8).pin_memory()
+        for f0 in range(0, Be, B):
+            h_img[f0:f0 + B].copy_(d_img[:min(B, Be - f0)])
+        h_kps = torch.empty((Be, cap, 7), dtype=torch.float32).pin_memory()
+        h_desc = torch.empty((Be, cap, 32), dtype=torch.uint8).pin_memory()
+        h_n = torch.empty(Be, dtype=torch.int32).pin_memory()
+        h_nm = torch.empty(Be, dtype=torch.int32).pin_memory()
+        ex2 = orbx.ORBextractor(NFEAT, SCALE, NLEVELS, INI_TH, MIN_TH, device=local_rank, max_cols=COLS, max_rows=ROWS, max_batch=chunk)
+        ptrs = (C.c_void_p * Be)(*[h_img.data_ptr() + f * ROWS * COLS for f in range(Be)])
 
-    def e2e_step():
-        check(lib().orbx_extract_batch(ex2._h, ptrs, Be, ROWS, COLS, COLS, 0, 0, ptr(h_kps), ptr(h_desc), cap, ptr(h_n), ptr(h_nm)))
+        def e2e_step():
+            check(lib().orbx_extract_batch(ex2._h, ptrs, Be, ROWS, COLS, COLS, 0, 0, ptr(h_kps), ptr(h_desc), cap, ptr(h_n), ptr(h_nm)))
 
-    for _ in range(max(args.warmup, 1)):
-        e2e_step()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        e2e_step()
-    e2e_s = max_over_ranks(time.perf_counter() - t0)
-    e2e_value = world * Be * args.steps / e2e_s
-    assert int(h_n.sum()) == int(d_n[:Be].sum().item()), "host-buffer API and device API disagree"
+        for _ in range(max(args.warmup, 1)):
+            e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            e2e_step()
+        e2e_s = max_over_ranks(time.perf_counter() - t0)
+        assert torch.equal(h_n, d_n.cpu().repeat((Be + B - 1) // B)[:Be]), "host-buffer API and device API disagree"
+        ex2.close()
+        return world * Be * args.steps / e2e_s
+
+    Be = args.e2e_batch
+    e2e_value = run_e2e(Be, args.e2e_chunk)
     e2e = {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": Be * ROWS * COLS,
-           "d2h_bytes_per_step": Be * cap * 60 + Be * 8, "frames_per_step": Be, "api": "orbx_extract_batch (pinned host buffers)"}
+           "d2h_bytes_per_step": Be * cap * 60 + Be * 8, "frames_per_step": Be, "pipeline_chunk": args.e2e_chunk,
+           "api": "orbx_extract_batch (pinned host buffers; one call = one step)"}
+    e2e_small = None
+    if Be > B:      # the same call with only as many frames as the resident step, for comparison
+        e2e_small = {"value": run_e2e(B, 64), "unit": "frames/s", "frames_per_step": B, "pipeline_chunk": 64}
 
     # ---- roofline of the dominant kernel ----------------------------------------------------------------------------------
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -285,6 +296,8 @@ def run_ours(args, rank, world, local_rank):
     pipeline_gbs = whole_bytes * B * args.steps / (ms * 1e-3) / 1e9
     extra = {"stages": stages, "pipeline": {"algorithmic_bytes_per_frame": whole_bytes, "achieved_GBps": pipeline_gbs, "frac_of_hbm_peak": pipeline_gbs / peak},
              "mean_keypoints_per_frame": kp_mean}
+    if e2e_small is not None:
+        extra["e2e_small_call"] = e2e_small
 
     # ---- 2-NN Hamming: 100k x 10M, database sharded over the ranks, NCCL all-gather + merge -------------------------------
     knn = None
@@ -295,9 +308,9 @@ def run_ours(args, rank, world, local_rank):
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         threads = os.cpu_count() or 1
-        nfr = max(64, 12 * threads)
+        nfr = 384 * threads                     # ~10 s of work on all host threads
         fps, dt, kp = cpu_oracle_throughput(nfr, threads)
-        fps1, dt1, _ = cpu_oracle_throughput(24, 1)
+        fps1, dt1, _ = cpu_oracle_throughput(240, 1)
         cpu = {"value": fps, "unit": "frames/s", "cores": threads, "kind": "port",
                "sample": "%d frames of the same 752x480/1000kp workload in %.1f s on %d threads (single thread: %.1f frames/s)" % (nfr, dt, threads, fps1),
                "single_thread_value": fps1}
@@ -378,8 +391,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=512, help="frames per GPU per step")
-    ap.add_argument("--e2e-batch", type=int, default=512)
-    ap.add_argument("--e2e-chunk", type=int, default=64)
+    ap.add_argument("--e2e-batch", type=int, default=4096, help="frames per host-API call (configs[3] streams 8192 frames)")
+    ap.add_argument("--e2e-chunk", type=int, default=256, help="pipeline chunk of the host API (max_batch of its extractor)")
     ap.add_argument("--no-knn2", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--knn-nq", type=int, default=NQ)
