@@ -299,6 +299,13 @@ def run_ours(args, rank, world, local_rank):
     if e2e_small is not None:
         extra["e2e_small_call"] = e2e_small
 
+    # ---- the other BASELINE.json configs (parity-test shapes), measured briefly on rank 0 for context ---------------------------
+    if rank == 0 and not args.no_other:
+        ex.close()
+        del d_kps, d_desc
+        torch.cuda.empty_cache()
+        extra["other_configs"] = run_other_configs(local_rank, dev)
+
     # ---- 2-NN Hamming: 100k x 10M, database sharded over the ranks, NCCL all-gather + merge -------------------------------
     knn = None
     if not args.no_knn2:
@@ -328,6 +335,83 @@ def run_ours(args, rank, world, local_rank):
         if knn is not None:
             line["knn2"] = knn
         print(json.dumps(line), flush=True)
+
+
+def run_other_configs(local_rank, dev):
+    """configs[1..3] of BASELINE.json as short measurements (host image in -> results out, median of repeated calls):
+    EuRoC-shape stereo pair + ComputeStereoMatches, KITTI-shape stereo pair + brute-force 2-NN + ratio test, and the
+    resident 1280x720 / 2000-feature batch."""
+    import numpy as np
+    import torch
+
+    import wut_cuda_orb_slam3_b200 as orbx
+    from wut_cuda_orb_slam3_b200 import synth
+
+    def med_ms(fn, reps=30, warm=5):
+        for _ in range(warm):
+            fn()
+        ts = []
+        for _ in range(reps):
+            t0 = time.perf_counter(); fn(); ts.append(time.perf_counter() - t0)
+        return 1e3 * float(np.median(ts))
+
+    out = {}
+    # configs[1]: 752x480 stereo pair, 1200 features per image, extraction x2 + ComputeStereoMatches
+    L, R = synth.image(31, 752, 480, view=0, max_disp=40), synth.image(31, 752, 480, view=1, max_disp=40)
+    exL = orbx.ORBextractor(1200, SCALE, NLEVELS, INI_TH, MIN_TH, device=local_rank, max_cols=752, max_rows=480, max_batch=1)
+    exR = orbx.ORBextractor(1200, SCALE, NLEVELS, INI_TH, MIN_TH, device=local_rank, max_cols=752, max_rows=480, max_batch=1)
+    res = {}
+
+    from concurrent.futures import ThreadPoolExecutor
+    pool = ThreadPoolExecutor(2)          # the reference extracts left and right on two threads (src/Frame.cc:124-127)
+
+    def stereo():
+        fl, fr = pool.submit(exL, L), pool.submit(exR, R)
+        (_, kl, dl), (_, kr, dr) = fl.result(), fr.result()
+        res["u"], res["d"] = orbx.compute_stereo_matches(exL, exR, kl, dl, kr, dr, 47.9, 435.2)
+    ms = med_ms(stereo)
+    out["euroc_stereo_pair_1200"] = {"ms_per_pair": ms, "pairs_per_s": 1e3 / ms, "stereo_matches": int((res["u"] >= 0).sum()),
+                                     "what": "orbx_extract left | right on two host threads + orbx_stereo_match"}
+    exL.close(); exR.close()
+    # configs[2]: 1241x376 stereo pair, 2000 features, extraction x2 + brute-force 2-NN L->R + 0.7 ratio test
+    L, R = synth.image(32, 1241, 376, view=0, max_disp=60), synth.image(32, 1241, 376, view=1, max_disp=60)
+    exL = orbx.ORBextractor(2000, SCALE, NLEVELS, INI_TH, MIN_TH, device=local_rank, max_cols=1241, max_rows=376, max_batch=1)
+    exR = orbx.ORBextractor(2000, SCALE, NLEVELS, INI_TH, MIN_TH, device=local_rank, max_cols=1241, max_rows=376, max_batch=1)
+    m = orbx.ORBmatcher(0.7, True, device=local_rank)
+
+    def kitti():
+        fl, fr = pool.submit(exL, L), pool.submit(exR, R)
+        (_, kl, dl), (_, kr, dr) = fl.result(), fr.result()
+        idx, dist = m.knn2(dl, dr)
+        res["acc"] = m.ratio_test(dist, mode=2, ratio=0.7)
+    ms = med_ms(kitti)
+    out["kitti_stereo_pair_2000"] = {"ms_per_pair": ms, "pairs_per_s": 1e3 / ms, "ratio_test_matches": int(res["acc"].sum()),
+                                     "what": "orbx_extract left | right on two host threads + orbx_knn2 + orbx_ratio_test (Frame.cc:1174-1181 form)"}
+    exL.close(); exR.close()
+    # configs[3] (per-GPU share): resident 1280x720 frames, 2000 features
+    Bh = 256
+    d_img = torch.empty((Bh, 720, 1280), dtype=torch.uint8, device=dev)
+    synth.images_device(d_img, 9000, Bh, 1280, 720, 1280, 720 * 1280, device=local_rank)
+    ex = orbx.ORBextractor(2000, SCALE, NLEVELS, INI_TH, MIN_TH, device=local_rank, max_cols=1280, max_rows=720, max_batch=Bh)
+    cap = ex.max_keypoints()
+    d_kps = torch.zeros((Bh, cap, 7), dtype=torch.float32, device=dev); d_desc = torch.zeros((Bh, cap, 32), dtype=torch.uint8, device=dev)
+    d_n = torch.zeros(Bh, dtype=torch.int32, device=dev); d_nm = torch.zeros(Bh, dtype=torch.int32, device=dev)
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def step():
+        ex.extract_batch_device(d_img, Bh, 720, 1280, 1280, 720 * 1280, d_kps, d_desc, cap, d_n, d_nm, (0, 0), stream=stream)
+    for _ in range(3):
+        step()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize(); e0.record()
+    for _ in range(5):
+        step()
+    e1.record(); torch.cuda.synchronize()
+    msb = e0.elapsed_time(e1) / 5
+    out["hd720_batch_2000"] = {"frames_per_s": Bh / msb * 1e3, "ms_per_step": msb, "frames_per_step": Bh, "mean_keypoints_per_frame": float(d_n.float().mean().item()),
+                               "algorithmic_bytes_per_frame": 11532352, "what": "orbx_extract_batch_device, frames resident in HBM"}
+    ex.close()
+    return out
 
 
 def run_knn2(args, rank, world, local_rank, dev, barrier, max_over_ranks):
@@ -395,6 +479,7 @@ def main():
     ap.add_argument("--e2e-chunk", type=int, default=256, help="pipeline chunk of the host API (max_batch of its extractor)")
     ap.add_argument("--no-knn2", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-other", action="store_true", help="skip the short measurements of the other BASELINE configs")
     ap.add_argument("--knn-nq", type=int, default=NQ)
     ap.add_argument("--knn-ndb", type=int, default=NDB)
     ap.add_argument("--knn-reps", type=int, default=2)

@@ -7,12 +7,12 @@ OUT=gpurun_out
 mkdir -p $OUT profiles
 python bench.py --steps 10 --warmup 3 > $OUT/${TAG}_bench.json 2> $OUT/${TAG}_bench.err
 # launch list of the bench's own batch (512 frames per launch)
-LARGS="--steps 2 --warmup 1 --no-knn2 --no-cpu"
+LARGS="--steps 2 --warmup 1 --no-knn2 --no-cpu --no-other"
 python bench.py $LARGS > $OUT/plain.log 2>&1 && \
 ncu --metrics gpu__time_duration.sum --clock-control none -c 120 --csv --log-file $OUT/${TAG}_launches_b512.csv python bench.py $LARGS > $OUT/ncu_l.log 2>&1
 python tools/launch_shares.py $OUT/${TAG}_launches_b512.csv $OUT/${TAG}_bench.json 512 > $OUT/${TAG}_launch_shares_b512.txt 2>&1
 # full captures of the dominant extraction kernel and of the matcher (small batch: ncu replays each kernel ~40 times)
-ARGS="--steps 1 --warmup 1 --batch 64 --no-knn2 --no-cpu"
+ARGS="--steps 1 --warmup 1 --batch 64 --no-knn2 --no-cpu --no-other"
 python bench.py $ARGS > $OUT/plain.log 2>&1 && \
 ncu --set full --clock-control none --import-source on -k regex:fast_cells_warp -s 3 -c 1 -f -o $OUT/${TAG}_fast_cells_warp python bench.py $ARGS > $OUT/ncu_f.log 2>&1
 KARGS="--steps 1 --warmup 1 --batch 32 --no-cpu --knn-ndb 1000000 --knn-reps 1"

@@ -490,6 +490,40 @@ static int run_chunk(orbx_extractor* ex, Slot& s, const uint8_t* d_images, size_
     return ORBX_OK;
 }
 
+// Grow-only device scratch per device for the matcher entry points that take host buffers (orbx_knn2, orbx_stereo_match): a
+// cudaMalloc/cudaFree pair per call costs more than the kernels on frame-sized inputs.  One call at a time per device holds it.
+struct ScratchArena {
+    std::mutex mu;
+    unsigned char* base = nullptr;
+    size_t bytes = 0;
+};
+static ScratchArena g_scratch[64];
+
+struct ScratchLease {
+    ScratchArena& a;
+    std::unique_lock<std::mutex> lock;
+    size_t off = 0;
+    explicit ScratchLease(int device) : a(g_scratch[device & 63]), lock(a.mu) {}
+    int reserve(size_t total)
+    {
+        total += 4096;
+        if (a.bytes >= total) return ORBX_OK;
+        if (a.base) cudaFree(a.base);
+        a.base = nullptr; a.bytes = 0;
+        cudaError_t e = cudaMalloc(&a.base, total);
+        if (e != cudaSuccess) return fail(ORBX_ERR_OOM, "cudaMalloc(%zu): %s", total, cudaGetErrorString(e));
+        a.bytes = total;
+        return ORBX_OK;
+    }
+    template <typename T> T* take(size_t count)
+    {
+        off = (off + 255) & ~(size_t)255;
+        T* p = reinterpret_cast<T*>(a.base + off);
+        off += std::max<size_t>(count, 1) * sizeof(T);
+        return p;
+    }
+};
+
 }  // namespace orbx
 
 // =====================================================================================================================
@@ -992,21 +1026,17 @@ int orbx_knn2(int device, const uint8_t* queries, int nq, const uint8_t* databas
     if (nq == 0) return ORBX_OK;
     int rc = set_device(device);
     if (rc) return rc;
-    uint8_t *dq = nullptr, *ddb = nullptr;
-    int32_t *di = nullptr, *dd = nullptr;
-    auto cleanup = [&] { cudaFree(dq); cudaFree(ddb); cudaFree(di); cudaFree(dd); };
-    cudaError_t e;
-    if ((e = cudaMalloc(&dq, (size_t)nq * 32)) || (e = cudaMalloc(&ddb, std::max<size_t>((size_t)ndb * 32, 32))) ||
-        (e = cudaMalloc(&di, (size_t)nq * 8)) || (e = cudaMalloc(&dd, (size_t)nq * 8))) {
-        cleanup();
-        return fail(ORBX_ERR_OOM, "cudaMalloc: %s", cudaGetErrorString(e));
-    }
-    cudaMemcpy(dq, queries, (size_t)nq * 32, cudaMemcpyHostToDevice);
-    if (ndb > 0) cudaMemcpy(ddb, database, (size_t)ndb * 32, cudaMemcpyHostToDevice);
-    e = launch_knn2(dq, nq, ddb, ndb, 0, di, dd, 0);
+    ScratchLease L(device);
+    if ((rc = L.reserve((size_t)nq * 32 + (size_t)std::max<int64_t>(ndb, 1) * 32 + (size_t)nq * 16 + 4 * 256))) return rc;
+    uint8_t* dq = L.take<uint8_t>((size_t)nq * 32);
+    uint8_t* ddb = L.take<uint8_t>((size_t)std::max<int64_t>(ndb, 1) * 32);
+    int32_t* di = L.take<int32_t>((size_t)nq * 2);
+    int32_t* dd = L.take<int32_t>((size_t)nq * 2);
+    cudaError_t e = cudaMemcpy(dq, queries, (size_t)nq * 32, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess && ndb > 0) e = cudaMemcpy(ddb, database, (size_t)ndb * 32, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = launch_knn2(dq, nq, ddb, ndb, 0, di, dd, 0);
     if (e == cudaSuccess) e = cudaMemcpy(idx, di, (size_t)nq * 8, cudaMemcpyDeviceToHost);
     if (e == cudaSuccess) e = cudaMemcpy(dist, dd, (size_t)nq * 8, cudaMemcpyDeviceToHost);
-    cleanup();
     if (e != cudaSuccess) return fail(ORBX_ERR_CUDA, "knn2: %s", cudaGetErrorString(e));
     return ORBX_OK;
 }
@@ -1084,17 +1114,16 @@ int orbx_stereo_match(orbx_extractor* exL, int frameL, orbx_extractor* exR, int 
         if (kpL[i].octave < 0 || kpL[i].octave >= exL->nlevels) return fail(ORBX_ERR_INVALID_ARG, "left keypoint %d octave", i);
     for (int i = 0; i < nR; ++i)
         if (kpR[i].octave < 0 || kpR[i].octave >= exL->nlevels) return fail(ORBX_ERR_INVALID_ARG, "right keypoint %d octave", i);
-    Slot tmp;
     StereoArgs A{};
-    orbx_keypoint *dkL = nullptr, *dkR = nullptr;
-    uint8_t *ddL = nullptr, *ddR = nullptr;
-    auto cleanup = [&] { free_slot(tmp); };
-    if ((rc = dev_alloc(tmp, &dkL, (size_t)nL)) || (rc = dev_alloc(tmp, &ddL, (size_t)nL * 32)) ||
-        (rc = dev_alloc(tmp, &dkR, (size_t)std::max(nR, 1))) || (rc = dev_alloc(tmp, &ddR, (size_t)std::max(nR, 1) * 32)) ||
-        (rc = dev_alloc(tmp, &A.uRight, (size_t)nL)) || (rc = dev_alloc(tmp, &A.depth, (size_t)nL)) || (rc = dev_alloc(tmp, &A.sad, (size_t)nL))) {
-        cleanup();
-        return rc;
-    }
+    ScratchLease Ls(exL->device);
+    const size_t nRa = (size_t)std::max(nR, 1);
+    if ((rc = Ls.reserve(((size_t)nL + nRa) * (sizeof(orbx_keypoint) + 32) + (size_t)nL * 12 + 8 * 256))) return rc;
+    orbx_keypoint* dkL = Ls.take<orbx_keypoint>((size_t)nL);
+    uint8_t* ddL = Ls.take<uint8_t>((size_t)nL * 32);
+    orbx_keypoint* dkR = Ls.take<orbx_keypoint>(nRa);
+    uint8_t* ddR = Ls.take<uint8_t>(nRa * 32);
+    A.uRight = Ls.take<float>((size_t)nL); A.depth = Ls.take<float>((size_t)nL); A.sad = Ls.take<int>((size_t)nL);
+    auto cleanup = [] {};
     cudaMemcpy(dkL, kpL, sizeof(orbx_keypoint) * nL, cudaMemcpyHostToDevice);
     cudaMemcpy(ddL, descL, (size_t)nL * 32, cudaMemcpyHostToDevice);
     if (nR > 0) {
