@@ -18,5 +18,9 @@ ncu --set full --clock-control none --import-source on -k regex:fast_cells_warp 
 KARGS="--steps 1 --warmup 1 --batch 32 --no-cpu --knn-ndb 1000000 --knn-reps 1"
 python bench.py $KARGS > $OUT/plain.log 2>&1 && \
 ncu --set full --clock-control none --import-source on -k regex:knn2_kernel -s 1 -c 1 -f -o $OUT/${TAG}_knn2 python bench.py $KARGS > $OUT/ncu_k.log 2>&1
+python bench.py $ARGS > $OUT/plain.log 2>&1 && \
+ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -k regex:fast_cells_warp -s 3 -c 3 --csv --log-file $OUT/${TAG}_fast_dram.csv python bench.py $ARGS > $OUT/ncu_d.log 2>&1
+python bench.py $ARGS > $OUT/plain.log 2>&1 && \
+ncu --set full --clock-control none --import-source on -k regex:blur_pipe -s 1 -c 1 -f -o $OUT/${TAG}_blur_pipe python bench.py $ARGS > $OUT/ncu_b.log 2>&1
 python tools/latency.py > $OUT/${TAG}_single_frame_latency.txt 2>&1
 tail -n 2 $OUT/ncu_f.log; tail -n 2 $OUT/ncu_k.log; tail -n 3 $OUT/${TAG}_launch_shares_b512.txt
