@@ -336,13 +336,11 @@ __device__ __forceinline__ int fast_score16(uint32_t c /* byte address of the ce
 }
 
 constexpr int kWarpsPerCta = 1;
-constexpr int kMaxBmWordsPerLane = (kRoiRows * kRoiPitch / 32 + 31) / 32;   // 6: bitmap words a lane may own
 
 // per-warp shared-memory carve-up for a plane of `rows` x PA pixels and `list_cap` pre-test survivors
 struct WarpSmem {
     int a_bytes;      // u16 plane (+ slack: the pre-test reads up to 4 pixels past the end of a row)
     int list_bytes;   // u16 positions of pre-test survivors
-    int bm_bytes;     // one position-indexed bitmap
     int total;
 };
 __host__ __device__ inline WarpSmem warp_smem(int rows, int pa, int list_cap)
@@ -350,8 +348,7 @@ __host__ __device__ inline WarpSmem warp_smem(int rows, int pa, int list_cap)
     WarpSmem s;
     s.a_bytes = (rows * pa * 2 + 16 + 15) & ~15;
     s.list_bytes = (list_cap * 2 + 15) & ~15;
-    s.bm_bytes = (((rows * pa + 31) >> 5) * 4 + 15) & ~15;
-    s.total = s.a_bytes + s.list_bytes + 2 * s.bm_bytes;
+    s.total = s.a_bytes + s.list_bytes;
     return s;
 }
 
@@ -371,7 +368,7 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta) fast_cells_warp_kernel(cons
     const int frame = blockIdx.y;
     const WarpSmem sm = warp_smem(wlc.rows_alloc, PA, wlc.list_cap);
     const uint32_t A_s = (uint32_t)__cvta_generic_to_shared(smem_raw) + (uint32_t)(warp * sm.total);
-    const uint32_t list_s = A_s + sm.a_bytes, selA_s = list_s + sm.list_bytes, selH_s = selA_s + sm.bm_bytes;
+    const uint32_t list_s = A_s + sm.a_bytes;
 
     const uint32_t ct = __ldg(fg.cell_tab + gcell);
     const int level = ct & 15, ci = (ct >> 4) & 0xfff, cj = ct >> 16;
@@ -418,8 +415,6 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta) fast_cells_warp_kernel(cons
                 }
             }
         }
-        const int nbw = (rh * PA + 31) >> 5;
-        for (int i = lane; i < nbw; i += 32) { sts_u32(selA_s + i * 4, 0); sts_u32(selH_s + i * 4, 0); }
     }
     __syncwarp();
 
@@ -503,71 +498,63 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta) fast_cells_warp_kernel(cons
     }
     __syncwarp();
 
-    // 4. 3x3 strict NMS inside the cell (pixels outside the evaluated region keep score 0 = cv::FAST's zeroed buffer);
-    //    survivors set their bit in position-indexed bitmaps
-    for (int i = lane; i < nl; i += 32) {
-        const uint32_t pos = lds_u16(list_s + 2 * i);
-        const uint32_t b = A_s + (pos - PA - 1) * 2 + 1;
-        uint32_t s;
-        asm volatile("ld.shared.u8 %0, [%1+%2];" : "=r"(s) : "r"(b), "n"((PA + 1) * 2));
-        if (s > 0) {
-            uint32_t n0, n1, n2, n3, n4, n5, n6, n7;
-#define ORBX_LDS_B(dst, off) asm volatile("ld.shared.u8 %0, [%1+%2];" : "=r"(dst) : "r"(b), "n"((off) * 2))
-            ORBX_LDS_B(n0, 0);          ORBX_LDS_B(n1, 1);          ORBX_LDS_B(n2, 2);
-            ORBX_LDS_B(n3, PA);         ORBX_LDS_B(n4, PA + 2);
-            ORBX_LDS_B(n5, 2 * PA);     ORBX_LDS_B(n6, 2 * PA + 1); ORBX_LDS_B(n7, 2 * PA + 2);
-#undef ORBX_LDS_B
-            const uint32_t mx = max(max(max(n0, n1), max(n2, n3)), max(max(n4, n5), max(n6, n7)));
-            if (s > mx) {
-                atom_or(selA_s + (pos >> 5) * 4, 1u << (pos & 31));
-                if ((int)s >= iniTh) atom_or(selH_s + (pos >> 5) * 4, 1u << (pos & 31));
+    // 4. 3x3 strict NMS inside the cell (pixels outside the evaluated region keep score 0 = cv::FAST's zeroed buffer).  The
+    //    list is sorted by plane position (the pre-test compacts lane-major, lanes walk the cell row-major), so a ballot
+    //    compaction of the survivors IN PLACE keeps (y, x) order: no bitmaps, no atomics.  nh counts the survivors >= iniTh.
+    int ns = 0, nh = 0;
+    {
+        const uint32_t ltmask = (1u << lane) - 1u;
+        for (int base = 0; base < nl; base += 32) {
+            const int i = base + lane;
+            uint32_t pos = 0, s = 0;
+            if (i < nl) {
+                pos = lds_u16(list_s + 2 * i);
+                s = lds_u8(A_s + pos * 2 + 1);
             }
+            bool keep = false;
+            if (s > 0) {
+                const uint32_t b = A_s + (pos - PA - 1) * 2 + 1;
+                uint32_t n0, n1, n2, n3, n4, n5, n6, n7;
+#define ORBX_LDS_B(dst, off) asm volatile("ld.shared.u8 %0, [%1+%2];" : "=r"(dst) : "r"(b), "n"((off) * 2))
+                ORBX_LDS_B(n0, 0);          ORBX_LDS_B(n1, 1);          ORBX_LDS_B(n2, 2);
+                ORBX_LDS_B(n3, PA);         ORBX_LDS_B(n4, PA + 2);
+                ORBX_LDS_B(n5, 2 * PA);     ORBX_LDS_B(n6, 2 * PA + 1); ORBX_LDS_B(n7, 2 * PA + 2);
+#undef ORBX_LDS_B
+                keep = s > max(max(max(n0, n1), max(n2, n3)), max(max(n4, n5), max(n6, n7)));
+            }
+            const uint32_t mk = __ballot_sync(0xffffffffu, keep);
+            nh += __popc(__ballot_sync(0xffffffffu, keep && (int)s >= iniTh));
+            // every entry of this iteration is in registers and ns <= base: the in-place write cannot hit an unread entry
+            if (keep) sts_u16(list_s + 2 * (ns + __popc(mk & ltmask)), pos);
+            ns += __popc(mk);
         }
     }
     __syncwarp();
 
-    // 5. per-cell threshold selection (ini if it yields anything, else min) + exclusive offsets, all in registers
-    const int nwordsB = ((rh * PA) + 31) >> 5;
-    uint32_t anyH = 0;
-    for (int w = lane; w < nwordsB; w += 32) anyH |= lds_u32(selH_s + w * 4);
-    anyH = __ballot_sync(0xffffffffu, anyH != 0);
-    const uint32_t sel_s = anyH ? selH_s : selA_s;
-    uint32_t mkreg[kMaxBmWordsPerLane];
-    int offreg[kMaxBmWordsPerLane];
-    int running = 0;
-#pragma unroll
-    for (int k = 0; k < kMaxBmWordsPerLane; ++k) {
-        mkreg[k] = 0; offreg[k] = 0;
-        if (k * 32 < nwordsB) {                                  // warp-uniform
-            const int w = k * 32 + lane;
-            if (w < nwordsB) mkreg[k] = lds_u32(sel_s + w * 4);
-            const int cnt = __popc(mkreg[k]);
-            int incl = cnt;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const int t = __shfl_up_sync(0xffffffffu, incl, d);
-                if (lane >= d) incl += t;
-            }
-            offreg[k] = running + incl - cnt;
-            running += __shfl_sync(0xffffffffu, incl, 31);
-        }
-    }
-    if (lane == 0) *count_out = running;
-    if (running == 0) return;
-
-    // 6. ordered scatter: plane position order == (y, x) order
+    // 5. per-cell threshold selection (ini if it yields anything, else min) and ordered output
+    const int total = nh > 0 ? nh : ns;
+    if (lane == 0) *count_out = total;
+    if (total == 0) return;
     uint32_t* out = ws.cand + (size_t)frame * fg.cand_frame_stride + g.cand_off + (size_t)cell * g.cell_cap;
     const int xbase = cj * g.wCell - m, ybase = ci * g.hCell;
-#pragma unroll
-    for (int k = 0; k < kMaxBmWordsPerLane; ++k) {
-        uint32_t mk = mkreg[k];
-        int o = offreg[k];
-        while (mk) {
-            const int bit = __ffs(mk) - 1;
-            mk &= mk - 1;
-            const int pos = ((k * 32 + lane) << 5) + bit;
-            const int y = pos / PA, x = pos - y * PA;
-            out[o++] = (uint32_t)(xbase + x) | ((uint32_t)(ybase + y) << 12) | (lds_u8(A_s + pos * 2 + 1) << 24);
+    {
+        const uint32_t ltmask = (1u << lane) - 1u;
+        int o = 0;
+        for (int base = 0; base < ns; base += 32) {
+            const int i = base + lane;
+            uint32_t pos = 0, sc8 = 0;
+            bool sel = false;
+            if (i < ns) {
+                pos = lds_u16(list_s + 2 * i);
+                sc8 = lds_u8(A_s + pos * 2 + 1);
+                sel = nh == 0 || (int)sc8 >= iniTh;
+            }
+            const uint32_t mk = __ballot_sync(0xffffffffu, sel);
+            if (sel) {
+                const int y = (int)pos / PA, x = (int)pos - y * PA;
+                out[o + __popc(mk & ltmask)] = (uint32_t)(xbase + x) | ((uint32_t)(ybase + y) << 12) | (sc8 << 24);
+            }
+            o += __popc(mk);
         }
     }
 }
