@@ -261,6 +261,83 @@ int orbx_search_for_triangulation(int device, const orbx_keypoint* kp_a, const u
                                   const float* sigma2_b, int n_levels, int only_stereo, int coarse, int check_orientation,
                                   int32_t* match_a, int* n_matches);
 
+/* ---- the frame grid and the projection-guided searches ---------------------------------- */
+
+#define ORBX_FRAME_GRID_ROWS 48   /* include/Frame.h:44 */
+#define ORBX_FRAME_GRID_COLS 64   /* include/Frame.h:45 */
+
+/* The slice of ORB_SLAM3::Frame the searches read (HOST pointers; Nleft == -1: one camera, rectified stereo or RGB-D). */
+typedef struct orbx_frame_view {
+    int n;                          /* Frame::N */
+    const orbx_keypoint* keys_un;   /* mvKeysUn (pt, octave, angle are read) */
+    const uint8_t* descriptors;     /* mDescriptors, n x 32 */
+    const float* u_right;           /* mvuRight, NULL = none (monocular: all -1) */
+    const uint8_t* occupied;        /* [n] or NULL: the feature's map point on entry makes later queries skip it (each function
+                                     * says what that means: Observations() > 0, or merely non-NULL) */
+    float min_x, min_y, max_x, max_y;   /* mnMinX, mnMinY, mnMaxX, mnMaxY (src/Frame.cc:150-162) */
+    float grid_w_inv, grid_h_inv;   /* mfGridElementWidthInv / HeightInv = 64 / (maxX - minX), 48 / (maxY - minY) */
+    const float* scale_factors;     /* mvScaleFactors, n_levels entries */
+    int n_levels;
+} orbx_frame_view;
+
+/* Frame::AssignFeaturesToGrid (src/Frame.cc:387-418, PosInGrid :755-766) as CSR over cell id = ix * 48 + iy:
+ * cell_start[64*48 + 1], items[n] (only cell_start[64*48] entries are written: features outside the grid are dropped), the
+ * features of a cell in push_back order = ascending index.  Runs on the GPU (the same kernel the searches use). */
+int orbx_assign_features_to_grid(int device, const orbx_frame_view* frame, int32_t* cell_start, int32_t* items);
+/* vector<size_t> Frame::GetFeaturesInArea(x, y, r, minLevel, maxLevel) (src/Frame.cc:687-753): indices in the reference's
+ * order (cell column, cell row, in-cell order).  ORBX_ERR_CAPACITY with *n_out = needed count if out is too small. */
+int orbx_get_features_in_area(int device, const orbx_frame_view* frame, float x, float y, float r, int min_level, int max_level,
+                              int32_t* out, int capacity, int* n_out);
+
+/* The map points of Tracking::SearchLocalPoints as the fields SearchByProjection reads (HOST arrays of n entries). */
+typedef struct orbx_track_points {
+    int n;
+    const uint8_t* in_view;         /* pMP->mbTrackInView */
+    const uint8_t* bad;             /* pMP->isBad() */
+    const float* proj_x;            /* mTrackProjX */
+    const float* proj_y;            /* mTrackProjY */
+    const float* proj_xr;           /* mTrackProjXR */
+    const float* view_cos;          /* mTrackViewCos */
+    const float* track_depth;       /* mTrackDepth (read only with far_points) */
+    const int32_t* scale_level;     /* mnTrackScaleLevel */
+    const int32_t* n_obs;           /* Observations() */
+    const uint8_t* descriptors;     /* GetDescriptor(), n x 32 */
+} orbx_track_points;
+
+/* int ORBmatcher::SearchByProjection(Frame& F, const vector<MapPoint*>& vpMapPoints, th, bFarPoints, thFarPoints)
+ * — src/ORBmatcher1.cc:45-215 (Nleft == -1).  frame->occupied[idx] != 0 <=> F.mvpMapPoints[idx] && Observations() > 0 on entry.
+ * Window radius = RadiusByViewingCos(viewCos) [* th] * mvScaleFactors[level] (:68-74), levels [level-1, level], mvuRight gate
+ * (:95-100), best/second with the same-level ratio test against nn_ratio (mfNNratio) and TH_HIGH (:125-131).  Features taken by
+ * an earlier map point of the call are skipped by later ones exactly as the sequential loop does.
+ * Output: match_f[frame->n] = index of the map point assigned to the feature by THIS call, -1 = untouched;
+ * *n_matches = the return value. */
+int orbx_search_by_projection_map(int device, const orbx_frame_view* frame, const orbx_track_points* points, float th,
+                                  int far_points, float th_far_points, float nn_ratio, int32_t* match_f, int* n_matches);
+
+/* int ORBmatcher::SearchByProjection(Frame& CurrentFrame, const Frame& LastFrame, th, bMono) — src/ORBmatcher3.cc:256-467
+ * (Nleft == -1).  The Sophus/Eigen part stays with the caller: per last-frame feature i
+ *   valid[i]   = LastFrame.mvpMapPoints[i] && !LastFrame.mvbOutlier[i]           (:278-281)
+ *   u, v, invz = mpCamera->project(Tcw * x3Dw) and 1 / x3Dc(2)                   (:284-294)
+ *   octave, angle = the last frame's key point (:304, :358-365), n_obs = pMP->Observations(), desc = pMP->GetDescriptor()
+ *   forward / backward = bForward / bBackward (:272-273); mbf = CurrentFrame.mbf
+ * cur->occupied as above.  Output: match_f[cur->n] = last-frame index i assigned to the feature (after the rotation filter),
+ * *n_matches = the return value. */
+int orbx_search_by_projection_last(int device, const orbx_frame_view* cur, float mbf, int n_last, const uint8_t* valid,
+                                   const float* u, const float* v, const float* invz, const int32_t* octave, const float* angle,
+                                   const int32_t* n_obs, const uint8_t* desc, float th, int forward, int backward,
+                                   int check_orientation, int32_t* match_f, int* n_matches);
+
+/* int ORBmatcher::SearchByProjection(Frame& CurrentFrame, KeyFrame* pKF, sAlreadyFound, th, ORBdist) — src/ORBmatcher3.cc:469-578.
+ *   valid[i] = pMP && !pMP->isBad() && !sAlreadyFound.count(pMP); u, v = projection by the caller; dist3d = |x3Dw - Ow| with the
+ *   map point's min/max distance invariance (:508-514); level = pMP->PredictScale(dist3D, &CurrentFrame) (:516); angle = pKF->mvKeysUn[i].angle.
+ * cur->occupied[idx] != 0 <=> CurrentFrame.mvpMapPoints[idx] != NULL (:533), and every assignment of the call occupies. */
+int orbx_search_by_projection_kf(int device, const orbx_frame_view* cur, int n_kf, const uint8_t* valid, const float* u,
+                                 const float* v, const float* dist3d, const float* min_dist, const float* max_dist,
+                                 const int32_t* level, const float* angle, const uint8_t* desc, float th, int orb_dist,
+                                 int check_orientation, int32_t* match_f, int* n_matches);
+/* Speculation rounds the last projection search on this thread needed (diagnostics; 0 = every query was final at once). */
+int orbx_projection_rounds(void);
+
 /* ---- measurement helpers ----------------------------------------------------------------------------------- */
 
 /* Per-stage device timing: between begin and end every extraction on `ex` records CUDA events around its stages on the

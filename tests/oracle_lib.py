@@ -211,6 +211,70 @@ class Oracle:
                                                     int(check_ori), _ptr(out))
         return out, nm
 
+    # ---- frame grid / projection-guided searches (oracle/projection_oracle.cpp) -----------------
+    def assign_features_to_grid(self, kp, bounds_grid):
+        kp = np.ascontiguousarray(kp, KP_DTYPE); bg = np.ascontiguousarray(bounds_grid, np.float32)
+        cs = np.zeros(64 * 48 + 1, np.int32); items = np.zeros(max(len(kp), 1), np.int32)
+        self.lib.orbo_assign_features_to_grid.restype = None
+        self.lib.orbo_assign_features_to_grid(_ptr(kp), len(kp), _ptr(bg), _ptr(cs), _ptr(items))
+        return cs, items[:cs[-1]]
+
+    def get_features_in_area(self, kp, bounds_grid, x, y, r, min_level=-1, max_level=-1):
+        kp = np.ascontiguousarray(kp, KP_DTYPE); bg = np.ascontiguousarray(bounds_grid, np.float32)
+        out = np.zeros(max(len(kp), 1), np.int32)
+        n = self.lib.orbo_get_features_in_area(_ptr(kp), len(kp), _ptr(bg), C.c_float(x), C.c_float(y), C.c_float(r), int(min_level),
+                                               int(max_level), _ptr(out))
+        return out[:n]
+
+    @staticmethod
+    def _opt(a, dt):
+        return None if a is None else np.ascontiguousarray(a, dt)
+
+    def search_by_projection_map(self, kp, desc, uright, occupied, bounds_grid, scale, in_view, bad, projx, projy, projxr, viewcos,
+                                 depth, level, nobs, mpdesc, th=1.0, far=False, th_far=0.0, nnratio=0.8):
+        kp = np.ascontiguousarray(kp, KP_DTYPE); desc = np.ascontiguousarray(desc, np.uint8)
+        ur = self._opt(uright, np.float32); oc = self._opt(occupied, np.uint8)
+        bg = np.ascontiguousarray(bounds_grid, np.float32); sc = np.ascontiguousarray(scale, np.float32)
+        f32 = lambda a: np.ascontiguousarray(a, np.float32)   # noqa: E731
+        iv = np.ascontiguousarray(in_view, np.uint8); bd = np.ascontiguousarray(bad, np.uint8)
+        px, py, pxr, vc, dp = f32(projx), f32(projy), f32(projxr), f32(viewcos), f32(depth)
+        lv = np.ascontiguousarray(level, np.int32); no = np.ascontiguousarray(nobs, np.int32); md = np.ascontiguousarray(mpdesc, np.uint8)
+        out = np.full(max(len(kp), 1), -1, np.int32)
+        nm = self.lib.orbo_search_by_projection_map(_ptr(kp), _ptr(desc), None if ur is None else _ptr(ur), None if oc is None else _ptr(oc),
+                                                    len(kp), _ptr(bg), _ptr(sc), _ptr(iv), _ptr(bd), _ptr(px), _ptr(py), _ptr(pxr), _ptr(vc),
+                                                    _ptr(dp), _ptr(lv), _ptr(no), _ptr(md), len(iv), C.c_float(th), int(far), C.c_float(th_far),
+                                                    C.c_float(nnratio), _ptr(out))
+        return out[:len(kp)], nm
+
+    def search_by_projection_last(self, kp, desc, uright, occupied, bounds_grid, scale, mbf, valid, u, v, invz, octave, angle, nobs, mpdesc,
+                                  th, forward=False, backward=False, check_ori=True):
+        kp = np.ascontiguousarray(kp, KP_DTYPE); desc = np.ascontiguousarray(desc, np.uint8)
+        ur = self._opt(uright, np.float32); oc = self._opt(occupied, np.uint8)
+        bg = np.ascontiguousarray(bounds_grid, np.float32); sc = np.ascontiguousarray(scale, np.float32)
+        f32 = lambda a: np.ascontiguousarray(a, np.float32)   # noqa: E731
+        va = np.ascontiguousarray(valid, np.uint8); uu, vv, iz, an = f32(u), f32(v), f32(invz), f32(angle)
+        oct_ = np.ascontiguousarray(octave, np.int32); no = np.ascontiguousarray(nobs, np.int32); md = np.ascontiguousarray(mpdesc, np.uint8)
+        out = np.full(max(len(kp), 1), -1, np.int32)
+        nm = self.lib.orbo_search_by_projection_last(_ptr(kp), _ptr(desc), None if ur is None else _ptr(ur), None if oc is None else _ptr(oc),
+                                                     len(kp), _ptr(bg), _ptr(sc), C.c_float(mbf), _ptr(va), _ptr(uu), _ptr(vv), _ptr(iz),
+                                                     _ptr(oct_), _ptr(an), _ptr(no), _ptr(md), len(va), C.c_float(th), int(forward),
+                                                     int(backward), int(check_ori), _ptr(out))
+        return out[:len(kp)], nm
+
+    def search_by_projection_kf(self, kp, desc, occupied, bounds_grid, scale, valid, u, v, dist3d, mind, maxd, level, angle, mpdesc, th,
+                                orb_dist, check_ori=True):
+        kp = np.ascontiguousarray(kp, KP_DTYPE); desc = np.ascontiguousarray(desc, np.uint8)
+        oc = self._opt(occupied, np.uint8)
+        bg = np.ascontiguousarray(bounds_grid, np.float32); sc = np.ascontiguousarray(scale, np.float32)
+        f32 = lambda a: np.ascontiguousarray(a, np.float32)   # noqa: E731
+        va = np.ascontiguousarray(valid, np.uint8); uu, vv, d3, mn, mx, an = f32(u), f32(v), f32(dist3d), f32(mind), f32(maxd), f32(angle)
+        lv = np.ascontiguousarray(level, np.int32); md = np.ascontiguousarray(mpdesc, np.uint8)
+        out = np.full(max(len(kp), 1), -1, np.int32)
+        nm = self.lib.orbo_search_by_projection_kf(_ptr(kp), _ptr(desc), None if oc is None else _ptr(oc), len(kp), _ptr(bg), _ptr(sc),
+                                                   _ptr(va), _ptr(uu), _ptr(vv), _ptr(d3), _ptr(mn), _ptr(mx), _ptr(lv), _ptr(an), _ptr(md),
+                                                   len(va), C.c_float(th), int(orb_dist), int(check_ori), _ptr(out))
+        return out[:len(kp)], nm
+
     # ---- extractor --------------------------------------------------------------------------
     def extractor(self, nfeatures=1000, scale_factor=1.2, nlevels=8, ini_th=20, min_th=7):
         return OracleExtractor(self, nfeatures, scale_factor, nlevels, ini_th, min_th)

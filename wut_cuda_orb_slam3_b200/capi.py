@@ -69,6 +69,12 @@ SIGNATURES = {
     "orbx_search_by_bow": (_i, [_i, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _i, _vp, _i, _f, _i, _vp, _vp, _vp]),
     "orbx_search_for_triangulation": (_i, [_i, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _i, _i,
                                            _i, _i, _vp, _vp]),
+    "orbx_assign_features_to_grid": (_i, [_i, _vp, _vp, _vp]),
+    "orbx_get_features_in_area": (_i, [_i, _vp, _f, _f, _f, _i, _i, _vp, _i, _vp]),
+    "orbx_search_by_projection_map": (_i, [_i, _vp, _vp, _f, _i, _f, _f, _vp, _vp]),
+    "orbx_search_by_projection_last": (_i, [_i, _vp, _f, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _f, _i, _i, _i, _vp, _vp]),
+    "orbx_search_by_projection_kf": (_i, [_i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _f, _i, _i, _vp, _vp]),
+    "orbx_projection_rounds": (_i, []),
     "orbx_profile_begin": (_i, [_vp]),
     "orbx_profile_end": (_i, [_vp, _vp, _vp]),
     "orbx_measure_popc_peak": (_i, [_i, C.POINTER(C.c_double)]),
@@ -83,6 +89,19 @@ SIGNATURES = {
 class FeatureVectorC(C.Structure):
     """orbx_feature_vector (include/orbx.h): a DBoW2::FeatureVector in CSR form."""
     _fields_ = [("n_nodes", C.c_int), ("node_ids", _vp), ("offsets", _vp), ("indices", _vp)]
+
+
+class FrameViewC(C.Structure):
+    """orbx_frame_view (include/orbx.h): the slice of ORB_SLAM3::Frame the projection searches read."""
+    _fields_ = [("n", C.c_int), ("keys_un", _vp), ("descriptors", _vp), ("u_right", _vp), ("occupied", _vp),
+                ("min_x", _f), ("min_y", _f), ("max_x", _f), ("max_y", _f), ("grid_w_inv", _f), ("grid_h_inv", _f),
+                ("scale_factors", _vp), ("n_levels", C.c_int)]
+
+
+class TrackPointsC(C.Structure):
+    """orbx_track_points (include/orbx.h)."""
+    _fields_ = [("n", C.c_int), ("in_view", _vp), ("bad", _vp), ("proj_x", _vp), ("proj_y", _vp), ("proj_xr", _vp),
+                ("view_cos", _vp), ("track_depth", _vp), ("scale_level", _vp), ("n_obs", _vp), ("descriptors", _vp)]
 
 
 class OrbxError(RuntimeError):

@@ -192,7 +192,39 @@ struct TriSearchArgs {
 };
 cudaError_t launch_search_triangulation(const TriSearchArgs& a, cudaStream_t st);
 
-// host helpers shared by api.cu / api_bow.cu
+
+// ---- frame grid + projection-guided window searches (kernels_proj.cu, api_proj.cu) ----------------------------------------
+enum { PROJ_Q_VALID = 1, PROJ_Q_CHECK_RIGHT = 2, PROJ_Q_TAKES = 4 };
+struct ProjQuery {               // one GetFeaturesInArea window + what the scan needs (32 bytes)
+    float x, y, r;               // window centre and half size (already multiplied by the level's scale factor)
+    float ur;                    // predicted right-image coordinate for the mvuRight gate (PROJ_Q_CHECK_RIGHT)
+    int min_level, max_level;    // GetFeaturesInArea minLevel / maxLevel (-1 = open)
+    int flags;                   // PROJ_Q_*: VALID = passes the reference's pre-checks; TAKES = the assigned map point has Observations() > 0
+    int pad;
+};
+struct ProjArgs {
+    int n;                       // features of the frame
+    const orbx_keypoint* kp; const uint8_t* desc; const float* u_right;   // u_right may be null
+    float min_x, min_y, grid_w_inv, grid_h_inv;
+    int* cell_start;             // [64*48 + 1] CSR over cell id = ix * 48 + iy
+    int* items;                  // [n] feature indices by cell, ascending inside a cell
+    unsigned short* cell_of;     // [n] cell id or 0xffff
+    int* taken_by;               // [n] INT_MAX = free, -1 = holds an observed map point on entry, else the query that took it
+    int* claim;                  // [n] least undecided query index that could take the feature
+    int nq; const ProjQuery* q; const uint8_t* qdesc;
+    int mode;                    // 0: best/second + level-aware ratio (ORBmatcher1.cc:45-215); 1: 1-NN (ORBmatcher3.cc:256-578)
+    int th_dist; float nn_ratio;
+    unsigned long long* keys;    // [nq][2] top-2 (distance << 48 | cell << 32 | index)
+    int* qmatch;                 // [nq] init -1: feature assigned to the query
+    int* list_a; int* list_b;    // [nq] undecided queries, ping-pong
+    int* rounds_out;             // speculation rounds used (diagnostics; may be null)
+};
+cudaError_t launch_frame_grid(const ProjArgs& a, cudaStream_t st);
+cudaError_t launch_proj_search(const ProjArgs& a, cudaStream_t st);
+cudaError_t launch_features_in_area(const ProjArgs& a, float x, float y, float r, int min_level, int max_level,
+                                    unsigned long long* d_out, int capacity, int* d_n_out, cudaStream_t st);
+
+// host helpers shared by api.cu / api_bow.cu / api_proj.cu
 int fail(int code, const char* fmt, ...);
 int set_device(int device);
 void three_maxima(const int* count, int L, int& ind1, int& ind2, int& ind3);   // ORBmatcher::ComputeThreeMaxima (src/ORBmatcher3.cc:592-633)
