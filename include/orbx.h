@@ -338,6 +338,29 @@ int orbx_search_by_projection_kf(int device, const orbx_frame_view* cur, int n_k
 /* Speculation rounds the last projection search on this thread needed (diagnostics; 0 = every query was final at once). */
 int orbx_projection_rounds(void);
 
+/* ---- preparation steps either side of the extractor ------------------------------------- */
+
+/* void Frame::UndistortKeyPoints() — src/Frame.cc:777-810 = cv::undistortPoints(mvKeys, K, mDistCoef, cv::Mat(), mK).
+ *   K[4] / new_K[4] = (fx, fy, cx, cy) of Pinhole::toK() and of mK; dist = mDistCoef (CV_32F: k1 k2 p1 p2 [k3 [k4 k5 k6]]),
+ *   n_dist in {0, 4, 5, 8, 12}.  dist[0] == 0 (or n_dist == 0) copies the key points, as the reference does (:779-783).
+ * HOST arrays; out may alias keypoints.  Computes on the GPU in double, bit-identical to OpenCV's scalar code. */
+int orbx_undistort_keypoints(int device, const orbx_keypoint* keypoints, int n, const float* K, const float* dist, int n_dist,
+                             const float* new_K, orbx_keypoint* out);
+
+/* Stereo rectification of System::TrackStereo (src/System.cc:253-260): cv::remap(im, out, M1, M2, cv::INTER_LINEAR) with the
+ * CV_32FC1 maps of cv::initUndistortRectifyMap (src/Settings.cc:488-491), BORDER_CONSTANT 0.  The maps are quantised to
+ * OpenCV's 1/32-pixel fixed point once, at creation, and stay on the device. */
+typedef struct orbx_rectifier orbx_rectifier;
+int orbx_rectifier_create(int device, const float* map_x, const float* map_y, size_t map_step_bytes, int dst_rows, int dst_cols,
+                          orbx_rectifier** out);
+void orbx_rectifier_destroy(orbx_rectifier* r);
+/* One HOST image (src_rows x src_cols, 8UC1) -> HOST dst (dst_rows x dst_cols of the rectifier). */
+int orbx_remap(orbx_rectifier* r, const uint8_t* src, int src_rows, int src_cols, size_t src_step, uint8_t* dst, size_t dst_step);
+/* Device-resident frames (frame f at d_src + f * src_frame_stride), on `stream` (a cudaStream_t or NULL); chain it in front of
+ * orbx_extract_batch_device on the same stream to keep the rectified images on the device. */
+int orbx_remap_device(orbx_rectifier* r, const uint8_t* d_src, int src_rows, int src_cols, size_t src_pitch, size_t src_frame_stride,
+                      int n_frames, uint8_t* d_dst, size_t dst_pitch, size_t dst_frame_stride, void* stream);
+
 /* ---- measurement helpers ----------------------------------------------------------------------------------- */
 
 /* Per-stage device timing: between begin and end every extraction on `ex` records CUDA events around its stages on the

@@ -275,6 +275,33 @@ class Oracle:
                                                    len(va), C.c_float(th), int(orb_dist), int(check_ori), _ptr(out))
         return out[:len(kp)], nm
 
+    # ---- preparation steps (oracle/prep_oracle.cpp) ----------------------------------------------
+    def undistort_points(self, pts, K, dist, P):
+        pts = np.ascontiguousarray(pts, np.float32).reshape(-1, 2)
+        K = np.ascontiguousarray(K, np.float64); P = np.ascontiguousarray(P, np.float64); d = np.ascontiguousarray(dist, np.float64)
+        out = np.zeros_like(pts)
+        self.lib.orbo_undistort_points.restype = None
+        self.lib.orbo_undistort_points(_ptr(pts), len(pts), _ptr(K), _ptr(d), len(d), _ptr(P), _ptr(out))
+        return out
+
+    def undistort_keypoints(self, kps, K, dist, new_K):
+        kps = np.ascontiguousarray(kps, KP_DTYPE)
+        K = np.ascontiguousarray(np.asarray(K, np.float32), np.float64); P = np.ascontiguousarray(np.asarray(new_K, np.float32), np.float64)
+        d = np.ascontiguousarray(dist, np.float32)
+        out = np.zeros_like(kps)
+        self.lib.orbo_undistort_keypoints.restype = None
+        self.lib.orbo_undistort_keypoints(_ptr(kps), len(kps), _ptr(K), _ptr(d), len(d), _ptr(P), _ptr(out))
+        return out
+
+    def remap(self, src, mapx, mapy):
+        src = np.ascontiguousarray(src, np.uint8); mx = np.ascontiguousarray(mapx, np.float32); my = np.ascontiguousarray(mapy, np.float32)
+        dh, dw = mx.shape
+        out = np.zeros((dh, dw), np.uint8)
+        self.lib.orbo_remap_linear_u8.restype = None
+        self.lib.orbo_remap_linear_u8(_ptr(src), src.shape[1], src.shape[0], _sz(src.shape[1]), _ptr(mx), _ptr(my), _sz(dw), _ptr(out), dw, dh,
+                                      _sz(dw))
+        return out
+
     # ---- extractor --------------------------------------------------------------------------
     def extractor(self, nfeatures=1000, scale_factor=1.2, nlevels=8, ini_th=20, min_th=7):
         return OracleExtractor(self, nfeatures, scale_factor, nlevels, ini_th, min_th)

@@ -219,3 +219,60 @@ def test_cvt_gray_bit_exact(oracle, code, ch, rgb):
     for c2 in (0, 1, 127, 255):
         img = np.concatenate([ramp, np.full((256, 256, ch - 2), c2, np.uint8)], -1)
         assert np.array_equal(oracle.cvt_gray(img, rgb), cv2.cvtColor(img, code))
+
+
+def _camera(rng, trial):
+    K = np.array([rng.uniform(300, 900), rng.uniform(300, 900), rng.uniform(300, 400), rng.uniform(200, 280)], np.float32)
+    nd = [4, 5, 8][trial % 3]
+    d = np.zeros(nd, np.float32)
+    d[0] = rng.uniform(-0.4, 0.1); d[1] = rng.uniform(-0.1, 0.2); d[2:4] = rng.uniform(-1e-3, 1e-3, 2)
+    if nd >= 5:
+        d[4] = rng.uniform(-0.05, 0.05)
+    if nd == 8:
+        d[5:8] = rng.uniform(-0.05, 0.05, 3)
+    P = K.copy() if trial % 2 == 0 else np.array([rng.uniform(300, 900), rng.uniform(300, 900), rng.uniform(300, 400), rng.uniform(200, 280)], np.float32)
+    return K, d, P
+
+
+def _mat(k):
+    return np.array([[k[0], 0, k[2]], [0, k[1], k[3]], [0, 0, 1]], np.float32)
+
+
+def test_undistort_points_bit_exact():
+    """cv::undistortPoints as called by Frame::UndistortKeyPoints (src/Frame.cc:797): pinhole + radtan, R = I, P = mK."""
+    from tests import oracle_lib
+    oracle = oracle_lib.load()
+    rng = np.random.default_rng(0)
+    for trial in range(24):
+        K, d, P = _camera(rng, trial)
+        pts = np.stack([rng.uniform(-20, 772, 1500), rng.uniform(-20, 500, 1500)], 1).astype(np.float32)
+        want = cv2.undistortPoints(pts.reshape(-1, 1, 2), _mat(K), d.reshape(1, -1), None, _mat(P)).reshape(-1, 2)
+        got = oracle.undistort_points(pts, K.astype(np.float64), d.astype(np.float64), P.astype(np.float64))
+        assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), trial
+
+
+def _maps(rng, sw, sh, dw, dh, shift=0.0, noise=3.0):
+    yy, xx = np.mgrid[0:dh, 0:dw].astype(np.float32)
+    mx = (xx * sw / dw + rng.normal(0, noise, (dh, dw)) + 5 * np.sin(yy / 30) - shift).astype(np.float32)
+    my = (yy * sh / dh + rng.normal(0, noise, (dh, dw)) + shift).astype(np.float32)
+    return mx, my
+
+
+@pytest.mark.parametrize("case", range(8))
+def test_remap_linear_bit_exact(case):
+    """cv::remap(INTER_LINEAR, CV_32FC1 maps, BORDER_CONSTANT 0) as called by System::TrackStereo (src/System.cc:259-260)."""
+    from tests import oracle_lib
+    oracle = oracle_lib.load()
+    rng = np.random.default_rng(100 + case)
+    sh, sw = [(480, 752), (376, 1241), (61, 47), (480, 752)][case % 4]
+    dh, dw = [(480, 752), (300, 500), (70, 90), (481, 750)][case % 4]
+    src = rng.integers(0, 256, (sh, sw), dtype=np.uint8)
+    if case == 6:      # identity and exact half-pixel positions: the saturated (0,0) weight and round-half-to-even of the map
+        yy, xx = np.mgrid[0:dh, 0:dw].astype(np.float32)
+        mx = (xx + np.float32(0.5) * (yy.astype(np.int32) % 2)).astype(np.float32)
+        my = (yy + np.float32(1.0 / 64) * (xx.astype(np.int32) % 3)).astype(np.float32)
+    else:
+        mx, my = _maps(rng, sw, sh, dw, dh, shift=20.0 if case >= 4 else 0.0)
+    want = cv2.remap(src, mx, my, cv2.INTER_LINEAR)
+    got = oracle.remap(src, mx, my)
+    assert np.array_equal(got, want)

@@ -8,6 +8,7 @@ from . import capi, synth  # noqa: F401
 from .capi import KP_DTYPE, OrbxError, lib  # noqa: F401
 from .bow import FeatureVector, ORBVocabulary, search_by_bow, search_for_triangulation  # noqa: F401
 from .extractor import ORBextractor, compute_tables, distribute_octree  # noqa: F401
+from .prep import Rectifier, undistort_keypoints  # noqa: F401
 from .projection import (FrameView, projection_rounds, search_by_projection_kf, search_by_projection_last,  # noqa: F401
                          search_by_projection_map)
 from .matcher import (ORBmatcher, compute_stereo_matches, distinctive_descriptor, knn2_device,  # noqa: F401

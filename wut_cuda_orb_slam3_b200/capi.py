@@ -75,6 +75,11 @@ SIGNATURES = {
     "orbx_search_by_projection_last": (_i, [_i, _vp, _f, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _f, _i, _i, _i, _vp, _vp]),
     "orbx_search_by_projection_kf": (_i, [_i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _f, _i, _i, _vp, _vp]),
     "orbx_projection_rounds": (_i, []),
+    "orbx_undistort_keypoints": (_i, [_i, _vp, _i, _vp, _vp, _i, _vp, _vp]),
+    "orbx_rectifier_create": (_i, [_i, _vp, _vp, _sz, _i, _i, C.POINTER(_vp)]),
+    "orbx_rectifier_destroy": (None, [_vp]),
+    "orbx_remap": (_i, [_vp, _vp, _i, _i, _sz, _vp, _sz]),
+    "orbx_remap_device": (_i, [_vp, _vp, _i, _i, _sz, _sz, _i, _vp, _sz, _sz, _vp]),
     "orbx_profile_begin": (_i, [_vp]),
     "orbx_profile_end": (_i, [_vp, _vp, _vp]),
     "orbx_measure_popc_peak": (_i, [_i, C.POINTER(C.c_double)]),

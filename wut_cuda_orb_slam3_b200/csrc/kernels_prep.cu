@@ -1,0 +1,122 @@
+// kernels_prep.cu — preparation steps either side of the extractor.
+//
+//   * Frame::UndistortKeyPoints (src/Frame.cc:777-810) = cv::undistortPoints(pts, K, mDistCoef, R = I, P = mK): normalise,
+//     5 fixed-point iterations of the inverse radial-tangential distortion, re-project; double arithmetic, float results.
+//     One thread per key point; --fmad=false keeps every multiply and add separately rounded like the x86-64 build of OpenCV.
+//   * System::TrackStereo rectification (src/System.cc:253-260) = cv::remap(im, out, M1, M2, INTER_LINEAR) with CV_32FC1 maps:
+//     the map is quantised ONCE to OpenCV's 1/32-pixel fixed point (remap_quantise_kernel), every frame then costs four
+//     gathers and one 15-bit fixed-point blend per pixel.  The packed map (8 bytes per pixel) stays L2-resident across a
+//     batch, so HBM sees the source and destination bytes only; a thread produces 4 adjacent pixels and stores them as one word.
+#include "orbx_internal.cuh"
+
+namespace orbx {
+
+__global__ void __launch_bounds__(128) undistort_kernel(const orbx_keypoint* __restrict__ in, int n, UndistortParams p,
+                                                        orbx_keypoint* __restrict__ out)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    orbx_keypoint kp = in[i];
+    const double* k = p.k;
+    const double ifx = 1. / p.fx, ify = 1. / p.fy;
+    const double u = kp.x, v = kp.y;
+    double x = (u - p.cx) * ifx, y = (v - p.cy) * ify;
+    if (p.n_dist > 0) {
+        const double x0 = x, y0 = y;
+        for (int j = 0; j < 5; ++j) {
+            const double r2 = x * x + y * y;
+            const double icdist = (1 + ((k[7] * r2 + k[6]) * r2 + k[5]) * r2) / (1 + ((k[4] * r2 + k[1]) * r2 + k[0]) * r2);
+            if (icdist < 0) { x = (u - p.cx) * ifx; y = (v - p.cy) * ify; break; }
+            const double deltaX = 2 * k[2] * x * y + k[3] * (r2 + 2 * x * x) + k[8] * r2 + k[9] * r2 * r2;
+            const double deltaY = k[2] * (r2 + 2 * y * y) + 2 * k[3] * x * y + k[10] * r2 + k[11] * r2 * r2;
+            x = (x0 - deltaX) * icdist;
+            y = (y0 - deltaY) * icdist;
+        }
+    }
+    const double xx = p.nfx * x + 0.0 * y + p.ncx;
+    const double yy = 0.0 * x + p.nfy * y + p.ncy;
+    const double ww = 1. / (0.0 * x + 0.0 * y + 1.0);
+    kp.x = (float)(xx * ww);
+    kp.y = (float)(yy * ww);
+    out[i] = kp;
+}
+
+// cvRound(map * 32) -> (sx | sy << 16, fx | fy << 5); sx, sy saturate to int16 like OpenCV's XY buffer.
+__global__ void __launch_bounds__(256) remap_quantise_kernel(const float* __restrict__ mapx, const float* __restrict__ mapy,
+                                                             size_t map_step, int dw, int dh, uint2* __restrict__ packed)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= dw || y >= dh) return;
+    const int sxq = __float2int_rn(__fmul_rn(mapx[(size_t)y * map_step + x], 32.0f));
+    const int syq = __float2int_rn(__fmul_rn(mapy[(size_t)y * map_step + x], 32.0f));
+    const int sx = max(-32768, min(32767, sxq >> 5)), sy = max(-32768, min(32767, syq >> 5));
+    packed[(size_t)y * dw + x] = make_uint2(((uint32_t)sx & 0xffffu) | ((uint32_t)sy << 16), (uint32_t)(sxq & 31) | ((uint32_t)(syq & 31) << 5));
+}
+
+__device__ __forceinline__ uint32_t remap_pixel(const uint8_t* __restrict__ src, int sw, int sh, size_t spitch, uint2 m)
+{
+    const int sx = (int)(short)(m.x & 0xffffu), sy = (int)(short)(m.x >> 16);
+    const int fx = (int)(m.y & 31u), fy = (int)(m.y >> 5);
+    int w0 = (32 - fy) * (32 - fx) * 32, w3 = fy * fx * 32;
+    const int w1 = (32 - fy) * fx * 32, w2 = fy * (32 - fx) * 32;
+    if (w0 == 32768) { w0 = 32767; w3 = 1; }                 // saturate_cast<short>(32768) and OpenCV's sum fix-up
+    int p00 = 0, p01 = 0, p10 = 0, p11 = 0;
+    if ((unsigned)sx < (unsigned)(sw - 1) && (unsigned)sy < (unsigned)(sh - 1)) {
+        const uint8_t* s = src + (size_t)sy * spitch + sx;
+        p00 = __ldg(s); p01 = __ldg(s + 1); p10 = __ldg(s + spitch); p11 = __ldg(s + spitch + 1);
+    } else {                                                 // BORDER_CONSTANT, value 0: taps outside the image read 0
+        const bool x0 = (unsigned)sx < (unsigned)sw, x1 = (unsigned)(sx + 1) < (unsigned)sw;
+        const bool y0 = (unsigned)sy < (unsigned)sh, y1 = (unsigned)(sy + 1) < (unsigned)sh;
+        if (x0 && y0) p00 = __ldg(src + (size_t)sy * spitch + sx);
+        if (x1 && y0) p01 = __ldg(src + (size_t)sy * spitch + sx + 1);
+        if (x0 && y1) p10 = __ldg(src + (size_t)(sy + 1) * spitch + sx);
+        if (x1 && y1) p11 = __ldg(src + (size_t)(sy + 1) * spitch + sx + 1);
+    }
+    return (uint32_t)((p00 * w0 + p01 * w1 + p10 * w2 + p11 * w3 + (1 << 14)) >> 15);
+}
+
+// grid (ceil(dw / 4 / 128), dh, frames): a thread = 4 adjacent destination pixels.
+__global__ void __launch_bounds__(128) remap_kernel(const uint8_t* __restrict__ src, int sw, int sh, size_t spitch, size_t sframe,
+                                                    const uint2* __restrict__ packed, uint8_t* __restrict__ dst, int dw, int dh,
+                                                    size_t dpitch, size_t dframe)
+{
+    const int x4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4, y = blockIdx.y;
+    if (x4 >= dw) return;
+    const uint8_t* s = src + (size_t)blockIdx.z * sframe;
+    uint8_t* d = dst + (size_t)blockIdx.z * dframe + (size_t)y * dpitch + x4;
+    const uint2* m = packed + (size_t)y * dw + x4;
+    if (x4 + 4 <= dw && ((dw & 3) == 0) && ((reinterpret_cast<size_t>(d) & 3) == 0)) {
+        const uint4 ma = __ldg(reinterpret_cast<const uint4*>(m)), mb = __ldg(reinterpret_cast<const uint4*>(m) + 1);
+        const uint32_t a = remap_pixel(s, sw, sh, spitch, make_uint2(ma.x, ma.y)), b = remap_pixel(s, sw, sh, spitch, make_uint2(ma.z, ma.w));
+        const uint32_t c = remap_pixel(s, sw, sh, spitch, make_uint2(mb.x, mb.y)), e = remap_pixel(s, sw, sh, spitch, make_uint2(mb.z, mb.w));
+        *reinterpret_cast<uint32_t*>(d) = a | (b << 8) | (c << 16) | (e << 24);
+    } else {
+        for (int t = 0; t < 4 && x4 + t < dw; ++t) d[t] = (uint8_t)remap_pixel(s, sw, sh, spitch, __ldg(m + t));
+    }
+}
+
+cudaError_t launch_undistort(const orbx_keypoint* d_in, int n, const UndistortParams& p, orbx_keypoint* d_out, cudaStream_t st)
+{
+    if (n <= 0) return cudaSuccess;
+    undistort_kernel<<<(n + 127) / 128, 128, 0, st>>>(d_in, n, p, d_out);
+    count_launch();
+    return cudaGetLastError();
+}
+
+cudaError_t launch_remap_quantise(const float* d_mapx, const float* d_mapy, size_t map_step, int dw, int dh, uint2* d_packed, cudaStream_t st)
+{
+    remap_quantise_kernel<<<dim3((dw + 255) / 256, dh), 256, 0, st>>>(d_mapx, d_mapy, map_step, dw, dh, d_packed);
+    count_launch();
+    return cudaGetLastError();
+}
+
+cudaError_t launch_remap(const uint8_t* d_src, int sw, int sh, size_t spitch, size_t sframe, const uint2* d_packed, uint8_t* d_dst, int dw,
+                         int dh, size_t dpitch, size_t dframe, int n_frames, cudaStream_t st)
+{
+    if (n_frames <= 0) return cudaSuccess;
+    remap_kernel<<<dim3((dw + 511) / 512, dh, n_frames), 128, 0, st>>>(d_src, sw, sh, spitch, sframe, d_packed, d_dst, dw, dh, dpitch, dframe);
+    count_launch();
+    return cudaGetLastError();
+}
+
+}  // namespace orbx

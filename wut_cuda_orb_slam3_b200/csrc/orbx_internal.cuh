@@ -224,6 +224,18 @@ cudaError_t launch_proj_search(const ProjArgs& a, cudaStream_t st);
 cudaError_t launch_features_in_area(const ProjArgs& a, float x, float y, float r, int min_level, int max_level,
                                     unsigned long long* d_out, int capacity, int* d_n_out, cudaStream_t st);
 
+// ---- preparation steps either side of the extractor (kernels_prep.cu, api_prep.cu) ------------------------------------------
+struct UndistortParams {
+    double fx, fy, cx, cy;       // K of the distorted camera
+    double nfx, nfy, ncx, ncy;   // P = new camera matrix (mK)
+    double k[14];                // k1 k2 p1 p2 k3 k4 k5 k6 s1..s4 (tilt unused); missing = 0
+    int n_dist;
+};
+cudaError_t launch_undistort(const orbx_keypoint* d_in, int n, const UndistortParams& p, orbx_keypoint* d_out, cudaStream_t st);
+cudaError_t launch_remap_quantise(const float* d_mapx, const float* d_mapy, size_t map_step, int dw, int dh, uint2* d_packed, cudaStream_t st);
+cudaError_t launch_remap(const uint8_t* d_src, int sw, int sh, size_t spitch, size_t sframe, const uint2* d_packed, uint8_t* d_dst, int dw,
+                         int dh, size_t dpitch, size_t dframe, int n_frames, cudaStream_t st);
+
 // host helpers shared by api.cu / api_bow.cu / api_proj.cu
 int fail(int code, const char* fmt, ...);
 int set_device(int device);
