@@ -353,6 +353,10 @@ int orbx_undistort_keypoints(int device, const orbx_keypoint* keypoints, int n, 
 typedef struct orbx_rectifier orbx_rectifier;
 int orbx_rectifier_create(int device, const float* map_x, const float* map_y, size_t map_step_bytes, int dst_rows, int dst_cols,
                           orbx_rectifier** out);
+/* The other branch of System::TrackStereo / TrackMonocular / TrackRGBD (src/System.cc:261-263, 330, 407, settings_->needToResize()):
+ * cv::resize(im, out, newImSize) — INTER_LINEAR on 8UC1 (OpenCV's 11-bit fixed point; exact 2x takes the INTER_AREA average).
+ * Returns a rectifier whose orbx_remap / orbx_remap_device calls resize src_rows x src_cols images to dst_rows x dst_cols. */
+int orbx_resizer_create(int device, int src_rows, int src_cols, int dst_rows, int dst_cols, orbx_rectifier** out);
 void orbx_rectifier_destroy(orbx_rectifier* r);
 /* One HOST image (src_rows x src_cols, 8UC1) -> HOST dst (dst_rows x dst_cols of the rectifier). */
 int orbx_remap(orbx_rectifier* r, const uint8_t* src, int src_rows, int src_cols, size_t src_step, uint8_t* dst, size_t dst_step);

@@ -81,10 +81,20 @@ void resize_linear_u8(const uint8_t* src, int sw, int sh, size_t sstep, uint8_t*
         c1 = (short)cvRoundF(f * 2048.f);
     };
     for (int x = 0; x < dw; ++x) coeffs(x, scale_x, sw, xofs[x], a0[x], a1[x]);
-    for (int y = 0; y < dh; ++y) coeffs(y, scale_y, sh, yofs[y], b0[y], b1[y]);
+    // The vertical direction is NOT clamped like the horizontal one: cv::resize keeps sy and fy as computed and the row
+    // loop clips the two row indices into the image (resizeGeneric_Invoker: clip(sy + k, 0, ssize.height)).  Identical for
+    // every down-scale (the pyramid); on up-scales the first/last rows blend a row with itself with split truncation.
+    for (int y = 0; y < dh; ++y) {
+        float f = (float)((y + 0.5) * scale_y - 0.5);
+        const int s = cvFloorD(f);
+        f -= s;
+        yofs[y] = s;
+        b0[y] = (short)cvRoundF((1.f - f) * 2048.f);
+        b1[y] = (short)cvRoundF(f * 2048.f);
+    }
     std::vector<int> r0(dw), r1(dw);
     for (int y = 0; y < dh; ++y) {
-        int sy0 = yofs[y], sy1 = std::min(sy0 + 1, sh - 1);
+        int sy0 = std::min(std::max(yofs[y], 0), sh - 1), sy1 = std::min(std::max(yofs[y] + 1, 0), sh - 1);
         const uint8_t* S0 = src + (size_t)sy0 * sstep;
         const uint8_t* S1 = src + (size_t)sy1 * sstep;
         for (int x = 0; x < dw; ++x) {

@@ -76,3 +76,18 @@ def test_remap_device_batch_feeds_extractor(oracle):
         kp = hk[f, :n[f]].copy().view(KP_DTYPE).reshape(-1)
         assert np.array_equal(kp["x"], okp["x"]) and np.array_equal(kp["y"], okp["y"]) and np.array_equal(kp["octave"], okp["octave"])
         assert (d_desc[f, :n[f]].cpu().numpy() != odesc).any(axis=1).mean() <= 0.005
+
+
+@pytest.mark.parametrize("src,dst", [((480, 752), (400, 627)), ((480, 752), (240, 376)), ((376, 1241), (480, 752)), ((100, 90), (37, 201)),
+                                     ((480, 640), (960, 1280))])
+def test_resize_matches_oracle(oracle, src, dst):
+    """cv::resize(im, out, newImSize) (src/System.cc:261-263): the oracle's resize is pinned against cv2 in tests/test_oracle_cv2.py."""
+    rng = np.random.default_rng(400)
+    img = rng.integers(0, 256, src, dtype=np.uint8)
+    r = orbx.Rectifier(resize=(src[0], src[1], dst[0], dst[1]))
+    got = r.remap(img)
+    want = oracle.resize(img, dst[1], dst[0])
+    assert np.array_equal(got, want)
+    with pytest.raises(orbx.OrbxError):
+        r.remap(img[:-1])
+    r.close()

@@ -276,3 +276,13 @@ def test_remap_linear_bit_exact(case):
     want = cv2.remap(src, mx, my, cv2.INTER_LINEAR)
     got = oracle.remap(src, mx, my)
     assert np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("src,dst", [((480, 752), (400, 627)), ((376, 1241), (480, 752)), ((100, 90), (37, 201)), ((480, 640), (960, 1280)),
+                                     ((48, 64), (96, 128)), ((480, 752), (240, 376)), ((60, 80), (61, 79))])
+def test_resize_to_new_size_bit_exact(oracle, src, dst):
+    """cv::resize(im, out, newImSize) of System::TrackStereo (src/System.cc:261-263), up- and down-scales (rows are not clamped
+    like columns: the first/last rows of an up-scale blend a row with itself)."""
+    rng = np.random.default_rng(400)
+    img = rng.integers(0, 256, src, dtype=np.uint8)
+    assert np.array_equal(oracle.resize(img, dst[1], dst[0]), cv2.resize(img, (dst[1], dst[0])))

@@ -77,6 +77,7 @@ SIGNATURES = {
     "orbx_projection_rounds": (_i, []),
     "orbx_undistort_keypoints": (_i, [_i, _vp, _i, _vp, _vp, _i, _vp, _vp]),
     "orbx_rectifier_create": (_i, [_i, _vp, _vp, _sz, _i, _i, C.POINTER(_vp)]),
+    "orbx_resizer_create": (_i, [_i, _i, _i, _i, _i, C.POINTER(_vp)]),
     "orbx_rectifier_destroy": (None, [_vp]),
     "orbx_remap": (_i, [_vp, _vp, _i, _i, _sz, _vp, _sz]),
     "orbx_remap_device": (_i, [_vp, _vp, _i, _i, _sz, _sz, _i, _vp, _sz, _sz, _vp]),

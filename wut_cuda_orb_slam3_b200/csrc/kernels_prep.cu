@@ -95,6 +95,41 @@ __global__ void __launch_bounds__(128) remap_kernel(const uint8_t* __restrict__ 
     }
 }
 
+
+// cv::resize(src, dst, newImSize) (INTER_LINEAR, 8UC1) of System::TrackStereo / TrackMonocular (src/System.cc:261-263, 330, 407):
+// OpenCV's 11-bit fixed-point bilinear (or the exact-2x INTER_AREA average) from per-column / per-row tables
+// {s0 | s1 << 16, c0 | c1 << 16} evaluated once on the host with OpenCV's float formula — the same arithmetic as the pyramid.
+__global__ void __launch_bounds__(128) resize_kernel(const uint8_t* __restrict__ src, size_t spitch, size_t sframe,
+                                                     const uint2* __restrict__ xtab, const uint2* __restrict__ ytab, int area2x,
+                                                     uint8_t* __restrict__ dst, int dw, int dh, size_t dpitch, size_t dframe)
+{
+    const int x4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4, y = blockIdx.y;
+    if (x4 >= dw) return;
+    const uint2 yt = __ldg(ytab + y);
+    const uint8_t* S0 = src + (size_t)blockIdx.z * sframe + (size_t)(yt.x & 0xffff) * spitch;
+    const uint8_t* S1 = src + (size_t)blockIdx.z * sframe + (size_t)(yt.x >> 16) * spitch;
+    const int b0 = (int)(short)(yt.y & 0xffff), b1 = (int)(short)(yt.y >> 16);
+    uint8_t* d = dst + (size_t)blockIdx.z * dframe + (size_t)y * dpitch + x4;
+    uint32_t out = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        if (x4 + j >= dw) break;
+        const uint2 xt = __ldg(xtab + x4 + j);
+        const int sx0 = xt.x & 0xffff, sx1 = xt.x >> 16;
+        const int a0 = (int)(short)(xt.y & 0xffff), a1 = (int)(short)(xt.y >> 16);
+        const int p00 = __ldg(S0 + sx0), p01 = __ldg(S0 + sx1), p10 = __ldg(S1 + sx0), p11 = __ldg(S1 + sx1);
+        uint32_t v;
+        if (area2x) v = (uint32_t)((p00 + p01 + p10 + p11 + 2) >> 2);
+        else {
+            const int r0 = p00 * a0 + p01 * a1, r1 = p10 * a0 + p11 * a1;
+            v = (uint32_t)((((b0 * (r0 >> 4)) >> 16) + ((b1 * (r1 >> 4)) >> 16) + 2) >> 2) & 0xffu;
+        }
+        out |= v << (8 * j);
+    }
+    if (x4 + 4 <= dw && (reinterpret_cast<size_t>(d) & 3) == 0) *reinterpret_cast<uint32_t*>(d) = out;
+    else for (int j = 0; j < 4 && x4 + j < dw; ++j) d[j] = (uint8_t)(out >> (8 * j));
+}
+
 cudaError_t launch_undistort(const orbx_keypoint* d_in, int n, const UndistortParams& p, orbx_keypoint* d_out, cudaStream_t st)
 {
     if (n <= 0) return cudaSuccess;
@@ -115,6 +150,15 @@ cudaError_t launch_remap(const uint8_t* d_src, int sw, int sh, size_t spitch, si
 {
     if (n_frames <= 0) return cudaSuccess;
     remap_kernel<<<dim3((dw + 511) / 512, dh, n_frames), 128, 0, st>>>(d_src, sw, sh, spitch, sframe, d_packed, d_dst, dw, dh, dpitch, dframe);
+    count_launch();
+    return cudaGetLastError();
+}
+
+cudaError_t launch_resize(const uint8_t* d_src, size_t spitch, size_t sframe, const uint2* d_xtab, const uint2* d_ytab, int area2x,
+                          uint8_t* d_dst, int dw, int dh, size_t dpitch, size_t dframe, int n_frames, cudaStream_t st)
+{
+    if (n_frames <= 0) return cudaSuccess;
+    resize_kernel<<<dim3((dw + 511) / 512, dh, n_frames), 128, 0, st>>>(d_src, spitch, sframe, d_xtab, d_ytab, area2x, d_dst, dw, dh, dpitch, dframe);
     count_launch();
     return cudaGetLastError();
 }

@@ -235,6 +235,8 @@ cudaError_t launch_undistort(const orbx_keypoint* d_in, int n, const UndistortPa
 cudaError_t launch_remap_quantise(const float* d_mapx, const float* d_mapy, size_t map_step, int dw, int dh, uint2* d_packed, cudaStream_t st);
 cudaError_t launch_remap(const uint8_t* d_src, int sw, int sh, size_t spitch, size_t sframe, const uint2* d_packed, uint8_t* d_dst, int dw,
                          int dh, size_t dpitch, size_t dframe, int n_frames, cudaStream_t st);
+cudaError_t launch_resize(const uint8_t* d_src, size_t spitch, size_t sframe, const uint2* d_xtab, const uint2* d_ytab, int area2x,
+                          uint8_t* d_dst, int dw, int dh, size_t dpitch, size_t dframe, int n_frames, cudaStream_t st);
 
 // host helpers shared by api.cu / api_bow.cu / api_proj.cu
 int fail(int code, const char* fmt, ...);

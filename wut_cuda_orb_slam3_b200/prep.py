@@ -22,7 +22,16 @@ def undistort_keypoints(keypoints, K, dist, new_K=None, device=0):
 class Rectifier:
     """cv::remap(im, out, M1, M2, INTER_LINEAR) with fixed CV_32FC1 maps (cv::initUndistortRectifyMap), maps kept on the device."""
 
-    def __init__(self, map_x, map_y, device=0):
+    def __init__(self, map_x=None, map_y=None, device=0, resize=None):
+        """resize=(src_rows, src_cols, dst_rows, dst_cols) builds the cv::resize(im, out, newImSize) variant instead."""
+        self.device = device
+        if resize is not None:
+            sr, sc, dr, dc = resize
+            self.shape = (dr, dc)
+            h = C.c_void_p()
+            check(lib().orbx_resizer_create(device, sr, sc, dr, dc, C.byref(h)))
+            self._h = h
+            return
         mx = np.ascontiguousarray(map_x, np.float32); my = np.ascontiguousarray(map_y, np.float32)
         assert mx.shape == my.shape and mx.ndim == 2
         self.shape = mx.shape
