@@ -1,0 +1,44 @@
+#!/bin/sh
+# build_ref.sh — compiles the REFERENCE's own functions of the hot path into oracle/_ref/libref.so (test infrastructure).
+#
+# The reference as a whole cannot be built here (OpenCV / OpenCL / boost / Eigen / Sophus headers and its cmake build are not in
+# this image), but the functions that carry the reference-owned logic of the path are plain C++ over a handful of OpenCV
+# containers.  This recipe slices them — by line range, from the sources WHERE THEY LIE under /root/reference, at build time —
+# into oracle/_ref/gen/*.inc (git-ignored, never committed) and compiles them against oracle/ref_shim/ (container types only;
+# the one OpenCV algorithm a slice calls, cv::FAST, is forwarded to the cv2-pinned oracle).  tests/test_ref_pin.py then checks
+# the oracle against this library and tests/golden/make_ref_golden.py freezes its answers as fixtures for the GPU box.
+#
+# Without /root/reference (the GPU box) the script keeps whatever oracle/_ref/libref.so travelled with the snapshot.
+set -e
+HERE=$(cd "$(dirname "$0")" && pwd)
+REF=${ORB_REFERENCE_ROOT:-/root/reference}
+OUT="$HERE/_ref"
+if [ ! -d "$REF/src" ]; then
+    echo "build_ref: $REF not present, keeping prebuilt $OUT/libref.so (if any)"
+    exit 0
+fi
+mkdir -p "$OUT/gen"
+slice() { sed -n "$2,$3p" "$REF/$1" > "$OUT/gen/$4"; }
+# --- extractor ---------------------------------------------------------------------------------------------------------
+slice include/ORBextractor.h   39 120 ORBextractor_classes.inc       # class ExtractorNode, class ORBextractor
+slice src/ORBextractor.cc      99 149 orb_constants_descriptor.inc   # PATCH_SIZE..factorPI, computeOrbDescriptor
+slice src/ORBextractor.cc     151 408 orb_bit_pattern.inc            # bit_pattern_31_
+slice src/ORBextractor.cc     410 468 orb_ctor.inc                   # ORBextractor::ORBextractor (tables, umax)
+slice src/ORBextractor.cc     515 582 orb_divide_compare.inc         # ExtractorNode::DivideNode, compareNodes
+slice src/ORBextractor.cc     584 774 orb_distribute_octree.inc      # ORBextractor::DistributeOctTree
+slice src/ORBextractor.cc     867 950 orb_tile_calc_keypoints.inc    # tileCalcKeypoints (the CPU cell loop)
+slice src/ORBextractor.cc    1283 1303 orb_pack_loop.inc             # operator(): scale + lapping-area placement loop
+# --- matcher / frame grid ----------------------------------------------------------------------------------------------
+slice src/ORBmatcher3.cc      592 653 matcher_maxima_distance.inc    # ComputeThreeMaxima, DescriptorDistance
+slice src/ORBmatcher1.cc       45 223 matcher_projection_map.inc     # SearchByProjection(Frame, MapPoints), RadiusByViewingCos
+slice src/ORBmatcher3.cc      256 590 matcher_projection_frames.inc  # SearchByProjection(Current, Last) and (Current, KeyFrame)
+slice src/ORBmatcher1.cc      225 427 matcher_bow_kf_frame.inc       # SearchByBoW(KeyFrame*, Frame&, ...)
+slice src/ORBmatcher2.cc       36 177 matcher_bow_kf_kf.inc          # SearchByBoW(KeyFrame*, KeyFrame*, ...)
+slice src/Frame.cc            841 1011 frame_stereo_matches.inc      # Frame::ComputeStereoMatches
+slice src/Frame.cc            387 418 frame_assign_grid.inc          # Frame::AssignFeaturesToGrid
+slice src/Frame.cc            687 766 frame_area_posingrid.inc       # Frame::GetFeaturesInArea, Frame::PosInGrid
+CXX=${CXX:-g++}
+# plain -O3 as the reference builds (CMakeLists.txt:105-107), no FMA contraction
+$CXX -O3 -std=c++17 -fPIC -ffp-contract=off -w -I"$HERE/ref_shim" -I"$OUT/gen" -shared -o "$OUT/libref.so" \
+    "$HERE/ref_shim/ref_wrapper.cpp" -L"$HERE/_build" -lorb_oracle -Wl,-rpath,'$ORIGIN/../_build'
+echo "build_ref: built $OUT/libref.so from $REF"

@@ -4,12 +4,17 @@
 // (kpmrozowski/wut-cuda-orb-slam3).  Only tests/, __graft_entry__.smoke() and bench.py's
 // cpu_baseline / --impl reference legs may load this library, and only as the checker / baseline.
 //
-// Parity pinning status: the reference ships NO golden vectors or value-asserting tests for this
-// path and cannot be compiled here (needs OpenCV/OpenCL/boost C++ headers), so the
-// reference-owned logic below (tables, cell grid, octree, packing, stereo, matcher) is pinned only
-// by line-by-line restatement => "parity unpinned" for those parts.  The OpenCV-owned arithmetic
-// (resize, copyMakeBorder, FAST, GaussianBlur, fastAtan2, BFMatcher.knnMatch) IS pinned: tests/
-// check every primitive bit-exact against cv2 4.13 (the same third-party code the reference calls).
+// Parity pinning status: PINNED on both sides.
+//  * OpenCV-owned arithmetic (resize, copyMakeBorder, FAST, GaussianBlur, fastAtan2, BFMatcher.knnMatch, cvtColor) is checked
+//    bit-exact against cv2 4.13 — the same third-party code the reference calls — in tests/test_oracle_cv2.py.
+//  * Reference-owned logic (constructor tables, DistributeOctTree incl. its std::sort tie behaviour, the cell loop
+//    tileCalcKeypoints, computeOrbDescriptor + bit_pattern_31_, operator()'s placement loop, DescriptorDistance,
+//    ComputeThreeMaxima, ComputeStereoMatches, both SearchByBoW overloads) is checked against the REFERENCE'S OWN FUNCTIONS,
+//    compiled from the sources where they lie by oracle/build_ref.sh into oracle/_ref/libref.so (tests/test_ref_pin.py), and
+//    against tests/golden/ref_golden.json, frozen from that library (tests/golden/make_ref_golden.py).
+//  * Not pinned against compiled reference code (restatement only): SearchForTriangulation (needs Eigen/Sophus and the camera
+//    models), the DBoW2 transform (checked against an independent Python restatement), IC_Angle (the fork deleted the CPU
+//    function; the oracle follows the OpenCL kernel's summation and OpenCV's fastAtan2, which is cv2-pinned).
 //
 // Every function cites the reference file:line (paths relative to /root/reference) it follows.
 #include <algorithm>

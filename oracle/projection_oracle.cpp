@@ -8,8 +8,9 @@
 //   ORBmatcher::SearchByProjection(Frame& Current, KeyFrame*, sAlreadyFound, th, ORBdist)       src/ORBmatcher3.cc:469-578
 // Only the Nleft == -1 paths (one camera, rectified stereo, RGB-D) are restated; the two-fisheye rig (Nleft != -1) is out of
 // scope.  Eigen/Sophus arithmetic (the projection of the map point into the frame) stays with the caller: the
-// functions take the projected coordinates.  Parity pinning: reference-owned logic with no reference fixtures => "parity
-// unpinned" (restatement only), like the other matcher functions in orb_oracle.cpp.
+// functions take the projected coordinates.  Parity pinning: PINNED — tests/test_ref_pin.py checks every function of this
+// file against the reference's own AssignFeaturesToGrid / GetFeaturesInArea / PosInGrid / SearchByProjection code, compiled
+// from /root/reference by oracle/build_ref.sh (oracle/_ref/libref.so), and tests/golden/ref_golden.json freezes its answers.
 #include <algorithm>
 #include <cmath>
 #include <cstdint>

@@ -73,3 +73,18 @@ def test_cuda_knn2_golden():
     idx, dist = orbx.ORBmatcher().knn2(q, db)
     assert crc(idx) == g["idx_crc"] and crc(dist) == g["dist_crc"]
     assert idx[:8].tolist() == g["first"][0] and dist[:8].tolist() == g["first"][1]
+
+
+def test_oracle_reproduces_reference_golden(oracle):
+    """tests/golden/ref_golden.json holds answers of the REFERENCE's own compiled functions (oracle/_ref, made by
+    tests/golden/make_ref_golden.py in the dev container); the oracle must reproduce every one of them."""
+    import json
+    import os
+
+    from tests import ref_cases
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_golden.json")) as f:
+        gold = json.load(f)["cases"]
+    got = ref_cases.run_all(oracle)
+    assert set(got) == set(gold)
+    bad = [k for k in gold if got[k] != gold[k]]
+    assert not bad, bad
