@@ -34,11 +34,25 @@ slice src/ORBmatcher1.cc       45 223 matcher_projection_map.inc     # SearchByP
 slice src/ORBmatcher3.cc      256 590 matcher_projection_frames.inc  # SearchByProjection(Current, Last) and (Current, KeyFrame)
 slice src/ORBmatcher1.cc      225 427 matcher_bow_kf_frame.inc       # SearchByBoW(KeyFrame*, Frame&, ...)
 slice src/ORBmatcher2.cc       36 177 matcher_bow_kf_kf.inc          # SearchByBoW(KeyFrame*, KeyFrame*, ...)
+slice src/ORBmatcher2.cc      179 418 matcher_triangulation.inc      # SearchForTriangulation
+slice src/CameraModels/Pinhole.cpp 114 128 pinhole_epipolar_tail.inc # Pinhole::epipolarConstrain after F12 (line test)
+slice src/MapPoint.cc         368 397 mappoint_distinctive_core.inc  # ComputeDistinctiveDescriptors: distance matrix, least median
 slice src/Frame.cc            841 1011 frame_stereo_matches.inc      # Frame::ComputeStereoMatches
 slice src/Frame.cc            387 418 frame_assign_grid.inc          # Frame::AssignFeaturesToGrid
 slice src/Frame.cc            687 766 frame_area_posingrid.inc       # Frame::GetFeaturesInArea, Frame::PosInGrid
-CXX=${CXX:-g++}
+# --- DBoW2 (vendored under Thirdparty/DBoW2) -----------------------------------------------------------------------------
+D=Thirdparty/DBoW2/DBoW2
+slice $D/BowVector.cpp         34 84 dbow2_bowvector.inc             # addWeight, addIfNotExist, normalize
+slice $D/FeatureVector.cpp     31 45 dbow2_featurevector.inc         # addFeature
+slice $D/FORB.cpp              81 101 dbow2_forb_distance.inc        # FORB::distance
+slice $D/FORB.cpp             120 135 dbow2_forb_fromstring.inc      # FORB::fromString
+slice $D/ScoringObject.cpp     23 68 dbow2_l1_score.inc              # L1Scoring::score
+slice $D/TemplatedVocabulary.h 1126 1196 dbow2_transform_all.inc     # transform(features, BowVector, FeatureVector, levelsup)
+slice $D/TemplatedVocabulary.h 1217 1259 dbow2_transform_one.inc     # transform(feature, word_id, weight, nid, levelsup)
+slice $D/TemplatedVocabulary.h 1337 1424 dbow2_load_text.inc         # loadFromTextFile
+# the system compiler links libstdc++ dynamically; a toolchain that links it statically breaks iostreams in a dlopen()ed library
+if [ -x /usr/bin/g++ ]; then CXX=/usr/bin/g++; else CXX=${CXX:-g++}; fi
 # plain -O3 as the reference builds (CMakeLists.txt:105-107), no FMA contraction
 $CXX -O3 -std=c++17 -fPIC -ffp-contract=off -w -I"$HERE/ref_shim" -I"$OUT/gen" -shared -o "$OUT/libref.so" \
-    "$HERE/ref_shim/ref_wrapper.cpp" -L"$HERE/_build" -lorb_oracle -Wl,-rpath,'$ORIGIN/../_build'
+    "$HERE/ref_shim/ref_wrapper.cpp" "$HERE/ref_shim/ref_dbow2_wrapper.cpp" -L"$HERE/_build" -lorb_oracle -Wl,-rpath,'$ORIGIN/../_build'
 echo "build_ref: built $OUT/libref.so from $REF"

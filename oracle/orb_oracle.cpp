@@ -9,12 +9,12 @@
 //    bit-exact against cv2 4.13 — the same third-party code the reference calls — in tests/test_oracle_cv2.py.
 //  * Reference-owned logic (constructor tables, DistributeOctTree incl. its std::sort tie behaviour, the cell loop
 //    tileCalcKeypoints, computeOrbDescriptor + bit_pattern_31_, operator()'s placement loop, DescriptorDistance,
-//    ComputeThreeMaxima, ComputeStereoMatches, both SearchByBoW overloads) is checked against the REFERENCE'S OWN FUNCTIONS,
-//    compiled from the sources where they lie by oracle/build_ref.sh into oracle/_ref/libref.so (tests/test_ref_pin.py), and
-//    against tests/golden/ref_golden.json, frozen from that library (tests/golden/make_ref_golden.py).
-//  * Not pinned against compiled reference code (restatement only): SearchForTriangulation (needs Eigen/Sophus and the camera
-//    models), the DBoW2 transform (checked against an independent Python restatement), IC_Angle (the fork deleted the CPU
-//    function; the oracle follows the OpenCL kernel's summation and OpenCV's fastAtan2, which is cv2-pinned).
+//    ComputeThreeMaxima, ComputeStereoMatches, both SearchByBoW overloads, SearchForTriangulation, ComputeDistinctiveDescriptors,
+//    the DBoW2 transform / L1 score / text loader) is checked against the REFERENCE'S OWN FUNCTIONS, compiled from the sources
+//    where they lie by oracle/build_ref.sh into oracle/_ref/libref.so (tests/test_ref_pin.py), and against
+//    tests/golden/ref_golden.json, frozen from that library (tests/golden/make_ref_golden.py).
+//  * Not pinned against compiled reference code (restatement only): IC_Angle (the fork deleted the CPU function; the oracle
+//    follows upstream's summation pattern and OpenCV's fastAtan2, which is cv2-pinned) and ComputePyramid's glue.
 //
 // Every function cites the reference file:line (paths relative to /root/reference) it follows.
 #include <algorithm>

@@ -56,6 +56,7 @@ struct Mat {
     Mat() {}
     Mat(int r, int c, int /*type*/) : store(std::make_shared<std::vector<uchar>>((size_t)r * c)), data(store->data()), rows(r), cols(c), step((size_t)c) {}
     Mat(int r, int c, int /*type*/, void* d, size_t s = 0) : data((uchar*)d), rows(r), cols(c), step(s ? s : (size_t)c) {}
+    void create(int r, int c, int /*type*/) { store = std::make_shared<std::vector<uchar>>((size_t)r * c); data = store->data(); rows = r; cols = c; step = (size_t)c; }
     bool empty() const { return !data || rows == 0 || cols == 0; }
     int type() const { return CV_8UC1; }
     template <typename T> T& at(int y, int x) { return *(T*)(data + (size_t)y * step + x * sizeof(T)); }

@@ -20,6 +20,10 @@ struct Vector3f {
     Vector3f operator-(const Vector3f& o) const { return Vector3f(v[0] - o.v[0], v[1] - o.v[1], v[2] - o.v[2]); }
     float norm() const { return std::sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]); }
 };
+struct Matrix3f {
+    float m[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
+    float operator()(int i, int j) const { return m[i][j]; }
+};
 struct Vector2f { float v[2] = {0, 0}; Vector2f() {} Vector2f(float a, float b) { v[0] = a; v[1] = b; } float operator()(int i) const { return v[i]; } };
 }  // namespace Eigen
 namespace Sophus {
@@ -29,6 +33,8 @@ struct SE3f {
     Eigen::Vector3f t;
     SE3f inverse() const { SE3f r; r.t = Eigen::Vector3f(-t(0), -t(1), -t(2)); return r; }
     Eigen::Vector3f translation() const { return t; }
+    Eigen::Matrix3f rotationMatrix() const { return Eigen::Matrix3f(); }
+    SE3f operator*(const SE3f& o) const { SE3f r; r.t = Eigen::Vector3f(t(0) + o.t(0), t(1) + o.t(1), t(2) + o.t(2)); return r; }
     Eigen::Vector3f operator*(const Eigen::Vector3f& p) const { return Eigen::Vector3f(p(0) + t(0), p(1) + t(1), p(2) + t(2)); }
 };
 }  // namespace Sophus
@@ -78,7 +84,17 @@ public:
     float GetMaxDistanceInvariance() { return mfMaxDistance; }
     int PredictScale(const float&, Frame*) { return predictedLevel; }
 };
-struct GeometricCamera { Eigen::Vector2f project(const Eigen::Vector3f& p) { return Eigen::Vector2f(p(0), p(1)); } };
+struct GeometricCamera {
+    Eigen::Matrix3f mF12;                                // K1^-T [t12]x R12 K2^-1, evaluated by the caller (Eigen) in the reference
+    Eigen::Vector2f project(const Eigen::Vector3f& p) { return Eigen::Vector2f(p(0), p(1)); }
+    // Pinhole::epipolarConstrain (src/CameraModels/Pinhole.cpp:107-129): the slice starts after the Eigen evaluation of F12
+    bool epipolarConstrain(GeometricCamera* /*pCamera2*/, const cv::KeyPoint& kp1, const cv::KeyPoint& kp2, const Eigen::Matrix3f& /*R12*/,
+                           const Eigen::Vector3f& /*t12*/, const float sigmaLevel, const float unc)
+    {
+        const Eigen::Matrix3f& F12 = mF12;
+#include "pinhole_epipolar_tail.inc"
+    }
+};
 
 class Frame {                                           // the members the slices read (include/Frame.h)
 public:
@@ -115,8 +131,17 @@ public:
     std::vector<cv::KeyPoint> mvKeysUn, mvKeys, mvKeysRight;
     DBoW2::FeatureVector mFeatVec;
     cv::Mat mDescriptors;
-    int NLeft = -1;
+    int NLeft = -1, N = 0;
     GeometricCamera *mpCamera = nullptr, *mpCamera2 = nullptr;
+    std::vector<float> mvuRight, mvScaleFactors, mvLevelSigma2;
+    Sophus::SE3f mTcw, mTwc, mTrw, mTwr;
+    Eigen::Vector3f mOw;
+    Sophus::SE3f GetPose() { return mTcw; }
+    Sophus::SE3f GetPoseInverse() { return mTwc; }
+    Sophus::SE3f GetRightPose() { return mTrw; }
+    Sophus::SE3f GetRightPoseInverse() { return mTwr; }
+    Eigen::Vector3f GetCameraCenter() { return mOw; }
+    MapPoint* GetMapPoint(const size_t& idx) { return mvpMapPoints[idx]; }
     std::vector<MapPoint*> GetMapPointMatches() { return mvpMapPoints; }
 };
 
@@ -126,6 +151,8 @@ public:
     static int DescriptorDistance(const cv::Mat& a, const cv::Mat& b);
     int SearchByBoW(KeyFrame* pKF, Frame& F, std::vector<MapPoint*>& vpMapPointMatches);
     int SearchByBoW(KeyFrame* pKF1, KeyFrame* pKF2, std::vector<MapPoint*>& vpMatches12);
+    int SearchForTriangulation(KeyFrame* pKF1, KeyFrame* pKF2, std::vector<std::pair<size_t, size_t>>& vMatchedPairs, const bool bOnlyStereo,
+                               const bool bCoarse = false);
     int SearchByProjection(Frame& F, const std::vector<MapPoint*>& vpMapPoints, const float th = 3, const bool bFarPoints = false,
                            const float thFarPoints = 50.0f);
     int SearchByProjection(Frame& CurrentFrame, const Frame& LastFrame, const float th, const bool bMono);
@@ -148,6 +175,7 @@ const int ORBmatcher::HISTO_LENGTH = 30;
 #include "matcher_bow_kf_frame.inc"
 #include "matcher_bow_kf_kf.inc"
 #include "frame_stereo_matches.inc"
+#include "matcher_triangulation.inc"
 
 }  // namespace ORB_SLAM3
 
@@ -459,6 +487,54 @@ int refc_search_by_bow_kf_kf(const uint8_t* desc1, const float* angle1, const ui
     std::vector<MapPoint*> matches;
     const int nm = matcher.SearchByBoW(&K1, &K2, matches);
     for (int i = 0; i < n1; ++i) out[i] = matches[i] ? (int32_t)(matches[i] - m2.data()) : -1;
+    return nm;
+}
+
+// MapPoint::ComputeDistinctiveDescriptors (src/MapPoint.cc:329-401) from the point where the observed descriptors are gathered.
+int refc_distinctive_descriptor(const uint8_t* desc, int n)
+{
+    std::vector<cv::Mat> vDescriptors;
+    for (int i = 0; i < n; ++i) vDescriptors.push_back(cv::Mat(1, 32, CV_8U, (void*)(desc + (size_t)i * 32)));
+#include "mappoint_distinctive_core.inc"
+    return BestIdx;
+}
+
+// SearchForTriangulation(pKF1, pKF2, vMatchedPairs, bOnlyStereo, bCoarse), single pinhole camera on both key frames.  F12 and the
+// epipole are supplied (the reference evaluates them with Eigen/Sophus); out[i] = matched feature of KF2 or -1.
+int refc_search_for_triangulation(const KP28* kp1, const uint8_t* desc1, const uint8_t* free1, const uint8_t* stereo1, int n1, int fv1_n,
+                                  const uint32_t* fv1_nodes, const int32_t* fv1_off, const uint32_t* fv1_idx, const KP28* kp2,
+                                  const uint8_t* desc2, const uint8_t* free2, const uint8_t* stereo2, int n2, int fv2_n,
+                                  const uint32_t* fv2_nodes, const int32_t* fv2_off, const uint32_t* fv2_idx, const float* F12,
+                                  const float* ep, const float* scale2, const float* sigma2_2, int nlev, int bOnlyStereo, int bCoarse,
+                                  int checkOri, int32_t* out)
+{
+    KeyFrame K1, K2;
+    GeometricCamera cam1, cam2;
+    for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) cam1.mF12.m[r][c] = F12[r * 3 + c];
+    K1.mpCamera = &cam1; K2.mpCamera = &cam2;
+    MapPoint some;
+    auto fill = [&](KeyFrame& K, const KP28* kp, const uint8_t* desc, const uint8_t* fr, const uint8_t* st, int n) {
+        K.N = n;
+        K.mvKeysUn.resize(n);
+        for (int i = 0; i < n; ++i) K.mvKeysUn[i] = to_cv(kp[i]);
+        K.mvKeys = K.mvKeysUn;
+        K.mvpMapPoints.assign(n, nullptr);
+        K.mvuRight.assign(n, -1.0f);
+        for (int i = 0; i < n; ++i) { if (!fr[i]) K.mvpMapPoints[i] = &some; if (st[i]) K.mvuRight[i] = 1.0f; }
+        K.mDescriptors = cv::Mat(n, 32, CV_8U, (void*)desc);
+    };
+    fill(K1, kp1, desc1, free1, stereo1, n1);
+    fill(K2, kp2, desc2, free2, stereo2, n2);
+    K2.mvScaleFactors.assign(scale2, scale2 + nlev); K2.mvLevelSigma2.assign(sigma2_2, sigma2_2 + nlev);
+    K1.mvScaleFactors = K2.mvScaleFactors; K1.mvLevelSigma2 = K2.mvLevelSigma2;
+    K1.mOw = Eigen::Vector3f(ep[0], ep[1], 1.0f);          // identity poses: C2 = Cw, project() keeps (x, y) => ep as given
+    fill_featvec(K1.mFeatVec, fv1_n, fv1_nodes, fv1_off, fv1_idx);
+    fill_featvec(K2.mFeatVec, fv2_n, fv2_nodes, fv2_off, fv2_idx);
+    ORBmatcher matcher(0.6f, checkOri != 0);
+    std::vector<std::pair<size_t, size_t>> pairs;
+    const int nm = matcher.SearchForTriangulation(&K1, &K2, pairs, bOnlyStereo != 0, bCoarse != 0);
+    for (int i = 0; i < n1; ++i) out[i] = -1;
+    for (auto& pr : pairs) out[pr.first] = (int32_t)pr.second;
     return nm;
 }
 

@@ -104,4 +104,36 @@ def run_all(oracle, ref=None):
     out["bow_kf_frame"] = crc(m, np.int32(nm))
     m, nm = impl.search_by_bow_kf_kf(B["desc_a"], B["angle_a"], B["valid_a"], fva, B["desc_b"], B["angle_b"], B["valid_b"], fvb, 0.8, True)
     out["bow_kf_kf"] = crc(m, np.int32(nm))
+    # SearchForTriangulation (F12 / epipole supplied)
+    from tests import test_bow_cpu
+    kpa, kpb, F, ep, scale, sigma2, fa, fb, sa, sb = test_bow_cpu.tri_inputs(B, 91)
+    m, nm = impl.search_for_triangulation(kpa, B["desc_a"], fa, sa, fva, kpb, B["desc_b"], fb, sb, fvb, F, ep, scale, sigma2, False, False, True)
+    out["triangulation"] = crc(m, np.int32(nm))
+    # ComputeDistinctiveDescriptors
+    rng = np.random.default_rng(17)
+    best = []
+    for n in (1, 2, 5, 20, 61):
+        base = rng.integers(0, 256, 32, dtype=np.uint8)
+        d = np.stack([base ^ (rng.integers(0, 256, 32, dtype=np.uint8) & rng.integers(0, 256, 32, dtype=np.uint8)) for _ in range(n)])
+        best.append(impl.distinctive_descriptor(d))
+    out["distinctive"] = crc(np.array(best, np.int32))
+    # DBoW2 transform + L1 score (the reference side loads the vocabulary with DBoW2's own loadFromTextFile)
+    import os
+    import tempfile
+    if use_ref:
+        from tests import ref_lib
+        with tempfile.TemporaryDirectory() as td:
+            path = os.path.join(td, "voc.txt")
+            bow_synth.write_vocab_text(path, parent, vdesc, weights, k, L, 0, 0)
+            txt = open(path).read().rstrip()
+            open(path, "w").write(txt)
+            v = ref_lib.RefVocabulary(ref, path)
+            (ids, vals), fv = v.transform(B["desc_a"], 2)
+            (ids2, vals2), _ = v.transform(B["desc_b"], 2)
+            sc = v.score((ids, vals), (ids2, vals2))
+    else:
+        (ids, vals), fv = voc.transform(B["desc_a"], 2)
+        (ids2, vals2), _ = voc.transform(B["desc_b"], 2)
+        sc = oracle.bow_score_l1((ids, vals), (ids2, vals2))
+    out["dbow2_transform"] = crc(ids, vals, *fv, np.float64(sc))
     return out

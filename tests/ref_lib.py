@@ -73,6 +73,10 @@ class Ref:
         a = np.ascontiguousarray(a, np.uint8); b = np.ascontiguousarray(b, np.uint8)
         return self.lib.refc_descriptor_distance(_p(a), _p(b))
 
+    def distinctive_descriptor(self, desc):
+        desc = np.ascontiguousarray(desc, np.uint8)
+        return self.lib.refc_distinctive_descriptor(_p(desc), len(desc))
+
     def three_maxima(self, counts):
         c = np.ascontiguousarray(counts, np.int32); ind = np.zeros(3, np.int32)
         self.lib.refc_three_maxima(_p(c), len(c), _p(ind))
@@ -177,6 +181,64 @@ class Ref:
         nm = self.lib.refc_search_by_bow_kf_kf(_p(d1), _p(a1), _p(v1), len(d1), len(n1), _p(n1), _p(o1), _p(i1), _p(d2), _p(a2), _p(v2), len(d2),
                                                len(n2), _p(n2), _p(o2), _p(i2), _f(nnratio), int(check_ori), _p(out))
         return out, nm
+
+    def search_for_triangulation(self, kp1, d1, free1, st1, fv1, kp2, d2, free2, st2, fv2, F12, ep, scale2, sigma2_2, only_stereo=False,
+                                 coarse=False, check_ori=True):
+        kp1 = np.ascontiguousarray(kp1, KP_DTYPE); kp2 = np.ascontiguousarray(kp2, KP_DTYPE)
+        d1 = np.ascontiguousarray(d1, np.uint8); d2 = np.ascontiguousarray(d2, np.uint8)
+        free1 = np.ascontiguousarray(free1, np.uint8); free2 = np.ascontiguousarray(free2, np.uint8)
+        st1 = np.ascontiguousarray(st1, np.uint8); st2 = np.ascontiguousarray(st2, np.uint8)
+        n1, o1, i1 = self._fv(fv1); n2, o2, i2 = self._fv(fv2)
+        F = np.ascontiguousarray(F12, np.float32).reshape(9); e = np.ascontiguousarray(ep, np.float32)
+        sc = np.ascontiguousarray(scale2, np.float32); sg = np.ascontiguousarray(sigma2_2, np.float32)
+        out = np.full(len(d1), -1, np.int32)
+        nm = self.lib.refc_search_for_triangulation(_p(kp1), _p(d1), _p(free1), _p(st1), len(d1), len(n1), _p(n1), _p(o1), _p(i1), _p(kp2), _p(d2),
+                                                    _p(free2), _p(st2), len(d2), len(n2), _p(n2), _p(o2), _p(i2), _p(F), _p(e), _p(sc), _p(sg),
+                                                    len(sc), int(only_stereo), int(coarse), int(check_ori), _p(out))
+        return out, nm
+
+
+class RefVocabulary:
+    """DBoW2's own loadFromTextFile + transform + L1 score (Thirdparty/DBoW2/DBoW2, compiled by oracle/build_ref.sh)."""
+
+    def __init__(self, ref, path):
+        self.lib = ref.lib
+        self.lib.refd_vocab_load_text.restype = _vp
+        self.h = _vp(self.lib.refd_vocab_load_text(str(path).encode()))
+        assert self.h.value, "loadFromTextFile failed"
+
+    def __del__(self):
+        try:
+            self.lib.refd_vocab_destroy(self.h)
+        except Exception:
+            pass
+
+    def info(self):
+        v = [C.c_int(0) for _ in range(5)]
+        self.lib.refd_vocab_info(self.h, *[C.byref(x) for x in v])
+        return dict(n_nodes=v[0].value, n_words=v[1].value, k=v[2].value, L=v[3].value, weighting=v[4].value)
+
+    def transform_features(self, desc, levelsup=4):
+        d = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32)
+        n = len(d)
+        word = np.zeros(n, np.uint32); weight = np.zeros(n, np.float64); node = np.zeros(n, np.uint32)
+        self.lib.refd_transform_features(self.h, _p(d), n, levelsup, _p(word), _p(weight), _p(node))
+        return word, weight, node
+
+    def transform(self, desc, levelsup=4):
+        d = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32)
+        n = len(d)
+        ids = np.zeros(max(n, 1), np.uint32); vals = np.zeros(max(n, 1), np.float64)
+        nodes = np.zeros(max(n, 1), np.uint32); offs = np.zeros(n + 1, np.int32); idx = np.zeros(max(n, 1), np.uint32)
+        nb = C.c_int(0); nf = C.c_int(0)
+        self.lib.refd_transform(self.h, _p(d), n, levelsup, _p(ids), _p(vals), C.byref(nb), _p(nodes), _p(offs), _p(idx), C.byref(nf))
+        return (ids[:nb.value].copy(), vals[:nb.value].copy()), (nodes[:nf.value].copy(), offs[:nf.value + 1].copy(), idx[:offs[nf.value]].copy())
+
+    def score(self, a, b):
+        ia = np.ascontiguousarray(a[0], np.uint32); va = np.ascontiguousarray(a[1], np.float64)
+        ib = np.ascontiguousarray(b[0], np.uint32); vb = np.ascontiguousarray(b[1], np.float64)
+        self.lib.refd_score_l1.restype = C.c_double
+        return self.lib.refd_score_l1(_p(ia), _p(va), len(ia), _p(ib), _p(vb), len(ib))
 
 
 _cached = None

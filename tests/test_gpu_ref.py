@@ -119,3 +119,25 @@ def test_search_by_bow_vs_reference(ref, oracle):
                                     nnratio=0.8)
     want, wnm = ref.search_by_bow_kf_kf(B["desc_a"], B["angle_a"], B["valid_a"], t(fva), B["desc_b"], B["angle_b"], B["valid_b"], t(fvb), 0.8, True)
     assert nm == wnm and nm > 50 and np.array_equal(ma, want)
+
+
+def test_bow_transform_vs_dbow2(ref, tmp_path):
+    """The CUDA vocabulary descent + host BowVector / FeatureVector assembly against DBoW2's own compiled transform, both
+    loading the same ORBvoc-format file (no trailing newline: see tests/test_ref_pin.py)."""
+    k, L = 10, 4
+    parent, vdesc, weights = bow_synth.make_vocab(611, k, L)
+    path = tmp_path / "voc.txt"
+    bow_synth.write_vocab_text(path, parent, vdesc, weights, k, L, 0, 0)
+    open(path, "w").write(open(path).read().rstrip())
+    rv = ref_lib.RefVocabulary(ref, path)
+    voc = orbx.ORBVocabulary.loadFromTextFile(path)
+    feats = bow_synth.make_features(612, vdesc, parent, 3000)
+    for a, b in zip(voc.transform_features(feats, 4), rv.transform_features(feats, 4)):
+        assert np.array_equal(a, b)
+    (ids, vals), fv = voc.transform(feats, 4)
+    (rid, rval), rfv = rv.transform(feats, 4)
+    assert np.array_equal(ids, rid) and vals.tobytes() == rval.tobytes()
+    for a, b in zip((fv.node_ids, fv.offsets, fv.indices), rfv):
+        assert np.array_equal(a, b)
+    (ids2, vals2), _ = voc.transform(bow_synth.make_features(613, vdesc, parent, 2500), 4)
+    assert voc.score((ids, vals), (ids2, vals2)) == rv.score((rid, rval), (ids2, vals2))

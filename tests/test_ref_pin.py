@@ -224,3 +224,57 @@ def test_search_by_bow_kf_kf_matches_reference(oracle, ref, check_ori, ratio, se
     got, nm = oracle.search_by_bow_kf_kf(*a)
     want, wnm = ref.search_by_bow_kf_kf(*a)
     assert nm == wnm and nm > 20 and np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("only_stereo,coarse,check_ori,seed", [(False, False, True, 91), (True, False, True, 92), (False, True, True, 93),
+                                                               (False, False, False, 94)])
+def test_search_for_triangulation_matches_reference(oracle, ref, only_stereo, coarse, check_ori, seed):
+    """ORBmatcher::SearchForTriangulation + the line test of Pinhole::epipolarConstrain (F12 and the epipole supplied)."""
+    from tests import test_bow_cpu
+    k, L = 4, 3
+    parent, desc, weights = bow_synth.make_vocab(seed, k, L)
+    voc = oracle.vocabulary(parent, desc, weights, k, L)
+    P = bow_synth.make_pair(seed + 100, desc, parent, 900, 900)
+    _, fva = voc.transform(P["desc_a"], 2); _, fvb = voc.transform(P["desc_b"], 2)
+    kpa, kpb, F, ep, scale, sigma2, fa, fb, sa, sb = test_bow_cpu.tri_inputs(P, seed)
+    a = (kpa, P["desc_a"], fa, sa, fva, kpb, P["desc_b"], fb, sb, fvb, F, ep, scale, sigma2, only_stereo, coarse, check_ori)
+    got, nm = oracle.search_for_triangulation(*a)
+    want, wnm = ref.search_for_triangulation(*a)
+    assert nm == wnm and nm > (3 if not coarse else 30) and np.array_equal(got, want)
+
+
+def test_distinctive_descriptor_matches_reference(oracle, ref):
+    rng = np.random.default_rng(17)
+    for n in [1, 2, 3, 4, 7, 20, 61, 150]:
+        for _ in range(20):
+            base = rng.integers(0, 256, 32, dtype=np.uint8)
+            d = np.stack([base ^ (rng.integers(0, 256, 32, dtype=np.uint8) & rng.integers(0, 256, 32, dtype=np.uint8) & rng.integers(0, 256, 32, dtype=np.uint8))
+                          for _ in range(n)])
+            if n > 3:
+                d[n - 1] = d[0]                      # duplicates: equal medians, the first index must win
+            assert oracle.distinctive_descriptor(d) == ref.distinctive_descriptor(d)
+
+
+@pytest.mark.parametrize("k,L,levelsup,weighting,seed", [(10, 4, 4, 0, 5), (10, 4, 2, 0, 6), (4, 3, 1, 1, 7), (3, 6, 4, 2, 8), (5, 3, 2, 3, 9)])
+def test_dbow2_transform_and_score_match_reference(oracle, ref, tmp_path, k, L, levelsup, weighting, seed):
+    """DBoW2's own loadFromTextFile / transform / L1 score on a synthetic ORBvoc-format file (written without a trailing newline:
+    loadFromTextFile's `while(!f.eof())` loop turns a trailing empty line into a bogus root child with an uninitialised
+    descriptor — undefined behaviour that the product loader does not reproduce, it skips the empty line)."""
+    parent, desc, weights = bow_synth.make_vocab(seed, k, L)
+    path = tmp_path / "voc.txt"
+    bow_synth.write_vocab_text(path, parent, desc, weights, k, L, 0, weighting)
+    txt = open(path).read().rstrip("\n")
+    open(path, "w").write(txt)
+    rv = ref_lib.RefVocabulary(ref, path)
+    ov = oracle.vocabulary(parent, desc, weights, k, L, 0, weighting)
+    assert rv.info()["n_nodes"] == len(parent) and rv.info()["k"] == k and rv.info()["L"] == L
+    feats = bow_synth.make_features(seed + 50, desc, parent, 1500)
+    for a, b in zip(rv.transform_features(feats, levelsup), ov.transform_features(feats, levelsup)):
+        assert np.array_equal(a, b)
+    (rid, rval), rfv = rv.transform(feats, levelsup)
+    (oid, oval), ofv = ov.transform(feats, levelsup)
+    assert np.array_equal(rid, oid) and rval.tobytes() == oval.tobytes()          # identical doubles
+    for a, b in zip(rfv, ofv):
+        assert np.array_equal(a, b)
+    other = ov.transform(bow_synth.make_features(seed + 51, desc, parent, 1200), levelsup)[0]
+    assert rv.score((rid, rval), other) == oracle.bow_score_l1((oid, oval), other)
