@@ -128,7 +128,8 @@ def test_bow_transform_vs_dbow2(ref, tmp_path):
     parent, vdesc, weights = bow_synth.make_vocab(611, k, L)
     path = tmp_path / "voc.txt"
     bow_synth.write_vocab_text(path, parent, vdesc, weights, k, L, 0, 0)
-    open(path, "w").write(open(path).read().rstrip())
+    txt = open(path).read().rstrip()
+    open(path, "w").write(txt)
     rv = ref_lib.RefVocabulary(ref, path)
     voc = orbx.ORBVocabulary.loadFromTextFile(path)
     feats = bow_synth.make_features(612, vdesc, parent, 3000)
