@@ -107,7 +107,7 @@ static EncodeTiledFn get_encode_tiled()
 struct Slot {
     Workspace ws{};
     cudaStream_t stream = nullptr;
-    cudaEvent_t ev_in = nullptr, ev_done = nullptr;     // H2D complete / compute complete (serial-compute pipeline)
+    cudaEvent_t ev_in = nullptr, ev_done = nullptr, ev_out = nullptr;   // H2D complete / compute complete / D2H complete (serial-compute pipeline)
     int cap_frames = 0;
     // staging for the host-buffer API
     uint8_t* d_in = nullptr; size_t d_in_bytes = 0;
@@ -157,7 +157,7 @@ struct orbx_extractor {
     int max_batch = 0;
     static const int kSlots = 6;
     Slot slots[kSlots];
-    cudaStream_t compute = nullptr;                 // serial-compute pipeline of orbx_extract_batch
+    cudaStream_t compute = nullptr, copy_in = nullptr, copy_out = nullptr;   // serial-compute pipeline of orbx_extract_batch (3 streams)
     int last_frames = 0;           // frames of the last call that are probe-able (slot 0)
     int max_kp = 0;
     // per-stage CUDA-event timing (orbx_profile_begin / orbx_profile_end)
@@ -356,6 +356,7 @@ static int ensure_slot(orbx_extractor* ex, Slot& s, int frames)
     if (!s.ev_in) {
         CU(cudaEventCreateWithFlags(&s.ev_in, cudaEventDisableTiming));
         CU(cudaEventCreateWithFlags(&s.ev_done, cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&s.ev_out, cudaEventDisableTiming));
     }
     if (s.cap_frames >= frames) return ORBX_OK;
     cudaStreamSynchronize(s.stream);
@@ -591,11 +592,13 @@ void orbx_destroy(orbx_extractor* ex)
     if (!ex) return;
     cudaSetDevice(ex->device);
     if (ex->compute) { cudaStreamSynchronize(ex->compute); cudaStreamDestroy(ex->compute); ex->compute = nullptr; }
+    if (ex->copy_in) { cudaStreamSynchronize(ex->copy_in); cudaStreamDestroy(ex->copy_in); ex->copy_in = nullptr; }
+    if (ex->copy_out) { cudaStreamSynchronize(ex->copy_out); cudaStreamDestroy(ex->copy_out); ex->copy_out = nullptr; }
     for (int i = 0; i < orbx_extractor::kSlots; ++i) {
         if (ex->slots[i].stream) cudaStreamSynchronize(ex->slots[i].stream);
         free_slot(ex->slots[i]);
         if (ex->slots[i].stream) cudaStreamDestroy(ex->slots[i].stream);
-        if (ex->slots[i].ev_in) { cudaEventDestroy(ex->slots[i].ev_in); cudaEventDestroy(ex->slots[i].ev_done); }
+        if (ex->slots[i].ev_in) { cudaEventDestroy(ex->slots[i].ev_in); cudaEventDestroy(ex->slots[i].ev_done); cudaEventDestroy(ex->slots[i].ev_out); }
     }
     if (ex->d_tables) cudaFree(ex->d_tables);
     for (cudaEvent_t e : ex->ev_pool) cudaEventDestroy(e);
@@ -711,39 +714,52 @@ int orbx_extract_batch(orbx_extractor* ex, const uint8_t* const* images, int n_f
     std::vector<cudaEvent_t> tev;
     auto mark = [&](cudaStream_t st) { if (trace) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, st); tev.push_back(e); } };
     // Two pipelines.  Small chunks (< 128 frames) run whole on their slot's stream, so that chunks overlap each other (a small
-    // chunk under-fills the GPU: its octree is one partial wave).  Large chunks compute on ONE stream in order, the slot
-    // streams only copy: interleaving the kernels of two big chunks costs ~20 % (measured: 80 k vs 98 k frames/s at 256-frame
-    // chunks), while copies overlap compute either way.  ORBX_BATCH_SERIAL=0/1 overrides.
+    // chunk under-fills the GPU: its octree is one partial wave).  Large chunks compute on ONE stream in order: interleaving the
+    // kernels of two big chunks costs ~20 % (measured: 80 k vs 98 k frames/s at 256-frame chunks).  The serial pipeline uses
+    // exactly three streams — H2D, compute, D2H — tied by per-slot events: with one copy stream per slot (seven streams) two of
+    // them regularly landed on the same hardware connection (8 by default) and a chunk's D2H or the next H2D queued behind an
+    // unrelated copy (90.5 k frames/s; 97.9 k with CUDA_DEVICE_MAX_CONNECTIONS=32; 98 k with three streams at any setting).
+    // ORBX_BATCH_SERIAL=0/1 overrides.
     static const char* serial_env = getenv("ORBX_BATCH_SERIAL");
     const bool serial = serial_env ? atoi(serial_env) != 0 : max_chunk >= 128;
-    if (serial && !ex->compute) CU(cudaStreamCreateWithFlags(&ex->compute, cudaStreamNonBlocking));
+    if (serial && !ex->compute) {
+        CU(cudaStreamCreateWithFlags(&ex->compute, cudaStreamNonBlocking));
+        CU(cudaStreamCreateWithFlags(&ex->copy_in, cudaStreamNonBlocking));
+        CU(cudaStreamCreateWithFlags(&ex->copy_out, cudaStreamNonBlocking));
+    }
+    if (serial)      // earlier work of this extractor on the slot streams (single-frame calls, small batches) must be complete
+        for (int i = 0; i < nslots; ++i) CU(cudaStreamSynchronize(ex->slots[i].stream));
     for (int c = 0; c < nchunks; ++c) {
         Slot& s = ex->slots[c % nslots];
         const int f0 = sched[c].first, nf = sched[c].second;
         cudaStream_t cst = serial ? ex->compute : s.stream;
-        mark(s.stream);
-        // stream order makes reuse of the slot's staging safe: the previous D2H on this stream precedes these H2D copies
-        // (and, in the serial pipeline, that D2H waited for the compute that read the staging)
+        cudaStream_t ist = serial ? ex->copy_in : s.stream, ost = serial ? ex->copy_out : s.stream;
+        // reuse of a slot: its input staging is free once the chunk that used it has been computed, its output staging once
+        // that chunk's D2H has completed (one slot stream orders all of this by itself in the other pipeline)
+        if (serial && c >= nslots) { CU(cudaStreamWaitEvent(ist, s.ev_done, 0)); CU(cudaStreamWaitEvent(cst, s.ev_out, 0)); }
+        mark(ist);
         bool contiguous = step == (size_t)cols;
         for (int f = 1; f < nf && contiguous; ++f) contiguous = images[f0 + f] == images[f0 + f - 1] + dframe;
         if (contiguous) {
-            CU(cudaMemcpyAsync(s.d_in, images[f0], dframe * nf, cudaMemcpyHostToDevice, s.stream));
+            CU(cudaMemcpyAsync(s.d_in, images[f0], dframe * nf, cudaMemcpyHostToDevice, ist));
         } else {
             for (int f = 0; f < nf; ++f)
-                CU(cudaMemcpy2DAsync(s.d_in + (size_t)f * dframe, dpitch, images[f0 + f], step, cols, rows, cudaMemcpyHostToDevice, s.stream));
+                CU(cudaMemcpy2DAsync(s.d_in + (size_t)f * dframe, dpitch, images[f0 + f], step, cols, rows, cudaMemcpyHostToDevice, ist));
         }
-        mark(s.stream);
-        if (serial) { CU(cudaEventRecord(s.ev_in, s.stream)); CU(cudaStreamWaitEvent(cst, s.ev_in, 0)); }
+        mark(ist);
+        if (serial) { CU(cudaEventRecord(s.ev_in, ist)); CU(cudaStreamWaitEvent(cst, s.ev_in, 0)); }
         if ((rc = run_chunk(ex, s, s.d_in, dframe, dpitch, nf, lap0, lap1, s.d_kps, s.d_desc, capacity, s.d_n, s.d_nm, cst))) return rc;
-        if (serial) { CU(cudaEventRecord(s.ev_done, cst)); CU(cudaStreamWaitEvent(s.stream, s.ev_done, 0)); }
-        mark(s.stream);
-        CU(cudaMemcpyAsync(keypoints + (size_t)f0 * capacity, s.d_kps, sizeof(orbx_keypoint) * (size_t)nf * capacity, cudaMemcpyDeviceToHost, s.stream));
-        CU(cudaMemcpyAsync(descriptors + (size_t)f0 * capacity * 32, s.d_desc, (size_t)nf * capacity * 32, cudaMemcpyDeviceToHost, s.stream));
-        CU(cudaMemcpyAsync(n_out + f0, s.d_n, sizeof(int) * nf, cudaMemcpyDeviceToHost, s.stream));
-        CU(cudaMemcpyAsync(n_mono + f0, s.d_nm, sizeof(int) * nf, cudaMemcpyDeviceToHost, s.stream));
-        mark(s.stream);
+        if (serial) { CU(cudaEventRecord(s.ev_done, cst)); CU(cudaStreamWaitEvent(ost, s.ev_done, 0)); }
+        mark(ost);
+        CU(cudaMemcpyAsync(keypoints + (size_t)f0 * capacity, s.d_kps, sizeof(orbx_keypoint) * (size_t)nf * capacity, cudaMemcpyDeviceToHost, ost));
+        CU(cudaMemcpyAsync(descriptors + (size_t)f0 * capacity * 32, s.d_desc, (size_t)nf * capacity * 32, cudaMemcpyDeviceToHost, ost));
+        CU(cudaMemcpyAsync(n_out + f0, s.d_n, sizeof(int) * nf, cudaMemcpyDeviceToHost, ost));
+        CU(cudaMemcpyAsync(n_mono + f0, s.d_nm, sizeof(int) * nf, cudaMemcpyDeviceToHost, ost));
+        mark(ost);
+        if (serial) CU(cudaEventRecord(s.ev_out, ost));
         if (c % nslots == 0) ex->last_frames = nf;
     }
+    if (serial) { CU(cudaStreamSynchronize(ex->copy_out)); CU(cudaStreamSynchronize(ex->compute)); CU(cudaStreamSynchronize(ex->copy_in)); }
     for (int i = 0; i < nslots; ++i) CU(cudaStreamSynchronize(ex->slots[i].stream));
     if (trace) {
         for (int c = 0; c < nchunks; ++c) {

@@ -53,48 +53,82 @@ __global__ void __launch_bounds__(256) remap_quantise_kernel(const float* __rest
     packed[(size_t)y * dw + x] = make_uint2(((uint32_t)sx & 0xffffu) | ((uint32_t)sy << 16), (uint32_t)(sxq & 31) | ((uint32_t)(syq & 31) << 5));
 }
 
-__device__ __forceinline__ uint32_t remap_pixel(const uint8_t* __restrict__ src, int sw, int sh, size_t spitch, uint2 m)
+// grid (ceil(dw / 4 / 128), dh, ceil(frames / FPT)): a thread = 4 adjacent destination pixels of FPT consecutive frames.  The
+// four map entries (32 bytes) and the 16 bilinear weights are loaded / computed once and reused for every frame of the group:
+// the packed map is 8 bytes per pixel against 2 bytes of image traffic, so reading it per frame made L2 the bottleneck.
+struct RemapTap { int off; int w0, w1, w2, w3; unsigned valid; };     // valid: bit0..3 = taps 00, 01, 10, 11 inside the image
+__device__ __forceinline__ RemapTap remap_tap(uint2 m, int sw, int sh, size_t spitch)
 {
+    RemapTap t;
     const int sx = (int)(short)(m.x & 0xffffu), sy = (int)(short)(m.x >> 16);
     const int fx = (int)(m.y & 31u), fy = (int)(m.y >> 5);
-    int w0 = (32 - fy) * (32 - fx) * 32, w3 = fy * fx * 32;
-    const int w1 = (32 - fy) * fx * 32, w2 = fy * (32 - fx) * 32;
-    if (w0 == 32768) { w0 = 32767; w3 = 1; }                 // saturate_cast<short>(32768) and OpenCV's sum fix-up
+    t.w0 = (32 - fy) * (32 - fx) * 32; t.w3 = fy * fx * 32;
+    t.w1 = (32 - fy) * fx * 32; t.w2 = fy * (32 - fx) * 32;
+    if (t.w0 == 32768) { t.w0 = 32767; t.w3 = 1; }          // saturate_cast<short>(32768) and OpenCV's sum fix-up
+    const bool x0 = (unsigned)sx < (unsigned)sw, x1 = (unsigned)(sx + 1) < (unsigned)sw;
+    const bool y0 = (unsigned)sy < (unsigned)sh, y1 = (unsigned)(sy + 1) < (unsigned)sh;
+    t.valid = (x0 && y0 ? 1u : 0u) | (x1 && y0 ? 2u : 0u) | (x0 && y1 ? 4u : 0u) | (x1 && y1 ? 8u : 0u);
+    t.off = t.valid ? sy * (int)spitch + sx : 0;            // BORDER_CONSTANT 0: taps outside the image read 0
+    return t;
+}
+__device__ __forceinline__ uint32_t remap_apply(const uint8_t* __restrict__ s, const RemapTap& t, int spitch)
+{
     int p00 = 0, p01 = 0, p10 = 0, p11 = 0;
-    if ((unsigned)sx < (unsigned)(sw - 1) && (unsigned)sy < (unsigned)(sh - 1)) {
-        const uint8_t* s = src + (size_t)sy * spitch + sx;
-        p00 = __ldg(s); p01 = __ldg(s + 1); p10 = __ldg(s + spitch); p11 = __ldg(s + spitch + 1);
-    } else {                                                 // BORDER_CONSTANT, value 0: taps outside the image read 0
-        const bool x0 = (unsigned)sx < (unsigned)sw, x1 = (unsigned)(sx + 1) < (unsigned)sw;
-        const bool y0 = (unsigned)sy < (unsigned)sh, y1 = (unsigned)(sy + 1) < (unsigned)sh;
-        if (x0 && y0) p00 = __ldg(src + (size_t)sy * spitch + sx);
-        if (x1 && y0) p01 = __ldg(src + (size_t)sy * spitch + sx + 1);
-        if (x0 && y1) p10 = __ldg(src + (size_t)(sy + 1) * spitch + sx);
-        if (x1 && y1) p11 = __ldg(src + (size_t)(sy + 1) * spitch + sx + 1);
+    const uint8_t* q = s + t.off;
+    if (t.valid == 15u) { p00 = __ldg(q); p01 = __ldg(q + 1); p10 = __ldg(q + spitch); p11 = __ldg(q + spitch + 1); }
+    else {
+        if (t.valid & 1u) p00 = __ldg(q);
+        if (t.valid & 2u) p01 = __ldg(q + 1);
+        if (t.valid & 4u) p10 = __ldg(q + spitch);
+        if (t.valid & 8u) p11 = __ldg(q + spitch + 1);
     }
-    return (uint32_t)((p00 * w0 + p01 * w1 + p10 * w2 + p11 * w3 + (1 << 14)) >> 15);
+    return (uint32_t)((p00 * t.w0 + p01 * t.w1 + p10 * t.w2 + p11 * t.w3 + (1 << 14)) >> 15);
 }
 
-// grid (ceil(dw / 4 / 128), dh, frames): a thread = 4 adjacent destination pixels.
-__global__ void __launch_bounds__(128) remap_kernel(const uint8_t* __restrict__ src, int sw, int sh, size_t spitch, size_t sframe,
-                                                    const uint2* __restrict__ packed, uint8_t* __restrict__ dst, int dw, int dh,
-                                                    size_t dpitch, size_t dframe)
+template <int FPT>
+__global__ void __launch_bounds__(128, 8) remap_kernel(const uint8_t* __restrict__ src, int sw, int sh, size_t spitch, size_t sframe,
+                                                       const uint2* __restrict__ packed, uint8_t* __restrict__ dst, int dw, int dh,
+                                                       size_t dpitch, size_t dframe, int n_frames)
 {
     const int x4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4, y = blockIdx.y;
     if (x4 >= dw) return;
-    const uint8_t* s = src + (size_t)blockIdx.z * sframe;
-    uint8_t* d = dst + (size_t)blockIdx.z * dframe + (size_t)y * dpitch + x4;
+    const int f0 = blockIdx.z * FPT, nf = min(FPT, n_frames - f0);
     const uint2* m = packed + (size_t)y * dw + x4;
-    if (x4 + 4 <= dw && ((dw & 3) == 0) && ((reinterpret_cast<size_t>(d) & 3) == 0)) {
+    const int npx = min(4, dw - x4);
+    RemapTap t[4];
+    if (npx == 4 && ((dw & 1) == 0)) {                       // 16-byte aligned pair of entries
         const uint4 ma = __ldg(reinterpret_cast<const uint4*>(m)), mb = __ldg(reinterpret_cast<const uint4*>(m) + 1);
-        const uint32_t a = remap_pixel(s, sw, sh, spitch, make_uint2(ma.x, ma.y)), b = remap_pixel(s, sw, sh, spitch, make_uint2(ma.z, ma.w));
-        const uint32_t c = remap_pixel(s, sw, sh, spitch, make_uint2(mb.x, mb.y)), e = remap_pixel(s, sw, sh, spitch, make_uint2(mb.z, mb.w));
-        *reinterpret_cast<uint32_t*>(d) = a | (b << 8) | (c << 16) | (e << 24);
+        t[0] = remap_tap(make_uint2(ma.x, ma.y), sw, sh, spitch); t[1] = remap_tap(make_uint2(ma.z, ma.w), sw, sh, spitch);
+        t[2] = remap_tap(make_uint2(mb.x, mb.y), sw, sh, spitch); t[3] = remap_tap(make_uint2(mb.z, mb.w), sw, sh, spitch);
     } else {
-        for (int t = 0; t < 4 && x4 + t < dw; ++t) d[t] = (uint8_t)remap_pixel(s, sw, sh, spitch, __ldg(m + t));
+#pragma unroll
+        for (int j = 0; j < 4; ++j) t[j] = remap_tap(j < npx ? __ldg(m + j) : make_uint2(0, 0), sw, sh, spitch);
+    }
+    const uint8_t* s = src + (size_t)f0 * sframe;
+    uint8_t* d = dst + (size_t)f0 * dframe + (size_t)y * dpitch + x4;
+    const int sp = (int)spitch;
+    if (npx == 4 && (t[0].valid & t[1].valid & t[2].valid & t[3].valid) == 15u && ((reinterpret_cast<size_t>(d) | dframe) & 3) == 0) {
+        // interior: all 16 taps inside the image, one word store per frame; every frame's loads are independent of the others
+        const uint8_t *q0 = s + t[0].off, *q1 = s + t[1].off, *q2 = s + t[2].off, *q3 = s + t[3].off;
+#pragma unroll
+        for (int f = 0; f < FPT; ++f) {
+            if (f < nf) {
+                const int a = __ldg(q0) * t[0].w0 + __ldg(q0 + 1) * t[0].w1 + __ldg(q0 + sp) * t[0].w2 + __ldg(q0 + sp + 1) * t[0].w3;
+                const int b = __ldg(q1) * t[1].w0 + __ldg(q1 + 1) * t[1].w1 + __ldg(q1 + sp) * t[1].w2 + __ldg(q1 + sp + 1) * t[1].w3;
+                const int c = __ldg(q2) * t[2].w0 + __ldg(q2 + 1) * t[2].w1 + __ldg(q2 + sp) * t[2].w2 + __ldg(q2 + sp + 1) * t[2].w3;
+                const int e = __ldg(q3) * t[3].w0 + __ldg(q3 + 1) * t[3].w1 + __ldg(q3 + sp) * t[3].w2 + __ldg(q3 + sp + 1) * t[3].w3;
+                *reinterpret_cast<uint32_t*>(d) = (uint32_t)((a + 16384) >> 15) | ((uint32_t)((b + 16384) >> 15) << 8) |
+                                                  ((uint32_t)((c + 16384) >> 15) << 16) | ((uint32_t)((e + 16384) >> 15) << 24);
+                q0 += sframe; q1 += sframe; q2 += sframe; q3 += sframe; d += dframe;
+            }
+        }
+        return;
+    }
+    for (int f = 0; f < nf; ++f, s += sframe, d += dframe) {
+        const uint32_t v[4] = {remap_apply(s, t[0], sp), remap_apply(s, t[1], sp), remap_apply(s, t[2], sp), remap_apply(s, t[3], sp)};
+        for (int j = 0; j < npx; ++j) d[j] = (uint8_t)v[j];
     }
 }
-
 
 // cv::resize(src, dst, newImSize) (INTER_LINEAR, 8UC1) of System::TrackStereo / TrackMonocular (src/System.cc:261-263, 330, 407):
 // OpenCV's 11-bit fixed-point bilinear (or the exact-2x INTER_AREA average) from per-column / per-row tables
@@ -149,7 +183,13 @@ cudaError_t launch_remap(const uint8_t* d_src, int sw, int sh, size_t spitch, si
                          int dh, size_t dpitch, size_t dframe, int n_frames, cudaStream_t st)
 {
     if (n_frames <= 0) return cudaSuccess;
-    remap_kernel<<<dim3((dw + 511) / 512, dh, n_frames), 128, 0, st>>>(d_src, sw, sh, spitch, sframe, d_packed, d_dst, dw, dh, dpitch, dframe);
+    if ((size_t)sh * spitch >= (size_t)1 << 31) return cudaErrorInvalidValue;       // tap offsets are 32-bit
+    if (n_frames >= 4)
+        remap_kernel<4><<<dim3((dw + 511) / 512, dh, (n_frames + 3) / 4), 128, 0, st>>>(d_src, sw, sh, spitch, sframe, d_packed, d_dst, dw, dh,
+                                                                                     dpitch, dframe, n_frames);
+    else
+        remap_kernel<1><<<dim3((dw + 511) / 512, dh, n_frames), 128, 0, st>>>(d_src, sw, sh, spitch, sframe, d_packed, d_dst, dw, dh, dpitch,
+                                                                             dframe, n_frames);
     count_launch();
     return cudaGetLastError();
 }
