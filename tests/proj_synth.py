@@ -41,12 +41,16 @@ def make_frame(rng, n, w=752.0, h=480.0, stereo_frac=0.6, occupied_frac=0.1, out
     return kp, desc, ur, occ, bounds
 
 
-def make_points(rng, kp, desc, ur, n_pts, jitter=2.0, max_flip=70, dup_frac=0.3, level_slop=True):
-    """Map points aimed at frame features: position jitter, descriptor bit flips, several points per feature (dup_frac)."""
+def make_points(rng, kp, desc, ur, n_pts, jitter=2.0, max_flip=70, dup_frac=0.3, level_slop=True, unique=False):
+    """Map points aimed at frame features: position jitter, descriptor bit flips, several points per feature (dup_frac), or
+    every point at its own feature (unique=True, n_pts <= len(kp): what a well-tracked frame looks like)."""
     n = len(kp)
-    base = rng.integers(0, n, max(1, int(n_pts * (1 - dup_frac))))
-    tgt = np.concatenate([base, rng.choice(base, n_pts - len(base))]) if n_pts > len(base) else base[:n_pts]
-    rng.shuffle(tgt)
+    if unique:
+        tgt = rng.permutation(n)[:n_pts]
+    else:
+        base = rng.integers(0, n, max(1, int(n_pts * (1 - dup_frac))))
+        tgt = np.concatenate([base, rng.choice(base, n_pts - len(base))]) if n_pts > len(base) else base[:n_pts]
+        rng.shuffle(tgt)
     P = {}
     P["target"] = tgt
     P["x"] = (kp["x"][tgt] + rng.normal(0, jitter, n_pts)).astype(np.float32)

@@ -79,6 +79,14 @@ def main():
     out["search_by_projection_last_1200x2000_us"] = lat(lambda: orbx.search_by_projection_last(
         fv, 40.0, P["valid"], P["x"], P["y"], P["invz"], P["level"], P["angle"], P["n_obs"], P["desc"], 15.0))
     out["search_by_projection_last_rounds"] = orbx.projection_rounds()
+    # a well-tracked frame: 1000 map points, each aimed at its own feature (few competing claims)
+    U = make_points(rng, kp, desc, ur, 1000, unique=True, max_flip=50)
+    out["search_by_projection_map_1200x1000_unique_us"] = lat(lambda: orbx.search_by_projection_map(
+        fv, U["in_view"], U["bad"], U["x"], U["y"], U["xr"], U["view_cos"], U["depth"], U["level"], U["n_obs"], U["desc"]))
+    out["search_by_projection_map_unique_rounds"] = orbx.projection_rounds()
+    out["search_by_projection_last_1200x1000_unique_us"] = lat(lambda: orbx.search_by_projection_last(
+        fv, 40.0, U["valid"], U["x"], U["y"], U["invz"], U["level"], U["angle"], U["n_obs"], U["desc"], 15.0))
+    out["search_by_projection_last_unique_rounds"] = orbx.projection_rounds()
     kps = np.zeros(1200, orbx.KP_DTYPE); kps["x"] = rng.uniform(0, 752, 1200); kps["y"] = rng.uniform(0, 480, 1200)
     out["undistort_keypoints_1200_us"] = lat(lambda: orbx.undistort_keypoints(kps, [458.6, 457.3, 367.2, 248.4], [-0.283, 0.074, 1.9e-4, 1.8e-5]))
     print(json.dumps(out, indent=1))

@@ -6,6 +6,7 @@
 #include <cfloat>
 #include <cmath>
 #include <cstring>
+#include <mutex>
 #include <vector>
 
 #include "orbx_internal.cuh"
@@ -21,6 +22,19 @@ struct orbx_rectifier {
 };
 
 using namespace orbx;
+
+namespace {
+// Grow-only device + pinned staging per device for orbx_undistort_keypoints: the call sits on the per-frame path of the
+// tracking thread (Frame constructor), a cudaMalloc / cudaFree pair per call cost more than everything else in it.
+struct UndistortArena {
+    std::mutex mu;
+    orbx_keypoint* d = nullptr;
+    orbx_keypoint* h = nullptr;
+    size_t cap = 0;
+    cudaStream_t st = nullptr;
+};
+UndistortArena g_undistort[64];
+}  // namespace
 
 extern "C" {
 
@@ -41,13 +55,28 @@ int orbx_undistort_keypoints(int device, const orbx_keypoint* keypoints, int n, 
     p.nfx = new_K[0]; p.nfy = new_K[1]; p.ncx = new_K[2]; p.ncy = new_K[3];
     for (int i = 0; i < n_dist; ++i) p.k[i] = dist[i];
     p.n_dist = n_dist;
-    orbx_keypoint* d = nullptr;
-    cudaError_t e = cudaMalloc(&d, (size_t)n * sizeof(orbx_keypoint));
-    if (e != cudaSuccess) return fail(ORBX_ERR_OOM, "cudaMalloc: %s", cudaGetErrorString(e));
-    e = cudaMemcpy(d, keypoints, (size_t)n * sizeof(orbx_keypoint), cudaMemcpyHostToDevice);
-    if (e == cudaSuccess) e = launch_undistort(d, n, p, d, 0);
-    if (e == cudaSuccess) e = cudaMemcpy(out, d, (size_t)n * sizeof(orbx_keypoint), cudaMemcpyDeviceToHost);
-    cudaFree(d);
+    UndistortArena& A = g_undistort[device & 63];
+    std::lock_guard<std::mutex> lock(A.mu);
+    cudaError_t e = cudaSuccess;
+    if (!A.st) e = cudaStreamCreateWithFlags(&A.st, cudaStreamNonBlocking);
+    if (e == cudaSuccess && A.cap < (size_t)n) {
+        if (A.d) cudaFree(A.d);
+        if (A.h) cudaFreeHost(A.h);
+        A.d = A.h = nullptr; A.cap = 0;
+        const size_t want = (size_t)n + (size_t)n / 2 + 256;
+        e = cudaMalloc(&A.d, want * sizeof(orbx_keypoint));
+        if (e == cudaSuccess) e = cudaMallocHost(&A.h, want * sizeof(orbx_keypoint));
+        if (e != cudaSuccess) return fail(ORBX_ERR_OOM, "undistort scratch: %s", cudaGetErrorString(e));
+        A.cap = want;
+    }
+    if (e == cudaSuccess) {
+        memcpy(A.h, keypoints, (size_t)n * sizeof(orbx_keypoint));
+        e = cudaMemcpyAsync(A.d, A.h, (size_t)n * sizeof(orbx_keypoint), cudaMemcpyHostToDevice, A.st);
+    }
+    if (e == cudaSuccess) e = launch_undistort(A.d, n, p, A.d, A.st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(A.h, A.d, (size_t)n * sizeof(orbx_keypoint), cudaMemcpyDeviceToHost, A.st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(A.st);
+    if (e == cudaSuccess) memcpy(out, A.h, (size_t)n * sizeof(orbx_keypoint));
     if (e != cudaSuccess) return fail(ORBX_ERR_CUDA, "undistort_keypoints: %s", cudaGetErrorString(e));
     return ORBX_OK;
 }
