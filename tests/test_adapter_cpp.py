@@ -54,3 +54,55 @@ def test_adapter_matches_c_abi():
     assert m.group(6) == "%016x" % hp
     assert int(m.group(7)) == -1                      # empty image -> -1, like the reference
     assert int(m.group(8)) == orbx.ORBmatcher.DescriptorDistance(desc[0], desc[1])
+
+
+MSRC = os.path.join(ROOT, "tests", "cpp", "matcher_adapter_test.cpp")
+MEXE = os.path.join(ROOT, "build", "matcher_adapter_test")
+
+
+def build_matcher_exe():
+    os.makedirs(os.path.dirname(MEXE), exist_ok=True)
+    subprocess.check_call(["g++", "-std=c++17", "-O2", "-I" + os.path.join(ROOT, "tests", "cpp", "cv_stub"), "-I" + os.path.join(ROOT, "include"),
+                           "-I" + os.path.join(ROOT, "wut_cuda_orb_slam3_b200", "csrc", "adapter"), "-o", MEXE, MSRC,
+                           "-L" + os.path.join(ROOT, "wut_cuda_orb_slam3_b200"), "-lorbx",
+                           "-Wl,-rpath," + os.path.join(ROOT, "wut_cuda_orb_slam3_b200")])
+
+
+def test_matcher_adapter_compiles():
+    """CPU: csrc/adapter/ORBmatcherProjection.h compiles against Frame / MapPoint stand-ins and links (no compute call)."""
+    build_matcher_exe()
+    assert os.path.exists(MEXE)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode", [0, 1])
+def test_matcher_adapter_matches_oracle(oracle, tmp_path, mode):
+    """The C++ adapter, driven like Tracking::SearchLocalPoints / TrackWithMotionModel, against the oracle's sequential loop."""
+    from tests.proj_synth import SCALE, make_frame, make_points
+    build_matcher_exe()
+    rng = np.random.default_rng(500 + mode)
+    kp, desc, ur, occ, bounds = make_frame(rng, 900, crowd=6)
+    P = make_points(rng, kp, desc, ur, 1500, dup_frac=0.5, max_flip=90)
+    b = [np.float32(v) for v in bounds]
+    bg = np.array(b + [np.float32(64) / (b[2] - b[0]), np.float32(48) / (b[3] - b[1])], np.float32)
+    th, ratio, mbf = 3.0, 0.8, 40.0
+    fl = np.array(list(bg) + [15.0 if mode else th, mbf if mode else ratio, 1.0, 20.0], np.float32)
+    scene = tmp_path / "scene.bin"; result = tmp_path / "result.bin"
+    with open(scene, "wb") as f:
+        f.write(np.array([len(kp), len(P["x"]), len(SCALE), mode], np.int32).tobytes()); f.write(fl.tobytes())
+        f.write(kp.tobytes()); f.write(desc.tobytes()); f.write(ur.tobytes()); f.write(occ.tobytes()); f.write(SCALE.tobytes())
+        fa, fb = (P["valid"], np.zeros_like(P["valid"])) if mode else (P["in_view"], P["bad"])
+        f.write(fa.tobytes()); f.write(fb.tobytes())
+        for a in (P["x"], P["y"], P["xr"], P["view_cos"], P["invz"] if mode else P["depth"], P["angle"]):
+            f.write(np.ascontiguousarray(a, np.float32).tobytes())
+        f.write(P["level"].astype(np.int32).tobytes()); f.write(P["n_obs"].astype(np.int32).tobytes()); f.write(P["desc"].tobytes())
+    subprocess.check_call([MEXE, str(scene), str(result)])
+    raw = np.fromfile(result, np.int32)
+    nm, got = int(raw[0]), raw[1:]
+    if mode == 0:
+        want, wnm = oracle.search_by_projection_map(kp, desc, ur, occ, bg, SCALE, P["in_view"], P["bad"], P["x"], P["y"], P["xr"], P["view_cos"],
+                                                    P["depth"], P["level"], P["n_obs"], P["desc"], th=th, far=True, th_far=20.0, nnratio=ratio)
+    else:
+        want, wnm = oracle.search_by_projection_last(kp, desc, ur, occ, bg, SCALE, mbf, P["valid"], P["x"], P["y"], P["invz"], P["level"],
+                                                     P["angle"], P["n_obs"], P["desc"], 15.0, False, False, True)
+    assert nm == wnm and nm > 50 and np.array_equal(got, want)
