@@ -91,3 +91,26 @@ def test_resize_matches_oracle(oracle, src, dst):
     with pytest.raises(orbx.OrbxError):
         r.remap(img[:-1])
     r.close()
+
+
+@pytest.mark.parametrize("case", range(5))
+def test_remap_device_batch_tiled_matches_oracle(oracle, case):
+    """>= 8 resident frames take the tiled shared-memory kernel: smooth maps, maps leaving the image, noisy maps (window too
+    large -> gather fallback inside the kernel), odd destination sizes."""
+    rng = np.random.default_rng(700 + case)
+    sh, sw = [(480, 752), (376, 1248), (480, 752), (128, 160), (480, 752)][case]
+    dh, dw = [(480, 752), (300, 501), (481, 750), (70, 90), (240, 376)][case]
+    nf = [9, 8, 17, 33, 16][case]
+    src = rng.integers(0, 256, (nf, sh, sw), dtype=np.uint8)
+    noise = [0.0, 0.3, 0.0, 40.0, 0.0][case]
+    mx, my = _maps(rng, sw, sh, dw, dh, shift=[0.0, 0.0, 30.0, 0.0, -12.0][case], noise=noise)
+    r = orbx.Rectifier(mx, my)
+    d_src = torch.from_numpy(src).cuda()
+    d_dst = torch.full((nf, dh, dw), 7, dtype=torch.uint8, device="cuda")
+    torch.cuda.synchronize()
+    r.remap_device(d_src, sh, sw, sw, sh * sw, nf, d_dst, dw, dh * dw)
+    torch.cuda.synchronize()
+    got = d_dst.cpu().numpy()
+    for f in range(nf):
+        assert np.array_equal(got[f], oracle.remap(src[f], mx, my)), (case, f)
+    r.close()

@@ -7,6 +7,8 @@
 //     the map is quantised ONCE to OpenCV's 1/32-pixel fixed point (remap_quantise_kernel), every frame then costs four
 //     gathers and one 15-bit fixed-point blend per pixel.  The packed map (8 bytes per pixel) stays L2-resident across a
 //     batch, so HBM sees the source and destination bytes only; a thread produces 4 adjacent pixels and stores them as one word.
+#include <climits>
+
 #include "orbx_internal.cuh"
 
 namespace orbx {
@@ -130,6 +132,115 @@ __global__ void __launch_bounds__(128, 8) remap_kernel(const uint8_t* __restrict
     }
 }
 
+// ---- tiled variant for batches: the source window of a 128 x 8 destination tile is staged in shared memory --------------------
+// A rectification map is smooth, so the taps of a destination tile fall into a compact source window (a few KB).  Per CTA: map
+// entries, weights and the window are worked out ONCE, then for every frame of the group the window is copied with coalesced
+// 16-byte loads (double buffered: frame f + 1 is fetched while frame f is blended) and the four taps per pixel come from shared
+// memory instead of four scattered byte loads through L1/L2.  Tiles whose window does not fit (wild maps) or whose source is
+// not 16-byte aligned take the gather path of remap_kernel.
+constexpr int RT_W = 128, RT_H = 8, RT_THREADS = 256, RT_SMEM = 4096, RT_STAGES = 4, RT_FPC = 32;
+
+__device__ __forceinline__ int nitems_of(int SP, int nrow) { return (SP >> 4) * nrow; }
+
+__global__ void __launch_bounds__(RT_THREADS, 4) remap_tiled_kernel(const uint8_t* __restrict__ src, int sw, int sh, size_t spitch, size_t sframe,
+                                                                 const uint2* __restrict__ packed, uint8_t* __restrict__ dst, int dw, int dh,
+                                                                 size_t dpitch, size_t dframe, int n_frames)
+{
+    __shared__ __align__(16) uint8_t win[RT_STAGES][RT_SMEM];
+    __shared__ int s_box[4];                                  // min sx, max sx + 1, min sy, max sy + 1 over the taps inside the image
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int x4 = blockIdx.x * RT_W + lane * 4, y = blockIdx.y * RT_H + (tid >> 5);
+    const int f0 = blockIdx.z * RT_FPC, nf = min(RT_FPC, n_frames - f0);
+    const bool row_ok = y < dh;
+    const int npx = row_ok ? max(0, min(4, dw - x4)) : 0;
+    if (tid == 0) { s_box[0] = INT_MAX; s_box[1] = -1; s_box[2] = INT_MAX; s_box[3] = -1; }
+    __syncthreads();
+    RemapTap t[4];
+    int bx0 = INT_MAX, bx1 = -1, by0 = INT_MAX, by1 = -1;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const uint2 m = j < npx ? __ldg(packed + (size_t)y * dw + x4 + j) : make_uint2(0x80008000u, 0);   // sx = sy = -32768: no tap inside
+        t[j] = remap_tap(m, sw, sh, spitch);
+        if (t[j].valid) {
+            const int sx = (int)(short)(m.x & 0xffffu), sy = (int)(short)(m.x >> 16);
+            bx0 = min(bx0, max(sx, 0)); bx1 = max(bx1, min(sx + 1, sw - 1));
+            by0 = min(by0, max(sy, 0)); by1 = max(by1, min(sy + 1, sh - 1));
+        }
+    }
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) {
+        bx0 = min(bx0, __shfl_xor_sync(0xffffffffu, bx0, d)); bx1 = max(bx1, __shfl_xor_sync(0xffffffffu, bx1, d));
+        by0 = min(by0, __shfl_xor_sync(0xffffffffu, by0, d)); by1 = max(by1, __shfl_xor_sync(0xffffffffu, by1, d));
+    }
+    if (lane == 0 && bx1 >= 0) { atomicMin(&s_box[0], bx0); atomicMax(&s_box[1], bx1); atomicMin(&s_box[2], by0); atomicMax(&s_box[3], by1); }
+    __syncthreads();
+    const int X0 = s_box[0] & ~15, X1 = s_box[1], Y0 = s_box[2], Y1 = s_box[3];
+    const bool any = X1 >= 0;
+    const int nvec = any ? ((X1 - X0) >> 4) + 1 : 0, nrow = any ? Y1 - Y0 + 1 : 0, SP = nvec * 16;
+    uint8_t* d = dst + (size_t)f0 * dframe + (size_t)y * dpitch + x4;
+    const uint8_t* s = src + (size_t)f0 * sframe;
+    const bool word_store = npx == 4 && ((reinterpret_cast<size_t>(d) | dframe) & 3) == 0;
+    if (!any) {                                               // the whole tile maps outside the image: BORDER_CONSTANT 0
+        for (int f = 0; f < nf; ++f, d += dframe)
+            for (int j = 0; j < npx; ++j) d[j] = 0;
+        return;
+    }
+    if (SP * nrow > RT_SMEM || nitems_of(SP, nrow) > RT_THREADS || (size_t)X0 + (size_t)SP > spitch) {   // window too large / would run over the row pitch: gather
+        for (int f = 0; f < nf; ++f, s += sframe, d += dframe) {
+            const uint32_t v[4] = {remap_apply(s, t[0], (int)spitch), remap_apply(s, t[1], (int)spitch), remap_apply(s, t[2], (int)spitch),
+                                   remap_apply(s, t[3], (int)spitch)};
+            for (int j = 0; j < npx; ++j) d[j] = (uint8_t)v[j];
+        }
+        return;
+    }
+    // tap offsets inside the staged window
+    int off[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const uint2 m = j < npx ? __ldg(packed + (size_t)y * dw + x4 + j) : make_uint2(0x80008000u, 0);
+        const int sx = (int)(short)(m.x & 0xffffu), sy = (int)(short)(m.x >> 16);
+        off[j] = (sy - Y0) * SP + (sx - X0);                 // may be negative / past the window for taps whose valid bit is clear
+    }
+    const uint8_t* wsrc = s + (size_t)Y0 * spitch + X0;
+    const int nitems = nrow * nvec;
+    // RT_STAGES-deep cp.async ring: a thread moves at most RT_SMEM / 16 / RT_THREADS = 1 vector of the window per frame, straight
+    // from global to shared memory; the copy of frame f + RT_STAGES - 1 is in flight while frame f is blended, which covers the
+    // DRAM latency (a two-buffer version that waited for every frame's window ran at one DRAM round trip per frame: 0.41 ms).
+    const int r0 = tid / nvec, v0 = tid - r0 * nvec;
+    const bool h0 = tid < nitems;
+    const size_t g0 = (size_t)r0 * spitch + (size_t)v0 * 16;
+    const uint32_t q0 = (uint32_t)__cvta_generic_to_shared(&win[0][0]) + (uint32_t)(r0 * SP + v0 * 16);
+    auto issue = [&](int f) {
+        if (h0 && f < nf)
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(q0 + (uint32_t)((f % RT_STAGES) * RT_SMEM)), "l"(wsrc + (size_t)f * sframe + g0) : "memory");
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+#pragma unroll
+    for (int f = 0; f < RT_STAGES - 1; ++f) issue(f);
+    for (int f = 0; f < nf; ++f, d += dframe) {
+        asm volatile("cp.async.wait_group %0;" ::"n"(RT_STAGES - 2) : "memory");     // this thread's part of frame f has landed
+        __syncthreads();                                      // ... everybody's has, and everybody is done with frame f - 1
+        issue(f + RT_STAGES - 1);                             // into the buffer frame f - 1 used
+        const uint8_t* W = win[f % RT_STAGES];
+        uint32_t v[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const RemapTap& q = t[j];
+            int p00 = 0, p01 = 0, p10 = 0, p11 = 0;
+            if (q.valid == 15u) { p00 = W[off[j]]; p01 = W[off[j] + 1]; p10 = W[off[j] + SP]; p11 = W[off[j] + SP + 1]; }
+            else {
+                if (q.valid & 1u) p00 = W[off[j]];
+                if (q.valid & 2u) p01 = W[off[j] + 1];
+                if (q.valid & 4u) p10 = W[off[j] + SP];
+                if (q.valid & 8u) p11 = W[off[j] + SP + 1];
+            }
+            v[j] = (uint32_t)((p00 * q.w0 + p01 * q.w1 + p10 * q.w2 + p11 * q.w3 + (1 << 14)) >> 15);
+        }
+        if (word_store) *reinterpret_cast<uint32_t*>(d) = v[0] | (v[1] << 8) | (v[2] << 16) | (v[3] << 24);
+        else for (int j = 0; j < npx; ++j) d[j] = (uint8_t)v[j];
+    }
+}
+
 // cv::resize(src, dst, newImSize) (INTER_LINEAR, 8UC1) of System::TrackStereo / TrackMonocular (src/System.cc:261-263, 330, 407):
 // OpenCV's 11-bit fixed-point bilinear (or the exact-2x INTER_AREA average) from per-column / per-row tables
 // {s0 | s1 << 16, c0 | c1 << 16} evaluated once on the host with OpenCV's float formula — the same arithmetic as the pyramid.
@@ -184,6 +295,12 @@ cudaError_t launch_remap(const uint8_t* d_src, int sw, int sh, size_t spitch, si
 {
     if (n_frames <= 0) return cudaSuccess;
     if ((size_t)sh * spitch >= (size_t)1 << 31) return cudaErrorInvalidValue;       // tap offsets are 32-bit
+    if (n_frames >= 8 && ((reinterpret_cast<size_t>(d_src) | spitch | sframe) & 15) == 0) {
+        remap_tiled_kernel<<<dim3((dw + RT_W - 1) / RT_W, (dh + RT_H - 1) / RT_H, (n_frames + RT_FPC - 1) / RT_FPC), RT_THREADS, 0, st>>>(
+            d_src, sw, sh, spitch, sframe, d_packed, d_dst, dw, dh, dpitch, dframe, n_frames);
+        count_launch();
+        return cudaGetLastError();
+    }
     if (n_frames >= 4)
         remap_kernel<4><<<dim3((dw + 511) / 512, dh, (n_frames + 3) / 4), 128, 0, st>>>(d_src, sw, sh, spitch, sframe, d_packed, d_dst, dw, dh,
                                                                                      dpitch, dframe, n_frames);
