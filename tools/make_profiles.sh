@@ -25,7 +25,7 @@ ncu --set full --clock-control none --import-source on -k regex:blur_pipe -s 1 -
 python tools/latency.py > $OUT/${TAG}_single_frame_latency.txt 2>&1
 # rectification / resize kernels and the projection-guided searches
 python tools/prep_bench.py > $OUT/${TAG}_prep_bench.json 2> $OUT/prep_bench.err && \
-ncu --set full --clock-control none --import-source on -k regex:remap_kernel -s 3 -c 1 -f -o $OUT/${TAG}_remap python tools/prep_bench.py > $OUT/ncu_r.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:remap_tiled_kernel -s 3 -c 1 -f -o $OUT/${TAG}_remap_tiled python tools/prep_bench.py > $OUT/ncu_r.log 2>&1
 python tools/prep_bench.py > $OUT/plain.log 2>&1 && \
 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"proj_|frame_grid" -c 40 --csv --log-file $OUT/${TAG}_proj_launches.csv python tools/prep_bench.py > $OUT/ncu_p.log 2>&1
 tail -n 2 $OUT/ncu_f.log; tail -n 2 $OUT/ncu_k.log; tail -n 3 $OUT/${TAG}_launch_shares_b512.txt

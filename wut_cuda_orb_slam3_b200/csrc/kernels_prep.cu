@@ -203,6 +203,7 @@ __global__ void __launch_bounds__(RT_THREADS, 4) remap_tiled_kernel(const uint8_
     }
     const uint8_t* wsrc = s + (size_t)Y0 * spitch + X0;
     const int nitems = nrow * nvec;
+    const bool interior = word_store && (t[0].valid & t[1].valid & t[2].valid & t[3].valid) == 15u;
     // RT_STAGES-deep cp.async ring: a thread moves at most RT_SMEM / 16 / RT_THREADS = 1 vector of the window per frame, straight
     // from global to shared memory; the copy of frame f + RT_STAGES - 1 is in flight while frame f is blended, which covers the
     // DRAM latency (a two-buffer version that waited for every frame's window ran at one DRAM round trip per frame: 0.41 ms).
@@ -223,17 +224,23 @@ __global__ void __launch_bounds__(RT_THREADS, 4) remap_tiled_kernel(const uint8_
         issue(f + RT_STAGES - 1);                             // into the buffer frame f - 1 used
         const uint8_t* W = win[f % RT_STAGES];
         uint32_t v[4];
+        if (interior) {                                       // decided once per thread: no per-tap tests inside the frame loop
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const uint8_t* w = W + off[j];
+                v[j] = (uint32_t)(((int)w[0] * t[j].w0 + (int)w[1] * t[j].w1 + (int)w[SP] * t[j].w2 + (int)w[SP + 1] * t[j].w3 + (1 << 14)) >> 15);
+            }
+            *reinterpret_cast<uint32_t*>(d) = v[0] | (v[1] << 8) | (v[2] << 16) | (v[3] << 24);
+            continue;
+        }
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const RemapTap& q = t[j];
             int p00 = 0, p01 = 0, p10 = 0, p11 = 0;
-            if (q.valid == 15u) { p00 = W[off[j]]; p01 = W[off[j] + 1]; p10 = W[off[j] + SP]; p11 = W[off[j] + SP + 1]; }
-            else {
-                if (q.valid & 1u) p00 = W[off[j]];
-                if (q.valid & 2u) p01 = W[off[j] + 1];
-                if (q.valid & 4u) p10 = W[off[j] + SP];
-                if (q.valid & 8u) p11 = W[off[j] + SP + 1];
-            }
+            if (q.valid & 1u) p00 = W[off[j]];
+            if (q.valid & 2u) p01 = W[off[j] + 1];
+            if (q.valid & 4u) p10 = W[off[j] + SP];
+            if (q.valid & 8u) p11 = W[off[j] + SP + 1];
             v[j] = (uint32_t)((p00 * q.w0 + p01 * q.w1 + p10 * q.w2 + p11 * q.w3 + (1 << 14)) >> 15);
         }
         if (word_store) *reinterpret_cast<uint32_t*>(d) = v[0] | (v[1] << 8) | (v[2] << 16) | (v[3] << 24);
