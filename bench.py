@@ -373,6 +373,20 @@ def run_other_configs(local_rank, dev):
     out["euroc_stereo_pair_1200"] = {"ms_per_pair": ms, "pairs_per_s": 1e3 / ms, "stereo_matches": int((res["u"] >= 0).sum()),
                                      "what": "orbx_extract left | right on two host threads + orbx_stereo_match"}
     exL.close(); exR.close()
+    # the same pair as ONE two-frame call on one extractor (both pyramids stay on the device as frames 0 and 1): what a
+    # stereo front end built on the batch API does instead of two extractor threads
+    exS = orbx.ORBextractor(1200, SCALE, NLEVELS, INI_TH, MIN_TH, device=local_rank, max_cols=752, max_rows=480, max_batch=2)
+    LR = np.stack([L, R])
+
+    def stereo_batched():
+        nm, n, kps, desc = exS.extract_batch(LR)
+        res["u2"], res["d2"] = orbx.compute_stereo_matches(exS, exS, kps[0, :n[0]], desc[0, :n[0]], kps[1, :n[1]], desc[1, :n[1]], 47.9, 435.2,
+                                                           frameL=0, frameR=1)
+    ms = med_ms(stereo_batched)
+    assert np.array_equal(res["u2"], res["u"]) and np.array_equal(res["d2"], res["d"]), "two-frame call and two-extractor path disagree"
+    out["euroc_stereo_pair_1200_one_call"] = {"ms_per_pair": ms, "pairs_per_s": 1e3 / ms, "stereo_matches": int((res["u2"] >= 0).sum()),
+                                              "what": "orbx_extract_batch([left, right]) on one extractor + orbx_stereo_match(frames 0, 1)"}
+    exS.close()
     # configs[2]: 1241x376 stereo pair, 2000 features, extraction x2 + brute-force 2-NN L->R + 0.7 ratio test
     L, R = synth.image(32, 1241, 376, view=0, max_disp=60), synth.image(32, 1241, 376, view=1, max_disp=60)
     exL = orbx.ORBextractor(2000, SCALE, NLEVELS, INI_TH, MIN_TH, device=local_rank, max_cols=1241, max_rows=376, max_batch=1)
