@@ -259,3 +259,27 @@ def test_color_input_cvt_gray(oracle, ch, rgb):
     ex = orbx.ORBextractor(300, 1.2, 8, 20, 7)
     nm, kps, desc = ex.extract_color(view, rgb)
     assert np.array_equal(ex.pyramid_level(0), oracle.cvt_gray(np.ascontiguousarray(view), rgb))
+
+
+def test_host_batch_serial_pipeline_matches_single_frames(oracle):
+    """orbx_extract_batch with >= 128-frame chunks takes the three-stream serial pipeline (H2D / compute / D2H streams, slots
+    reused through events): every frame of a 700-frame call must equal the single-frame result, bit for bit, also on a second
+    call that reuses the slots, and a sample of frames must equal the oracle."""
+    cols, rows, F = 200, 150, 700
+    imgs = np.stack([synth.image(4000 + f, cols, rows) for f in range(F)])
+    ex = orbx.ORBextractor(300, 1.2, 6, 20, 7, max_cols=cols, max_rows=rows, max_batch=128)
+    single = orbx.ORBextractor(300, 1.2, 6, 20, 7)
+    for rep in range(2):
+        nm, n, kps, desc = ex.extract_batch(imgs if rep == 0 else imgs[::-1].copy())
+        order = range(F) if rep == 0 else range(F - 1, -1, -1)
+        for slot, f in enumerate(order):
+            if f % 7 and rep:          # second pass: a sample is enough
+                continue
+            m1, k1, d1 = single(imgs[f])
+            assert nm[slot] == m1 and n[slot] == len(k1), (rep, f)
+            assert kps[slot, :n[slot]].tobytes() == k1.tobytes() and np.array_equal(desc[slot, :n[slot]], d1), (rep, f)
+    oex = oracle.extractor(300, 1.2, 6, 20, 7)
+    for f in (0, 333, 699):
+        ok, od, onm = oex.extract(imgs[f], (0, 0))
+        slot = F - 1 - f
+        assert n[slot] == len(ok) and np.array_equal(kps[slot, :n[slot]]["x"], ok["x"]) and np.array_equal(kps[slot, :n[slot]]["y"], ok["y"])
