@@ -160,6 +160,19 @@ struct orbx_extractor {
     cudaStream_t compute = nullptr, copy_in = nullptr, copy_out = nullptr;   // serial-compute pipeline of orbx_extract_batch (3 streams)
     int last_frames = 0;           // frames of the last call that are probe-able (slot 0)
     int max_kp = 0;
+    // single-frame calls replay a captured CUDA graph of the 15 kernel launches (orbx_extract is the tracking thread's per-frame call:
+    // launch gaps, not kernels, dominate it).  The graph is keyed by everything the captured launches bake in.
+    struct GraphKey {
+        int rows = 0, cols = 0, lap0 = 0, lap1 = 0, capacity = 0;
+        const void* pyr = nullptr; const void* d_in = nullptr; const void* d_kps = nullptr; const void* cand = nullptr;
+        bool operator==(const GraphKey& o) const
+        {
+            return rows == o.rows && cols == o.cols && lap0 == o.lap0 && lap1 == o.lap1 && capacity == o.capacity && pyr == o.pyr && d_in == o.d_in &&
+                   d_kps == o.d_kps && cand == o.cand;
+        }
+    } graph_key;
+    cudaGraphExec_t graph_exec = nullptr;
+    int single_calls = 0;          // the first single-frame call runs un-captured (lazy one-time initialisation inside the launchers)
     // per-stage CUDA-event timing (orbx_profile_begin / orbx_profile_end)
     bool profiling = false;
     std::vector<cudaEvent_t> ev_pool;   // kStages+1 events per profiled chunk
@@ -600,6 +613,7 @@ void orbx_destroy(orbx_extractor* ex)
         if (ex->slots[i].stream) cudaStreamDestroy(ex->slots[i].stream);
         if (ex->slots[i].ev_in) { cudaEventDestroy(ex->slots[i].ev_in); cudaEventDestroy(ex->slots[i].ev_done); cudaEventDestroy(ex->slots[i].ev_out); }
     }
+    if (ex->graph_exec) cudaGraphExecDestroy(ex->graph_exec);
     if (ex->d_tables) cudaFree(ex->d_tables);
     for (cudaEvent_t e : ex->ev_pool) cudaEventDestroy(e);
     delete ex;
@@ -748,7 +762,27 @@ int orbx_extract_batch(orbx_extractor* ex, const uint8_t* const* images, int n_f
         }
         mark(ist);
         if (serial) { CU(cudaEventRecord(s.ev_in, ist)); CU(cudaStreamWaitEvent(cst, s.ev_in, 0)); }
-        if ((rc = run_chunk(ex, s, s.d_in, dframe, dpitch, nf, lap0, lap1, s.d_kps, s.d_desc, capacity, s.d_n, s.d_nm, cst))) return rc;
+        static const bool graphs = !(getenv("ORBX_GRAPH") && atoi(getenv("ORBX_GRAPH")) == 0);
+        if (n_frames == 1 && graphs && !trace && !ex->profiling && ex->single_calls++ > 0) {
+            orbx_extractor::GraphKey key;
+            key.rows = rows; key.cols = cols; key.lap0 = lap0; key.lap1 = lap1; key.capacity = capacity;
+            key.pyr = s.ws.pyr; key.d_in = s.d_in; key.d_kps = s.d_kps; key.cand = s.ws.cand;
+            if (!ex->graph_exec || !(key == ex->graph_key)) {
+                if (ex->graph_exec) { cudaGraphExecDestroy(ex->graph_exec); ex->graph_exec = nullptr; }
+                cudaGraph_t g = nullptr;
+                CU(cudaStreamBeginCapture(cst, cudaStreamCaptureModeThreadLocal));
+                rc = run_chunk(ex, s, s.d_in, dframe, dpitch, 1, lap0, lap1, s.d_kps, s.d_desc, capacity, s.d_n, s.d_nm, cst);
+                cudaError_t ce = cudaStreamEndCapture(cst, &g);
+                if (rc) { if (g) cudaGraphDestroy(g); return rc; }
+                if (ce != cudaSuccess) return fail(ORBX_ERR_CUDA, "graph capture: %s", cudaGetErrorString(ce));
+                ce = cudaGraphInstantiate(&ex->graph_exec, g, 0);
+                cudaGraphDestroy(g);
+                if (ce != cudaSuccess) { ex->graph_exec = nullptr; return fail(ORBX_ERR_CUDA, "graph instantiate: %s", cudaGetErrorString(ce)); }
+                ex->graph_key = key;
+            }
+            CU(cudaGraphLaunch(ex->graph_exec, cst));
+            count_launch(15);
+        } else if ((rc = run_chunk(ex, s, s.d_in, dframe, dpitch, nf, lap0, lap1, s.d_kps, s.d_desc, capacity, s.d_n, s.d_nm, cst))) return rc;
         if (serial) { CU(cudaEventRecord(s.ev_done, cst)); CU(cudaStreamWaitEvent(ost, s.ev_done, 0)); }
         mark(ost);
         CU(cudaMemcpyAsync(keypoints + (size_t)f0 * capacity, s.d_kps, sizeof(orbx_keypoint) * (size_t)nf * capacity, cudaMemcpyDeviceToHost, ost));
