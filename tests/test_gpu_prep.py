@@ -114,3 +114,22 @@ def test_remap_device_batch_tiled_matches_oracle(oracle, case):
     for f in range(nf):
         assert np.array_equal(got[f], oracle.remap(src[f], mx, my)), (case, f)
     r.close()
+
+
+@pytest.mark.parametrize("src,dst,nf", [((480, 752), (400, 627), 9), ((480, 752), (240, 376), 8), ((376, 1248), (480, 752), 17), ((96, 80), (37, 201), 33),
+                                        ((480, 640), (960, 1280), 8), ((480, 752), (30, 47), 12)])
+def test_resize_device_batch_tiled_matches_oracle(oracle, src, dst, nf):
+    """>= 8 resident frames take the tiled cp.async kernel: down-scales, the exact-2x area path, up-scales, odd sizes and a
+    16x down-scale whose source window does not fit the ring (global fallback inside the kernel)."""
+    rng = np.random.default_rng(800 + nf)
+    imgs = rng.integers(0, 256, (nf,) + src, dtype=np.uint8)
+    r = orbx.Rectifier(resize=(src[0], src[1], dst[0], dst[1]))
+    d_src = torch.from_numpy(imgs).cuda()
+    d_dst = torch.full((nf,) + dst, 9, dtype=torch.uint8, device="cuda")
+    torch.cuda.synchronize()
+    r.remap_device(d_src, src[0], src[1], src[1], src[0] * src[1], nf, d_dst, dst[1], dst[0] * dst[1])
+    torch.cuda.synchronize()
+    got = d_dst.cpu().numpy()
+    for f in range(nf):
+        assert np.array_equal(got[f], oracle.resize(imgs[f], dst[1], dst[0])), f
+    r.close()

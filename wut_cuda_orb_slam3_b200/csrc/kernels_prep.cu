@@ -282,6 +282,81 @@ __global__ void __launch_bounds__(128) resize_kernel(const uint8_t* __restrict__
     else for (int j = 0; j < 4 && x4 + j < dw; ++j) d[j] = (uint8_t)(out >> (8 * j));
 }
 
+// Tiled variant of resize_kernel for batches, same structure as remap_tiled_kernel: the source window of a 128 x 8 destination
+// tile is a plain rectangle (rows sy0(first) .. sy1(last), columns sx0(first) .. sx1(last): the tables are monotone), staged
+// per frame through a cp.async ring; every tap index in the tables is already clamped into the image, so there is no border case.
+__global__ void __launch_bounds__(RT_THREADS, 4) resize_tiled_kernel(const uint8_t* __restrict__ src, size_t spitch, size_t sframe,
+                                                                     const uint2* __restrict__ xtab, const uint2* __restrict__ ytab,
+                                                                     int area2x, uint8_t* __restrict__ dst, int dw, int dh,
+                                                                     size_t dpitch, size_t dframe, int n_frames)
+{
+    __shared__ __align__(16) uint8_t win[RT_STAGES][RT_SMEM];
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int tx0 = blockIdx.x * RT_W, ty0 = blockIdx.y * RT_H;
+    const int x4 = tx0 + lane * 4, y = ty0 + (tid >> 5);
+    const int f0 = blockIdx.z * RT_FPC, nf = min(RT_FPC, n_frames - f0);
+    const int npx = y < dh ? max(0, min(4, dw - x4)) : 0;
+    const int txl = min(tx0 + RT_W, dw) - 1, tyl = min(ty0 + RT_H, dh) - 1;
+    const int X0 = (int)(__ldg(xtab + tx0).x & 0xffff) & ~15, X1 = (int)(__ldg(xtab + txl).x >> 16);
+    const int Y0 = (int)(__ldg(ytab + ty0).x & 0xffff), Y1 = (int)(__ldg(ytab + tyl).x >> 16);
+    const int nvec = ((X1 - X0) >> 4) + 1, nrow = Y1 - Y0 + 1, SP = nvec * 16, nitems = nvec * nrow;
+    const uint2 yt = __ldg(ytab + min(y, dh - 1));
+    const int b0 = (int)(short)(yt.y & 0xffff), b1 = (int)(short)(yt.y >> 16);
+    const int ro0 = ((int)(yt.x & 0xffff) - Y0) * SP, ro1 = ((int)(yt.x >> 16) - Y0) * SP;
+    int c0[4], c1[4], a0[4], a1[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const uint2 xt = __ldg(xtab + min(x4 + j, dw - 1));
+        c0[j] = (int)(xt.x & 0xffff) - X0; c1[j] = (int)(xt.x >> 16) - X0;
+        a0[j] = (int)(short)(xt.y & 0xffff); a1[j] = (int)(short)(xt.y >> 16);
+    }
+    uint8_t* d = dst + (size_t)f0 * dframe + (size_t)y * dpitch + x4;
+    const uint8_t* wsrc = src + (size_t)f0 * sframe + (size_t)Y0 * spitch + X0;
+    const bool word_store = npx == 4 && ((reinterpret_cast<size_t>(d) | dframe) & 3) == 0;
+    const bool staged = SP * nrow <= RT_SMEM && nitems <= RT_THREADS && (size_t)X0 + (size_t)SP <= spitch;
+    const int r0 = tid / nvec, v0 = tid - r0 * nvec;
+    const bool h0 = staged && tid < nitems;
+    const size_t g0 = (size_t)r0 * spitch + (size_t)v0 * 16;
+    const uint32_t q0 = (uint32_t)__cvta_generic_to_shared(&win[0][0]) + (uint32_t)(r0 * SP + v0 * 16);
+    auto issue = [&](int f) {
+        if (h0 && f < nf)
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(q0 + (uint32_t)((f % RT_STAGES) * RT_SMEM)), "l"(wsrc + (size_t)f * sframe + g0) : "memory");
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    if (staged) {
+#pragma unroll
+        for (int f = 0; f < RT_STAGES - 1; ++f) issue(f);
+    }
+    for (int f = 0; f < nf; ++f, d += dframe) {
+        const uint8_t* W;
+        int sp;
+        if (staged) {
+            asm volatile("cp.async.wait_group %0;" ::"n"(RT_STAGES - 2) : "memory");
+            __syncthreads();
+            issue(f + RT_STAGES - 1);
+            W = win[f % RT_STAGES]; sp = SP;
+        } else {                                              // window too large for the ring (huge down-scales): read global
+            W = wsrc + (size_t)f * sframe; sp = (int)spitch;
+        }
+        const uint8_t* S0 = W + (staged ? ro0 : (ro0 / SP) * sp);
+        const uint8_t* S1 = W + (staged ? ro1 : (ro1 / SP) * sp);
+        uint32_t out = 0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int p00 = S0[c0[j]], p01 = S0[c1[j]], p10 = S1[c0[j]], p11 = S1[c1[j]];
+            uint32_t v;
+            if (area2x) v = (uint32_t)((p00 + p01 + p10 + p11 + 2) >> 2);
+            else {
+                const int h0v = p00 * a0[j] + p01 * a1[j], h1v = p10 * a0[j] + p11 * a1[j];
+                v = (uint32_t)((((b0 * (h0v >> 4)) >> 16) + ((b1 * (h1v >> 4)) >> 16) + 2) >> 2) & 0xffu;
+            }
+            out |= v << (8 * j);
+        }
+        if (word_store) *reinterpret_cast<uint32_t*>(d) = out;
+        else for (int j = 0; j < npx; ++j) d[j] = (uint8_t)(out >> (8 * j));
+    }
+}
+
 cudaError_t launch_undistort(const orbx_keypoint* d_in, int n, const UndistortParams& p, orbx_keypoint* d_out, cudaStream_t st)
 {
     if (n <= 0) return cudaSuccess;
@@ -322,6 +397,12 @@ cudaError_t launch_resize(const uint8_t* d_src, size_t spitch, size_t sframe, co
                           uint8_t* d_dst, int dw, int dh, size_t dpitch, size_t dframe, int n_frames, cudaStream_t st)
 {
     if (n_frames <= 0) return cudaSuccess;
+    if (n_frames >= 8 && ((reinterpret_cast<size_t>(d_src) | spitch | sframe) & 15) == 0) {
+        resize_tiled_kernel<<<dim3((dw + RT_W - 1) / RT_W, (dh + RT_H - 1) / RT_H, (n_frames + RT_FPC - 1) / RT_FPC), RT_THREADS, 0, st>>>(
+            d_src, spitch, sframe, d_xtab, d_ytab, area2x, d_dst, dw, dh, dpitch, dframe, n_frames);
+        count_launch();
+        return cudaGetLastError();
+    }
     resize_kernel<<<dim3((dw + 511) / 512, dh, n_frames), 128, 0, st>>>(d_src, spitch, sframe, d_xtab, d_ytab, area2x, d_dst, dw, dh, dpitch, dframe);
     count_launch();
     return cudaGetLastError();
