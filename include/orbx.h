@@ -82,8 +82,13 @@ int orbx_compute_tables(int nfeatures, float scaleFactor, int nlevels, float* sc
                         float* inv_sigma2, int* nfeatures_per_level);
 /* Level size for an input of cols x rows: cvRound(cols * mvInvScaleFactor[level]) (src/ORBextractor.cc:1312-1313). */
 int orbx_level_size(const orbx_extractor* ex, int cols, int rows, int level, int* level_cols, int* level_rows);
-/* Upper bound on keypoints per frame (sum over levels of mnFeaturesPerLevel + 3): size outputs with this. */
+/* Upper bound on keypoints per frame for the shape the handle is configured for (sum over levels of
+ * max(mnFeaturesPerLevel + 4, 4 * nIni + 1)); before the first image it cannot know nIni = round(width / height) of
+ * DistributeOctTree (src/ORBextractor.cc:589) and returns the sum of mnFeaturesPerLevel + 4 only. */
 int orbx_max_keypoints(const orbx_extractor* ex);
+/* The same bound for a rows x cols image, from the shape alone (host arithmetic, handle unchanged): size outputs with
+ * this.  Wide images matter: the octree's first sweep splits all nIni roots into four before it compares with N. */
+int orbx_max_keypoints_for(const orbx_extractor* ex, int rows, int cols);
 
 /* ---- extraction ------------------------------------------------------------------------------------------ */
 

@@ -283,3 +283,27 @@ def test_host_batch_serial_pipeline_matches_single_frames(oracle):
         ok, od, onm = oex.extract(imgs[f], (0, 0))
         slot = F - 1 - f
         assert n[slot] == len(ok) and np.array_equal(kps[slot, :n[slot]]["x"], ok["x"]) and np.array_equal(kps[slot, :n[slot]]["y"], ok["y"])
+
+
+@pytest.mark.parametrize("cols,rows,nfeatures,nlevels", [(1300, 100, 100, 4), (1390, 84, 60, 3)])
+def test_wide_image_small_nfeatures_capacity(oracle, cols, rows, nfeatures, nlevels):
+    """DistributeOctTree splits all nIni = round(width / height) roots before it compares with N (src/ORBextractor.cc:589-608,
+    635-698): a strip image returns up to 4 * nIni keypoints per level, far more than mnFeaturesPerLevel + 3.  Outputs sized by
+    orbx_max_keypoints_for(rows, cols) must hold them on a fresh handle — single frame and host batch."""
+    imgs = np.stack([synth.image(4000 + f, cols, rows) for f in range(3)])
+    oex = oracle.extractor(nfeatures, 1.2, nlevels, 20, 7)
+    ex = orbx.ORBextractor(nfeatures, 1.2, nlevels, 20, 7)
+    assert ex.max_keypoints(rows, cols) > ex.max_keypoints()        # fresh handle: the shape-free figure is too small
+    kps, _, _, _ = compare_full(oracle, ex, oex, imgs[0], (0, 0))
+    assert len(kps) > nfeatures + 3 * nlevels                       # the case the old bound could not hold
+    assert ex.max_keypoints() == ex.max_keypoints(rows, cols)       # configured handle agrees with the shape-only bound
+    ex.close()
+    ex = orbx.ORBextractor(nfeatures, 1.2, nlevels, 20, 7)
+    nmv, nv, kb, db = ex.extract_batch(imgs)
+    for f in range(3):
+        ko, do, nmo = oex.extract(imgs[f], (0, 0))
+        assert int(nmv[f]) == nmo and int(nv[f]) == len(ko)
+        for fld in ("x", "y", "size", "response", "octave"):
+            assert np.array_equal(kb[f][:nv[f]][fld], ko[fld]), fld
+        assert np.array_equal(db[f][:nv[f]], do)
+    ex.close()

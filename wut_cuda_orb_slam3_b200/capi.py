@@ -40,6 +40,7 @@ SIGNATURES = {
     "orbx_compute_tables": (_i, [_i, _f, _i, _vp, _vp, _vp, _vp, _vp]),
     "orbx_level_size": (_i, [_vp, _i, _i, _i, _vp, _vp]),
     "orbx_max_keypoints": (_i, [_vp]),
+    "orbx_max_keypoints_for": (_i, [_vp, _i, _i]),
     "orbx_extract": (_i, [_vp, _vp, _i, _i, _sz, _i, _i, _vp, _vp, _i, _vp, _vp]),
     "orbx_extract_color": (_i, [_vp, _vp, _i, _i, _sz, _i, _i, _i, _i, _vp, _vp, _i, _vp, _vp]),
     "orbx_cvt_gray_device": (_i, [_i, _vp, _sz, _sz, _i, _i, _i, _i, _i, _vp, _sz, _sz, _vp]),

@@ -50,7 +50,7 @@ public:
         if (_image.empty()) return -1;
         cv::Mat image = _image.getMat();
         assert(image.type() == CV_8UC1);
-        const int cap = orbx_max_keypoints(handle);
+        const int cap = orbx_max_keypoints_for(handle, image.rows, image.cols);
         std::vector<cv::KeyPoint> kps(cap);
         std::vector<unsigned char> desc((size_t)cap * 32);
         int n = 0, nMono = 0;

@@ -647,6 +647,22 @@ int orbx_level_size(const orbx_extractor* ex, int cols, int rows, int level, int
 
 int orbx_max_keypoints(const orbx_extractor* ex) { return ex ? ex->max_kp : 0; }
 
+// The first sweep of DistributeOctTree splits all nIni = round(width / height) root nodes before it looks at N (src
+// 589-608, 635-698), so a level of a wide image can return up to 4 * nIni keypoints however small mnFeaturesPerLevel is.
+// Same per-level bound as configure() (kp_cap), from the shape alone: no GPU work, no change of the handle.
+int orbx_max_keypoints_for(const orbx_extractor* ex, int rows, int cols)
+{
+    if (!ex || rows <= 0 || cols <= 0) return 0;
+    int kp = 0;
+    for (int l = 0; l < ex->nlevels; ++l) {
+        const int w = cvRoundF((float)cols * ex->tab.inv[l]), h = cvRoundF((float)rows * ex->tab.inv[l]);
+        const float width = (float)(w - kEdge + 3 - kWinBorder), height = (float)(h - kEdge + 3 - kWinBorder);
+        const int nIni = (width > 0 && height > 0) ? (int)round(width / height) : 0;
+        kp += std::max(ex->tab.nfeat[l] + 4, 4 * nIni + 1);
+    }
+    return kp;
+}
+
 int orbx_sync(orbx_extractor* ex)
 {
     if (!ex) return fail(ORBX_ERR_INVALID_ARG, "extractor is NULL");

@@ -63,7 +63,11 @@ class ORBextractor:
     def GetFeaturesPerLevel(self):
         return self._tables()[4]
 
-    def max_keypoints(self):
+    def max_keypoints(self, rows=None, cols=None):
+        """Upper bound on keypoints per frame; pass the image shape (the bound depends on nIni = round(width / height) of
+        DistributeOctTree, src/ORBextractor.cc:589, which a handle that has not seen an image yet cannot know)."""
+        if rows is not None and cols is not None:
+            return lib().orbx_max_keypoints_for(self._h, int(rows), int(cols))
         return lib().orbx_max_keypoints(self._h)
 
     def level_size(self, cols, rows, level):
@@ -83,7 +87,7 @@ class ORBextractor:
         if image.strides[1] != 1:
             image = np.ascontiguousarray(image)
         rows, cols = image.shape
-        cap = self.max_keypoints()
+        cap = self.max_keypoints(rows, cols)
         kps = np.zeros(cap, KP_DTYPE)
         desc = np.zeros((cap, 32), np.uint8)
         n, nm = C.c_int(0), C.c_int(0)
@@ -99,7 +103,7 @@ class ORBextractor:
         if image.strides[2] != 1 or image.strides[1] != image.shape[2]:
             image = np.ascontiguousarray(image)
         rows, cols, ch = image.shape
-        cap = self.max_keypoints()
+        cap = self.max_keypoints(rows, cols)
         kps = np.zeros(cap, KP_DTYPE)
         desc = np.zeros((cap, 32), np.uint8)
         n, nm = C.c_int(0), C.c_int(0)
@@ -112,7 +116,7 @@ class ORBextractor:
         """images: [F,H,W] uint8 numpy array (host, ideally page-locked).  Returns (n_mono[F], n[F], kps[F,cap], desc[F,cap,32])."""
         assert images.dtype == np.uint8 and images.ndim == 3 and images.strides[2] == 1
         F, rows, cols = images.shape
-        cap = self.max_keypoints()
+        cap = self.max_keypoints(rows, cols)
         kps = np.zeros((F, cap), KP_DTYPE)
         desc = np.zeros((F, cap, 32), np.uint8)
         n = np.zeros(F, np.int32)
@@ -188,7 +192,7 @@ class ORBextractor:
 def distribute_octree(xs, ys, scores, minX, maxX, minY, maxY, nFeatures, device=0):
     """ORBextractor::DistributeOctTree (src/ORBextractor.cc:584-774) on the GPU kernel; returns retained input indices."""
     xs = np.ascontiguousarray(xs, np.int32); ys = np.ascontiguousarray(ys, np.int32); scores = np.ascontiguousarray(scores, np.int32)
-    cap = max(nFeatures + 8, 64)
+    cap = max(nFeatures + 8, 4 * 64 + 1)               # max(N + 4, 4 * nIni + 1), nIni <= 64
     out = np.zeros(cap, np.int32)
     n = C.c_int(0)
     check(lib().orbx_distribute_octree(device, ptr(xs), ptr(ys), ptr(scores), len(xs), minX, maxX, minY, maxY, nFeatures, ptr(out), cap,
