@@ -31,7 +31,12 @@ try:
     h = next(i for i, r in enumerate(rows) if "Source" in r and "Instructions Executed" in r)
 except StopIteration:
     sys.exit(0)
-hdr = rows[h]; data = [r for r in rows[h + 1:] if len(r) == len(hdr)]
+hdr = rows[h]; data = []
+for r in rows[h + 1:]:                      # a report with several kernels repeats the header: summarise the first kernel only
+    if r == hdr:
+        break
+    if len(r) == len(hdr):
+        data.append(r)
 ia, ii, isamp = hdr.index("Source"), hdr.index("Instructions Executed"), hdr.index("# Samples")
 tot = sum(int(r[ii]) for r in data); cur = 0; cs = 0; start = 0
 print("total warp instructions", tot)

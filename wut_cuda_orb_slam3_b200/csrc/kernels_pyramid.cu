@@ -225,36 +225,49 @@ __global__ void __launch_bounds__(PT_THREADS) pyr_resize_tiled_kernel(const __gr
         __syncthreads();
     }
 
-    // horizontal pass: thread = output column, every other source row
+    // horizontal pass: thread = output column, every other source row.  The vertical rule only ever uses (r >> 4), so the
+    // shift is applied once here (the exact-2x path adds the raw sums and keeps them unshifted); sums are non-negative
+    // (coefficients in [0, 2048]).  Pointer-stepped and unrolled: 2 LDS + 2 IMAD + SHF + STS per row.
     {
-        const int c0 = (int)(xt.x & 0xffff) - cbase, c1 = (int)(xt.x >> 16) - cbase;
-        const int a0 = (int)(xt.y & 0xffff), a1 = (int)(xt.y >> 16);
-        const uint8_t* s0 = src + c0;
-        const uint8_t* s1 = src + c1;
-        int* hb = hbuf + tx;
-        for (int r = tid >> 7; r < nrows; r += PT_THREADS / PT_W)
-            hb[r * PT_W] = (int)s0[r * spitch] * a0 + (int)s1[r * spitch] * a1;
+        // second tap = first tap + 1, except where the table clamps it to the last source column — and there its
+        // coefficient is 0 (f = 0), so reading the byte after it changes nothing: one pointer, two immediate offsets
+        const int c0 = (int)(xt.x & 0xffff) - cbase;
+        const bool same = (xt.x >> 16) == (xt.x & 0xffff);
+        const uint32_t a0 = (xt.y & 0xffff) + (same ? (xt.y >> 16) : 0u), a1 = same ? 0u : (xt.y >> 16);
+        const int rfirst = tid >> 7;
+        const uint8_t* q0 = src + c0 + rfirst * spitch;
+        uint32_t* hb = reinterpret_cast<uint32_t*>(hbuf) + tx + rfirst * PT_W;
+        const int step = (PT_THREADS / PT_W) * spitch;
+        const int n = (nrows - rfirst + (PT_THREADS / PT_W) - 1) / (PT_THREADS / PT_W);
+        const int sh = g.area2x ? 0 : 4;
+#pragma unroll 4
+        for (int i = 0; i < n; ++i) {
+            *hb = ((uint32_t)q0[0] * a0 + (uint32_t)q0[1] * a1) >> sh;
+            q0 += step; hb += (PT_THREADS / PT_W) * PT_W;
+        }
     }
     __syncthreads();
 
-    // vertical pass: thread = 4 consecutive columns x PT_H/8 rows -> one 32-bit word per row of the output tile
+    // vertical pass: thread = 4 consecutive columns x PT_H/8 rows -> one 32-bit word per row of the output tile.
+    // ((b * (r >> 4)) >> 16) with b <= 2048 and (r >> 4) < 2^15 is the high word of (b << 16) * (r >> 4): one IMAD.HI.
     {
         const int xq = (tid & 31) * 4;
 #pragma unroll
         for (int k = 0; k < PT_H / 8; ++k) {
             const int ty = (tid >> 5) + 8 * k;
             const uint2 yt = ytl[ty];
-            const int4 r0 = *reinterpret_cast<const int4*>(hbuf + ((int)(yt.x & 0xffff) - symin) * PT_W + xq);
-            const int4 r1 = *reinterpret_cast<const int4*>(hbuf + ((int)(yt.x >> 16) - symin) * PT_W + xq);
-            const int b0 = (int)(yt.y & 0xffff), b1 = (int)(yt.y >> 16);
-            uint32_t o;
+            const uint4 r0 = *reinterpret_cast<const uint4*>(hbuf + ((int)(yt.x & 0xffff) - symin) * PT_W + xq);
+            const uint4 r1 = *reinterpret_cast<const uint4*>(hbuf + ((int)(yt.x >> 16) - symin) * PT_W + xq);
+            uint32_t p0, p1, p2, p3;
             if (g.area2x) {
-                o = (uint32_t)((r0.x + r1.x + 2) >> 2) | ((uint32_t)((r0.y + r1.y + 2) >> 2) << 8) |
-                    ((uint32_t)((r0.z + r1.z + 2) >> 2) << 16) | ((uint32_t)((r0.w + r1.w + 2) >> 2) << 24);
+                p0 = (r0.x + r1.x + 2) >> 2; p1 = (r0.y + r1.y + 2) >> 2; p2 = (r0.z + r1.z + 2) >> 2; p3 = (r0.w + r1.w + 2) >> 2;
             } else {
-                auto f = [&](int a, int b) { return (uint32_t)((((b0 * (a >> 4)) >> 16) + ((b1 * (b >> 4)) >> 16) + 2) >> 2) & 0xffu; };
-                o = f(r0.x, r1.x) | (f(r0.y, r1.y) << 8) | (f(r0.z, r1.z) << 16) | (f(r0.w, r1.w) << 24);
+                const uint32_t b0 = yt.y << 16, b1 = yt.y & 0xffff0000u;
+                auto f = [&](uint32_t a, uint32_t b) { return (__umulhi(b0, a) + __umulhi(b1, b) + 2) >> 2; };
+                p0 = f(r0.x, r1.x); p1 = f(r0.y, r1.y); p2 = f(r0.z, r1.z); p3 = f(r0.w, r1.w);
             }
+            // low bytes of p0..p3 -> one word (same truncation as the & 0xff of the scalar rule)
+            const uint32_t o = __byte_perm(__byte_perm(p0, p1, 0x0040), __byte_perm(p2, p3, 0x0040), 0x5410);
             *reinterpret_cast<uint32_t*>(outt + ty * PT_W + xq) = o;
         }
     }
