@@ -173,15 +173,89 @@ __global__ void __launch_bounds__(PT_THREADS) pyr_level0_tiled_kernel(const __gr
     write_border_mirrors<PT_W>(D, g.pitch, g.w, g.h, x0, y0, tw, th, t, tid, PT_THREADS);
 }
 
+// The two fixed-point passes, the interior stores and the border mirrors of one 128 x PT_H tile whose source window is already
+// staged in `src` (row pitch `spitch`, first staged column `cbase`, first staged row `symin`).  Shared by the one-tile-per-CTA
+// kernel (a persistent two-stage variant was measured and dropped).  Ends without a barrier.
+template <int PT_H>
+__device__ __forceinline__ void resize_tile_passes(const LevelGeom& g, const Workspace& ws, const uint8_t* src, uint16_t* hbuf, uint8_t* outt,
+                                                   const uint2* ytl, uint2 xt, int tid, int tx, int x0, int y0, int frame, int tw, int th,
+                                                   int cbase, int spitch, int symin, int nrows)
+{
+    // horizontal pass: thread = output column, every other source row.  The vertical rule only ever uses (r >> 4), so the
+    // shift is applied once here (the exact-2x path adds the raw sums and keeps them unshifted); sums are non-negative
+    // (coefficients in [0, 2048]).  Pointer-stepped and unrolled: 2 LDS + 2 IMAD + SHF + STS per row.
+    {
+        // second tap = first tap + 1, except where the table clamps it to the last source column — and there its
+        // coefficient is 0 (f = 0), so reading the byte after it changes nothing: one pointer, two immediate offsets
+        const int c0 = (int)(xt.x & 0xffff) - cbase;
+        const bool same = (xt.x >> 16) == (xt.x & 0xffff);
+        const uint32_t a0 = (xt.y & 0xffff) + (same ? (xt.y >> 16) : 0u), a1 = same ? 0u : (xt.y >> 16);
+        const int rfirst = tid >> 7;
+        const uint8_t* q0 = src + c0 + rfirst * spitch;
+        uint16_t* hb = hbuf + tx + rfirst * PT_W;
+        const int step = (PT_THREADS / PT_W) * spitch;
+        const int n = (nrows - rfirst + (PT_THREADS / PT_W) - 1) / (PT_THREADS / PT_W);
+        const int sh = g.area2x ? 0 : 4;
+#pragma unroll 4
+        for (int i = 0; i < n; ++i) {
+            *hb = (uint16_t)(((uint32_t)q0[0] * a0 + (uint32_t)q0[1] * a1) >> sh);
+            q0 += step; hb += (PT_THREADS / PT_W) * PT_W;
+        }
+    }
+    __syncthreads();
+
+    // vertical pass: thread = 4 consecutive columns x PT_H/8 rows -> one 32-bit word per row of the output tile.
+    // ((b * (r >> 4)) >> 16) with b <= 2048 and (r >> 4) < 2^15 is the high word of (b << 16) * (r >> 4): one IMAD.HI.
+    {
+        const int xq = (tid & 31) * 4;
+#pragma unroll
+        for (int k = 0; k < PT_H / 8; ++k) {
+            const int ty = (tid >> 5) + 8 * k;
+            const uint2 yt = ytl[ty];
+            const uint2 r0 = *reinterpret_cast<const uint2*>(hbuf + ((int)(yt.x & 0xffff) - symin) * PT_W + xq);     // 4 x u16
+            const uint2 r1 = *reinterpret_cast<const uint2*>(hbuf + ((int)(yt.x >> 16) - symin) * PT_W + xq);
+            uint32_t p0, p1, p2, p3;
+            if (g.area2x) {
+                const uint32_t s01 = r0.x + r1.x + 0x00020002u, s23 = r0.y + r1.y + 0x00020002u;   // halves <= 1022: no carry across
+                p0 = (s01 & 0xffffu) >> 2; p1 = s01 >> 18; p2 = (s23 & 0xffffu) >> 2; p3 = s23 >> 18;
+            } else {
+                const uint32_t b0 = yt.y << 16, b1 = yt.y & 0xffff0000u;
+                auto f = [&](uint32_t a, uint32_t b) { return (__umulhi(b0, a) + __umulhi(b1, b) + 2) >> 2; };
+                p0 = f(r0.x & 0xffffu, r1.x & 0xffffu); p1 = f(r0.x >> 16, r1.x >> 16);
+                p2 = f(r0.y & 0xffffu, r1.y & 0xffffu); p3 = f(r0.y >> 16, r1.y >> 16);
+            }
+            // low bytes of p0..p3 -> one word (same truncation as the & 0xff of the scalar rule)
+            const uint32_t o = __byte_perm(__byte_perm(p0, p1, 0x0040), __byte_perm(p2, p3, 0x0040), 0x5410);
+            *reinterpret_cast<uint32_t*>(outt + ty * PT_W + xq) = o;
+        }
+    }
+    __syncthreads();
+
+    // interior: 16-byte stores (interior rows are 16-byte aligned and x0 is a multiple of 128)
+    uint8_t* D = level_interior(ws.pyr, g, frame);
+    for (int i = tid; i < PT_H * (PT_W / 16); i += PT_THREADS) {
+        const int ty = i >> 3, v = i & 7;
+        if (ty < th && v * 16 < tw) {
+            uint8_t* dst = D + (size_t)(y0 + ty) * g.pitch + x0 + v * 16;
+            if (v * 16 + 16 <= tw) *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(outt + ty * PT_W + v * 16);
+            else for (int b = v * 16; b < tw; ++b) dst[b - v * 16] = outt[ty * PT_W + b];
+        }
+    }
+    const bool edge = x0 <= kEdge || x0 + tw >= g.w - kEdge - 1 || y0 <= kEdge || y0 + th >= g.h - kEdge - 1;
+    if (!edge) return;
+    write_border_mirrors<PT_W>(D, g.pitch, g.w, g.h, x0, y0, tw, th, outt, tid, PT_THREADS);
+}
+
 // Level l >= 1: one CTA produces a 128 x PT_H tile of the level interior (32 rows for scale <= 1.5, 16 rows up to 2).  The
 // source footprint is staged in shared memory with 16-byte loads, the horizontal fixed-point pass runs once per source row
-// into an int32 plane, the vertical pass combines two rows per output row (4 pixels per thread, 128-bit shared loads),
+// into a u16 plane (pre-shifted sums), the vertical pass combines two rows per output row (4 pixels per thread, 64-bit shared loads),
 // and the finished tile is written with 16-byte stores.
+constexpr int PT_MINB = 6;                     // CTAs per SM the register budget must allow (the kernel is occupancy-bound)
 template <int PT_H, int PT_SR, int PT_SP>      // tile rows, source rows, source pitch (bytes, multiple of 16)
-__global__ void __launch_bounds__(PT_THREADS) pyr_resize_tiled_kernel(const __grid_constant__ FrameGeom fg, Workspace ws, int level)
+__global__ void __launch_bounds__(PT_THREADS, PT_MINB) pyr_resize_tiled_kernel(const __grid_constant__ FrameGeom fg, Workspace ws, int level)
 {
     __shared__ __align__(128) uint8_t src[PT_SR * PT_SP];
-    __shared__ __align__(16) int hbuf[PT_SR * PT_W];
+    __shared__ __align__(16) uint16_t hbuf[PT_SR * PT_W];      // horizontal sums, pre-shifted: <= 255 * 2048 >> 4 = 32640
     __shared__ __align__(16) uint8_t outt[PT_H * PT_W];
     __shared__ uint2 ytl[PT_H];
 
@@ -225,67 +299,7 @@ __global__ void __launch_bounds__(PT_THREADS) pyr_resize_tiled_kernel(const __gr
         __syncthreads();
     }
 
-    // horizontal pass: thread = output column, every other source row.  The vertical rule only ever uses (r >> 4), so the
-    // shift is applied once here (the exact-2x path adds the raw sums and keeps them unshifted); sums are non-negative
-    // (coefficients in [0, 2048]).  Pointer-stepped and unrolled: 2 LDS + 2 IMAD + SHF + STS per row.
-    {
-        // second tap = first tap + 1, except where the table clamps it to the last source column — and there its
-        // coefficient is 0 (f = 0), so reading the byte after it changes nothing: one pointer, two immediate offsets
-        const int c0 = (int)(xt.x & 0xffff) - cbase;
-        const bool same = (xt.x >> 16) == (xt.x & 0xffff);
-        const uint32_t a0 = (xt.y & 0xffff) + (same ? (xt.y >> 16) : 0u), a1 = same ? 0u : (xt.y >> 16);
-        const int rfirst = tid >> 7;
-        const uint8_t* q0 = src + c0 + rfirst * spitch;
-        uint32_t* hb = reinterpret_cast<uint32_t*>(hbuf) + tx + rfirst * PT_W;
-        const int step = (PT_THREADS / PT_W) * spitch;
-        const int n = (nrows - rfirst + (PT_THREADS / PT_W) - 1) / (PT_THREADS / PT_W);
-        const int sh = g.area2x ? 0 : 4;
-#pragma unroll 4
-        for (int i = 0; i < n; ++i) {
-            *hb = ((uint32_t)q0[0] * a0 + (uint32_t)q0[1] * a1) >> sh;
-            q0 += step; hb += (PT_THREADS / PT_W) * PT_W;
-        }
-    }
-    __syncthreads();
-
-    // vertical pass: thread = 4 consecutive columns x PT_H/8 rows -> one 32-bit word per row of the output tile.
-    // ((b * (r >> 4)) >> 16) with b <= 2048 and (r >> 4) < 2^15 is the high word of (b << 16) * (r >> 4): one IMAD.HI.
-    {
-        const int xq = (tid & 31) * 4;
-#pragma unroll
-        for (int k = 0; k < PT_H / 8; ++k) {
-            const int ty = (tid >> 5) + 8 * k;
-            const uint2 yt = ytl[ty];
-            const uint4 r0 = *reinterpret_cast<const uint4*>(hbuf + ((int)(yt.x & 0xffff) - symin) * PT_W + xq);
-            const uint4 r1 = *reinterpret_cast<const uint4*>(hbuf + ((int)(yt.x >> 16) - symin) * PT_W + xq);
-            uint32_t p0, p1, p2, p3;
-            if (g.area2x) {
-                p0 = (r0.x + r1.x + 2) >> 2; p1 = (r0.y + r1.y + 2) >> 2; p2 = (r0.z + r1.z + 2) >> 2; p3 = (r0.w + r1.w + 2) >> 2;
-            } else {
-                const uint32_t b0 = yt.y << 16, b1 = yt.y & 0xffff0000u;
-                auto f = [&](uint32_t a, uint32_t b) { return (__umulhi(b0, a) + __umulhi(b1, b) + 2) >> 2; };
-                p0 = f(r0.x, r1.x); p1 = f(r0.y, r1.y); p2 = f(r0.z, r1.z); p3 = f(r0.w, r1.w);
-            }
-            // low bytes of p0..p3 -> one word (same truncation as the & 0xff of the scalar rule)
-            const uint32_t o = __byte_perm(__byte_perm(p0, p1, 0x0040), __byte_perm(p2, p3, 0x0040), 0x5410);
-            *reinterpret_cast<uint32_t*>(outt + ty * PT_W + xq) = o;
-        }
-    }
-    __syncthreads();
-
-    // interior: 16-byte stores (interior rows are 16-byte aligned and x0 is a multiple of 128)
-    uint8_t* D = level_interior(ws.pyr, g, frame);
-    for (int i = tid; i < PT_H * (PT_W / 16); i += PT_THREADS) {
-        const int ty = i >> 3, v = i & 7;
-        if (ty < th && v * 16 < tw) {
-            uint8_t* dst = D + (size_t)(y0 + ty) * g.pitch + x0 + v * 16;
-            if (v * 16 + 16 <= tw) *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(outt + ty * PT_W + v * 16);
-            else for (int b = v * 16; b < tw; ++b) dst[b - v * 16] = outt[ty * PT_W + b];
-        }
-    }
-    const bool edge = x0 <= kEdge || x0 + tw >= g.w - kEdge - 1 || y0 <= kEdge || y0 + th >= g.h - kEdge - 1;
-    if (!edge) return;
-    write_border_mirrors<PT_W>(D, g.pitch, g.w, g.h, x0, y0, tw, th, outt, tid, PT_THREADS);
+    resize_tile_passes<PT_H>(g, ws, src, hbuf, outt, ytl, xt, tid, tx, x0, y0, frame, tw, th, cbase, spitch, symin, nrows);
 }
 
 cudaError_t launch_pyramid(const FrameGeom& fg, const Workspace& ws, const uint8_t* d_images, size_t frame_stride,
