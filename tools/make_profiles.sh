@@ -15,7 +15,7 @@ python tools/launch_shares.py $OUT/${TAG}_launches_b512.csv $OUT/${TAG}_bench.js
 ARGS="--steps 1 --warmup 1 --batch 64 --no-knn2 --no-cpu --no-other"
 python bench.py $ARGS > $OUT/plain.log 2>&1 && \
 ncu --set full --clock-control none --import-source on -k regex:fast_cells_warp -s 3 -c 1 -f -o $OUT/${TAG}_fast_cells_warp python bench.py $ARGS > $OUT/ncu_f.log 2>&1
-KARGS="--steps 1 --warmup 1 --batch 32 --no-cpu --knn-ndb 1000000 --knn-reps 1"
+KARGS="--steps 1 --warmup 1 --batch 32 --no-cpu --no-other --knn-ndb 1000000 --knn-reps 1"   # --no-other: the KITTI pair of the other configs launches knn2_kernel first (4 CTAs)
 python bench.py $KARGS > $OUT/plain.log 2>&1 && \
 ncu --set full --clock-control none --import-source on -k regex:knn2_kernel -s 1 -c 1 -f -o $OUT/${TAG}_knn2 python bench.py $KARGS > $OUT/ncu_k.log 2>&1
 python bench.py $ARGS > $OUT/plain.log 2>&1 && \
