@@ -96,6 +96,8 @@ int orbx_max_keypoints_for(const orbx_extractor* ex, int rows, int cols);
  * src/ORBextractor.cc:1227-1307.  image: CV_8UC1 rows x cols, `step` bytes per row, HOST memory.  (lap0, lap1) =
  * vLappingArea.  Writes *n_out keypoints (28 B) + descriptors (32 B) in the reference's packing order (non-lapping
  * from the front, lapping from the back) and *n_mono = the reference's return value (monoIndex).
+ * `capacity` = room in keypoints / descriptors, sized with orbx_max_keypoints_for(ex, rows, cols); a frame with more
+ * keypoints than that fails with ORBX_ERR_CAPACITY and writes nothing past the buffers.
  * Returns ORBX_ERR_EMPTY_IMAGE for a NULL/empty image. */
 int orbx_extract(orbx_extractor* ex, const uint8_t* image, int rows, int cols, size_t step, int lap0, int lap1,
                  orbx_keypoint* keypoints, uint8_t* descriptors, int capacity, int* n_out, int* n_mono);
