@@ -122,7 +122,8 @@ int orbx_extract_batch(orbx_extractor* ex, const uint8_t* const* images, int n_f
 
 /* Device-resident batched operator(): frame f starts at d_images + f*frame_stride, `pitch` bytes per row; all
  * output pointers are DEVICE memory with the same slab layout.  Asynchronous on `stream` (a cudaStream_t, or NULL
- * for the extractor's own stream); call orbx_sync to wait. */
+ * for the extractor's own stream).  orbx_sync waits for it whichever stream was used (an event is recorded behind the last
+ * launch), and so do the probes, orbx_stereo_match and the next call on this handle. */
 int orbx_extract_batch_device(orbx_extractor* ex, const uint8_t* d_images, size_t frame_stride, int n_frames, int rows,
                               int cols, size_t pitch, int lap0, int lap1, orbx_keypoint* d_keypoints,
                               uint8_t* d_descriptors, int capacity, int* d_n_out, int* d_n_mono, void* stream);
@@ -158,13 +159,41 @@ int orbx_descriptor_distance(const uint8_t* a, const uint8_t* b);
  * HOST buffers; idx/dist are [nq][2], ascending distance, ties -> lower database index; missing = (-1, INT32_MAX). */
 int orbx_knn2(int device, const uint8_t* queries, int nq, const uint8_t* database, int64_t ndb, int32_t* idx,
               int32_t* dist);
-/* Device-resident variant on `stream`; database rows are numbered index_base + row (for sharded databases). */
+/* Device-resident variant on `stream`; database rows are numbered index_base + row (for sharded databases).  Re-entrant:
+ * scratch is a stream-ordered allocation private to the call, so Tracking / LocalMapping / LoopClosing threads (all of which
+ * match descriptors, src/ORBmatcher3.cc:637-653 callers) may run it concurrently on their own streams. */
 int orbx_knn2_device(int device, const uint8_t* d_queries, int nq, const uint8_t* d_database, int64_t ndb,
                      int32_t index_base, int32_t* d_idx, int32_t* d_dist, void* stream);
 /* Merge per-shard 2-NN candidates (e.g. after an NCCL all-gather): inputs [n_shards][nq][2]; lexicographic
  * (distance, index) order reproduces the single-GPU / BFMatcher tie rule exactly. */
 int orbx_knn2_merge_device(int device, const int32_t* d_idx_shards, const int32_t* d_dist_shards, int n_shards, int nq,
                            int32_t* d_idx, int32_t* d_dist, void* stream);
+
+/* ---- database-sharded 2-NN over several GPUs (BASELINE config 5; SURVEY.md §8(b) "a sharded variant taking an
+ * ncclComm_t/rank/world", §8(e)) --------------------------------------------------------------------------------------------
+ * The reference's brute-force matcher (cv::BFMatcher(NORM_HAMMING).knnMatch(k=2) + the ratio test, src/Frame.cc:45, 1174-1181)
+ * on a database too large for one GPU: queries replicated, database rows split in contiguous shards (orbx_shard_rows), one
+ * process per GPU.  NCCL is bound at run time (the copy already loaded into the process, else libnccl.so.2 / $ORBX_NCCL_LIB). */
+typedef struct orbx_comm orbx_comm;
+#define ORBX_COMM_ID_BYTES 128
+/* ncclGetUniqueId: call on one rank, hand the 128 bytes to every rank by any means (MPI, torch.distributed, a file). */
+int orbx_comm_unique_id(uint8_t id[ORBX_COMM_ID_BYTES]);
+/* ncclCommInitRank on `device`; collective: every rank of `world` must call it with the same id. */
+int orbx_comm_create(int device, int rank, int world, const uint8_t id[ORBX_COMM_ID_BYTES], orbx_comm** out);
+/* Wrap a communicator the caller already owns (an ncclComm_t from the SAME libnccl the process has loaded); not destroyed by
+ * orbx_comm_destroy. */
+int orbx_comm_from_nccl(int device, void* nccl_comm, int rank, int world, orbx_comm** out);
+void orbx_comm_destroy(orbx_comm* comm);
+int orbx_comm_info(const orbx_comm* comm, int* rank, int* world, int* nccl_version);
+/* The contiguous shard [first, first + count) of n_rows that `rank` of `world` owns (trailing shards may be empty). Host. */
+void orbx_shard_rows(int64_t n_rows, int world, int rank, int64_t* first, int64_t* count);
+/* One collective call per rank: d_db_shard holds rows [first_row, first_row + n_shard_rows) of the global database; every rank
+ * passes the same nq queries.  On return (asynchronously on `stream`) EVERY rank's d_idx / d_dist [nq][2] hold the 2-NN over the
+ * whole database with GLOBAL row indices: local scan, ONE ncclAllGather of the packed 16 B / query candidates, lexicographic
+ * (distance, index) merge = the single-GPU / BFMatcher answer bit for bit.  Calls on one communicator are serialised. */
+int orbx_knn2_sharded(orbx_comm* comm, const uint8_t* d_queries, int nq, const uint8_t* d_db_shard, int64_t n_shard_rows,
+                      int64_t first_row, int32_t* d_idx, int32_t* d_dist, void* stream);
+
 /* Ratio-test acceptance on 2-NN output, host: mode 0 = src/ORBmatcher1.cc:329-333 (d1 <= th_low && (float)d1 <
  * ratio*(float)d2), mode 1 = src/ORBmatcher2.cc:120-125 (d1 < th_low && ...), mode 2 = src/Frame.cc:1181
  * (d1 < d2 * ratio, no gate).  accept[i] = 0/1. */
@@ -186,6 +215,21 @@ int orbx_distinctive_descriptor(const uint8_t* descriptors, int n, int* best_idx
 int orbx_stereo_match(orbx_extractor* exL, int frameL, orbx_extractor* exR, int frameR, const orbx_keypoint* kpL,
                       const uint8_t* descL, int nL, const orbx_keypoint* kpR, const uint8_t* descR, int nR, float bf,
                       float maxD, float* uRight, float* depth);
+
+/* The same on DEVICE-resident features, asynchronous on `stream`: d_kp* / d_desc* are [cap*] rows as written by
+ * orbx_extract_batch_device (or any device copy of orbx_extract's output), *d_nL / *d_nR the device-resident counts (read by the
+ * kernel, so the call can be queued behind an extraction that is still running on the same stream); d_uRight / d_depth receive
+ * capL floats (rows >= *d_nL are left untouched).  No host round trip, no re-upload. */
+int orbx_stereo_match_device(orbx_extractor* exL, int frameL, orbx_extractor* exR, int frameR, const orbx_keypoint* d_kpL,
+                             const uint8_t* d_descL, const int* d_nL, int capL, const orbx_keypoint* d_kpR, const uint8_t* d_descR,
+                             const int* d_nR, int capR, float bf, float maxD, float* d_uRight, float* d_depth, void* stream);
+/* The stereo Frame constructor in one call — src/Frame.cc:124-143: ExtractORB(0, imLeft) and ExtractORB(1, imRight) (two
+ * std::threads in the reference, two CUDA streams here, vLappingArea = {0, 0}) followed by ComputeStereoMatches().  HOST images
+ * in; HOST keypoints / descriptors of both sides (capacity rows each, *nL / *nR valid), mvuRight / mvDepth [capacity] out.
+ * The matcher reads keypoints, descriptors and pyramids where the extractors left them on the device. */
+int orbx_extract_stereo(orbx_extractor* exL, orbx_extractor* exR, const uint8_t* imageL, const uint8_t* imageR, int rows, int cols,
+                        size_t step, orbx_keypoint* kpL, uint8_t* descL, int* nL, orbx_keypoint* kpR, uint8_t* descR, int* nR,
+                        int capacity, float bf, float maxD, float* uRight, float* depth);
 
 /* ---- bag-of-words transform and vocabulary-guided matching -------------------- */
 

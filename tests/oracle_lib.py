@@ -63,6 +63,14 @@ class Oracle:
         L.orbo_stereo_match.argtypes = [_vp, _vp, C.c_int, _vp, _vp, C.c_int, _vp, _vp, _vp, _vp, C.c_int, _vp, _vp,
                                         C.c_float, C.c_float, _vp, _vp]
 
+    def synth_image(self, seed, cols, rows, view=0, max_disp=48):
+        """csrc/synth.h's image generator, from the oracle library (no CUDA library needed)."""
+        a = np.zeros((rows, cols), np.uint8)
+        self.lib.orbo_synth_image.argtypes = [C.c_uint32, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _sz]
+        self.lib.orbo_synth_image.restype = None
+        self.lib.orbo_synth_image(seed, view, cols, rows, max_disp, _ptr(a), a.strides[0])
+        return a
+
     def rotation_consistency(self, a, b):
         a = np.ascontiguousarray(a, np.float32); b = np.ascontiguousarray(b, np.float32)
         keep = np.zeros(len(a), np.uint8)
@@ -427,7 +435,8 @@ def load():
     global _cached
     if _cached is None:
         src = os.path.join(ROOT, "oracle", "orb_oracle.cpp")
-        if not os.path.exists(SO) or (os.path.exists(src) and os.path.getmtime(src) > os.path.getmtime(SO)):
+        srcs = [src, os.path.join(ROOT, "oracle", "synth_oracle.cpp")]
+        if not os.path.exists(SO) or any(os.path.exists(f) and os.path.getmtime(f) > os.path.getmtime(SO) for f in srcs):
             build()
         _cached = Oracle(C.CDLL(SO))
     return _cached

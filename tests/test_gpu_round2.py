@@ -1,0 +1,184 @@
+"""GPU tests of the round-2 entry points and robustness fixes: re-entrant matcher, device-resident stereo matching, the
+one-call stereo frame, the sharded 2-NN behind the C ABI, handle state after a failed configuration, orbx_sync with a
+caller's stream.  Everything goes through the C ABI (liborbx.so) and is compared with the CPU oracle, bit for bit."""
+import ctypes as C
+import threading
+
+import numpy as np
+import pytest
+
+import wut_cuda_orb_slam3_b200 as orbx
+from wut_cuda_orb_slam3_b200 import synth
+from wut_cuda_orb_slam3_b200.capi import OrbxError, check, lib, ptr
+
+pytestmark = pytest.mark.gpu
+
+
+def test_knn2_device_is_reentrant_two_threads_two_streams(oracle):
+    """ORBmatcher::DescriptorDistance users run on the Tracking, LocalMapping and LoopClosing threads at once:
+    two host threads, two streams, different databases (both chunked, so both need scratch), 200 calls each."""
+    import torch
+    dev = torch.device("cuda:0")
+    cases = []
+    for t, (nq, ndb, seed) in enumerate([(700, 300_000, 21), (1100, 260_000, 22)]):
+        db = synth.descriptors(seed, ndb); q = synth.descriptors(seed, nq, is_query=True, ndb=ndb, plant_every=3)
+        db[ndb // 2] = db[5]; q[0] = db[5]                         # a tie
+        ridx, rdist = oracle.knn2(q, db)
+        cases.append((torch.from_numpy(q).to(dev), torch.from_numpy(db).to(dev), nq, ndb, ridx, rdist))
+    errors = []
+
+    def worker(t):
+        try:
+            d_q, d_db, nq, ndb, ridx, rdist = cases[t]
+            st = torch.cuda.Stream(device=dev)
+            d_idx = torch.empty((nq, 2), dtype=torch.int32, device=dev); d_dist = torch.empty_like(d_idx)
+            for it in range(200):
+                d_idx.fill_(-7); d_dist.fill_(-7)
+                st.wait_stream(torch.cuda.current_stream(dev))
+                orbx.knn2_device(d_q, nq, d_db, ndb, d_idx, d_dist, stream=st.cuda_stream)
+                st.synchronize()
+                if not (np.array_equal(d_idx.cpu().numpy(), ridx) and np.array_equal(d_dist.cpu().numpy(), rdist)):
+                    errors.append((t, it))
+                    return
+        except Exception as e:          # noqa: BLE001
+            errors.append((t, repr(e)))
+
+    ths = [threading.Thread(target=worker, args=(t,)) for t in range(2)]
+    for th in ths:
+        th.start()
+    for th in ths:
+        th.join()
+    assert not errors, errors
+
+
+def _pair(seed=31, cols=752, rows=480):
+    return synth.image(seed, cols, rows, view=0, max_disp=40), synth.image(seed, cols, rows, view=1, max_disp=40)
+
+
+def test_stereo_match_extractors_with_different_capacity(oracle):
+    """exL sized for 4 frames, exR for 1: the level slabs of the two pyramids lie at different offsets."""
+    L, R = _pair()
+    exL = orbx.ORBextractor(1200, 1.2, 8, 20, 7, max_cols=752, max_rows=480, max_batch=4)
+    exR = orbx.ORBextractor(1200, 1.2, 8, 20, 7, max_cols=752, max_rows=480, max_batch=1)
+    nm, n, kps, desc = exL.extract_batch(np.stack([L, L, L, L]))          # grows exL's slot to 4 frames
+    _, kL, dL = exL(L, None, (0, 0)); _, kR, dR = exR(R, None, (0, 0))
+    u, d = orbx.compute_stereo_matches(exL, exR, kL, dL, kR, dR, 47.9, 435.2)
+    oL = oracle.extractor(1200, 1.2, 8, 20, 7); oR = oracle.extractor(1200, 1.2, 8, 20, 7)
+    okL, odL, _ = oL.extract(L, (0, 0)); okR, odR, _ = oR.extract(R, (0, 0))
+    ou, od, kept = oracle.stereo_match(oL, oR, okL, odL, okR, odR, 47.9, 435.2)
+    assert kept > 50 and np.array_equal(u, ou) and np.array_equal(d, od)
+    # the other way round
+    u2, d2 = orbx.compute_stereo_matches(exR, exL, kR, dR, kL, dL, 47.9, 435.2)
+    ou2, od2, _ = oracle.stereo_match(oR, oL, okR, odR, okL, odL, 47.9, 435.2)
+    assert np.array_equal(u2, ou2) and np.array_equal(d2, od2)
+
+
+@pytest.mark.parametrize("cols,rows,nf", [(752, 480, 1200), (1241, 376, 2000)])
+def test_extract_stereo_one_call_equals_separate_calls(oracle, cols, rows, nf):
+    """orbx_extract_stereo (Frame.cc:124-143 in one call, matcher on device-resident features) against the three-call path
+    and against the oracle; repeated so that the captured graphs and the second-call state are exercised."""
+    exL = orbx.ORBextractor(nf, 1.2, 8, 20, 7); exR = orbx.ORBextractor(nf, 1.2, 8, 20, 7)
+    sL = orbx.ORBextractor(nf, 1.2, 8, 20, 7); sR = orbx.ORBextractor(nf, 1.2, 8, 20, 7)
+    oL = oracle.extractor(nf, 1.2, 8, 20, 7); oR = oracle.extractor(nf, 1.2, 8, 20, 7)
+    for rep, seed in enumerate([31, 32, 31, 33]):
+        L, R = _pair(seed, cols, rows)
+        kL, dL, kR, dR, u, d = orbx.extract_stereo(exL, exR, L, R, 47.9, 435.2)
+        _, k1, d1 = sL(L, None, (0, 0)); _, k2, d2 = sR(R, None, (0, 0))
+        assert kL.tobytes() == k1.tobytes() and kR.tobytes() == k2.tobytes()
+        assert np.array_equal(dL, d1) and np.array_equal(dR, d2)
+        u1, dd1 = orbx.compute_stereo_matches(sL, sR, k1, d1, k2, d2, 47.9, 435.2)
+        assert np.array_equal(u, u1) and np.array_equal(d, dd1), rep
+        if rep < 2:
+            okL, odL, _ = oL.extract(L, (0, 0)); okR, odR, _ = oR.extract(R, (0, 0))
+            ou, od, kept = oracle.stereo_match(oL, oR, okL, odL, okR, odR, 47.9, 435.2)
+            assert kept > 50 and np.array_equal(u, ou) and np.array_equal(d, od)
+
+
+def test_stereo_match_device_on_batch_outputs(oracle):
+    """orbx_stereo_match_device queued behind orbx_extract_batch_device on one stream: counts are read on the device."""
+    import torch
+    dev = torch.device("cuda:0")
+    L, R = _pair(35)
+    ex = orbx.ORBextractor(1200, 1.2, 8, 20, 7, max_cols=752, max_rows=480, max_batch=2)
+    cap = ex.max_keypoints(480, 752)
+    d_img = torch.from_numpy(np.stack([L, R])).to(dev)
+    d_kps = torch.zeros((2, cap, 7), dtype=torch.float32, device=dev); d_desc = torch.zeros((2, cap, 32), dtype=torch.uint8, device=dev)
+    d_n = torch.zeros(2, dtype=torch.int32, device=dev); d_nm = torch.zeros(2, dtype=torch.int32, device=dev)
+    d_u = torch.full((cap,), -5.0, dtype=torch.float32, device=dev); d_d = torch.full((cap,), -5.0, dtype=torch.float32, device=dev)
+    st = torch.cuda.Stream(device=dev)
+    st.wait_stream(torch.cuda.current_stream(dev))
+    ex.extract_batch_device(d_img, 2, 480, 752, 752, 480 * 752, d_kps, d_desc, cap, d_n, d_nm, (0, 0), stream=st.cuda_stream)
+    check(lib().orbx_stereo_match_device(ex._h, 0, ex._h, 1, ptr(d_kps[0]), ptr(d_desc[0]), ptr(d_n[0:]), cap, ptr(d_kps[1]), ptr(d_desc[1]),
+                                         ptr(d_n[1:]), cap, 47.9, 435.2, ptr(d_u), ptr(d_d), C.c_void_p(st.cuda_stream)))
+    check(lib().orbx_sync(ex._h))          # must cover the caller's stream too
+    n = d_n.cpu().numpy()
+    oL = oracle.extractor(1200, 1.2, 8, 20, 7); oR = oracle.extractor(1200, 1.2, 8, 20, 7)
+    okL, odL, _ = oL.extract(L, (0, 0)); okR, odR, _ = oR.extract(R, (0, 0))
+    ou, od, kept = oracle.stereo_match(oL, oR, okL, odL, okR, odR, 47.9, 435.2)
+    assert n[0] == len(okL) and n[1] == len(okR)
+    assert np.array_equal(d_u.cpu().numpy()[:n[0]], ou) and np.array_equal(d_d.cpu().numpy()[:n[0]], od)
+    assert (d_u.cpu().numpy()[n[0]:] == -5.0).all()
+    # the probes wait for the caller's stream as well and refuse frames the last call did not produce
+    assert np.array_equal(ex.pyramid_level(0, frame=1), R)
+    with pytest.raises(OrbxError):
+        ex.pyramid_level(0, frame=2)
+
+
+def test_sharded_knn2_world1_through_nccl(oracle):
+    """orbx_comm_* + orbx_knn2_sharded with a one-rank NCCL communicator (the 2..8-rank run is tools/sharded_check.py)."""
+    import torch
+    dev = torch.device("cuda:0")
+    ndb, nq = 120_001, 999
+    db = synth.descriptors(9, ndb); q = synth.descriptors(9, nq, is_query=True, ndb=ndb, plant_every=2)
+    sm = orbx.ShardedMatcher(0, 1, 0, lambda b: b)
+    assert sm.nccl_version() > 20000
+    first, cnt = sm.shard_rows(ndb, 1, 0)
+    assert (first, cnt) == (0, ndb)
+    d_db = torch.from_numpy(db).to(dev); d_q = torch.from_numpy(q).to(dev)
+    d_idx = torch.empty((nq, 2), dtype=torch.int32, device=dev); d_dist = torch.empty_like(d_idx)
+    for _ in range(3):
+        sm.knn2(d_q, nq, d_db, ndb, 0, d_idx, d_dist)
+    torch.cuda.synchronize()
+    ridx, rdist = oracle.knn2(q, db)
+    assert np.array_equal(d_idx.cpu().numpy(), ridx) and np.array_equal(d_dist.cpu().numpy(), rdist)
+    sm.close()
+
+
+def test_failed_configuration_leaves_handle_usable(oracle):
+    """A shape the extractor cannot take (aspect ratio > 64:1) must fail every time it is offered — not only the first — and
+    the handle must keep working for supported shapes afterwards (half-built geometry with geom_valid set)."""
+    ex = orbx.ORBextractor(500, 1.2, 4, 20, 7)
+    good = synth.image(3, 320, 240)
+    nm0, k0, d0 = ex(good)
+    bad = synth.image(4, 4000, 70)
+    for _ in range(3):
+        with pytest.raises(OrbxError):
+            ex(bad)
+        with pytest.raises(OrbxError):
+            ex.pyramid_level(0)                    # nothing is probe-able after a failed call
+    nm1, k1, d1 = ex(good)
+    assert nm1 == nm0 and k1.tobytes() == k0.tobytes() and np.array_equal(d1, d0)
+
+
+def test_distribute_octree_rejects_duplicate_pixels():
+    xs = np.array([10, 50, 10, 70], np.int32); ys = np.array([20, 30, 20, 90], np.int32); sc = np.array([30, 40, 50, 60], np.int32)
+    with pytest.raises(OrbxError):
+        orbx.distribute_octree(xs, ys, sc, 0, 200, 0, 100, 10)
+
+
+def test_single_frame_forked_graph_equals_serial(oracle, monkeypatch):
+    """The per-level fork/join graph of orbx_extract against the serial launch order (profiling forces the serial path) on the
+    same handle, several frames and shapes (graph re-capture on a shape change)."""
+    ex = orbx.ORBextractor(1000, 1.2, 8, 20, 7)
+    for (cols, rows, seed) in [(752, 480, 1), (752, 480, 2), (640, 480, 3), (752, 480, 4), (752, 480, 5)]:
+        img = synth.image(seed, cols, rows)
+        r1 = ex(img)
+        ex.profile_begin()
+        r2 = ex(img)
+        ex.profile_end()
+        r3 = ex(img)
+        for r in (r2, r3):
+            assert r[0] == r1[0] and r[1].tobytes() == r1[1].tobytes() and np.array_equal(r[2], r1[2])
+        oex = oracle.extractor(1000, 1.2, 8, 20, 7)
+        ok, od, onm = oex.extract(img, (0, 0))
+        assert r1[0] == onm and np.array_equal(r1[1]["x"], ok["x"]) and np.array_equal(r1[1]["y"], ok["y"]) and np.array_equal(r1[2], od)

@@ -9,7 +9,8 @@ L.orbx_debug_octree_timing.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int,
 img = synth.image(1000, 752, 480)
 ex = orbx.ORBextractor(1000, 1.2, 8, 20, 7)
 ex(img, None, (0, 0))
-names = ["gather+codes", "radix sort", "roots", "phase1 sweeps", "introsort", "phase2 rest", "retain", "#sweeps", "#p2 rounds", "n", "m max"]
+names = ["codes+count+scan", "bin scatter", "roots", "phase1 sweeps", "introsort", "phase2 rest", "retain", "#sweeps", "#p2 rounds", "n", "m max"]
+# NB: the batch path inside orbx_debug_octree_timing (ORBX_DBG_REPLICAS) still uses 256-thread CTAs; a single frame gets 1024
 for level in (0, 3, 7):
     out = np.zeros(16, np.int64)
     check(L.orbx_debug_octree_timing(ex._h, ptr(img), 480, 752, 752, level, ptr(out)))

@@ -60,6 +60,15 @@ SIGNATURES = {
     "orbx_rotation_consistency": (_i, [_vp, _vp, _i, _vp]),
     "orbx_distinctive_descriptor": (_i, [_vp, _i, _vp]),
     "orbx_stereo_match": (_i, [_vp, _i, _vp, _i, _vp, _vp, _i, _vp, _vp, _i, _f, _f, _vp, _vp]),
+    "orbx_stereo_match_device": (_i, [_vp, _i, _vp, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp, _i, _f, _f, _vp, _vp, _vp]),
+    "orbx_extract_stereo": (_i, [_vp, _vp, _vp, _vp, _i, _i, _sz, _vp, _vp, _vp, _vp, _vp, _vp, _i, _f, _f, _vp, _vp]),
+    "orbx_comm_unique_id": (_i, [_vp]),
+    "orbx_comm_create": (_i, [_i, _i, _i, _vp, C.POINTER(_vp)]),
+    "orbx_comm_from_nccl": (_i, [_i, _vp, _i, _i, C.POINTER(_vp)]),
+    "orbx_comm_destroy": (None, [_vp]),
+    "orbx_comm_info": (_i, [_vp, _vp, _vp, _vp]),
+    "orbx_shard_rows": (None, [_i64, _i, _i, _vp, _vp]),
+    "orbx_knn2_sharded": (_i, [_vp, _vp, _i, _vp, _i64, _i64, _vp, _vp, _vp]),
     "orbx_vocab_create": (_i, [_i, _i, _vp, _vp, _vp, _i, _i, _i, _i, C.POINTER(_vp)]),
     "orbx_vocab_load_text": (_i, [_i, C.c_char_p, C.POINTER(_vp)]),
     "orbx_vocab_destroy": (None, [_vp]),

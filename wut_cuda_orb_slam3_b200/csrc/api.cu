@@ -112,7 +112,9 @@ struct Slot {
     // staging for the host-buffer API
     uint8_t* d_in = nullptr; size_t d_in_bytes = 0;
     uint8_t* d_color = nullptr; size_t d_color_bytes = 0;      // colour input of orbx_extract_color
-    orbx_keypoint* d_kps = nullptr; uint8_t* d_desc = nullptr; int* d_n = nullptr; int* d_nm = nullptr; int out_cap = 0;
+    orbx_keypoint* d_kps = nullptr; uint8_t* d_desc = nullptr; int* d_n = nullptr; int* d_nm = nullptr;
+    size_t out_cap = 0;            // keypoint rows the output staging holds
+    int out_frames = 0;            // frames the per-frame counters hold
     std::vector<void*> allocs;
 };
 
@@ -159,20 +161,29 @@ struct orbx_extractor {
     Slot slots[kSlots];
     cudaStream_t compute = nullptr, copy_in = nullptr, copy_out = nullptr;   // serial-compute pipeline of orbx_extract_batch (3 streams)
     int last_frames = 0;           // frames of the last call that are probe-able (slot 0)
+    // orbx_extract_batch_device on a caller's stream: an event recorded behind its last launch.  orbx_sync, the probes,
+    // stereo matching, re-configuration and the next extraction on the extractor's own streams wait for it.
+    cudaEvent_t ev_user = nullptr;
+    bool user_pending = false;
     int max_kp = 0;
     // single-frame calls replay a captured CUDA graph of the 15 kernel launches (orbx_extract is the tracking thread's per-frame call:
     // launch gaps, not kernels, dominate it).  The graph is keyed by everything the captured launches bake in.
     struct GraphKey {
-        int rows = 0, cols = 0, lap0 = 0, lap1 = 0, capacity = 0;
+        int rows = 0, cols = 0, lap0 = 0, lap1 = 0, capacity = 0, cap_frames = 0;
         const void* pyr = nullptr; const void* d_in = nullptr; const void* d_kps = nullptr; const void* cand = nullptr;
+        const void* d_n = nullptr; const void* tables = nullptr;
         bool operator==(const GraphKey& o) const
         {
-            return rows == o.rows && cols == o.cols && lap0 == o.lap0 && lap1 == o.lap1 && capacity == o.capacity && pyr == o.pyr && d_in == o.d_in &&
-                   d_kps == o.d_kps && cand == o.cand;
+            return rows == o.rows && cols == o.cols && lap0 == o.lap0 && lap1 == o.lap1 && capacity == o.capacity && cap_frames == o.cap_frames &&
+                   pyr == o.pyr && d_in == o.d_in && d_kps == o.d_kps && cand == o.cand && d_n == o.d_n && tables == o.tables;
         }
     } graph_key;
     cudaGraphExec_t graph_exec = nullptr;
     int single_calls = 0;          // the first single-frame call runs un-captured (lazy one-time initialisation inside the launchers)
+    bool force_eager = false;      // debug hooks that patch the workspace (orbx_debug_octree_timing) must not replay a captured graph
+    // fork / join of the single-frame pipeline: FAST + octree of level l run on side[l] as soon as level l of the pyramid exists
+    cudaStream_t side[ORBX_MAX_LEVELS] = {nullptr};
+    cudaEvent_t ev_lvl[ORBX_MAX_LEVELS] = {nullptr}, ev_side[ORBX_MAX_LEVELS] = {nullptr};
     // per-stage CUDA-event timing (orbx_profile_begin / orbx_profile_end)
     bool profiling = false;
     std::vector<cudaEvent_t> ev_pool;   // kStages+1 events per profiled chunk
@@ -180,6 +191,13 @@ struct orbx_extractor {
 };
 
 namespace orbx {
+
+// Block the host until the last orbx_extract_batch_device call on a caller-supplied stream has finished with the workspace.
+static void wait_user_work(orbx_extractor* ex)
+{
+    if (ex->user_pending && ex->ev_user) cudaEventSynchronize(ex->ev_user);
+    ex->user_pending = false;
+}
 
 int set_device(int device)
 {
@@ -190,6 +208,17 @@ int set_device(int device)
     }
     if (device < 0 || device >= n) return fail(ORBX_ERR_INVALID_ARG, "device %d out of range (%d visible)", device, n);
     CU(cudaSetDevice(device));
+    // stream-ordered scratch (cudaMallocAsync in the matcher entry points) should stay in the pool between calls
+    static std::atomic<unsigned long long> pool_ready{0};
+    if (device < 64 && !(pool_ready.load(std::memory_order_relaxed) & (1ull << device))) {
+        cudaMemPool_t pool = nullptr;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess && pool) {
+            unsigned long long keep = ~0ull;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+        cudaGetLastError();
+        pool_ready.fetch_or(1ull << device, std::memory_order_relaxed);
+    }
     return ORBX_OK;
 }
 
@@ -199,7 +228,19 @@ static void free_slot(Slot& s)
     s.allocs.clear();
     s.ws = Workspace{};
     s.cap_frames = 0;
-    s.d_in = nullptr; s.d_in_bytes = 0; s.d_color = nullptr; s.d_color_bytes = 0; s.d_kps = nullptr; s.d_desc = nullptr; s.d_n = nullptr; s.d_nm = nullptr; s.out_cap = 0;
+    s.d_in = nullptr; s.d_in_bytes = 0; s.d_color = nullptr; s.d_color_bytes = 0; s.d_kps = nullptr; s.d_desc = nullptr; s.d_n = nullptr; s.d_nm = nullptr;
+    s.out_cap = 0; s.out_frames = 0;
+}
+
+// release one buffer of a slot early (a staging buffer that is being replaced by a larger one)
+template <typename T>
+static void dev_release(Slot& s, T*& p)
+{
+    if (!p) return;
+    for (size_t i = 0; i < s.allocs.size(); ++i)
+        if (s.allocs[i] == (void*)p) { s.allocs[i] = s.allocs.back(); s.allocs.pop_back(); break; }
+    cudaFree((void*)p);
+    p = nullptr;
 }
 
 template <typename T>
@@ -218,6 +259,12 @@ static int configure(orbx_extractor* ex, int rows, int cols)
 {
     if (ex->geom_valid && ex->fg.rows == rows && ex->fg.cols == cols) return ORBX_OK;
     if (cols > kMaxDim || rows > kMaxDim) return fail(ORBX_ERR_UNSUPPORTED, "image %dx%d exceeds %d px per side", cols, rows, kMaxDim);
+    // From here on the old geometry is gone: a failure below must leave the handle "unconfigured" (every entry point calls
+    // configure() first and probes / stereo matching check geom_valid), never half-built with the previous shape's flag set.
+    ex->geom_valid = false;
+    ex->last_frames = 0;
+    wait_user_work(ex);
+    if (ex->graph_exec) { cudaGraphExecDestroy(ex->graph_exec); ex->graph_exec = nullptr; }
     for (int i = 0; i < orbx_extractor::kSlots; ++i) {
         if (ex->slots[i].stream) cudaStreamSynchronize(ex->slots[i].stream);
         cudaStream_t st = ex->slots[i].stream;
@@ -268,6 +315,7 @@ static int configure(orbx_extractor* ex, int rows, int cols)
         g.cell_cap = ((g.wCell + 1) / 2) * ((g.hCell + 1) / 2);
         g.cand_off = cand_off;
         g.cand_max = g.nCols * g.nRows * g.cell_cap;
+        if ((long long)g.nCols * g.nRows * g.cell_cap >= (1 << 24)) return fail(ORBX_ERR_UNSUPPORTED, "level %d has too many candidate slots", l);
         cand_off += (unsigned long long)g.cand_max;
         g.oct_off = oct_off;
         oct_off += 5ull * g.cand_max + (unsigned long long)(g.nCols * g.nRows) + 16;
@@ -355,7 +403,7 @@ static int configure(orbx_extractor* ex, int rows, int cols)
         }
         fg.cell_tab = reinterpret_cast<const uint32_t*>(ex->d_tables + cell_tab_off);
     }
-    const size_t smem = octree_smem_bytes([&] { int M = 0; for (int l = 0; l < fg.nlevels; ++l) M = std::max(M, fg.L[l].kp_cap); return M; }());
+    const size_t smem = octree_smem_for(fg, 0, fg.nlevels);
     if (smem > 200 * 1024) return fail(ORBX_ERR_UNSUPPORTED, "nfeatures too large for the octree kernel (%zu B shared memory)", smem);
     CU(octree_prepare());
     ex->geom_valid = true;
@@ -435,6 +483,8 @@ static int ensure_capacity(orbx_extractor* ex, int frames, int nslots)
     int cap = ex->slots[0].cap_frames;
     bool grow = frames > cap;
     if (grow) {
+        wait_user_work(ex);
+        if (ex->graph_exec) { cudaGraphExecDestroy(ex->graph_exec); ex->graph_exec = nullptr; }
         for (int i = 0; i < orbx_extractor::kSlots; ++i) {
             cudaStream_t st = ex->slots[i].stream;
             if (st) cudaStreamSynchronize(st);
@@ -450,19 +500,30 @@ static int ensure_capacity(orbx_extractor* ex, int frames, int nslots)
     return ORBX_OK;
 }
 
+// Staging of the host-buffer API.  The caller has made sure no work is in flight on the slot when a buffer is replaced.
 static int ensure_host_staging(Slot& s, size_t in_bytes, int frames, int capacity)
 {
     int rc;
     if (s.d_in_bytes < in_bytes) {
+        dev_release(s, s.d_in);
+        s.d_in_bytes = 0;
         if ((rc = dev_alloc(s, &s.d_in, in_bytes))) return rc;
         s.d_in_bytes = in_bytes;
     }
-    if (s.out_cap < frames * capacity || !s.d_kps) {
-        if ((rc = dev_alloc(s, &s.d_kps, (size_t)frames * capacity))) return rc;
-        if ((rc = dev_alloc(s, &s.d_desc, (size_t)frames * capacity * 32))) return rc;
+    const size_t rows = (size_t)frames * capacity;
+    if (s.out_cap < rows || !s.d_kps) {
+        dev_release(s, s.d_kps); dev_release(s, s.d_desc);
+        s.out_cap = 0;
+        if ((rc = dev_alloc(s, &s.d_kps, rows))) return rc;
+        if ((rc = dev_alloc(s, &s.d_desc, rows * 32))) return rc;
+        s.out_cap = rows;
+    }
+    if (s.out_frames < frames || !s.d_n) {          // the per-frame counters follow the FRAME count, not rows
+        dev_release(s, s.d_n); dev_release(s, s.d_nm);
+        s.out_frames = 0;
         if ((rc = dev_alloc(s, &s.d_n, (size_t)frames))) return rc;
         if ((rc = dev_alloc(s, &s.d_nm, (size_t)frames))) return rc;
-        s.out_cap = frames * capacity;
+        s.out_frames = frames;
     }
     return ORBX_OK;
 }
@@ -501,6 +562,82 @@ static int run_chunk(orbx_extractor* ex, Slot& s, const uint8_t* d_images, size_
     if ((rc = prof_mark(ex, st))) return rc;
     CU(launch_pack(fg, s.ws, frames, lap0, lap1, d_kps, d_desc, capacity, d_n, d_nm, st));
     if ((rc = prof_mark(ex, st))) return rc;
+    return ORBX_OK;
+}
+
+// The single-frame pipeline (orbx_extract: what Frame::ExtractORB calls once per image, src/Frame.cc:420-455).  One frame
+// cannot fill the GPU, so the stages are forked per pyramid level: as soon as level l exists, FAST and the quadtree of that
+// level run on their own branch while the resize chain continues; the blur follows the chain; orientation + descriptors and
+// the packing join everything.  The critical path is level 0 (pyramid copy -> FAST -> octree), not the sum of all stages.
+// Works eagerly and under stream capture (the events become graph edges).
+static int run_single_forked(orbx_extractor* ex, Slot& s, const uint8_t* d_image, size_t pitch, int lap0, int lap1,
+                             orbx_keypoint* d_kps, uint8_t* d_desc, int capacity, int* d_n, int* d_nm, cudaStream_t st)
+{
+    const FrameGeom& fg = ex->fg;
+    for (int l = 0; l < fg.nlevels; ++l) {
+        if (!ex->side[l]) CU(cudaStreamCreateWithFlags(&ex->side[l], cudaStreamNonBlocking));
+        if (!ex->ev_lvl[l]) CU(cudaEventCreateWithFlags(&ex->ev_lvl[l], cudaEventDisableTiming));
+        if (!ex->ev_side[l]) CU(cudaEventCreateWithFlags(&ex->ev_side[l], cudaEventDisableTiming));
+    }
+    for (int l = 0; l < fg.nlevels; ++l) {
+        CU(launch_pyramid(fg, s.ws, d_image, pitch * fg.rows, pitch, 1, st, l, l + 1));
+        CU(cudaEventRecord(ex->ev_lvl[l], st));
+        CU(cudaStreamWaitEvent(ex->side[l], ex->ev_lvl[l], 0));
+        CU(launch_fast(fg, s.ws, 1, ex->side[l], l, l + 1));
+        CU(launch_octree(fg, s.ws, 1, ex->side[l], l, l + 1));
+        CU(cudaEventRecord(ex->ev_side[l], ex->side[l]));
+    }
+    CU(launch_blur(fg, s.ws, 1, st));
+    for (int l = 0; l < fg.nlevels; ++l) CU(cudaStreamWaitEvent(st, ex->ev_side[l], 0));
+    CU(launch_orient_describe(fg, s.ws, 1, st));
+    CU(launch_pack(fg, s.ws, 1, lap0, lap1, d_kps, d_desc, capacity, d_n, d_nm, st));
+    return ORBX_OK;
+}
+
+// Upload one host image into slot 0 and queue its extraction on the slot's stream (captured graph after the first call).
+// Results stay on the device (s.d_kps / s.d_desc / s.d_n / s.d_nm); nothing is copied back and nothing is waited for.
+static int enqueue_single(orbx_extractor* ex, const uint8_t* image, int rows, int cols, size_t step, int lap0, int lap1, int capacity)
+{
+    int rc = set_device(ex->device);
+    if (rc) return rc;
+    if ((rc = configure(ex, rows, cols))) return rc;
+    wait_user_work(ex);
+    if ((rc = ensure_capacity(ex, 1, 1))) return rc;
+    Slot& s = ex->slots[0];
+    const size_t dpitch = (size_t)cols, dframe = dpitch * rows;
+    if (s.d_in_bytes < dframe || s.out_cap < (size_t)capacity || s.out_frames < 1) CU(cudaStreamSynchronize(s.stream));
+    if ((rc = ensure_host_staging(s, dframe, 1, capacity))) return rc;
+    cudaStream_t st = s.stream;
+    if (step == (size_t)cols) CU(cudaMemcpyAsync(s.d_in, image, dframe, cudaMemcpyHostToDevice, st));
+    else CU(cudaMemcpy2DAsync(s.d_in, dpitch, image, step, cols, rows, cudaMemcpyHostToDevice, st));
+    static const bool graphs = !(getenv("ORBX_GRAPH") && atoi(getenv("ORBX_GRAPH")) == 0);
+    static const bool forked = !(getenv("ORBX_SINGLE_FORK") && atoi(getenv("ORBX_SINGLE_FORK")) == 0);   // A/B switch
+    auto body = [&](cudaStream_t cs) -> int {
+        if (forked && !ex->profiling) return run_single_forked(ex, s, s.d_in, dpitch, lap0, lap1, s.d_kps, s.d_desc, capacity, s.d_n, s.d_nm, cs);
+        return run_chunk(ex, s, s.d_in, dframe, dpitch, 1, lap0, lap1, s.d_kps, s.d_desc, capacity, s.d_n, s.d_nm, cs);
+    };
+    if (graphs && !ex->profiling && !ex->force_eager && ex->single_calls++ > 0) {
+        orbx_extractor::GraphKey key;
+        key.rows = rows; key.cols = cols; key.lap0 = lap0; key.lap1 = lap1; key.capacity = capacity;
+        key.pyr = s.ws.pyr; key.d_in = s.d_in; key.d_kps = s.d_kps; key.cand = s.ws.cand;
+        key.cap_frames = s.cap_frames; key.d_n = s.d_n; key.tables = ex->d_tables;
+        if (!ex->graph_exec || !(key == ex->graph_key)) {
+            if (ex->graph_exec) { cudaGraphExecDestroy(ex->graph_exec); ex->graph_exec = nullptr; }
+            cudaGraph_t g = nullptr;
+            CU(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+            rc = body(st);
+            cudaError_t ce = cudaStreamEndCapture(st, &g);
+            if (rc) { if (g) cudaGraphDestroy(g); cudaGetLastError(); return rc; }
+            if (ce != cudaSuccess) return fail(ORBX_ERR_CUDA, "graph capture: %s", cudaGetErrorString(ce));
+            ce = cudaGraphInstantiate(&ex->graph_exec, g, 0);
+            cudaGraphDestroy(g);
+            if (ce != cudaSuccess) { ex->graph_exec = nullptr; return fail(ORBX_ERR_CUDA, "graph instantiate: %s", cudaGetErrorString(ce)); }
+            ex->graph_key = key;
+        }
+        CU(cudaGraphLaunch(ex->graph_exec, st));
+        count_launch(forked ? 3 * ex->fg.nlevels + 3 : 15);
+    } else if ((rc = body(st))) return rc;
+    ex->last_frames = 1;
     return ORBX_OK;
 }
 
@@ -613,6 +750,12 @@ void orbx_destroy(orbx_extractor* ex)
         if (ex->slots[i].stream) cudaStreamDestroy(ex->slots[i].stream);
         if (ex->slots[i].ev_in) { cudaEventDestroy(ex->slots[i].ev_in); cudaEventDestroy(ex->slots[i].ev_done); cudaEventDestroy(ex->slots[i].ev_out); }
     }
+    if (ex->ev_user) { cudaEventSynchronize(ex->ev_user); cudaEventDestroy(ex->ev_user); }
+    for (int l = 0; l < ORBX_MAX_LEVELS; ++l) {
+        if (ex->side[l]) { cudaStreamSynchronize(ex->side[l]); cudaStreamDestroy(ex->side[l]); }
+        if (ex->ev_lvl[l]) cudaEventDestroy(ex->ev_lvl[l]);
+        if (ex->ev_side[l]) cudaEventDestroy(ex->ev_side[l]);
+    }
     if (ex->graph_exec) cudaGraphExecDestroy(ex->graph_exec);
     if (ex->d_tables) cudaFree(ex->d_tables);
     for (cudaEvent_t e : ex->ev_pool) cudaEventDestroy(e);
@@ -669,6 +812,8 @@ int orbx_sync(orbx_extractor* ex)
     CU(cudaSetDevice(ex->device));
     for (int i = 0; i < orbx_extractor::kSlots; ++i)
         if (ex->slots[i].stream) CU(cudaStreamSynchronize(ex->slots[i].stream));
+    if (ex->user_pending && ex->ev_user) CU(cudaEventSynchronize(ex->ev_user));    // work queued on a caller's stream
+    ex->user_pending = false;
     return ORBX_OK;
 }
 
@@ -687,6 +832,10 @@ int orbx_extract_batch_device(orbx_extractor* ex, const uint8_t* d_images, size_
     if ((rc = ensure_capacity(ex, chunk, 1))) return rc;
     Slot& s = ex->slots[0];
     cudaStream_t st = stream ? (cudaStream_t)stream : s.stream;
+    if (!ex->ev_user) CU(cudaEventCreateWithFlags(&ex->ev_user, cudaEventDisableTiming));
+    // the workspace is shared with whatever ran before: earlier work on another stream must be complete first
+    if (ex->user_pending) CU(cudaStreamWaitEvent(st, ex->ev_user, 0));
+    if (st != s.stream) { CU(cudaEventRecord(s.ev_done, s.stream)); CU(cudaStreamWaitEvent(st, s.ev_done, 0)); }
     for (int f0 = 0; f0 < n_frames; f0 += chunk) {
         const int nf = std::min(chunk, n_frames - f0);
         rc = run_chunk(ex, s, d_images + (size_t)f0 * frame_stride, frame_stride, pitch, nf, lap0, lap1,
@@ -695,6 +844,7 @@ int orbx_extract_batch_device(orbx_extractor* ex, const uint8_t* d_images, size_
         if (rc) return rc;
         ex->last_frames = nf;
     }
+    if (st != s.stream) { CU(cudaEventRecord(ex->ev_user, st)); ex->user_pending = true; }
     return ORBX_OK;
 }
 
@@ -708,9 +858,11 @@ int orbx_extract_batch(orbx_extractor* ex, const uint8_t* const* images, int n_f
         if (!images[i]) return fail(ORBX_ERR_EMPTY_IMAGE, "image %d is NULL", i);
     if (!keypoints || !descriptors || !n_out || !n_mono || capacity <= 0 || step < (size_t)cols)
         return fail(ORBX_ERR_INVALID_ARG, "bad output buffers / step");
+    if (n_frames == 1) return orbx_extract(ex, images[0], rows, cols, step, lap0, lap1, keypoints, descriptors, capacity, n_out, n_mono);
     int rc = set_device(ex->device);
     if (rc) return rc;
     if ((rc = configure(ex, rows, cols))) return rc;
+    wait_user_work(ex);
     const int chunk = ex->max_batch > 0 ? std::min(ex->max_batch, n_frames) : std::min(n_frames, 64);
     // Chunk schedule: the first host->device copy cannot overlap any compute, so the pipeline ramps up with a quarter and a
     // half chunk before it settles on full chunks (shorter un-overlapped prologue; the tail is whatever remains).
@@ -778,27 +930,7 @@ int orbx_extract_batch(orbx_extractor* ex, const uint8_t* const* images, int n_f
         }
         mark(ist);
         if (serial) { CU(cudaEventRecord(s.ev_in, ist)); CU(cudaStreamWaitEvent(cst, s.ev_in, 0)); }
-        static const bool graphs = !(getenv("ORBX_GRAPH") && atoi(getenv("ORBX_GRAPH")) == 0);
-        if (n_frames == 1 && graphs && !trace && !ex->profiling && ex->single_calls++ > 0) {
-            orbx_extractor::GraphKey key;
-            key.rows = rows; key.cols = cols; key.lap0 = lap0; key.lap1 = lap1; key.capacity = capacity;
-            key.pyr = s.ws.pyr; key.d_in = s.d_in; key.d_kps = s.d_kps; key.cand = s.ws.cand;
-            if (!ex->graph_exec || !(key == ex->graph_key)) {
-                if (ex->graph_exec) { cudaGraphExecDestroy(ex->graph_exec); ex->graph_exec = nullptr; }
-                cudaGraph_t g = nullptr;
-                CU(cudaStreamBeginCapture(cst, cudaStreamCaptureModeThreadLocal));
-                rc = run_chunk(ex, s, s.d_in, dframe, dpitch, 1, lap0, lap1, s.d_kps, s.d_desc, capacity, s.d_n, s.d_nm, cst);
-                cudaError_t ce = cudaStreamEndCapture(cst, &g);
-                if (rc) { if (g) cudaGraphDestroy(g); return rc; }
-                if (ce != cudaSuccess) return fail(ORBX_ERR_CUDA, "graph capture: %s", cudaGetErrorString(ce));
-                ce = cudaGraphInstantiate(&ex->graph_exec, g, 0);
-                cudaGraphDestroy(g);
-                if (ce != cudaSuccess) { ex->graph_exec = nullptr; return fail(ORBX_ERR_CUDA, "graph instantiate: %s", cudaGetErrorString(ce)); }
-                ex->graph_key = key;
-            }
-            CU(cudaGraphLaunch(ex->graph_exec, cst));
-            count_launch(15);
-        } else if ((rc = run_chunk(ex, s, s.d_in, dframe, dpitch, nf, lap0, lap1, s.d_kps, s.d_desc, capacity, s.d_n, s.d_nm, cst))) return rc;
+        if ((rc = run_chunk(ex, s, s.d_in, dframe, dpitch, nf, lap0, lap1, s.d_kps, s.d_desc, capacity, s.d_n, s.d_nm, cst))) return rc;
         if (serial) { CU(cudaEventRecord(s.ev_done, cst)); CU(cudaStreamWaitEvent(ost, s.ev_done, 0)); }
         mark(ost);
         CU(cudaMemcpyAsync(keypoints + (size_t)f0 * capacity, s.d_kps, sizeof(orbx_keypoint) * (size_t)nf * capacity, cudaMemcpyDeviceToHost, ost));
@@ -827,9 +959,20 @@ int orbx_extract_batch(orbx_extractor* ex, const uint8_t* const* images, int n_f
 int orbx_extract(orbx_extractor* ex, const uint8_t* image, int rows, int cols, size_t step, int lap0, int lap1,
                  orbx_keypoint* keypoints, uint8_t* descriptors, int capacity, int* n_out, int* n_mono)
 {
-    const uint8_t* imgs[1] = {image};
-    if (!image) return fail(ORBX_ERR_EMPTY_IMAGE, "empty image");
-    return orbx_extract_batch(ex, imgs, 1, rows, cols, step, lap0, lap1, keypoints, descriptors, capacity, n_out, n_mono);
+    if (!ex) return fail(ORBX_ERR_INVALID_ARG, "extractor is NULL");
+    if (!image || rows <= 0 || cols <= 0) return fail(ORBX_ERR_EMPTY_IMAGE, "empty image");
+    if (!keypoints || !descriptors || !n_out || !n_mono || capacity <= 0 || step < (size_t)cols)
+        return fail(ORBX_ERR_INVALID_ARG, "bad output buffers / step");
+    int rc = enqueue_single(ex, image, rows, cols, step, lap0, lap1, capacity);
+    if (rc) return rc;
+    Slot& s = ex->slots[0];
+    CU(cudaMemcpyAsync(keypoints, s.d_kps, sizeof(orbx_keypoint) * (size_t)capacity, cudaMemcpyDeviceToHost, s.stream));
+    CU(cudaMemcpyAsync(descriptors, s.d_desc, (size_t)capacity * 32, cudaMemcpyDeviceToHost, s.stream));
+    CU(cudaMemcpyAsync(n_out, s.d_n, sizeof(int), cudaMemcpyDeviceToHost, s.stream));
+    CU(cudaMemcpyAsync(n_mono, s.d_nm, sizeof(int), cudaMemcpyDeviceToHost, s.stream));
+    CU(cudaStreamSynchronize(s.stream));
+    if (*n_out > capacity) return fail(ORBX_ERR_CAPACITY, "frame has %d keypoints, capacity %d", *n_out, capacity);
+    return ORBX_OK;
 }
 
 int orbx_cvt_gray_device(int device, const uint8_t* d_src, size_t src_pitch, size_t src_frame_stride, int channels, int rgb,
@@ -856,6 +999,7 @@ int orbx_extract_color(orbx_extractor* ex, const uint8_t* image, int rows, int c
     int rc = set_device(ex->device);
     if (rc) return rc;
     if ((rc = configure(ex, rows, cols))) return rc;
+    wait_user_work(ex);
     if ((rc = ensure_capacity(ex, 1, 1))) return rc;
     Slot& s = ex->slots[0];
     const size_t gpitch = (size_t)cols, cpitch = align_up((size_t)cols * channels, 16);
@@ -908,8 +1052,8 @@ int orbx_profile_end(orbx_extractor* ex, float* stage_ms, int* n_chunks)
 static int probe_check(orbx_extractor* ex, int frame, int level)
 {
     if (!ex || !ex->geom_valid) return fail(ORBX_ERR_INVALID_ARG, "no extraction has run on this handle");
-    if (level < 0 || level >= ex->nlevels || frame < 0 || frame >= ex->slots[0].cap_frames)
-        return fail(ORBX_ERR_INVALID_ARG, "frame/level out of range");
+    if (level < 0 || level >= ex->nlevels || frame < 0 || frame >= ex->last_frames)
+        return fail(ORBX_ERR_INVALID_ARG, "frame/level out of range (the last call processed %d frame(s))", ex->last_frames);
     int rc = set_device(ex->device);
     if (rc) return rc;
     return orbx_sync(ex);
@@ -1019,13 +1163,21 @@ int orbx_distribute_octree(int device, const int* xs, const int* ys, const int* 
     }
     g.kp_base = 0; g.kp_cap = std::max(nFeatures + 4, 4 * g.nIni + 1);
     fg.kp_slots = g.kp_cap; fg.cand_frame_stride = g.cand_max; fg.oct_frame_stride = 5ull * g.cand_max + 32;
-    if (octree_smem_bytes(g.kp_cap) > 200 * 1024) return fail(ORBX_ERR_UNSUPPORTED, "nFeatures too large");
+    if (g.cand_max >= (1 << 24)) return fail(ORBX_ERR_UNSUPPORTED, "too many candidates");
+    if (octree_smem_for(fg, 0, 1) > 200 * 1024) return fail(ORBX_ERR_UNSUPPORTED, "nFeatures too large");
     CU(octree_prepare());
     std::vector<uint32_t> packed(std::max(n, 1));
     for (int i = 0; i < n; ++i) {
         if (xs[i] < 0 || xs[i] > 4095 || ys[i] < 0 || ys[i] > 4095 || scores[i] < 0 || scores[i] > 255)
             return fail(ORBX_ERR_INVALID_ARG, "candidate %d out of range", i);
         packed[i] = (uint32_t)xs[i] | ((uint32_t)ys[i] << 12) | ((uint32_t)scores[i] << 24);
+    }
+    {   // the quadtree separates distinct pixels only; the reference would loop on two candidates at one pixel until its
+        // depth runs out, cv::FAST never produces them
+        std::vector<uint32_t> seen(packed.begin(), packed.begin() + n);
+        for (auto& v : seen) v &= 0xffffffu;
+        std::sort(seen.begin(), seen.end());
+        if (std::adjacent_find(seen.begin(), seen.end()) != seen.end()) return fail(ORBX_ERR_INVALID_ARG, "two candidates share a pixel");
     }
     Slot s;
     Workspace& ws = s.ws;
@@ -1039,6 +1191,7 @@ int orbx_distribute_octree(int device, const int* xs, const int* ys, const int* 
     cudaError_t e = launch_octree(fg, ws, 1, 0);
     if (e == cudaSuccess) e = cudaDeviceSynchronize();
     if (e != cudaSuccess) { cleanup(); return fail(ORBX_ERR_CUDA, "octree kernel: %s", cudaGetErrorString(e)); }
+    if (octree_take_error_flag()) { cleanup(); return fail(ORBX_ERR_INVALID_ARG, "quadtree depth exhausted (candidates not separable)"); }
     int m = 0;
     cudaMemcpy(&m, ws.lvl_n, sizeof(int), cudaMemcpyDeviceToHost);
     std::vector<uint32_t> keys(std::max(m, 1));
@@ -1093,14 +1246,16 @@ int orbx_knn2(int device, const uint8_t* queries, int nq, const uint8_t* databas
     int rc = set_device(device);
     if (rc) return rc;
     ScratchLease L(device);
-    if ((rc = L.reserve((size_t)nq * 32 + (size_t)std::max<int64_t>(ndb, 1) * 32 + (size_t)nq * 16 + 4 * 256))) return rc;
+    const size_t ws_bytes = knn2_workspace_bytes(nq, ndb);
+    if ((rc = L.reserve((size_t)nq * 32 + (size_t)std::max<int64_t>(ndb, 1) * 32 + (size_t)nq * 16 + ws_bytes + 5 * 256))) return rc;
     uint8_t* dq = L.take<uint8_t>((size_t)nq * 32);
     uint8_t* ddb = L.take<uint8_t>((size_t)std::max<int64_t>(ndb, 1) * 32);
     int32_t* di = L.take<int32_t>((size_t)nq * 2);
     int32_t* dd = L.take<int32_t>((size_t)nq * 2);
+    void* dws = ws_bytes ? (void*)L.take<uint8_t>(ws_bytes) : nullptr;
     cudaError_t e = cudaMemcpy(dq, queries, (size_t)nq * 32, cudaMemcpyHostToDevice);
     if (e == cudaSuccess && ndb > 0) e = cudaMemcpy(ddb, database, (size_t)ndb * 32, cudaMemcpyHostToDevice);
-    if (e == cudaSuccess) e = launch_knn2(dq, nq, ddb, ndb, 0, di, dd, 0);
+    if (e == cudaSuccess) e = launch_knn2(dq, nq, ddb, ndb, 0, di, dd, 0, dws);
     if (e == cudaSuccess) e = cudaMemcpy(idx, di, (size_t)nq * 8, cudaMemcpyDeviceToHost);
     if (e == cudaSuccess) e = cudaMemcpy(dist, dd, (size_t)nq * 8, cudaMemcpyDeviceToHost);
     if (e != cudaSuccess) return fail(ORBX_ERR_CUDA, "knn2: %s", cudaGetErrorString(e));
@@ -1160,27 +1315,40 @@ int orbx_distinctive_descriptor(const uint8_t* descriptors, int n, int* best_idx
     return ORBX_OK;
 }
 
+// Checks shared by the stereo entry points; fills the pyramid part of the kernel arguments.
+static int stereo_prepare(orbx_extractor* exL, int frameL, orbx_extractor* exR, int frameR, StereoArgs& A)
+{
+    if (!exL || !exR || !exL->geom_valid || !exR->geom_valid) return fail(ORBX_ERR_INVALID_ARG, "extractors have not run");
+    if (exL->device != exR->device || exL->fg.rows != exR->fg.rows || exL->fg.cols != exR->fg.cols || exL->nlevels != exR->nlevels ||
+        exL->scaleFactorF != exR->scaleFactorF)
+        return fail(ORBX_ERR_INVALID_ARG, "left/right extractors must share device, image shape, levels and scale factor");
+    if (frameL < 0 || frameL >= exL->last_frames || frameR < 0 || frameR >= exR->last_frames)
+        return fail(ORBX_ERR_INVALID_ARG, "frame out of range");
+    // Scale tables: the reference reads Frame::mvScaleFactors / mvInvScaleFactors — the LEFT extractor's — for both sides
+    // (src/Frame.cc:112-118, 859, 933); the level sizes and pitches follow from the shape, which is shared.  What is NOT
+    // shared is where each extractor put its level slabs (that depends on its own slot capacity).
+    A.pyrL = exL->slots[0].ws.pyr; A.pyrR = exR->slots[0].ws.pyr; A.frameL = frameL; A.frameR = frameR;
+    for (int l = 0; l < exR->nlevels; ++l) A.offR[l] = exR->fg.L[l].pyr_off;
+    return ORBX_OK;
+}
+
 int orbx_stereo_match(orbx_extractor* exL, int frameL, orbx_extractor* exR, int frameR, const orbx_keypoint* kpL,
                       const uint8_t* descL, int nL, const orbx_keypoint* kpR, const uint8_t* descR, int nR, float bf, float maxD,
                       float* uRight, float* depth)
 {
-    if (!exL || !exR || !exL->geom_valid || !exR->geom_valid) return fail(ORBX_ERR_INVALID_ARG, "extractors have not run");
-    if (exL->device != exR->device || exL->fg.rows != exR->fg.rows || exL->fg.cols != exR->fg.cols || exL->nlevels != exR->nlevels)
-        return fail(ORBX_ERR_INVALID_ARG, "left/right extractors must share device, image shape and levels");
+    StereoArgs A{};
+    int rc = stereo_prepare(exL, frameL, exR, frameR, A);
+    if (rc) return rc;
     if (nL < 0 || nR < 0 || (nL > 0 && (!kpL || !descL || !uRight || !depth)) || (nR > 0 && (!kpR || !descR)))
         return fail(ORBX_ERR_INVALID_ARG, "bad arguments");
-    if (frameL < 0 || frameL >= exL->slots[0].cap_frames || frameR < 0 || frameR >= exR->slots[0].cap_frames)
-        return fail(ORBX_ERR_INVALID_ARG, "frame out of range");
     if (nR >= (1 << 20)) return fail(ORBX_ERR_UNSUPPORTED, "too many right keypoints");
     if (nL == 0) return ORBX_OK;
-    int rc = set_device(exL->device);
-    if (rc) return rc;
+    if ((rc = set_device(exL->device))) return rc;
     if ((rc = orbx_sync(exL)) || (rc = orbx_sync(exR))) return rc;
     for (int i = 0; i < nL; ++i)
         if (kpL[i].octave < 0 || kpL[i].octave >= exL->nlevels) return fail(ORBX_ERR_INVALID_ARG, "left keypoint %d octave", i);
     for (int i = 0; i < nR; ++i)
         if (kpR[i].octave < 0 || kpR[i].octave >= exL->nlevels) return fail(ORBX_ERR_INVALID_ARG, "right keypoint %d octave", i);
-    StereoArgs A{};
     ScratchLease Ls(exL->device);
     const size_t nRa = (size_t)std::max(nR, 1);
     if ((rc = Ls.reserve(((size_t)nL + nRa) * (sizeof(orbx_keypoint) + 32) + (size_t)nL * 12 + 8 * 256))) return rc;
@@ -1189,20 +1357,88 @@ int orbx_stereo_match(orbx_extractor* exL, int frameL, orbx_extractor* exR, int 
     orbx_keypoint* dkR = Ls.take<orbx_keypoint>(nRa);
     uint8_t* ddR = Ls.take<uint8_t>(nRa * 32);
     A.uRight = Ls.take<float>((size_t)nL); A.depth = Ls.take<float>((size_t)nL); A.sad = Ls.take<int>((size_t)nL);
-    auto cleanup = [] {};
-    cudaMemcpy(dkL, kpL, sizeof(orbx_keypoint) * nL, cudaMemcpyHostToDevice);
-    cudaMemcpy(ddL, descL, (size_t)nL * 32, cudaMemcpyHostToDevice);
-    if (nR > 0) {
-        cudaMemcpy(dkR, kpR, sizeof(orbx_keypoint) * nR, cudaMemcpyHostToDevice);
-        cudaMemcpy(ddR, descR, (size_t)nR * 32, cudaMemcpyHostToDevice);
-    }
-    A.pyrL = exL->slots[0].ws.pyr; A.pyrR = exR->slots[0].ws.pyr; A.frameL = frameL; A.frameR = frameR;
+    cudaStream_t st = exL->slots[0].stream;          // idle: orbx_sync above
+    cudaError_t e = cudaMemcpyAsync(dkL, kpL, sizeof(orbx_keypoint) * nL, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(ddL, descL, (size_t)nL * 32, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess && nR > 0) e = cudaMemcpyAsync(dkR, kpR, sizeof(orbx_keypoint) * nR, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess && nR > 0) e = cudaMemcpyAsync(ddR, descR, (size_t)nR * 32, cudaMemcpyHostToDevice, st);
     A.kpL = dkL; A.descL = ddL; A.nL = nL; A.kpR = dkR; A.descR = ddR; A.nR = nR; A.bf = bf; A.maxD = maxD;
-    cudaError_t e = launch_stereo(exL->fg, A, 0);
-    if (e == cudaSuccess) e = cudaMemcpy(uRight, A.uRight, sizeof(float) * nL, cudaMemcpyDeviceToHost);
-    if (e == cudaSuccess) e = cudaMemcpy(depth, A.depth, sizeof(float) * nL, cudaMemcpyDeviceToHost);
-    cleanup();
+    if (e == cudaSuccess) e = launch_stereo(exL->fg, A, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(uRight, A.uRight, sizeof(float) * nL, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(depth, A.depth, sizeof(float) * nL, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);          // the lease (scratch) is released on return
     if (e != cudaSuccess) return fail(ORBX_ERR_CUDA, "stereo: %s", cudaGetErrorString(e));
+    return ORBX_OK;
+}
+
+int orbx_stereo_match_device(orbx_extractor* exL, int frameL, orbx_extractor* exR, int frameR, const orbx_keypoint* d_kpL,
+                             const uint8_t* d_descL, const int* d_nL, int capL, const orbx_keypoint* d_kpR, const uint8_t* d_descR,
+                             const int* d_nR, int capR, float bf, float maxD, float* d_uRight, float* d_depth, void* stream)
+{
+    StereoArgs A{};
+    int rc = stereo_prepare(exL, frameL, exR, frameR, A);
+    if (rc) return rc;
+    if (!d_kpL || !d_descL || !d_nL || !d_kpR || !d_descR || !d_nR || capL <= 0 || capR <= 0 || !d_uRight || !d_depth)
+        return fail(ORBX_ERR_INVALID_ARG, "bad arguments");
+    if (capR >= (1 << 20)) return fail(ORBX_ERR_UNSUPPORTED, "too many right keypoints");
+    if ((rc = set_device(exL->device))) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    int* sad = nullptr;
+    CU(cudaMallocAsync((void**)&sad, sizeof(int) * (size_t)capL, st));       // stream-ordered, private to the call
+    A.kpL = d_kpL; A.descL = d_descL; A.nL = capL; A.d_nL = d_nL; A.kpR = d_kpR; A.descR = d_descR; A.nR = capR; A.d_nR = d_nR;
+    A.bf = bf; A.maxD = maxD; A.uRight = d_uRight; A.depth = d_depth; A.sad = sad;
+    cudaError_t e = launch_stereo(exL->fg, A, st);
+    cudaError_t e2 = cudaFreeAsync(sad, st);
+    if (e == cudaSuccess) e = e2;
+    if (e != cudaSuccess) return fail(ORBX_ERR_CUDA, "stereo: %s", cudaGetErrorString(e));
+    return ORBX_OK;
+}
+
+// The stereo Frame constructor in one call (src/Frame.cc:124-143): both extractions run concurrently on their extractors'
+// streams (as the reference's two std::threads do), ComputeStereoMatches follows on the device as soon as both are done —
+// it reads the keypoints, descriptors and un-blurred pyramids where the extractors left them — and one wait at the end
+// covers all copies back.  No intermediate host round trip, no second upload of the features.
+int orbx_extract_stereo(orbx_extractor* exL, orbx_extractor* exR, const uint8_t* imageL, const uint8_t* imageR, int rows, int cols,
+                        size_t step, orbx_keypoint* kpL, uint8_t* descL, int* nL, orbx_keypoint* kpR, uint8_t* descR, int* nR,
+                        int capacity, float bf, float maxD, float* uRight, float* depth)
+{
+    if (!exL || !exR || exL == exR) return fail(ORBX_ERR_INVALID_ARG, "two distinct extractors are required");
+    if (!imageL || !imageR || rows <= 0 || cols <= 0) return fail(ORBX_ERR_EMPTY_IMAGE, "empty image");
+    if (!kpL || !descL || !nL || !kpR || !descR || !nR || !uRight || !depth || capacity <= 0 || step < (size_t)cols)
+        return fail(ORBX_ERR_INVALID_ARG, "bad output buffers / step");
+    if (exL->device != exR->device) return fail(ORBX_ERR_INVALID_ARG, "left/right extractors must share a device");
+    // vLappingArea = {0, 0} for both cameras of a rectified pair (src/Frame.cc:124-125)
+    int rc;
+    if ((rc = enqueue_single(exL, imageL, rows, cols, step, 0, 0, capacity))) return rc;
+    if ((rc = enqueue_single(exR, imageR, rows, cols, step, 0, 0, capacity))) return rc;
+    Slot& sL = exL->slots[0];
+    Slot& sR = exR->slots[0];
+    // right side: its results go home on its own stream while the matcher runs
+    CU(cudaEventRecord(sR.ev_done, sR.stream));
+    CU(cudaMemcpyAsync(kpR, sR.d_kps, sizeof(orbx_keypoint) * (size_t)capacity, cudaMemcpyDeviceToHost, sR.stream));
+    CU(cudaMemcpyAsync(descR, sR.d_desc, (size_t)capacity * 32, cudaMemcpyDeviceToHost, sR.stream));
+    CU(cudaMemcpyAsync(nR, sR.d_n, sizeof(int), cudaMemcpyDeviceToHost, sR.stream));
+    // left side: wait for the right extraction, match on the device, then copy everything back
+    CU(cudaStreamWaitEvent(sL.stream, sR.ev_done, 0));
+    ScratchLease Ls(exL->device);
+    if ((rc = Ls.reserve((size_t)capacity * 12 + 4 * 256))) return rc;
+    float* d_u = Ls.take<float>((size_t)capacity);
+    float* d_d = Ls.take<float>((size_t)capacity);
+    StereoArgs A{};
+    if ((rc = stereo_prepare(exL, 0, exR, 0, A))) return rc;
+    A.kpL = sL.d_kps; A.descL = sL.d_desc; A.nL = capacity; A.d_nL = sL.d_n;
+    A.kpR = sR.d_kps; A.descR = sR.d_desc; A.nR = capacity; A.d_nR = sR.d_n;
+    A.bf = bf; A.maxD = maxD; A.uRight = d_u; A.depth = d_d; A.sad = Ls.take<int>((size_t)capacity);
+    if (capacity >= (1 << 20)) return fail(ORBX_ERR_UNSUPPORTED, "too many right keypoints");
+    CU(launch_stereo(exL->fg, A, sL.stream));
+    CU(cudaMemcpyAsync(kpL, sL.d_kps, sizeof(orbx_keypoint) * (size_t)capacity, cudaMemcpyDeviceToHost, sL.stream));
+    CU(cudaMemcpyAsync(descL, sL.d_desc, (size_t)capacity * 32, cudaMemcpyDeviceToHost, sL.stream));
+    CU(cudaMemcpyAsync(nL, sL.d_n, sizeof(int), cudaMemcpyDeviceToHost, sL.stream));
+    CU(cudaMemcpyAsync(uRight, d_u, sizeof(float) * (size_t)capacity, cudaMemcpyDeviceToHost, sL.stream));
+    CU(cudaMemcpyAsync(depth, d_d, sizeof(float) * (size_t)capacity, cudaMemcpyDeviceToHost, sL.stream));
+    CU(cudaStreamSynchronize(sL.stream));
+    CU(cudaStreamSynchronize(sR.stream));
+    if (*nL > capacity || *nR > capacity) return fail(ORBX_ERR_CAPACITY, "%d / %d keypoints, capacity %d", *nL, *nR, capacity);
     return ORBX_OK;
 }
 
@@ -1275,7 +1511,7 @@ int orbx_synth_descriptors_device(int device, uint32_t seed, int is_query, int64
 }
 
 // Debug: per-phase clock64 cycles of the octree CTA of (frame 0, `level`) during one single-frame extraction of `image`.
-// out[0..6] = gather+codes, radix sort, roots, phase-1 sweeps, introsort replay, phase-2 rest, retain; out[7] = sweeps,
+// out[0..6] = codes + bin counts + scan, bin scatter, roots, phase-1 sweeps, introsort replay, phase-2 rest, retain; out[7] = sweeps,
 // out[8] = phase-2 rounds, out[9] = candidates, out[10] = largest sorted vector.
 int orbx_debug_octree_timing(orbx_extractor* ex, const uint8_t* image, int rows, int cols, size_t step, int level, long long* out16)
 {
@@ -1293,6 +1529,7 @@ int orbx_debug_octree_timing(orbx_extractor* ex, const uint8_t* image, int rows,
     std::vector<uint8_t> desc((size_t)cap * 32);
     int n = 0, nm = 0;
     s.ws.dbg = d_dbg; s.ws.dbg_level = level;
+    ex->force_eager = true;
     // ORBX_DBG_REPLICAS=R (<= 64): time the CTA of frame 0 while R copies of the frame are in flight (phase times under load)
     const int reps = getenv("ORBX_DBG_REPLICAS") ? std::min(std::max(atoi(getenv("ORBX_DBG_REPLICAS")), 1), 64) : 1;
     if (reps > 1) {
@@ -1306,6 +1543,7 @@ int orbx_debug_octree_timing(orbx_extractor* ex, const uint8_t* image, int rows,
     } else
     rc = orbx_extract(ex, image, rows, cols, step, 0, 0, kps.data(), desc.data(), cap, &n, &nm);
     ex->slots[0].ws.dbg = nullptr;
+    ex->force_eager = false;
     if (!rc) cudaMemcpy(out16, d_dbg, 16 * sizeof(long long), cudaMemcpyDeviceToHost);
     cudaFree(d_dbg);
     return rc;

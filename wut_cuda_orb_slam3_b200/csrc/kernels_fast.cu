@@ -98,7 +98,7 @@ static_assert(kRoiPitch == 80, "fast_score() hard-codes the 7x7 offsets for an 8
 
 }  // namespace
 
-__global__ void __launch_bounds__(128) fast_cells_kernel(const __grid_constant__ FrameGeom fg, Workspace ws)
+__global__ void __launch_bounds__(128) fast_cells_kernel(const __grid_constant__ FrameGeom fg, Workspace ws, int cell_lo)
 {
     __shared__ __align__(16) uint8_t roi[kPlane];
     __shared__ __align__(16) uint8_t sc[kPlane];
@@ -110,11 +110,12 @@ __global__ void __launch_bounds__(128) fast_cells_kernel(const __grid_constant__
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int frame = blockIdx.y;
     // cell -> (level, cell row, cell column) from a small table (built by the host with the geometry)
-    const uint32_t ct = __ldg(fg.cell_tab + blockIdx.x);
+    const int gcell = cell_lo + (int)blockIdx.x;
+    const uint32_t ct = __ldg(fg.cell_tab + gcell);
     const int level = ct & 15, ci = (ct >> 4) & 0xfff, cj = ct >> 16;
     const LevelGeom& g = fg.L[level];
-    const int cell = (int)blockIdx.x - g.cell_base;
-    int* count_out = ws.cell_count + (size_t)frame * fg.total_cells + blockIdx.x;
+    const int cell = gcell - g.cell_base;
+    int* count_out = ws.cell_count + (size_t)frame * fg.total_cells + gcell;
 
     const int maxBX = g.w - kWinBorder, maxBY = g.h - kWinBorder;
     const int iniX = kWinBorder + cj * g.wCell, iniY = kWinBorder + ci * g.hCell;
@@ -577,28 +578,33 @@ static cudaError_t launch_fast_warp(const FrameGeom& fg, const Workspace& ws, in
 
 static int plane_pitch_for(int wCell) { const int need = (3 + wCell + 6 + 3) & ~3; return need <= 48 ? 48 : (need <= 64 ? 64 : 80); }
 
-cudaError_t launch_fast(const FrameGeom& fg, const Workspace& ws, int n_frames, cudaStream_t st)
+// Levels [level_lo, level_hi) (level_hi <= 0: all).
+cudaError_t launch_fast(const FrameGeom& fg, const Workspace& ws, int n_frames, cudaStream_t st, int level_lo, int level_hi)
 {
-    if (fg.total_cells == 0) return cudaSuccess;
+    if (level_hi <= 0) level_hi = fg.nlevels;
+    if (fg.total_cells == 0 || level_lo >= level_hi) return cudaSuccess;
     // Small jobs (single frames: the SLAM tracking case) keep one CTA per cell for latency; batches use one warp per cell.
     static const char* force = getenv("ORBX_FAST_KERNEL");      // "cta" | "warp": A/B switch for tests and measurements
     bool use_warp = (long long)fg.total_cells * n_frames >= 8192;
     if (force) use_warp = force[0] == 'w';
     if (!use_warp) {
-        dim3 grid(fg.total_cells, n_frames);
-        fast_cells_kernel<<<grid, 128, 0, st>>>(fg, ws);
+        const int cell_lo = fg.L[level_lo].cell_base;
+        const int cell_hi = fg.L[level_hi - 1].cell_base + fg.L[level_hi - 1].nCols * fg.L[level_hi - 1].nRows;
+        if (cell_hi <= cell_lo) return cudaSuccess;
+        dim3 grid(cell_hi - cell_lo, n_frames);
+        fast_cells_kernel<<<grid, 128, 0, st>>>(fg, ws, cell_lo);
         count_launch();
         return cudaGetLastError();
     }
     // group consecutive levels whose cells have the same plane pitch and (within 10 %) the same height
-    int l = 0;
-    while (l < fg.nlevels) {
+    int l = level_lo;
+    while (l < level_hi) {
         const LevelGeom& g0 = fg.L[l];
         if (g0.nCols <= 0 || g0.nRows <= 0) { ++l; continue; }
         const int pa = plane_pitch_for(g0.wCell);
         int min_h = g0.hCell, max_h = g0.hCell, max_w = g0.wCell, e = l + 1;
         int cell_hi = g0.cell_base + g0.nCols * g0.nRows;
-        for (; e < fg.nlevels; ++e) {
+        for (; e < level_hi; ++e) {
             const LevelGeom& g = fg.L[e];
             if (g.nCols <= 0 || g.nRows <= 0) continue;
             const int nmin = std::min(min_h, g.hCell), nmax = std::max(max_h, g.hCell);

@@ -157,14 +157,15 @@ __global__ void __launch_bounds__(KNN_THREADS) knn2_kernel(const uint32_t* __res
     }
 }
 
+// shard s holds its [nq][2] candidates at idx_sh + s * shard_stride / dist_sh + s * shard_stride (int32 elements)
 __global__ void knn2_merge_kernel(const int32_t* __restrict__ idx_sh, const int32_t* __restrict__ dist_sh, int n_shards,
-                                  int nq, int32_t* __restrict__ idx, int32_t* __restrict__ dist)
+                                  int nq, int32_t* __restrict__ idx, int32_t* __restrict__ dist, size_t shard_stride)
 {
     const int qi = blockIdx.x * blockDim.x + threadIdx.x;
     if (qi >= nq) return;
     int d1 = INT_MAX, d2 = INT_MAX, i1 = -1, i2 = -1;
     for (int s = 0; s < n_shards; ++s) {
-        const size_t o = ((size_t)s * nq + qi) * 2;
+        const size_t o = (size_t)s * shard_stride + (size_t)qi * 2;
         top2_merge(dist_sh[o], idx_sh[o], d1, i1, d2, i2);
         top2_merge(dist_sh[o + 1], idx_sh[o + 1], d1, i1, d2, i2);
     }
@@ -172,17 +173,11 @@ __global__ void knn2_merge_kernel(const int32_t* __restrict__ idx_sh, const int3
     dist[2 * (size_t)qi] = d1; dist[2 * (size_t)qi + 1] = d2;
 }
 
-static uint8_t* g_knn_partial[64] = {nullptr};
-static size_t g_knn_partial_bytes[64] = {0};
-
-cudaError_t launch_knn2(const uint8_t* d_q, int nq, const uint8_t* d_db, long long ndb, int index_base, int32_t* d_idx,
-                        int32_t* d_dist, cudaStream_t st)
+// Database chunking of one launch: a few thousand CTAs, every chunk long enough to amortise the query load / result store.
+static void knn2_plan(int nq, long long ndb, int& qtiles, int& chunks, long long& rows_per_chunk)
 {
-    if (nq <= 0) return cudaSuccess;
-    const int qtiles = (nq + KNN_QTILE - 1) / KNN_QTILE;
-    // chunk the database so that the grid has a few thousand CTAs but every chunk is long enough to amortise the
-    // query load / result store
-    int chunks = 1;
+    qtiles = (nq + KNN_QTILE - 1) / KNN_QTILE;
+    chunks = 1;
     if (ndb > 0) {
         const long long target_ctas = 148LL * 16;
         long long want = (target_ctas + qtiles - 1) / qtiles;
@@ -192,24 +187,39 @@ cudaError_t launch_knn2(const uint8_t* d_q, int nq, const uint8_t* d_db, long lo
         if (want > 1024) want = 1024;
         chunks = (int)want;
     }
-    long long rows_per_chunk = ndb > 0 ? (ndb + chunks - 1) / chunks : 1;
+    rows_per_chunk = ndb > 0 ? (ndb + chunks - 1) / chunks : 1;
     rows_per_chunk = (rows_per_chunk + KNN_DTILE - 1) / KNN_DTILE * KNN_DTILE;
     chunks = ndb > 0 ? (int)((ndb + rows_per_chunk - 1) / rows_per_chunk) : 1;
+}
+
+size_t knn2_workspace_bytes(int nq, long long ndb)
+{
+    if (nq <= 0) return 0;
+    int qtiles, chunks; long long rpc;
+    knn2_plan(nq, ndb, qtiles, chunks, rpc);
+    return chunks > 1 ? (size_t)chunks * nq * 2 * sizeof(int32_t) * 2 : 0;
+}
+
+// The per-chunk partial results live in `workspace` (>= knn2_workspace_bytes, owned by the caller for the duration of the
+// launch) or, with workspace == nullptr, in a stream-ordered allocation made and released on `st` — either way private to
+// this call, so concurrent calls from several host threads / streams (Tracking, LocalMapping, LoopClosing all match
+// descriptors) never share scratch.
+cudaError_t launch_knn2(const uint8_t* d_q, int nq, const uint8_t* d_db, long long ndb, int index_base, int32_t* d_idx,
+                        int32_t* d_dist, cudaStream_t st, void* workspace)
+{
+    if (nq <= 0) return cudaSuccess;
+    int qtiles, chunks; long long rows_per_chunk;
+    knn2_plan(nq, ndb, qtiles, chunks, rows_per_chunk);
     int32_t* p_idx = d_idx;
     int32_t* p_dist = d_dist;
+    void* owned = nullptr;
     if (chunks > 1) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        dev &= 63;
-        const size_t need = (size_t)chunks * nq * 2 * sizeof(int32_t) * 2;
-        if (g_knn_partial_bytes[dev] < need) {
-            if (g_knn_partial[dev]) cudaFree(g_knn_partial[dev]);
-            g_knn_partial[dev] = nullptr; g_knn_partial_bytes[dev] = 0;
-            cudaError_t e = cudaMalloc(&g_knn_partial[dev], need);
+        if (!workspace) {
+            cudaError_t e = cudaMallocAsync(&owned, knn2_workspace_bytes(nq, ndb), st);
             if (e != cudaSuccess) return e;
-            g_knn_partial_bytes[dev] = need;
+            workspace = owned;
         }
-        p_idx = reinterpret_cast<int32_t*>(g_knn_partial[dev]);
+        p_idx = reinterpret_cast<int32_t*>(workspace);
         p_dist = p_idx + (size_t)chunks * nq * 2;
     }
     dim3 grid(qtiles, chunks);
@@ -218,17 +228,20 @@ cudaError_t launch_knn2(const uint8_t* d_q, int nq, const uint8_t* d_db, long lo
                                               p_dist);
     count_launch();
     if (chunks > 1) {
-        knn2_merge_kernel<<<(nq + 255) / 256, 256, 0, st>>>(p_idx, p_dist, chunks, nq, d_idx, d_dist);
+        knn2_merge_kernel<<<(nq + 255) / 256, 256, 0, st>>>(p_idx, p_dist, chunks, nq, d_idx, d_dist, (size_t)nq * 2);
         count_launch();
     }
-    return cudaGetLastError();
+    cudaError_t e = cudaGetLastError();
+    if (owned) { cudaError_t e2 = cudaFreeAsync(owned, st); if (e == cudaSuccess) e = e2; }
+    return e;
 }
 
 cudaError_t launch_knn2_merge(const int32_t* d_idx_sh, const int32_t* d_dist_sh, int n_shards, int nq, int32_t* d_idx,
-                              int32_t* d_dist, cudaStream_t st)
+                              int32_t* d_dist, cudaStream_t st, size_t shard_stride)
 {
     if (nq <= 0) return cudaSuccess;
-    knn2_merge_kernel<<<(nq + 255) / 256, 256, 0, st>>>(d_idx_sh, d_dist_sh, n_shards, nq, d_idx, d_dist);
+    knn2_merge_kernel<<<(nq + 255) / 256, 256, 0, st>>>(d_idx_sh, d_dist_sh, n_shards, nq, d_idx, d_dist,
+                                                        shard_stride ? shard_stride : (size_t)nq * 2);
     count_launch();
     return cudaGetLastError();
 }
@@ -275,11 +288,15 @@ __global__ void __launch_bounds__(256) stereo_match_kernel(const __grid_constant
     __shared__ int s_sad[8][12];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int iL = blockIdx.x * 8 + warp;
-    if (iL >= A.nL) return;
+    // device-resident counts: a frame that overflowed its capacity (count > bound) has no valid rows
+    int nL = A.nL, nR = A.nR;
+    if (A.d_nL) { const int c = __ldg(A.d_nL); nL = c > A.nL ? 0 : c; }
+    if (A.d_nR) { const int c = __ldg(A.d_nR); nR = c > A.nR ? 0 : c; }
+    if (iL >= nL) return;
     const int TH_HIGH = 100, TH_LOW = 50;
     const int thOrbDist = (TH_HIGH + TH_LOW) / 2;
     const orbx_keypoint kL = A.kpL[iL];
-    const int levelL = kL.octave;
+    const int levelL = min(max(kL.octave, 0), fg.nlevels - 1);      // host entry points validate; device-resident input is clamped
     const float vL = kL.y, uL = kL.x;
     float out_u = -1.0f, out_d = -1.0f;
     int out_sad = -1;
@@ -293,8 +310,9 @@ __global__ void __launch_bounds__(256) stereo_match_kernel(const __grid_constant
         for (int k = 0; k < 8; ++k) dl[k] = __ldg(pl + k);
         // best = min over (dist, iR): the reference scans row buckets in ascending iR with strict '<'
         unsigned best = 0xffffffffu;
-        for (int iR = lane; iR < A.nR; iR += 32) {
+        for (int iR = lane; iR < nR; iR += 32) {
             const orbx_keypoint kR = A.kpR[iR];
+            if ((unsigned)kR.octave >= (unsigned)fg.nlevels) continue;
             const float r = __fmul_rn(2.0f, fg.L[kR.octave].scale);
             const int maxr = (int)ceilf(__fadd_rn(kR.y, r));
             const int minr = (int)floorf(__fsub_rn(kR.y, r));
@@ -321,7 +339,8 @@ __global__ void __launch_bounds__(256) stereo_match_kernel(const __grid_constant
             const float endu = scaleduR0 + L + w + 1;
             if (!(iniu < 0 || endu >= g.w)) {
                 const uint8_t* IL = level_interior(A.pyrL, g, A.frameL);
-                const uint8_t* IR = level_interior(A.pyrR, g, A.frameR);
+                const uint8_t* IR = A.pyrR + A.offR[levelL] + (unsigned long long)A.frameR * g.pyr_frame_stride +
+                                    (unsigned long long)kEdge * g.pitch + kXPad;
                 if (lane < 11) s_sad[warp][lane] = 0;
                 __syncwarp();
                 const int cu = (int)scaleduL, cv = (int)scaledvL, cr = (int)scaleduR0;
@@ -368,21 +387,23 @@ __global__ void __launch_bounds__(1024) stereo_median_kernel(StereoArgs A)
 {
     __shared__ int s_n, s_median;
     const int tid = threadIdx.x;
+    int nL = A.nL;
+    if (A.d_nL) { const int c = __ldg(A.d_nL); nL = c > A.nL ? 0 : c; }
     if (tid == 0) { s_n = 0; s_median = -1; }
     __syncthreads();
     int cnt = 0;
-    for (int i = tid; i < A.nL; i += 1024) cnt += A.sad[i] >= 0;
+    for (int i = tid; i < nL; i += 1024) cnt += A.sad[i] >= 0;
     atomicAdd(&s_n, cnt);
     __syncthreads();
     const int n = s_n;
     if (n == 0) return;
     const int target = n / 2;
     // rank of element i in the sorted (sad, iL) list
-    for (int i = tid; i < A.nL; i += 1024) {
+    for (int i = tid; i < nL; i += 1024) {
         const int si = A.sad[i];
         if (si < 0) continue;
         int rank = 0;
-        for (int j = 0; j < A.nL; ++j) {
+        for (int j = 0; j < nL; ++j) {
             const int sj = A.sad[j];
             if (sj < 0) continue;
             rank += (sj < si) || (sj == si && j < i);
@@ -392,7 +413,7 @@ __global__ void __launch_bounds__(1024) stereo_median_kernel(StereoArgs A)
     __syncthreads();
     const float median = (float)s_median;
     const float thDist = 1.5f * 1.4f * median;
-    for (int i = tid; i < A.nL; i += 1024) {
+    for (int i = tid; i < nL; i += 1024) {
         const int si = A.sad[i];
         if (si >= 0 && !((float)si < thDist)) { A.uRight[i] = -1.f; A.depth[i] = -1.f; }
     }

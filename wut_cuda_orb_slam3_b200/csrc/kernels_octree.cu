@@ -4,10 +4,13 @@
 // Reformulation (bit-exact, see DESIGN.md "Octree"):
 //  * A key's path through the quadtree depends only on geometry: root = (int)(x / hX), then at every depth the
 //    quadrant given by x < UL.x + ceil(w/2), y < UL.y + ceil(h/2).  Every key gets a path code (root, 2 bits per depth,
-//    n1=0,n2=1,n3=2,n4=3).  One LSD radix sort of (path code, original index) makes every node of every depth a
-//    contiguous segment and the four children of a node its four sub-segments, found by binary search.  DivideNode's
-//    stable partition keeps a node's keys in original (cell-major, y, x) order; that order only matters for the
-//    "first key with maximal response" rule, which is evaluated on the carried original indices.
+//    n1=0,n2=1,n3=2,n4=3).  ONE counting sort on the leading root + 2*Dsort bits of the code (shared-memory atomics; Dsort = 5
+//    for the usual two roots) makes every node down to depth Dsort a contiguous segment whose child boundaries are plain
+//    look-ups in the scanned bin table — the tree of N ~ 200 nodes rarely goes deeper.  A node below depth Dsort covers a
+//    few pixels and holds a handful of keys: the lane that splits it partitions its segment in place by the next two code
+//    bits.  DivideNode's stable partition keeps a node's keys in original (cell-major, y, x) order; that order only matters
+//    for the "first key with maximal response" rule, which is evaluated on the carried original position (the key's slot in
+//    the FAST staging area is monotone in it), so the order inside a segment is free.
 //  * The std::list is an array in list order.  A sweep that splits a set of nodes processed in the order p=0..nS-1
 //    turns the list into [children(p=nS-1) n4..n1, ..., children(p=0) n4..n1, untouched nodes in old order]
 //    (every split push_front()s its non-empty children n1..n4 and erases the parent).  Positions come from prefix sums.
@@ -17,6 +20,8 @@
 //  * Retain (756-771): first key with maximal response per node, in list order.
 #include <stdlib.h>
 
+#include <mutex>
+
 #include "introsort_replay.h"
 #include "orbx_internal.cuh"
 
@@ -24,18 +29,19 @@ namespace orbx {
 
 namespace {
 
-constexpr int kMaxT = 1024;                 // largest CTA size the kernel is instantiated with
-constexpr int kHistWordsMax = 16 * kMaxT + (16 * kMaxT) / 32;
+constexpr int kSortBitsMax = 12;            // counting-sort bins: root bits + 2 * Dsort <= 12 (16 KB of bin starts)
 
 struct Smem {
     // carved from dynamic shared memory; M = node capacity
-    uint32_t* hist;        // [kHistWords]
+    int* bstart;           // [nb + 1] first sorted position of every bin (exclusive scan of the bin counts)
+    int* cursor;           // [nb] scatter cursors; aliases the node arrays below (dead before the roots are built)
     int* warp_tmp;         // [64]
     int* sort_stk;         // [3*72]
     uint32_t* nbeg[2];     // node segment begin           [M] x2 (ping-pong)
     uint32_t* ncnt[2];     // node key count
     uint32_t* nx[2];       // ULx | URx << 16
     uint32_t* ndep[2];     // depth
+    uint32_t* npre[2];     // path-code prefix of the node (root, 2 bits per depth)
     uint32_t* cc;          // [4*M] child counts of processed node p: cc[4*p+k]
     int* sa;               // [M] scan scratch a
     int* sb;               // [M] scan scratch b
@@ -75,6 +81,32 @@ __device__ int block_exclusive_scan(int* a, int n, int* warp_tmp)
     }
     const int total = carry;
     __syncthreads();            // nobody may re-enter (and reset carry) before everyone has read the total
+    return total;
+}
+
+// Exclusive prefix sum of a[0..n) in place, raking: thread t owns ceil(n / T) consecutive elements (one pass, three barriers
+// whatever n is).  Returns the total.  All T threads must call.
+template <int T>
+__device__ int block_exclusive_scan_raking(int* a, int n, int* warp_tmp)
+{
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int per = (n + T - 1) / T;
+    const int i0 = min(tid * per, n), i1 = min(i0 + per, n);
+    int sum = 0;
+    for (int i = i0; i < i1; ++i) sum += a[i];
+    int incl = sum;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += t;
+    }
+    if (lane == 31) warp_tmp[warp] = incl;
+    __syncthreads();
+    int woff = 0, total = 0;
+    for (int w = 0; w < T / 32; ++w) { const int v = warp_tmp[w]; if (w < warp) woff += v; total += v; }
+    int run = woff + incl - sum;
+    for (int i = i0; i < i1; ++i) { const int v = a[i]; a[i] = run; run += v; }
+    __syncthreads();
     return total;
 }
 
@@ -151,43 +183,40 @@ __device__ __forceinline__ uint32_t path_code(int x, int y, const LevelGeom& g, 
     return code;
 }
 
-// first index in [lo, hi) with (codes[i] >> shift) >= v
-__device__ __forceinline__ uint32_t lower_bound_code(const uint32_t* codes, uint32_t lo, uint32_t hi, int shift, uint32_t v)
-{
-    while (lo < hi) {
-        const uint32_t mid = (lo + hi) >> 1;
-        if ((codes[mid] >> shift) < v) lo = mid + 1; else hi = mid;
-    }
-    return lo;
-}
-
 }  // namespace
 
-size_t octree_smem_bytes(int M, int T)
+// counting-sort depth of a level: as many leading code bits as fit kSortBitsMax
+__host__ __device__ inline int octree_sort_depth(int depth, int root_bits)
 {
-    // the radix-sort histogram is dead once the sort is done: it shares its bytes with the node / scan arrays of the tree phases
-    const size_t hist = sizeof(uint32_t) * (16 * T + (16 * T) / 32);
+    const int d = (kSortBitsMax - root_bits) / 2;
+    return d < depth ? (d > 0 ? d : 0) : depth;
+}
+
+int octree_bins(const LevelGeom& g) { return 1 << (g.root_bits + 2 * octree_sort_depth(g.depth, g.root_bits)); }
+
+size_t octree_smem_bytes(int M, int NB)
+{
     size_t b = 0;
-    b += sizeof(uint32_t) * (size_t)M * 8;      // node arrays x2
+    b += sizeof(uint32_t) * (size_t)M * 10;     // node arrays x2
     b += sizeof(uint32_t) * (size_t)M * 4;      // cc
     b += sizeof(int) * (size_t)M * 5;           // sa, sb, sc, sd, procpos
     b += 8;                                     // alignment slack
     b += sizeof(unsigned long long) * (size_t)M * 2;
-    return sizeof(int) * (64 + 224) + (b > hist ? b : hist);
+    const size_t cur = sizeof(int) * (size_t)NB;
+    return sizeof(int) * (64 + 224) + sizeof(int) * ((size_t)NB + 2) + (b > cur ? b : cur);
 }
 
-// grid = (n_frames, nlevels); dynamic smem sized for the largest level's node capacity.
+// grid = (n_frames, levels of this launch); dynamic smem sized for the largest level's node capacity M and bin count NB.
 template <int T>
-__global__ void __launch_bounds__(T, 1024 / T) octree_kernel(const __grid_constant__ FrameGeom fg, Workspace ws, int M,
-                                                   int* __restrict__ err_flag)
+__global__ void __launch_bounds__(T, 1024 / T) octree_kernel(const __grid_constant__ FrameGeom fg, Workspace ws, int M, int NB,
+                                                   int level_base, int* __restrict__ err_flag)
 {
-    constexpr int kHistWords = 16 * T + (16 * T) / 32;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ int s_nL, s_nS, s_total;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     // level-major dispatch: the CTAs of level 0 (most candidates, longest) start first, the short deep levels pack the tail
-    const int frame = blockIdx.x, level = blockIdx.y;
+    const int frame = blockIdx.x, level = level_base + blockIdx.y;
     const LevelGeom& g = fg.L[level];
     const int N = g.nfeat;
     // optional phase timing of one CTA (orbx_debug_octree_timing): dbg[0..6] cycles, dbg[7..] counters
@@ -201,12 +230,14 @@ __global__ void __launch_bounds__(T, 1024 / T) octree_kernel(const __grid_consta
         unsigned char* p = smem_raw;
         S.warp_tmp = (int*)p; p += sizeof(int) * 64;
         S.sort_stk = (int*)p; p += sizeof(int) * 224;
-        S.hist = (uint32_t*)p;          // aliases the arrays below: used by the radix sort only, which ends with a barrier
+        S.bstart = (int*)p; p += sizeof(int) * ((size_t)NB + 2);
+        S.cursor = (int*)p;             // aliases the arrays below: used by the counting sort only, which ends with a barrier
         for (int b = 0; b < 2; ++b) {
             S.nbeg[b] = (uint32_t*)p; p += 4 * (size_t)M;
             S.ncnt[b] = (uint32_t*)p; p += 4 * (size_t)M;
             S.nx[b] = (uint32_t*)p; p += 4 * (size_t)M;
             S.ndep[b] = (uint32_t*)p; p += 4 * (size_t)M;
+            S.npre[b] = (uint32_t*)p; p += 4 * (size_t)M;
         }
         S.cc = (uint32_t*)p; p += 16 * (size_t)M;
         S.sa = (int*)p; p += 4 * (size_t)M;
@@ -229,149 +260,90 @@ __global__ void __launch_bounds__(T, 1024 / T) octree_kernel(const __grid_consta
         return;
     }
 
-    // ---- 0. gather the level's candidates in cell-major order, compute path codes ------------------------------
+    // ---- 0./1. counting sort of the level's candidates by the leading bits of their path codes -----------------------
+    // A candidate's identity is its slot in the FAST staging area, flat = cell * cell_cap + i: monotone in the reference's
+    // vToDistributeKeys order (cells row-major, (y, x) inside a cell), which is all the retain rule needs.
+    const int Dsort = octree_sort_depth(g.depth, g.root_bits);
+    const int lowbits = 2 * (g.depth - Dsort);                   // code bits below the sorted prefix
+    const int nb = 1 << (g.root_bits + 2 * Dsort);
     uint32_t* scratch = ws.oct + (size_t)frame * fg.oct_frame_stride + g.oct_off;
     const int nmax = g.cand_max;
-    // keys0 = packed candidates in original (cell-major, y, x) order; the sort permutes (code, original index) pairs
-    uint32_t* keys0 = scratch;
-    uint32_t* keys[2] = {scratch + nmax, scratch + 2 * (size_t)nmax};       // original indices, ping-pong
-    uint32_t* codes[2] = {scratch + 3 * (size_t)nmax, scratch + 4 * (size_t)nmax};
-    int* cell_off = (int*)(scratch + 5 * (size_t)nmax);                     // [ncells]
+    uint32_t* K = scratch;                                       // payload: flat staging slot | score << 24, bin-sorted
+    uint32_t* C = scratch + nmax;                                // path codes, same order
     const int* cell_count = ws.cell_count + (size_t)frame * fg.total_cells + g.cell_base;
-    for (int c = tid; c < ncells; c += T) cell_off[c] = cell_count[c];
+    const uint32_t* __restrict__ cand = ws.cand + (size_t)frame * fg.cand_frame_stride + g.cand_off;
+    for (int i = tid; i <= nb; i += T) S.bstart[i] = 0;
     __syncthreads();
-    const int n = block_exclusive_scan<T>(cell_off, ncells, S.warp_tmp);
-    if (tid == 0) *out_ncand = n;
+    // warp = 4 cells per iteration so that the dependent global loads (count -> candidates) of several cells overlap
+    for (int c0 = warp * 4; c0 < ncells; c0 += (T / 32) * 4) {
+        int cnt[4];
+        uint32_t k[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) cnt[u] = c0 + u < ncells ? cell_count[c0 + u] : 0;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) k[u] = lane < cnt[u] ? cand[(size_t)(c0 + u) * g.cell_cap + lane] : 0u;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            if (lane < cnt[u]) atomicAdd(&S.bstart[path_code((int)(k[u] & 0xfff), (int)((k[u] >> 12) & 0xfff), g, winH) >> lowbits], 1);
+            for (int i = lane + 32; i < cnt[u]; i += 32) {           // cells with more than 32 candidates (rare)
+                const uint32_t kk = cand[(size_t)(c0 + u) * g.cell_cap + i];
+                atomicAdd(&S.bstart[path_code((int)(kk & 0xfff), (int)((kk >> 12) & 0xfff), g, winH) >> lowbits], 1);
+            }
+        }
+    }
+    __syncthreads();
+    const int n = block_exclusive_scan_raking<T>(S.bstart, nb, S.warp_tmp);
+    if (tid == 0) { *out_ncand = n; S.bstart[nb] = n; }
     if (n == 0) {
         if (tid == 0) *out_n = 0;
         return;
     }
-    {
-        // warp = 4 cells per iteration so that the dependent global loads (offset -> candidates) of several cells overlap;
-        // payload = original index | score << 24 (the retain step needs only the payload)
-        const uint32_t* __restrict__ cand = ws.cand + (size_t)frame * fg.cand_frame_stride + g.cand_off;
-        for (int c0 = warp * 4; c0 < ncells; c0 += (T / 32) * 4) {
-            int cnt[4], o[4];
-            uint32_t k[4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int c = c0 + u;
-                cnt[u] = c < ncells ? cell_count[c] : 0;
-                o[u] = c < ncells ? cell_off[c] : 0;
-            }
-#pragma unroll
-            for (int u = 0; u < 4; ++u) k[u] = lane < cnt[u] ? cand[(size_t)(c0 + u) * g.cell_cap + lane] : 0u;
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                if (lane < cnt[u]) {
-                    keys0[o[u] + lane] = k[u];
-                    keys[0][o[u] + lane] = (uint32_t)(o[u] + lane) | (k[u] & 0xff000000u);
-                    codes[0][o[u] + lane] = path_code((int)(k[u] & 0xfff), (int)((k[u] >> 12) & 0xfff), g, winH);
-                }
-                for (int i = lane + 32; i < cnt[u]; i += 32) {           // cells with more than 32 candidates (rare)
-                    const uint32_t kk = cand[(size_t)(c0 + u) * g.cell_cap + i];
-                    keys0[o[u] + i] = kk;
-                    keys[0][o[u] + i] = (uint32_t)(o[u] + i) | (kk & 0xff000000u);
-                    codes[0][o[u] + i] = path_code((int)(kk & 0xfff), (int)((kk >> 12) & 0xfff), g, winH);
-                }
-            }
-        }
-    }
+    for (int i = tid; i < nb; i += T) S.cursor[i] = S.bstart[i];
     __syncthreads();
-
     OCT_MARK(0);
-    // ---- 1. stable LSD radix sort of (code, key) by code, 4 bits per pass ---------------------------------------
-    int cur = 0;
-    {
-        const int nbits = 2 * g.depth + g.root_bits;
-        const int ipt = (n + T - 1) / T;
-        const int i0 = min(tid * ipt, n), i1 = min(i0 + ipt, n);
-        for (int shift = 0; shift < nbits; shift += 4) {
-            for (int i = tid; i < kHistWords; i += T) S.hist[i] = 0;
-            __syncthreads();
-            const uint32_t* __restrict__ cin = codes[cur];
-            for (int i = i0; i < i1; i += 8) {                  // batches of 8 independent loads
-                uint32_t c8[8];
+    for (int c0 = warp * 4; c0 < ncells; c0 += (T / 32) * 4) {
+        int cnt[4];
+        uint32_t k[4];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) c8[j] = i + j < i1 ? cin[i + j] : 0u;
+        for (int u = 0; u < 4; ++u) cnt[u] = c0 + u < ncells ? cell_count[c0 + u] : 0;
 #pragma unroll
-                for (int j = 0; j < 8; ++j)
-                    if (i + j < i1) {
-                        const int idx = (int)((c8[j] >> shift) & 15) * T + tid;
-                        S.hist[idx + (idx >> 5)]++;
-                    }
+        for (int u = 0; u < 4; ++u) k[u] = lane < cnt[u] ? cand[(size_t)(c0 + u) * g.cell_cap + lane] : 0u;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            if (lane < cnt[u]) {
+                const uint32_t code = path_code((int)(k[u] & 0xfff), (int)((k[u] >> 12) & 0xfff), g, winH);
+                const int pos = atomicAdd(&S.cursor[code >> lowbits], 1);
+                C[pos] = code;
+                K[pos] = (uint32_t)((c0 + u) * g.cell_cap + lane) | (k[u] & 0xff000000u);
             }
-            __syncthreads();
-            // exclusive scan of the 16*T counters in (digit-major, thread-minor) order: padded raking
-            {
-                int sum = 0;
-                const int b = tid * 16;
-#pragma unroll
-                for (int k = 0; k < 16; ++k) sum += S.hist[b + k + ((b + k) >> 5)];
-                int incl = sum;
-#pragma unroll
-                for (int d = 1; d < 32; d <<= 1) {
-                    const int t = __shfl_up_sync(0xffffffffu, incl, d);
-                    if (lane >= d) incl += t;
-                }
-                if (lane == 31) S.warp_tmp[warp] = incl;
-                __syncthreads();
-                int woff = 0;
-                for (int w = 0; w < warp; ++w) woff += S.warp_tmp[w];
-                int run = woff + incl - sum;
-#pragma unroll
-                for (int k = 0; k < 16; ++k) {
-                    const int a = b + k + ((b + k) >> 5);
-                    const int v = S.hist[a];
-                    S.hist[a] = run;
-                    run += v;
-                }
+            for (int i = lane + 32; i < cnt[u]; i += 32) {
+                const uint32_t kk = cand[(size_t)(c0 + u) * g.cell_cap + i];
+                const uint32_t code = path_code((int)(kk & 0xfff), (int)((kk >> 12) & 0xfff), g, winH);
+                const int pos = atomicAdd(&S.cursor[code >> lowbits], 1);
+                C[pos] = code;
+                K[pos] = (uint32_t)((c0 + u) * g.cell_cap + i) | (kk & 0xff000000u);
             }
-            __syncthreads();
-            const uint32_t* __restrict__ kin = keys[cur];
-            uint32_t* __restrict__ cout_ = codes[cur ^ 1];
-            uint32_t* __restrict__ kout = keys[cur ^ 1];
-            for (int i = i0; i < i1; i += 8) {
-                uint32_t c8[8], k8[8];
-#pragma unroll
-                for (int j = 0; j < 8; ++j) { c8[j] = i + j < i1 ? cin[i + j] : 0u; k8[j] = i + j < i1 ? kin[i + j] : 0u; }
-#pragma unroll
-                for (int j = 0; j < 8; ++j)
-                    if (i + j < i1) {
-                        const int idx = (int)((c8[j] >> shift) & 15) * T + tid;
-                        const int pos = S.hist[idx + (idx >> 5)]++;
-                        cout_[pos] = c8[j];
-                        kout[pos] = k8[j];
-                    }
-            }
-            cur ^= 1;
-            __syncthreads();
         }
     }
-    const uint32_t* K = keys[cur];
-    const uint32_t* C = codes[cur];
+    __syncthreads();            // the cursors are dead from here on: their bytes become the node arrays
 
     OCT_MARK(1);
     // ---- 2. root nodes (src 589-626) --------------------------------------------------------------------------------
     int a = 0;   // active node buffer
     {
-        const int rshift = 2 * g.depth;
-        if (tid < g.nIni) {
-            const uint32_t lo = lower_bound_code(C, 0, n, rshift, tid), hi = lower_bound_code(C, 0, n, rshift, tid + 1);
-            S.sa[tid] = hi > lo ? 1 : 0;
-            S.cc[4 * tid] = lo; S.cc[4 * tid + 1] = hi - lo;
-        }
-        __syncthreads();
         if (tid == 0) {
             int m = 0;
-            for (int r = 0; r < g.nIni; ++r)
-                if (S.sa[r]) {
-                    S.nbeg[a][m] = S.cc[4 * r]; S.ncnt[a][m] = S.cc[4 * r + 1];
+            for (int r = 0; r < g.nIni; ++r) {
+                const int lo = S.bstart[r << (2 * Dsort)], hi = S.bstart[(r + 1) << (2 * Dsort)];
+                if (hi > lo) {
+                    S.nbeg[a][m] = (uint32_t)lo; S.ncnt[a][m] = (uint32_t)(hi - lo);
                     const int ulx = (int)__fmul_rn(g.hX, (float)r), urx = (int)__fmul_rn(g.hX, (float)(r + 1));
                     S.nx[a][m] = (uint32_t)ulx | ((uint32_t)urx << 16);
                     S.ndep[a][m] = 0;
+                    S.npre[a][m] = (uint32_t)r;
                     ++m;
                 }
+            }
             s_nL = m;
         }
         __syncthreads();
@@ -387,19 +359,36 @@ __global__ void __launch_bounds__(T, 1024 / T) octree_kernel(const __grid_consta
             S.cc[4 * p] = cnt; S.cc[4 * p + 1] = S.cc[4 * p + 2] = S.cc[4 * p + 3] = 0;
             return 1 | ((cnt > 1 ? 1 : 0) << 8);
         }
-        const int shift = 2 * (g.depth - 1 - dep);
-        const uint32_t prefix = (C[beg] >> shift) & ~3u;
         const uint32_t e = beg + cnt;
-        // three lower bounds in lock-step: the probes of one step are independent loads (chain length log2(cnt), not 3x)
-        uint32_t lo1 = beg, hi1 = e, lo2 = beg, hi2 = e, lo3 = beg, hi3 = e;
-        while (lo1 < hi1 || lo2 < hi2 || lo3 < hi3) {
-            const uint32_t m1 = (lo1 + hi1) >> 1, m2 = (lo2 + hi2) >> 1, m3 = (lo3 + hi3) >> 1;
-            const uint32_t v1 = C[min(m1, e - 1)] >> shift, v2 = C[min(m2, e - 1)] >> shift, v3 = C[min(m3, e - 1)] >> shift;
-            if (lo1 < hi1) { if (v1 < (prefix | 1u)) lo1 = m1 + 1; else hi1 = m1; }
-            if (lo2 < hi2) { if (v2 < (prefix | 2u)) lo2 = m2 + 1; else hi2 = m2; }
-            if (lo3 < hi3) { if (v3 < (prefix | 3u)) lo3 = m3 + 1; else hi3 = m3; }
+        uint32_t b1, b2, b3;
+        if (dep < Dsort) {
+            // the children are runs of whole bins: their boundaries are entries of the scanned bin table
+            const int sh = 2 * (Dsort - 1 - dep);
+            const uint32_t base = S.npre[a][pos] << 2;
+            b1 = (uint32_t)S.bstart[(base | 1u) << sh]; b2 = (uint32_t)S.bstart[(base | 2u) << sh]; b3 = (uint32_t)S.bstart[(base | 3u) << sh];
+        } else {
+            // below the sorted prefix: partition the (small) segment in place by the next two code bits.  Order inside a
+            // child is free, so an unstable American-flag pass does; re-partitioning an already partitioned segment (a
+            // phase-2 split that was computed but cut off) is a no-op.
+            const int shift = 2 * (g.depth - 1 - dep);
+            uint32_t c4[4] = {0, 0, 0, 0};
+            for (uint32_t i = beg; i < e; ++i) {
+                const uint32_t d = (C[i] >> shift) & 3u;
+                c4[0] += d == 0; c4[1] += d == 1; c4[2] += d == 2; c4[3] += d == 3;
+            }
+            b1 = beg + c4[0]; b2 = b1 + c4[1]; b3 = b2 + c4[2];
+            uint32_t nx0 = beg, nx1 = b1, nx2 = b2, nx3 = b3;
+            const uint32_t end0 = b1, end1 = b2, end2 = b3;
+            auto place = [&](uint32_t i, uint32_t d) {     // swap element i with the head of bucket d, advance that head
+                uint32_t& h = d == 0 ? nx0 : (d == 1 ? nx1 : (d == 2 ? nx2 : nx3));
+                const uint32_t tc = C[i], tk = K[i];
+                C[i] = C[h]; K[i] = K[h]; C[h] = tc; K[h] = tk;
+                ++h;
+            };
+            while (nx0 < end0) { const uint32_t d = (C[nx0] >> shift) & 3u; if (d == 0) ++nx0; else place(nx0, d); }
+            while (nx1 < end1) { const uint32_t d = (C[nx1] >> shift) & 3u; if (d == 1) ++nx1; else place(nx1, d); }
+            while (nx2 < end2) { const uint32_t d = (C[nx2] >> shift) & 3u; if (d == 2) ++nx2; else place(nx2, d); }
         }
-        const uint32_t b1 = lo1, b2 = lo2, b3 = lo3;
         const uint32_t c0 = b1 - beg, c1 = b2 - b1, c2 = b3 - b2, c3 = e - b3;
         S.cc[4 * p] = c0; S.cc[4 * p + 1] = c1; S.cc[4 * p + 2] = c2; S.cc[4 * p + 3] = c3;
         ne = (c0 > 0) + (c1 > 0) + (c2 > 0) + (c3 > 0);
@@ -435,6 +424,7 @@ __global__ void __launch_bounds__(T, 1024 / T) octree_kernel(const __grid_consta
             const int ulx = (int)(x & 0xffff), urx = (int)(x >> 16);
             const int mx = ulx + ((urx - ulx + 1) >> 1);
             const uint32_t dep = S.ndep[a][pos] + 1;
+            const uint32_t pre4 = S.npre[a][pos] << 2;
             const uint32_t c0 = S.cc[4 * p], c1 = S.cc[4 * p + 1], c2 = S.cc[4 * p + 2], c3 = S.cc[4 * p + 3];
             const uint32_t cb[4] = {beg, beg + c0, beg + c0 + c1, beg + c0 + c1 + c2};
             const uint32_t cn[4] = {c0, c1, c2, c3};
@@ -449,6 +439,7 @@ __global__ void __launch_bounds__(T, 1024 / T) octree_kernel(const __grid_consta
                 posk[k] = -1;
                 if (cn[k] > 0) {
                     S.nbeg[b][slot] = cb[k]; S.ncnt[b][slot] = cn[k]; S.nx[b][slot] = cx[k]; S.ndep[b][slot] = dep;
+                    S.npre[b][slot] = pre4 | (uint32_t)k;
                     posk[k] = slot++;
                 }
             }
@@ -462,7 +453,7 @@ __global__ void __launch_bounds__(T, 1024 / T) octree_kernel(const __grid_consta
             if (r >= 0) {
                 const int slot = Stot + r;
                 S.nbeg[b][slot] = S.nbeg[a][i]; S.ncnt[b][slot] = S.ncnt[a][i]; S.nx[b][slot] = S.nx[a][i];
-                S.ndep[b][slot] = S.ndep[a][i];
+                S.ndep[b][slot] = S.ndep[a][i]; S.npre[b][slot] = S.npre[a][i];
             }
         }
         __syncthreads();
@@ -560,12 +551,12 @@ __global__ void __launch_bounds__(T, 1024 / T) octree_kernel(const __grid_consta
         // = max score, then min ORIGINAL index: (score << 24) | (0xffffff - original index).
         uint32_t best = 0;
         for (uint32_t j = lane; j < cnt; j += 32) {
-            const uint32_t pl = K[beg + j];                      // original index | score << 24
+            const uint32_t pl = K[beg + j];                      // staging slot (monotone in the original index) | score << 24
             best = max(best, (pl & 0xff000000u) | (0xffffffu - (pl & 0xffffffu)));
         }
 #pragma unroll
         for (int d = 16; d >= 1; d >>= 1) best = max(best, __shfl_xor_sync(0xffffffffu, best, d));
-        if (lane == 0) out_kp[i] = keys0[0xffffffu - (best & 0xffffffu)];
+        if (lane == 0) out_kp[i] = cand[0xffffffu - (best & 0xffffffu)];
     }
     if (tid == 0) *out_n = nL;
     OCT_MARK(6);
@@ -579,40 +570,75 @@ cudaError_t octree_prepare()
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(octree_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (e != cudaSuccess) return e;
-
     e = cudaFuncSetAttribute(octree_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (e != cudaSuccess) return e;
     return cudaFuncSetAttribute(octree_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
 }
 
+size_t octree_smem_for(const FrameGeom& fg, int level_lo, int level_hi)
+{
+    int M = 1, NB = 1;
+    for (int l = level_lo; l < level_hi; ++l) {
+        M = M > fg.L[l].kp_cap ? M : fg.L[l].kp_cap;
+        const int nb = octree_bins(fg.L[l]);
+        NB = NB > nb ? NB : nb;
+    }
+    return octree_smem_bytes(M, NB);
+}
+
 static int* g_err_flag[64] = {nullptr};
 
-cudaError_t launch_octree(const FrameGeom& fg, const Workspace& ws, int n_frames, cudaStream_t st)
+// The depth-overflow flag of the last octree launches on the current device (set when two candidates share a pixel: the
+// quadtree cannot separate them); reading clears it.  Synchronises the device: test / stand-alone entry points only.
+int octree_take_error_flag()
 {
-    int M = 0;
-    for (int l = 0; l < fg.nlevels; ++l) M = M > fg.L[l].kp_cap ? M : fg.L[l].kp_cap;
-    // Batches: 256-thread CTAs (measured on 512-frame batches: 1.24 ms; 128 threads 1.33, 64 threads 1.69, 32 threads 1.93,
-    // 512 threads ~30 % slower: the parallel phases need the lanes, the single-lane sort replay needs many resident CTAs).
+    int dev = 0;
+    cudaGetDevice(&dev);
+    int* p = g_err_flag[dev & 63];
+    if (!p) return 0;
+    int v = 0;
+    if (cudaMemcpy(&v, p, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) return 0;
+    if (v) cudaMemset(p, 0, sizeof(int));
+    return v;
+}
+
+// Levels [level_lo, level_hi) of n_frames frames (level_hi <= 0: all levels).
+cudaError_t launch_octree(const FrameGeom& fg, const Workspace& ws, int n_frames, cudaStream_t st, int level_lo, int level_hi)
+{
+    if (level_hi <= 0) level_hi = fg.nlevels;
+    if (level_lo >= level_hi) return cudaSuccess;
+    int M = 1, NB = 1;
+    for (int l = level_lo; l < level_hi; ++l) {
+        M = M > fg.L[l].kp_cap ? M : fg.L[l].kp_cap;
+        const int nb = octree_bins(fg.L[l]);
+        NB = NB > nb ? NB : nb;
+    }
+    // Batches: 256-thread CTAs (measured on 512-frame batches: 128 threads +7 %, 64 threads +36 %, 512 threads ~30 % slower:
+    // the parallel phases need the lanes, the single-lane parts need many resident CTAs).
     // A few frames: the level-0 CTA is the critical path of the whole extraction, so give it more lanes.
     static const int t_override = getenv("ORBX_OCTREE_THREADS") ? atoi(getenv("ORBX_OCTREE_THREADS")) : 0;
     int T = n_frames >= 8 ? 256 : 1024;
     if (t_override == 128 || t_override == 256 || t_override == 512 || t_override == 1024) T = t_override;
-    const size_t smem = octree_smem_bytes(M, T);
+    const size_t smem = octree_smem_bytes(M, NB);
     if (smem > 200 * 1024) return cudaErrorInvalidConfiguration;
     int dev = 0;
     cudaGetDevice(&dev);
     if (!g_err_flag[dev & 63]) {
-        cudaError_t e = cudaMalloc(&g_err_flag[dev & 63], sizeof(int));
-        if (e != cudaSuccess) return e;
-        cudaMemset(g_err_flag[dev & 63], 0, sizeof(int));
+        static std::mutex mu;
+        std::lock_guard<std::mutex> lock(mu);
+        if (!g_err_flag[dev & 63]) {
+            int* p = nullptr;
+            cudaError_t e = cudaMalloc(&p, sizeof(int));
+            if (e != cudaSuccess) return e;
+            cudaMemset(p, 0, sizeof(int));
+            g_err_flag[dev & 63] = p;
+        }
     }
-    dim3 grid(n_frames, fg.nlevels);
-    // The kernel is latency-bound (sequential sort replay, dependent binary searches): big batches run more, smaller CTAs
-    // per SM to overlap those chains; a single frame gets the larger CTA for the shortest critical path.
-    if (T == 128) octree_kernel<128><<<grid, 128, smem, st>>>(fg, ws, M, g_err_flag[dev & 63]);
-    else if (T == 1024) octree_kernel<1024><<<grid, 1024, smem, st>>>(fg, ws, M, g_err_flag[dev & 63]);
-    else if (T == 512) octree_kernel<512><<<grid, 512, smem, st>>>(fg, ws, M, g_err_flag[dev & 63]);
-    else octree_kernel<256><<<grid, 256, smem, st>>>(fg, ws, M, g_err_flag[dev & 63]);
+    dim3 grid(n_frames, level_hi - level_lo);
+    if (T == 128) octree_kernel<128><<<grid, 128, smem, st>>>(fg, ws, M, NB, level_lo, g_err_flag[dev & 63]);
+    else if (T == 1024) octree_kernel<1024><<<grid, 1024, smem, st>>>(fg, ws, M, NB, level_lo, g_err_flag[dev & 63]);
+    else if (T == 512) octree_kernel<512><<<grid, 512, smem, st>>>(fg, ws, M, NB, level_lo, g_err_flag[dev & 63]);
+    else octree_kernel<256><<<grid, 256, smem, st>>>(fg, ws, M, NB, level_lo, g_err_flag[dev & 63]);
     count_launch();
     return cudaGetLastError();
 }

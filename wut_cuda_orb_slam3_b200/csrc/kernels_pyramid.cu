@@ -302,10 +302,12 @@ __global__ void __launch_bounds__(PT_THREADS, PT_MINB) pyr_resize_tiled_kernel(c
     resize_tile_passes<PT_H>(g, ws, src, hbuf, outt, ytl, xt, tid, tx, x0, y0, frame, tw, th, cbase, spitch, symin, nrows);
 }
 
+// Levels [level_lo, level_hi) (level_hi <= 0: all); level l >= 1 reads level l - 1, which must be complete on `st`.
 cudaError_t launch_pyramid(const FrameGeom& fg, const Workspace& ws, const uint8_t* d_images, size_t frame_stride,
-                           size_t pitch, int n_frames, cudaStream_t st)
+                           size_t pitch, int n_frames, cudaStream_t st, int level_lo, int level_hi)
 {
-    for (int l = 0; l < fg.nlevels; ++l) {
+    if (level_hi <= 0) level_hi = fg.nlevels;
+    for (int l = level_lo; l < level_hi; ++l) {
         const LevelGeom& g = fg.L[l];
         const int words = g.pitch / 4;
         dim3 grid((words + 127) / 128, g.rows_alloc, n_frames);

@@ -122,30 +122,34 @@ __device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* m
 void count_launch(int n = 1);
 
 cudaError_t launch_pyramid(const FrameGeom& fg, const Workspace& ws, const uint8_t* d_images, size_t frame_stride,
-                           size_t pitch, int n_frames, cudaStream_t st);
+                           size_t pitch, int n_frames, cudaStream_t st, int level_lo = 0, int level_hi = 0);
 cudaError_t launch_cvt_gray(const uint8_t* d_src, size_t src_pitch, size_t src_frame_stride, int channels, int rgb, int n_frames,
                             int rows, int cols, uint8_t* d_dst, size_t dst_pitch, size_t dst_frame_stride, cudaStream_t st);
-cudaError_t launch_fast(const FrameGeom& fg, const Workspace& ws, int n_frames, cudaStream_t st);
+cudaError_t launch_fast(const FrameGeom& fg, const Workspace& ws, int n_frames, cudaStream_t st, int level_lo = 0, int level_hi = 0);
 cudaError_t launch_blur(const FrameGeom& fg, const Workspace& ws, int n_frames, cudaStream_t st);
-cudaError_t launch_octree(const FrameGeom& fg, const Workspace& ws, int n_frames, cudaStream_t st);
+cudaError_t launch_octree(const FrameGeom& fg, const Workspace& ws, int n_frames, cudaStream_t st, int level_lo = 0, int level_hi = 0);
 cudaError_t launch_orient_describe(const FrameGeom& fg, const Workspace& ws, int n_frames, cudaStream_t st);
 cudaError_t launch_pack(const FrameGeom& fg, const Workspace& ws, int n_frames, int lap0, int lap1,
                         orbx_keypoint* d_kps, uint8_t* d_desc, int capacity, int* d_n_out, int* d_n_mono,
                         cudaStream_t st);
-size_t octree_smem_bytes(int node_capacity, int threads = 256);
+size_t octree_smem_for(const FrameGeom& fg, int level_lo, int level_hi);   // dynamic shared memory of octree_kernel for these levels
+int octree_take_error_flag();   // depth-overflow flag of the current device (duplicate pixels); reading clears it; synchronises
 cudaError_t octree_prepare();   // opt in to large dynamic shared memory
 
 cudaError_t launch_knn2(const uint8_t* d_q, int nq, const uint8_t* d_db, long long ndb, int index_base, int32_t* d_idx,
-                        int32_t* d_dist, cudaStream_t st);
+                        int32_t* d_dist, cudaStream_t st, void* workspace = nullptr);
+size_t knn2_workspace_bytes(int nq, long long ndb);
 cudaError_t launch_knn2_merge(const int32_t* d_idx_sh, const int32_t* d_dist_sh, int n_shards, int nq, int32_t* d_idx,
-                              int32_t* d_dist, cudaStream_t st);
+                              int32_t* d_dist, cudaStream_t st, size_t shard_stride = 0);   // stride in int32 elements, 0 = 2 * nq
 cudaError_t launch_popc_bench(unsigned long long* d_sink, int iters, int blocks, cudaStream_t st);
 
 struct StereoArgs {
-    const uint8_t* pyrL; const uint8_t* pyrR;       // pyramid allocations (same geometry)
+    const uint8_t* pyrL; const uint8_t* pyrR;       // pyramid allocations: same level sizes and pitches, but each extractor lays its
+    unsigned long long offR[kMaxLevels];            // level slabs out for its own slot capacity -> the right pyramid's level offsets
     int frameL, frameR;
-    const orbx_keypoint* kpL; const uint8_t* descL; int nL;
+    const orbx_keypoint* kpL; const uint8_t* descL; int nL;      // nL / nR: counts, or (with d_nL / d_nR) the capacity bound
     const orbx_keypoint* kpR; const uint8_t* descR; int nR;
+    const int* d_nL; const int* d_nR;               // optional device-resident counts (results of an extraction still in flight)
     float bf, maxD;
     float* uRight; float* depth;                    // [nL]
     int* sad;                                       // [nL] scratch: SAD of accepted matches, -1 otherwise

@@ -74,6 +74,63 @@ def compute_stereo_matches(exL, exR, kpL, descL, kpR, descR, bf, maxD, frameL=0,
     return u, d
 
 
+def extract_stereo(exL, exR, imgL, imgR, bf, maxD):
+    """The stereo Frame constructor in one call (src/Frame.cc:124-143): returns (kpL, descL, kpR, descR, mvuRight, mvDepth)."""
+    from .capi import KP_DTYPE
+    imgL = np.ascontiguousarray(imgL, np.uint8); imgR = np.ascontiguousarray(imgR, np.uint8)
+    rows, cols = imgL.shape
+    assert imgR.shape == imgL.shape
+    cap = max(exL.max_keypoints(rows, cols), exR.max_keypoints(rows, cols))
+    kL = np.zeros(cap, KP_DTYPE); kR = np.zeros(cap, KP_DTYPE)
+    dL = np.zeros((cap, 32), np.uint8); dR = np.zeros((cap, 32), np.uint8)
+    u = np.full(cap, -1.0, np.float32); d = np.full(cap, -1.0, np.float32)
+    nL = C.c_int(0); nR = C.c_int(0)
+    check(lib().orbx_extract_stereo(exL._h, exR._h, ptr(imgL), ptr(imgR), rows, cols, imgL.strides[0], ptr(kL), ptr(dL), C.byref(nL),
+                                    ptr(kR), ptr(dR), C.byref(nR), cap, float(bf), float(maxD), ptr(u), ptr(d)))
+    return kL[:nL.value], dL[:nL.value], kR[:nR.value], dR[:nR.value], u[:nL.value], d[:nL.value]
+
+
+class ShardedMatcher:
+    """Database-sharded brute-force 2-NN over the GPUs of one node (BASELINE config 5): one process per GPU, NCCL under the
+    C ABI (orbx_comm_* / orbx_knn2_sharded).  `broadcast_bytes(buf_or_None) -> bytes` hands rank 0's 128-byte id to every rank
+    (torch.distributed, MPI, ...)."""
+
+    def __init__(self, rank, world, device, broadcast_bytes):
+        ident = np.zeros(128, np.uint8)
+        if rank == 0:
+            check(lib().orbx_comm_unique_id(ptr(ident)))
+        ident = np.frombuffer(broadcast_bytes(ident.tobytes() if rank == 0 else None), np.uint8).copy()
+        self._h = C.c_void_p()
+        check(lib().orbx_comm_create(device, rank, world, ptr(ident), C.byref(self._h)))
+        self.rank, self.world, self.device = rank, world, device
+
+    def nccl_version(self):
+        v = C.c_int(0)
+        check(lib().orbx_comm_info(self._h, None, None, C.byref(v)))
+        return v.value
+
+    @staticmethod
+    def shard_rows(n_rows, world, rank):
+        f = C.c_int64(0); c = C.c_int64(0)
+        lib().orbx_shard_rows(n_rows, world, rank, C.byref(f), C.byref(c))
+        return f.value, c.value
+
+    def knn2(self, d_q, nq, d_db_shard, n_shard_rows, first_row, d_idx, d_dist, stream=None):
+        check(lib().orbx_knn2_sharded(self._h, ptr(d_q), nq, ptr(d_db_shard), n_shard_rows, first_row, ptr(d_idx), ptr(d_dist),
+                                      ptr(stream) if stream else None))
+
+    def close(self):
+        if self._h:
+            lib().orbx_comm_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 def measure_popc_peak(device=0):
     v = C.c_double(0)
     check(lib().orbx_measure_popc_peak(device, C.byref(v)))
