@@ -405,6 +405,24 @@ def run_other_configs(local_rank, dev):
     ms = med_ms(stereo)
     out["euroc_stereo_pair_1200"] = {"ms_per_pair": ms, "pairs_per_s": 1e3 / ms, "stereo_matches": int((res["u"] >= 0).sum()),
                                      "what": "orbx_extract left | right on two host threads + orbx_stereo_match"}
+    # the stereo Frame constructor as ONE C-ABI call (src/Frame.cc:124-143): two extractions on two streams + the matcher on the
+    # device-resident features, pinned host buffers in and out
+    import ctypes as C
+    from wut_cuda_orb_slam3_b200.capi import lib, ptr, check
+    hL = torch.from_numpy(L).pin_memory(); hR = torch.from_numpy(R).pin_memory()
+    cap = exL.max_keypoints(480, 752)
+    pk = [torch.empty((cap, 7), dtype=torch.float32).pin_memory() for _ in range(2)]
+    pd = [torch.empty((cap, 32), dtype=torch.uint8).pin_memory() for _ in range(2)]
+    pu = torch.empty(cap, dtype=torch.float32).pin_memory(); pz = torch.empty(cap, dtype=torch.float32).pin_memory()
+    nLc, nRc = C.c_int(0), C.c_int(0)
+
+    def stereo_one_call():
+        check(lib().orbx_extract_stereo(exL._h, exR._h, ptr(hL), ptr(hR), 480, 752, 752, ptr(pk[0]), ptr(pd[0]), C.byref(nLc), ptr(pk[1]), ptr(pd[1]),
+                                        C.byref(nRc), cap, 47.9, 435.2, ptr(pu), ptr(pz)))
+    ms = med_ms(stereo_one_call, reps=100)
+    assert np.array_equal(pu[:nLc.value].numpy(), res["u"]) and np.array_equal(pz[:nLc.value].numpy(), res["d"]), "orbx_extract_stereo disagrees"
+    out["euroc_stereo_pair_1200_extract_stereo"] = {"ms_per_pair": ms, "pairs_per_s": 1e3 / ms, "stereo_matches": int((pu[:nLc.value] >= 0).sum()),
+                                                    "what": "orbx_extract_stereo: one C-ABI call = ExtractORB left | right + ComputeStereoMatches (Frame.cc:124-143)"}
     exL.close(); exR.close()
     # the same pair as ONE two-frame call on one extractor (both pyramids stay on the device as frames 0 and 1): what a
     # stereo front end built on the batch API does instead of two extractor threads
@@ -463,7 +481,7 @@ def run_other_configs(local_rank, dev):
 
 # Checksums of configs[3] produced by ONE B200 over all 8192 frames (seeds 9000 .. 9000 + 8191): every N must reproduce them.
 # (total keypoints, sum n_out[f] * (f + 1), sum of the int32 words of all valid descriptors, same for the 28-byte keypoints)
-CFG4_EXPECTED = {8192: None}
+CFG4_EXPECTED = {8192: [16438361, 67339139679, 3427532576264195, 92368513198523344]}
 
 
 def run_cfg4(args, rank, world, local_rank, dev, barrier, max_over_ranks):

@@ -118,3 +118,54 @@ def test_range_parallel_32bit_items(oracle):
             items = np.ascontiguousarray((rank << np.uint32(16)) | np.arange(n, dtype=np.uint32))
             lib().orbx_debug_sort_replay_ranges32(ptr(items), n)
             assert np.array_equal(items & np.uint32(0xffff), (ref & np.uint64(0xffffff)).astype(np.uint32)), (n, nkeys)
+
+
+def replay_ranked(items):
+    a = np.ascontiguousarray(items, np.uint64).copy()
+    lib().orbx_debug_sort_replay_ranked.restype = None
+    lib().orbx_debug_sort_replay_ranked(ptr(a), len(a))
+    return a
+
+
+def test_rank_arithmetic_partition_matches_std_sort(oracle):
+    """The Hoare partition as rank arithmetic (k-th stop of the left scan pairs with the k-th stop of the right scan while they
+    have not crossed; csrc/introsort_replay.h unguarded_partition_ranked_) — the form a warp evaluates cooperatively in the
+    octree kernel — must give std::sort's permutation on everything the scan / swap loop is tested on."""
+    rng = np.random.default_rng(11)
+    for n in list(range(0, 48)) + [63, 64, 65, 100, 118, 217, 300, 434, 512, 1000, 4000]:
+        for nkeys in (1, 2, 3, 7, 50, 10 ** 6):
+            for rep in range(3):
+                items = make(rng.integers(0, nkeys, n))
+                assert np.array_equal(replay_ranked(items), oracle.std_sort_hi40(items)), (n, nkeys)
+    for n in (17, 33, 128, 1025, 4096):
+        for keys in (np.arange(n), np.arange(n)[::-1], np.zeros(n), np.arange(n) % 2, np.arange(n) // 3,
+                     np.concatenate([np.arange(n // 2), np.arange(n - n // 2)])):
+            items = make(keys)
+            assert np.array_equal(replay_ranked(items), oracle.std_sort_hi40(items))
+    for n in (20, 60, 150, 400):
+        for rep in range(20):
+            cnt = rng.integers(2, 12, n).astype(np.uint64)
+            ulx = (rng.integers(0, 8, n) * 45).astype(np.uint64)
+            items = make((cnt << np.uint64(13)) | ulx)
+            assert np.array_equal(replay_ranked(items), oracle.std_sort_hi40(items))
+    # median-of-three killer: depth limit -> heap-sort fallback on the way
+    n = 4096
+    k = n // 2
+    keys = np.zeros(n, np.int64)
+    for i in range(1, k + 1):
+        if i % 2 == 1:
+            keys[i - 1] = i
+            keys[i] = k + i
+        keys[k + i - 1] = 2 * i
+    items = make(keys)
+    assert np.array_equal(replay_ranked(items), oracle.std_sort_hi40(items))
+    # 32-bit rank items
+    lib().orbx_debug_sort_replay_ranked32.restype = None
+    for n in (1, 2, 17, 40, 118, 300, 512):
+        for nkeys in (1, 3, 20, 10 ** 6):
+            keys = rng.integers(0, nkeys, n).astype(np.uint64)
+            ref = oracle.std_sort_hi40(make(keys))
+            rank = np.array([(keys < k).sum() for k in keys], np.uint32)
+            items = np.ascontiguousarray((rank << np.uint32(16)) | np.arange(n, dtype=np.uint32))
+            lib().orbx_debug_sort_replay_ranked32(ptr(items), n)
+            assert np.array_equal(items & np.uint32(0xffff), (ref & np.uint64(0xffffff)).astype(np.uint32)), (n, nkeys)

@@ -1567,4 +1567,19 @@ void orbx_debug_sort_replay_ranges32(uint32_t* items, int n)
     orbx_sort::sort_replay_ranges_host(items, n, blk.data(), tmp.data());
 }
 
+// the same schedule with the rank-arithmetic partition the octree kernel evaluates per warp
+void orbx_debug_sort_replay_ranked(unsigned long long* items, int n)
+{
+    if (n <= 0 || n >= 4352) { orbx_sort::sort_replay(items, n); return; }
+    std::vector<uint32_t> blk(n);
+    std::vector<unsigned long long> tmp(n);
+    orbx_sort::sort_replay_ranges_host(items, n, blk.data(), tmp.data(), true);
+}
+void orbx_debug_sort_replay_ranked32(uint32_t* items, int n)
+{
+    if (n <= 0 || n >= 4352) { orbx_sort::sort_replay(items, n); return; }
+    std::vector<uint32_t> blk(n), tmp(n);
+    orbx_sort::sort_replay_ranges_host(items, n, blk.data(), tmp.data(), true);
+}
+
 }  // extern "C"

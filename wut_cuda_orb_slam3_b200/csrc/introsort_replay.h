@@ -128,6 +128,30 @@ template <typename item_t> ORBX_SORT_HD int unguarded_partition_(item_t* base, i
     }
 }
 
+// The same outcome from rank arithmetic instead of the scan / swap loop (the form a warp evaluates cooperatively, see
+// sort_replay_parallel in kernels_octree.cu).  Let L_0 < L_1 < ... be the positions in [first, last) whose element does NOT
+// compare less than the pivot (where the left scan can stop) and R_0 > R_1 > ... those whose element the pivot does NOT
+// compare less than (where the right scan can stop).  Between two swaps the scans only cross untouched elements, so swap k
+// exchanges L_k and R_k as long as L_k < R_k; with K such swaps the final left scan stops at the first CURRENT element that
+// is not less than the pivot to the right of L_{K-1}: the untouched L_K, or R_{K-1} (which now holds the old a[L_{K-1}]),
+// whichever comes first.  posL / posR: scratch for last - first positions each.
+template <typename item_t> ORBX_SORT_HD int unguarded_partition_ranked_(item_t* base, int first, int last, int pivot, int* posL, int* posR)
+{
+    const item_t pv = base[pivot];
+    int nl = 0, nr = 0;
+    for (int i = first; i < last; ++i)
+        if (!lt(base[i], pv)) posL[nl++] = i;
+    for (int i = last - 1; i >= first; --i)
+        if (!lt(pv, base[i])) posR[nr++] = i;
+    int K = 0;
+    while (K < nl && K < nr && posL[K] < posR[K]) ++K;
+    for (int k = 0; k < K; ++k) swp(base + posL[k], base + posR[k]);
+    int ret = last;                                     // (the median-of-three pivot guarantees a stop inside the range)
+    if (K < nl) ret = posL[K];
+    if (K > 0 && posR[K - 1] < ret) ret = posR[K - 1];
+    return ret;
+}
+
 template <typename item_t> ORBX_SORT_HD void unguarded_linear_insert_(item_t* base, int last)
 {
     const item_t val = base[last];
@@ -227,6 +251,22 @@ template <typename item_t> ORBX_SORT_HD int range_step(item_t* base, int n, Rang
     return 2;
 }
 
+// range_step with the ranked partition (host check of the formula the device evaluates per warp)
+template <typename item_t> inline int range_step_ranked(item_t* base, int n, Range r, Range out[2], int* posL, int* posR)
+{
+    if (r.depth == 0) {
+        heap_sort_(base + r.first, r.last - r.first);
+        return 0;
+    }
+    const int depth = r.depth - 1;
+    const int mid = r.first + (r.last - r.first) / 2;
+    move_median_to_first_(base + r.first, base + r.first + 1, base + mid, base + r.last - 1);
+    const int cut = unguarded_partition_ranked_(base, r.first + 1, r.last, r.first, posL, posR);
+    out[0] = Range{r.first, cut, depth};
+    out[1] = Range{cut, r.last, depth};
+    return 2;
+}
+
 // Position of element i after the stable sort of its block [f, l).
 template <typename item_t> ORBX_SORT_HD int block_stable_pos(const item_t* base, int f, int l, int i)
 {
@@ -246,9 +286,11 @@ ORBX_SORT_HD int initial_depth(int n)
 // Host-side sequential simulation of the range-parallel schedule (rounds of independent range steps, then the block-wise
 // stable placement): the device version in kernels_octree.cu runs the same steps with one lane per range / element.
 // blk[n]: packed block bounds (f | l << 16) per element; tmp[n]: output buffer.  n < 65536.
-template <typename item_t> inline void sort_replay_ranges_host(item_t* base, int n, uint32_t* blk, item_t* tmp)
+template <typename item_t> inline void sort_replay_ranges_host(item_t* base, int n, uint32_t* blk, item_t* tmp, bool ranked = false)
 {
     if (n <= 0) return;
+    int* posL = ranked ? new int[2 * (size_t)n] : nullptr;
+    int* posR = ranked ? posL + n : nullptr;
     Range cur[256], nxt[256];          // ranges longer than 16 elements: at most n / 17 of them
     int nc = 0, nn = 0;
     auto settle = [&](Range r, bool sorted) {
@@ -260,7 +302,7 @@ template <typename item_t> inline void sort_replay_ranges_host(item_t* base, int
         nn = 0;
         for (int q = 0; q < nc; ++q) {
             Range out[2];
-            const int k = range_step(base, n, cur[q], out);
+            const int k = ranked ? range_step_ranked(base, n, cur[q], out, posL, posR) : range_step(base, n, cur[q], out);
             if (k == 0) settle(cur[q], true);
             for (int c = 0; c < k; ++c) {
                 if (out[c].last - out[c].first > 16) nxt[nn++] = out[c];
@@ -272,6 +314,7 @@ template <typename item_t> inline void sort_replay_ranges_host(item_t* base, int
     }
     for (int i = 0; i < n; ++i) tmp[block_stable_pos(base, (int)(blk[i] & 0xffffu), (int)(blk[i] >> 16), i)] = base[i];
     for (int i = 0; i < n; ++i) base[i] = tmp[i];
+    delete[] posL;
 }
 
 }  // namespace orbx_sort

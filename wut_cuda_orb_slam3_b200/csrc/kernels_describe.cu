@@ -407,21 +407,31 @@ __global__ void __launch_bounds__(256) orient_describe_kernel(const __grid_const
     if (lane == 0) ws.lvl_angle[(size_t)frame * fg.kp_slots + slot] = angle;
 }
 
-// grid = n_frames, 256 threads: src/ORBextractor.cc:1283-1306.
-__global__ void __launch_bounds__(256) pack_kernel(const __grid_constant__ FrameGeom fg, Workspace ws, int lap0, int lap1,
-                                                   orbx_keypoint* __restrict__ kps, uint8_t* __restrict__ desc, int capacity,
-                                                   int* __restrict__ n_out, int* __restrict__ n_mono)
+// grid = n_frames, T threads: src/ORBextractor.cc:1283-1306.  T = 256 for batches (one CTA per frame, hundreds of frames in
+// flight), 1024 for a few frames: the whole frame is then one pass with two barriers — the kernel sits on the critical path
+// of the single-frame call.
+template <int T>
+__global__ void __launch_bounds__(T) pack_kernel(const __grid_constant__ FrameGeom fg, Workspace ws, int lap0, int lap1,
+                                                 orbx_keypoint* __restrict__ kps, uint8_t* __restrict__ desc, int capacity,
+                                                 int* __restrict__ n_out, int* __restrict__ n_mono)
 {
     __shared__ int lvl_off[kMaxLevels + 1];
-    __shared__ int warp_cnt[8];
+    __shared__ int warp_cnt[T / 32];
     __shared__ int carry;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int frame = blockIdx.x;
-    if (tid == 0) {
-        int o = 0;
-        for (int l = 0; l < fg.nlevels; ++l) { lvl_off[l] = o; o += ws.lvl_n[(size_t)frame * fg.nlevels + l]; }
-        lvl_off[fg.nlevels] = o;
-        carry = 0;
+    if (warp == 0) {                               // per-level counts -> offsets: independent loads + a shuffle scan
+        static_assert(kMaxLevels <= 32, "one lane per level");
+        const int c = lane < fg.nlevels ? ws.lvl_n[(size_t)frame * fg.nlevels + lane] : 0;
+        int incl = c;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += t;
+        }
+        if (lane < fg.nlevels) lvl_off[lane] = incl - c;
+        if (lane == fg.nlevels - 1) lvl_off[fg.nlevels] = incl;
+        if (lane == 0) carry = 0;
     }
     __syncthreads();
     const int nkp = lvl_off[fg.nlevels];
@@ -432,7 +442,7 @@ __global__ void __launch_bounds__(256) pack_kernel(const __grid_constant__ Frame
     orbx_keypoint* okp = kps + (size_t)frame * capacity;
     uint8_t* odesc = desc + (size_t)frame * capacity * 32;
     const float flap0 = (float)lap0, flap1 = (float)lap1;
-    for (int base = 0; base < nkp; base += 256) {
+    for (int base = 0; base < nkp; base += T) {
         const int t = base + tid;
         bool valid = t < nkp, stereo = false;
         orbx_keypoint kp;
@@ -453,10 +463,9 @@ __global__ void __launch_bounds__(256) pack_kernel(const __grid_constant__ Frame
             stereo = px >= flap0 && px <= flap1;
         }
         const uint32_t mS = __ballot_sync(0xffffffffu, valid && stereo);
-        const uint32_t mV = __ballot_sync(0xffffffffu, valid);
         if (lane == 0) warp_cnt[warp] = __popc(mS);
         __syncthreads();
-        int before = carry;            // stereo keypoints before this chunk
+        int before = carry;            // lapping-area keypoints before this chunk
         for (int w = 0; w < warp; ++w) before += warp_cnt[w];
         const int sBefore = before + __popc(mS & ((1u << lane) - 1));
         if (valid) {
@@ -467,9 +476,8 @@ __global__ void __launch_bounds__(256) pack_kernel(const __grid_constant__ Frame
             d[0] = s[0]; d[1] = s[1];
         }
         __syncthreads();
-        if (tid == 0) { int c = carry; for (int w = 0; w < 8; ++w) c += warp_cnt[w]; carry = c; }
+        if (tid == 0) { int c = carry; for (int w = 0; w < T / 32; ++w) c += warp_cnt[w]; carry = c; }
         __syncthreads();
-        (void)mV;
     }
     if (tid == 0) { n_out[frame] = nkp; n_mono[frame] = nkp - carry; }
 }
@@ -567,7 +575,8 @@ cudaError_t launch_orient_describe(const FrameGeom& fg, const Workspace& ws, int
 cudaError_t launch_pack(const FrameGeom& fg, const Workspace& ws, int n_frames, int lap0, int lap1, orbx_keypoint* d_kps,
                         uint8_t* d_desc, int capacity, int* d_n_out, int* d_n_mono, cudaStream_t st)
 {
-    pack_kernel<<<n_frames, 256, 0, st>>>(fg, ws, lap0, lap1, d_kps, d_desc, capacity, d_n_out, d_n_mono);
+    if (n_frames >= 8) pack_kernel<256><<<n_frames, 256, 0, st>>>(fg, ws, lap0, lap1, d_kps, d_desc, capacity, d_n_out, d_n_mono);
+    else pack_kernel<1024><<<n_frames, 1024, 0, st>>>(fg, ws, lap0, lap1, d_kps, d_desc, capacity, d_n_out, d_n_mono);
     count_launch();
     return cudaGetLastError();
 }

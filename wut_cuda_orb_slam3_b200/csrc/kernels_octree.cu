@@ -110,16 +110,61 @@ __device__ int block_exclusive_scan_raking(int* a, int n, int* warp_tmp)
     return total;
 }
 
+// One Hoare partition (libstdc++ __unguarded_partition) by ONE WARP, as rank arithmetic (introsort_replay.h,
+// unguarded_partition_ranked_, checked against std::sort on the host): ballots give every scan-stop position its rank from
+// the left / from the right, swap k pairs the k-th stops while they have not crossed.  posL / posR: scratch indexed by
+// absolute position (a range only touches its own span, so concurrent ranges never collide).
+__device__ __forceinline__ int warp_partition_ranked(uint32_t* base, int first, int last, int pivot, uint32_t* posL, uint32_t* posR, int lane)
+{
+    const uint32_t pv = base[pivot];
+    const uint32_t below = (1u << lane) - 1u;
+    int nl = 0, nr = 0;
+    for (int c = first; c < last; c += 32) {
+        const int i = c + lane;
+        const bool stop = i < last && !orbx_sort::lt(base[i], pv);
+        const uint32_t mk = __ballot_sync(0xffffffffu, stop);
+        if (stop) posL[first + nl + __popc(mk & below)] = (uint32_t)i;
+        nl += __popc(mk);
+    }
+    for (int c = last - 1; c >= first; c -= 32) {
+        const int i = c - lane;
+        const bool stop = i >= first && !orbx_sort::lt(pv, base[i]);
+        const uint32_t mk = __ballot_sync(0xffffffffu, stop);
+        if (stop) posR[first + nr + __popc(mk & below)] = (uint32_t)i;
+        nr += __popc(mk);
+    }
+    __syncwarp();
+    const int nm = min(nl, nr);
+    int K = 0;                                         // L_k < R_k is monotone in k: the pairs to swap form a prefix
+    for (int c = 0; c < nm; c += 32) {
+        const int k = c + lane;
+        const bool ok = k < nm && posL[first + k] < posR[first + k];
+        const uint32_t mk = __ballot_sync(0xffffffffu, ok);
+        K += __popc(mk);
+        if (mk != 0xffffffffu) break;                  // warp-uniform
+    }
+    for (int k = lane; k < K; k += 32) {
+        const uint32_t l = posL[first + k], r = posR[first + k];
+        const uint32_t x = base[l], y = base[r];
+        base[l] = y; base[r] = x;
+    }
+    int ret = last;
+    if (K < nl) ret = (int)posL[first + K];
+    if (K > 0) ret = min(ret, (int)posR[first + K - 1]);
+    __syncwarp();
+    return ret;
+}
+
 // std::sort replay, range-parallel (introsort_replay.h): all T threads call.  base[m] = 32-bit items in shared memory,
-// blk[m] / tmp[m] = shared scratch, q = 224 ints of shared scratch (three round counters + two queues of <= 32 ranges: a
-// range in a queue is longer than 16 elements and m <= 512).  Range r of a round is handled by lane r / NW of warp r % NW, so
-// that the longest partitions of a round run in different warps.  One barrier per round: the counters rotate (the one read
-// in round k is cleared in round k + 1 and refilled in round k + 2).
+// blk[m] / tmp[m] / aux[m] = shared scratch, q = 224 ints of shared scratch (three round counters + two queues of <= 32
+// ranges: a range in a queue is longer than 16 elements and m <= 512).  Every range of a round is partitioned by its own
+// warp (warp_partition_ranked).  One barrier per round: the counters rotate (the one read in round k is cleared in round
+// k + 1 and refilled in round k + 2).
 template <int T>
-__device__ void sort_replay_parallel(uint32_t* base, int m, uint32_t* blk, uint32_t* tmp, int* q)
+__device__ void sort_replay_parallel(uint32_t* base, int m, uint32_t* blk, uint32_t* tmp, uint32_t* aux, int* q)
 {
     constexpr int NW = T / 32;
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     int* cnt = q;
     int* Q[2] = {q + 8, q + 8 + 96};
     if (m <= 16) {
@@ -136,20 +181,29 @@ __device__ void sort_replay_parallel(uint32_t* base, int m, uint32_t* blk, uint3
         int* nxt_cnt = cnt + (round + 1) % 3;
         const int* qi = Q[round & 1];
         int* qo = Q[(round + 1) & 1];
-        const int r = (tid >> 5) + (tid & 31) * NW;
-        if (r < c) {
-            const orbx_sort::Range rg{qi[3 * r], qi[3 * r + 1], qi[3 * r + 2]};
-            orbx_sort::Range out[2];
-            const int k = orbx_sort::range_step(base, m, rg, out);
-            if (k == 0)
-                for (int i = rg.first; i < rg.last; ++i) blk[i] = (uint32_t)i | ((uint32_t)(i + 1) << 16);   // heap-sorted: final
-            for (int ch = 0; ch < k; ++ch) {
-                if (out[ch].last - out[ch].first > 16) {
-                    const int slot = atomicAdd(nxt_cnt, 1);
-                    qo[3 * slot] = out[ch].first; qo[3 * slot + 1] = out[ch].last; qo[3 * slot + 2] = out[ch].depth;
+        for (int r = warp; r < c; r += NW) {
+            const int first = qi[3 * r], last = qi[3 * r + 1], depth = qi[3 * r + 2];
+            if (depth == 0) {                                // depth budget exhausted: heap sort (one lane), final
+                if (lane == 0) orbx_sort::heap_sort_(base + first, last - first);
+                for (int i = first + lane; i < last; i += 32) blk[i] = (uint32_t)i | ((uint32_t)(i + 1) << 16);
+                __syncwarp();
+                continue;
+            }
+            if (lane == 0)
+                orbx_sort::move_median_to_first_(base + first, base + first + 1, base + first + (last - first) / 2, base + last - 1);
+            __syncwarp();
+            const int cut = warp_partition_ranked(base, first + 1, last, first, tmp, aux, lane);
+            const int cf[2] = {first, cut}, cl[2] = {cut, last};
+#pragma unroll
+            for (int ch = 0; ch < 2; ++ch) {
+                if (cl[ch] - cf[ch] > 16) {
+                    if (lane == 0) {
+                        const int slot = atomicAdd(nxt_cnt, 1);
+                        qo[3 * slot] = cf[ch]; qo[3 * slot + 1] = cl[ch]; qo[3 * slot + 2] = depth - 1;
+                    }
                 } else {
-                    const uint32_t b = (uint32_t)out[ch].first | ((uint32_t)out[ch].last << 16);
-                    for (int i = out[ch].first; i < out[ch].last; ++i) blk[i] = b;
+                    const uint32_t bb = (uint32_t)cf[ch] | ((uint32_t)cl[ch] << 16);
+                    for (int i = cf[ch] + lane; i < cl[ch]; i += 32) blk[i] = bb;
                 }
             }
         }
@@ -165,14 +219,14 @@ __device__ void sort_replay_parallel(uint32_t* base, int m, uint32_t* blk, uint3
     __syncthreads();
 }
 
-// Path code of a key (window-relative x, y).
-__device__ __forceinline__ uint32_t path_code(int x, int y, const LevelGeom& g, int winH)
+// Leading part of a key's path code (window-relative x, y): root index, then 2 bits per depth for `levels` depths.
+__device__ __forceinline__ uint32_t path_code_top(int x, int y, const LevelGeom& g, int winH, int levels)
 {
     const int r = (int)__fdiv_rn((float)x, g.hX);                      // vpIniNodes[kp.pt.x / hX]   (src 613)
     int ulx = (int)__fmul_rn(g.hX, (float)r), urx = (int)__fmul_rn(g.hX, (float)(r + 1));   // src 602-603
     int uly = 0, bry = winH;
     uint32_t code = (uint32_t)r;
-    for (int d = 0; d < g.depth; ++d) {
+    for (int d = 0; d < levels; ++d) {
         const int mx = ulx + ((urx - ulx + 1) >> 1);                   // UL.x + ceil((UR.x-UL.x)/2)   (src 517)
         const int my = uly + ((bry - uly + 1) >> 1);
         const uint32_t qx = x >= mx, qy = y >= my;                     // src 546-557
@@ -181,6 +235,26 @@ __device__ __forceinline__ uint32_t path_code(int x, int y, const LevelGeom& g, 
         if (qy) uly = my; else bry = my;
     }
     return code;
+}
+
+// Exclusive prefix sum of a[0..n) in place by ONE warp (lane-strided chunks, running carry).  Returns the total.
+__device__ __forceinline__ int warp_exclusive_scan(int* a, int n, int lane)
+{
+    int carry = 0;
+    for (int base = 0; base < n; base += 32) {
+        const int i = base + lane;
+        const int v = i < n ? a[i] : 0;
+        int incl = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += t;
+        }
+        if (i < n) a[i] = carry + incl - v;
+        carry += __shfl_sync(0xffffffffu, incl, 31);
+    }
+    __syncwarp();
+    return carry;
 }
 
 }  // namespace
@@ -264,17 +338,18 @@ __global__ void __launch_bounds__(T, 1024 / T) octree_kernel(const __grid_consta
     // A candidate's identity is its slot in the FAST staging area, flat = cell * cell_cap + i: monotone in the reference's
     // vToDistributeKeys order (cells row-major, (y, x) inside a cell), which is all the retain rule needs.
     const int Dsort = octree_sort_depth(g.depth, g.root_bits);
-    const int lowbits = 2 * (g.depth - Dsort);                   // code bits below the sorted prefix
     const int nb = 1 << (g.root_bits + 2 * Dsort);
     uint32_t* scratch = ws.oct + (size_t)frame * fg.oct_frame_stride + g.oct_off;
     const int nmax = g.cand_max;
     uint32_t* K = scratch;                                       // payload: flat staging slot | score << 24, bin-sorted
-    uint32_t* C = scratch + nmax;                                // path codes, same order
+    uint32_t* Bst = scratch + nmax;                              // per staging slot: bin | score << 24 (count pass -> scatter pass)
     const int* cell_count = ws.cell_count + (size_t)frame * fg.total_cells + g.cell_base;
     const uint32_t* __restrict__ cand = ws.cand + (size_t)frame * fg.cand_frame_stride + g.cand_off;
     for (int i = tid; i <= nb; i += T) S.bstart[i] = 0;
     __syncthreads();
-    // warp = 4 cells per iteration so that the dependent global loads (count -> candidates) of several cells overlap
+    // warp = 4 cells per iteration so that the dependent global loads (count -> candidates) of several cells overlap.  Only
+    // the Dsort leading depths of the path are evaluated (the deeper bits are needed by the rare splits below depth Dsort,
+    // which work them out on demand), once: the bin travels to the scatter pass through Bst.
     for (int c0 = warp * 4; c0 < ncells; c0 += (T / 32) * 4) {
         int cnt[4];
         uint32_t k[4];
@@ -284,10 +359,16 @@ __global__ void __launch_bounds__(T, 1024 / T) octree_kernel(const __grid_consta
         for (int u = 0; u < 4; ++u) k[u] = lane < cnt[u] ? cand[(size_t)(c0 + u) * g.cell_cap + lane] : 0u;
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-            if (lane < cnt[u]) atomicAdd(&S.bstart[path_code((int)(k[u] & 0xfff), (int)((k[u] >> 12) & 0xfff), g, winH) >> lowbits], 1);
+            if (lane < cnt[u]) {
+                const uint32_t bin = path_code_top((int)(k[u] & 0xfff), (int)((k[u] >> 12) & 0xfff), g, winH, Dsort);
+                atomicAdd(&S.bstart[bin], 1);
+                Bst[(size_t)(c0 + u) * g.cell_cap + lane] = bin | (k[u] & 0xff000000u);
+            }
             for (int i = lane + 32; i < cnt[u]; i += 32) {           // cells with more than 32 candidates (rare)
                 const uint32_t kk = cand[(size_t)(c0 + u) * g.cell_cap + i];
-                atomicAdd(&S.bstart[path_code((int)(kk & 0xfff), (int)((kk >> 12) & 0xfff), g, winH) >> lowbits], 1);
+                const uint32_t bin = path_code_top((int)(kk & 0xfff), (int)((kk >> 12) & 0xfff), g, winH, Dsort);
+                atomicAdd(&S.bstart[bin], 1);
+                Bst[(size_t)(c0 + u) * g.cell_cap + i] = bin | (kk & 0xff000000u);
             }
         }
     }
@@ -303,35 +384,32 @@ __global__ void __launch_bounds__(T, 1024 / T) octree_kernel(const __grid_consta
     OCT_MARK(0);
     for (int c0 = warp * 4; c0 < ncells; c0 += (T / 32) * 4) {
         int cnt[4];
-        uint32_t k[4];
+        uint32_t bs[4];
 #pragma unroll
         for (int u = 0; u < 4; ++u) cnt[u] = c0 + u < ncells ? cell_count[c0 + u] : 0;
 #pragma unroll
-        for (int u = 0; u < 4; ++u) k[u] = lane < cnt[u] ? cand[(size_t)(c0 + u) * g.cell_cap + lane] : 0u;
+        for (int u = 0; u < 4; ++u) bs[u] = lane < cnt[u] ? Bst[(size_t)(c0 + u) * g.cell_cap + lane] : 0u;
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
             if (lane < cnt[u]) {
-                const uint32_t code = path_code((int)(k[u] & 0xfff), (int)((k[u] >> 12) & 0xfff), g, winH);
-                const int pos = atomicAdd(&S.cursor[code >> lowbits], 1);
-                C[pos] = code;
-                K[pos] = (uint32_t)((c0 + u) * g.cell_cap + lane) | (k[u] & 0xff000000u);
+                const int pos = atomicAdd(&S.cursor[bs[u] & 0xffffffu], 1);
+                K[pos] = (uint32_t)((c0 + u) * g.cell_cap + lane) | (bs[u] & 0xff000000u);
             }
             for (int i = lane + 32; i < cnt[u]; i += 32) {
-                const uint32_t kk = cand[(size_t)(c0 + u) * g.cell_cap + i];
-                const uint32_t code = path_code((int)(kk & 0xfff), (int)((kk >> 12) & 0xfff), g, winH);
-                const int pos = atomicAdd(&S.cursor[code >> lowbits], 1);
-                C[pos] = code;
-                K[pos] = (uint32_t)((c0 + u) * g.cell_cap + i) | (kk & 0xff000000u);
+                const uint32_t b2 = Bst[(size_t)(c0 + u) * g.cell_cap + i];
+                const int pos = atomicAdd(&S.cursor[b2 & 0xffffffu], 1);
+                K[pos] = (uint32_t)((c0 + u) * g.cell_cap + i) | (b2 & 0xff000000u);
             }
         }
     }
     __syncthreads();            // the cursors are dead from here on: their bytes become the node arrays
 
     OCT_MARK(1);
-    // ---- 2. root nodes (src 589-626) --------------------------------------------------------------------------------
-    int a = 0;   // active node buffer
-    {
-        if (tid == 0) {
+    // ---- 2./3. the tree phases run in WARP 0 (a few hundred nodes: warp-wide scans and __syncwarp instead of CTA-wide
+    // barriers); the other warps join for the std::sort replay and the final retain step. -------------------------------
+    int a = 0;   // active node buffer (every thread tracks it)
+    if (warp == 0) {
+        if (lane == 0) {        // root nodes (src 589-626)
             int m = 0;
             for (int r = 0; r < g.nIni; ++r) {
                 const int lo = S.bstart[r << (2 * Dsort)], hi = S.bstart[(r + 1) << (2 * Dsort)];
@@ -346,8 +424,14 @@ __global__ void __launch_bounds__(T, 1024 / T) octree_kernel(const __grid_consta
             }
             s_nL = m;
         }
-        __syncthreads();
+        __syncwarp();
     }
+
+    // 2-bit quadrant of the key with payload `pl` at depth `dep` of its path (dep >= Dsort: not part of the sorted prefix)
+    auto quadrant_at = [&](uint32_t pl, int dep) -> uint32_t {
+        const uint32_t kk = cand[pl & 0xffffffu];
+        return path_code_top((int)(kk & 0xfff), (int)((kk >> 12) & 0xfff), g, winH, dep + 1) & 3u;
+    };
 
     // Computes the children of the node at list position `pos` into cc[4*p..]; returns (#non-empty) | (#expandable << 8).
     auto split_counts = [&](int p, int pos) -> int {
@@ -367,13 +451,12 @@ __global__ void __launch_bounds__(T, 1024 / T) octree_kernel(const __grid_consta
             const uint32_t base = S.npre[a][pos] << 2;
             b1 = (uint32_t)S.bstart[(base | 1u) << sh]; b2 = (uint32_t)S.bstart[(base | 2u) << sh]; b3 = (uint32_t)S.bstart[(base | 3u) << sh];
         } else {
-            // below the sorted prefix: partition the (small) segment in place by the next two code bits.  Order inside a
-            // child is free, so an unstable American-flag pass does; re-partitioning an already partitioned segment (a
-            // phase-2 split that was computed but cut off) is a no-op.
-            const int shift = 2 * (g.depth - 1 - dep);
+            // below the sorted prefix: partition the (small) segment in place by the key's quadrant at this depth.  Order
+            // inside a child is free, so an unstable American-flag pass does; re-partitioning an already partitioned segment
+            // (a phase-2 split that was computed but cut off) is a no-op.
             uint32_t c4[4] = {0, 0, 0, 0};
             for (uint32_t i = beg; i < e; ++i) {
-                const uint32_t d = (C[i] >> shift) & 3u;
+                const uint32_t d = quadrant_at(K[i], dep);
                 c4[0] += d == 0; c4[1] += d == 1; c4[2] += d == 2; c4[3] += d == 3;
             }
             b1 = beg + c4[0]; b2 = b1 + c4[1]; b3 = b2 + c4[2];
@@ -381,13 +464,13 @@ __global__ void __launch_bounds__(T, 1024 / T) octree_kernel(const __grid_consta
             const uint32_t end0 = b1, end1 = b2, end2 = b3;
             auto place = [&](uint32_t i, uint32_t d) {     // swap element i with the head of bucket d, advance that head
                 uint32_t& h = d == 0 ? nx0 : (d == 1 ? nx1 : (d == 2 ? nx2 : nx3));
-                const uint32_t tc = C[i], tk = K[i];
-                C[i] = C[h]; K[i] = K[h]; C[h] = tc; K[h] = tk;
+                const uint32_t tk = K[i];
+                K[i] = K[h]; K[h] = tk;
                 ++h;
             };
-            while (nx0 < end0) { const uint32_t d = (C[nx0] >> shift) & 3u; if (d == 0) ++nx0; else place(nx0, d); }
-            while (nx1 < end1) { const uint32_t d = (C[nx1] >> shift) & 3u; if (d == 1) ++nx1; else place(nx1, d); }
-            while (nx2 < end2) { const uint32_t d = (C[nx2] >> shift) & 3u; if (d == 2) ++nx2; else place(nx2, d); }
+            while (nx0 < end0) { const uint32_t d = quadrant_at(K[nx0], dep); if (d == 0) ++nx0; else place(nx0, d); }
+            while (nx1 < end1) { const uint32_t d = quadrant_at(K[nx1], dep); if (d == 1) ++nx1; else place(nx1, d); }
+            while (nx2 < end2) { const uint32_t d = quadrant_at(K[nx2], dep); if (d == 2) ++nx2; else place(nx2, d); }
         }
         const uint32_t c0 = b1 - beg, c1 = b2 - b1, c2 = b3 - b2, c3 = e - b3;
         S.cc[4 * p] = c0; S.cc[4 * p + 1] = c1; S.cc[4 * p + 2] = c2; S.cc[4 * p + 3] = c3;
@@ -396,27 +479,23 @@ __global__ void __launch_bounds__(T, 1024 / T) octree_kernel(const __grid_consta
         return ne | (nx << 8);
     };
 
-    // Applies the splits of processed nodes p = 0..nS-1 (list positions procpos[p], child counts in cc, sa[p] = #non-empty,
-    // sb[p] = #expandable), builds the new list in buffer a^1 and the new expandable vector in `vout`.
-    // Returns new list size via s_nL and the new vector length via s_total.
+    // WARP 0.  Applies the splits of processed nodes p = 0..nS-1 (list positions procpos[p], child counts in cc, sa[p] =
+    // #non-empty, sb[p] = #expandable), builds the new list in buffer a^1 and the new expandable vector in `vout`.
+    // Publishes the new list size in s_nL and the new vector length in s_total.
     auto apply_splits = [&](int nL, int nS, unsigned long long* vout) {
         const int b = a ^ 1;
-        // keep flags: sc[pos] = 1 for untouched nodes
-        for (int i = tid; i < nL; i += T) S.sc[i] = 1;
-        __syncthreads();
-        for (int p = tid; p < nS; p += T) S.sc[S.procpos[p]] = 0;
-        __syncthreads();
-        const int nKeep = block_exclusive_scan<T>(S.sc, nL, S.warp_tmp);          // sc[pos] = rank among kept (valid where kept)
-        // we still need to know which were kept: recompute from procpos by marking with -1-rank
-        for (int p = tid; p < nS; p += T) S.sc[S.procpos[p]] = -1;
-        __syncthreads();
-        // per-p child bookkeeping: stash ne/nx because the scans overwrite sa/sb
-        int* packed = S.sd;
-        for (int p = tid; p < nS; p += T) packed[p] = S.sa[p] | (S.sb[p] << 8);
-        __syncthreads();
-        const int Stot = block_exclusive_scan<T>(S.sa, nS, S.warp_tmp);           // sa[p] = sum_{p'<p} ne
-        const int Etot = block_exclusive_scan<T>(S.sb, nS, S.warp_tmp);           // sb[p] = sum_{p'<p} nx
-        for (int p = tid; p < nS; p += T) {
+        for (int i = lane; i < nL; i += 32) S.sc[i] = 1;                       // keep flags: sc[pos] = 1 for untouched nodes
+        __syncwarp();
+        for (int p = lane; p < nS; p += 32) S.sc[S.procpos[p]] = 0;
+        __syncwarp();
+        const int nKeep = warp_exclusive_scan(S.sc, nL, lane);                 // sc[pos] = rank among kept (valid where kept)
+        for (int p = lane; p < nS; p += 32) S.sc[S.procpos[p]] = -1;           // processed nodes are marked, not kept
+        int* packed = S.sd;                                                    // ne/nx survive the scans of sa/sb here
+        for (int p = lane; p < nS; p += 32) packed[p] = S.sa[p] | (S.sb[p] << 8);
+        __syncwarp();
+        const int Stot = warp_exclusive_scan(S.sa, nS, lane);                  // sa[p] = sum_{p'<p} ne
+        const int Etot = warp_exclusive_scan(S.sb, nS, lane);                  // sb[p] = sum_{p'<p} nx
+        for (int p = lane; p < nS; p += 32) {
             const int pos = S.procpos[p];
             const int ne = packed[p] & 0xff;
             const uint32_t beg = S.nbeg[a][pos];
@@ -448,7 +527,7 @@ __global__ void __launch_bounds__(T, 1024 / T) octree_kernel(const __grid_consta
                 if (cn[k] > 1)
                     vout[vslot++] = orbx_sort::make_item(((unsigned long long)cn[k] << 13) | (cx[k] & 0xffff), (uint32_t)posk[k]);
         }
-        for (int i = tid; i < nL; i += T) {
+        for (int i = lane; i < nL; i += 32) {
             const int r = S.sc[i];
             if (r >= 0) {
                 const int slot = Stot + r;
@@ -456,12 +535,11 @@ __global__ void __launch_bounds__(T, 1024 / T) octree_kernel(const __grid_consta
                 S.ndep[b][slot] = S.ndep[a][i]; S.npre[b][slot] = S.npre[a][i];
             }
         }
-        __syncthreads();
-        if (tid == 0) { s_nL = Stot + nKeep; s_total = Etot; }
-        __syncthreads();
-        a = b;
+        if (lane == 0) { s_nL = Stot + nKeep; s_total = Etot; }
+        __syncwarp();
     };
 
+    __syncthreads();
     OCT_MARK(2);
     // ---- 3. main loop (src 635-753) ---------------------------------------------------------------------------------
     bool finish = false;
@@ -469,19 +547,23 @@ __global__ void __launch_bounds__(T, 1024 / T) octree_kernel(const __grid_consta
         if (dbg) dbg[7] += 1;
         int nL = s_nL;
         const int prevSize = nL;
-        // phase-1 sweep: every node with more than one key, in list order
-        for (int i = tid; i < nL; i += T) S.sc[i] = S.ncnt[a][i] > 1 ? 1 : 0;
-        __syncthreads();
-        const int nS = block_exclusive_scan<T>(S.sc, nL, S.warp_tmp);
-        for (int i = tid; i < nL; i += T)
-            if (S.ncnt[a][i] > 1) S.procpos[S.sc[i]] = i;
-        __syncthreads();
-        for (int p = tid; p < nS; p += T) {
-            const int r = split_counts(p, S.procpos[p]);
-            S.sa[p] = r & 0xff; S.sb[p] = r >> 8;
+        if (warp == 0) {
+            // phase-1 sweep: every node with more than one key, in list order
+            for (int i = lane; i < nL; i += 32) S.sc[i] = S.ncnt[a][i] > 1 ? 1 : 0;
+            __syncwarp();
+            const int nS = warp_exclusive_scan(S.sc, nL, lane);
+            for (int i = lane; i < nL; i += 32)
+                if (S.ncnt[a][i] > 1) S.procpos[S.sc[i]] = i;
+            __syncwarp();
+            for (int p = lane; p < nS; p += 32) {
+                const int r = split_counts(p, S.procpos[p]);
+                S.sa[p] = r & 0xff; S.sb[p] = r >> 8;
+            }
+            __syncwarp();
+            apply_splits(nL, nS, S.vec);
         }
+        a ^= 1;
         __syncthreads();
-        apply_splits(nL, nS, S.vec);
         nL = s_nL;
         int nToExpand = s_total;
         OCT_MARK(3);
@@ -507,33 +589,39 @@ __global__ void __launch_bounds__(T, 1024 / T) octree_kernel(const __grid_consta
                         s32[i] = ((uint32_t)rank << 16) | (uint32_t)i;
                     }
                     __syncthreads();
-                    sort_replay_parallel<T>(s32, m, reinterpret_cast<uint32_t*>(S.sa), reinterpret_cast<uint32_t*>(S.sb), S.sort_stk);
+                    sort_replay_parallel<T>(s32, m, reinterpret_cast<uint32_t*>(S.sa), reinterpret_cast<uint32_t*>(S.sb),
+                                            reinterpret_cast<uint32_t*>(S.sc), S.sort_stk);
                 } else {
                     if (tid == 0) orbx_sort::sort_replay(vprev, m);
                 }
                 __syncthreads();
                 OCT_MARK(4);
-                // processing order p = 0..m-1 walks the sorted vector from the back (src 710)
-                for (int p = tid; p < m; p += T) {
-                    const int pos = (int)orbx_sort::payload(small ? vprev[s32[m - 1 - p] & 0xffffu] : vprev[m - 1 - p]);
-                    S.procpos[p] = pos;
-                    const int r = split_counts(p, pos);
-                    S.sa[p] = r & 0xff; S.sb[p] = r >> 8;
-                    S.sc[p] = (r & 0xff) - 1;                               // list growth of this split
+                if (warp == 0) {
+                    // processing order p = 0..m-1 walks the sorted vector from the back (src 710).  s32 lives in sd, which
+                    // apply_splits reuses: the positions are taken out first.
+                    for (int p = lane; p < m; p += 32)
+                        S.procpos[p] = (int)orbx_sort::payload(small ? vprev[s32[m - 1 - p] & 0xffffu] : vprev[m - 1 - p]);
+                    __syncwarp();
+                    for (int p = lane; p < m; p += 32) {
+                        const int r = split_counts(p, S.procpos[p]);
+                        S.sa[p] = r & 0xff; S.sb[p] = r >> 8;
+                        S.sc[p] = (r & 0xff) - 1;                               // list growth of this split
+                    }
+                    __syncwarp();
+                    // cut-off: stop right after the first split that makes size >= N (src 745-746)
+                    warp_exclusive_scan(S.sc, m, lane);                        // sc[p] = growth before p
+                    int cut = m;
+                    for (int p = lane; p < m; p += 32) {
+                        const int before = prev2 + S.sc[p];
+                        const int after = before + (S.sa[p] - 1);
+                        if (after >= N && before < N) cut = p + 1;             // at most one p satisfies this (growth >= 0)
+                    }
+#pragma unroll
+                    for (int d = 16; d >= 1; d >>= 1) cut = min(cut, __shfl_xor_sync(0xffffffffu, cut, d));
+                    apply_splits(prev2, cut, vnext);
                 }
+                a ^= 1;
                 __syncthreads();
-                // cut-off: stop right after the first split that makes size >= N (src 745-746)
-                block_exclusive_scan<T>(S.sc, m, S.warp_tmp);                  // sc[p] = growth before p
-                if (tid == 0) s_nS = m;
-                __syncthreads();
-                for (int p = tid; p < m; p += T) {
-                    const int after = prev2 + S.sc[p] + (S.sa[p] - 1);
-                    const int before = prev2 + S.sc[p];
-                    if (after >= N && before < N) s_nS = p + 1;
-                }
-                __syncthreads();
-                const int nS2 = s_nS;
-                apply_splits(prev2, nS2, vnext);
                 nL = s_nL;
                 nToExpand = s_total;
                 unsigned long long* t = vprev; vprev = vnext; vnext = t;
