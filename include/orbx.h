@@ -134,6 +134,14 @@ int orbx_sync(orbx_extractor* ex);
  * with_border = 0: interior (level_rows x level_cols); 1: the whole (rows+38) x (cols+38) bordered buffer. */
 int orbx_get_pyramid_level(orbx_extractor* ex, int frame, int level, uint8_t* dst, size_t dst_step, int with_border);
 
+/* The same member kept current without a blocking copy per level: with the mirror enabled every orbx_extract also sends the
+ * bordered levels to pinned host storage owned by the handle, level by level on a copy branch that overlaps FAST, the octree
+ * and the descriptors (the call returns when everything has arrived).  orbx_get_pyramid_mirror hands out the storage of one
+ * level: `bordered` = top-left of the (rows + 38) x (cols + 38) buffer, `step` bytes per row; the interior (the cv::Mat of
+ * mvImagePyramid[level]) starts at bordered + 19 * step + 19.  Valid until the next call on the handle. */
+int orbx_set_pyramid_mirror(orbx_extractor* ex, int enable);
+int orbx_get_pyramid_mirror(orbx_extractor* ex, int level, const uint8_t** bordered, size_t* step, int* level_cols, int* level_rows);
+
 /* Stage probes for parity tests (results of the LAST call, copied to host):
  *  blurred level (cv::GaussianBlur 7x7 sigma 2, src/ORBextractor.cc:1270-1273),
  *  FAST candidates handed to DistributeOctTree (vToDistributeKeys, src/ORBextractor.cc:867-950; window-relative),

@@ -40,6 +40,8 @@ slice src/MapPoint.cc         368 397 mappoint_distinctive_core.inc  # ComputeDi
 slice src/Frame.cc            841 1011 frame_stereo_matches.inc      # Frame::ComputeStereoMatches
 slice src/Frame.cc            387 418 frame_assign_grid.inc          # Frame::AssignFeaturesToGrid
 slice src/Frame.cc            687 766 frame_area_posingrid.inc       # Frame::GetFeaturesInArea, Frame::PosInGrid
+slice src/Frame.cc            111 127 frame_ctor_scale_extract.inc   # stereo Frame ctor: accessor block + the two ExtractORB threads
+slice src/Frame.cc            420 455 frame_extract_orb.inc          # extractorParenthesis, Frame::ExtractORB
 # --- DBoW2 (vendored under Thirdparty/DBoW2) -----------------------------------------------------------------------------
 D=Thirdparty/DBoW2/DBoW2
 slice $D/BowVector.cpp         34 84 dbow2_bowvector.inc             # addWeight, addIfNotExist, normalize
@@ -56,3 +58,12 @@ if [ -x /usr/bin/g++ ]; then CXX=/usr/bin/g++; else CXX=${CXX:-g++}; fi
 $CXX -O3 -std=c++17 -fPIC -ffp-contract=off -w -I"$HERE/ref_shim" -I"$OUT/gen" -shared -o "$OUT/libref.so" \
     "$HERE/ref_shim/ref_wrapper.cpp" "$HERE/ref_shim/ref_dbow2_wrapper.cpp" -L"$HERE/_build" -lorb_oracle -Wl,-rpath,'$ORIGIN/../_build'
 echo "build_ref: built $OUT/libref.so from $REF"
+# The reference's call site of the extractor (Frame ctor accessor block + Frame::ExtractORB) compiled UNCHANGED against the
+# drop-in adapter header; linked against the product library, run on the GPU box by tests/test_gpu_ref.py.
+ROOT=$(cd "$HERE/.." && pwd)
+if [ -f "$ROOT/wut_cuda_orb_slam3_b200/liborbx.so" ]; then
+    $CXX -O2 -std=c++17 -w -pthread -I"$ROOT/tests/cpp/cv_stub" -I"$ROOT/include" -I"$ROOT/wut_cuda_orb_slam3_b200/csrc/adapter" -I"$OUT/gen" \
+        -o "$OUT/frame_callsite_test" "$HERE/ref_shim/frame_callsite_main.cpp" -L"$ROOT/wut_cuda_orb_slam3_b200" -lorbx \
+        -Wl,-rpath,'$ORIGIN/../../wut_cuda_orb_slam3_b200'
+    echo "build_ref: built $OUT/frame_callsite_test (reference src/Frame.cc:111-127, 420-455 against csrc/adapter/ORBextractor.h)"
+fi

@@ -182,3 +182,63 @@ def test_single_frame_forked_graph_equals_serial(oracle, monkeypatch):
         oex = oracle.extractor(1000, 1.2, 8, 20, 7)
         ok, od, onm = oex.extract(img, (0, 0))
         assert r1[0] == onm and np.array_equal(r1[1]["x"], ok["x"]) and np.array_equal(r1[1]["y"], ok["y"]) and np.array_equal(r1[2], od)
+
+
+def test_pyramid_host_mirror_equals_probe(oracle):
+    """mvImagePyramid without blocking copies: the pinned host mirror filled during orbx_extract equals the probe copies and
+    the oracle pyramid, level by level with borders, across calls (graph replay) and a shape change."""
+    ex = orbx.ORBextractor(1000, 1.2, 8, 20, 7)
+    ex.set_pyramid_mirror(True)
+    plain = orbx.ORBextractor(1000, 1.2, 8, 20, 7)
+    for (cols, rows, seed) in [(752, 480, 11), (752, 480, 12), (640, 360, 13), (752, 480, 14)]:
+        img = synth.image(seed, cols, rows)
+        r1 = ex(img); r0 = plain(img)
+        assert r1[0] == r0[0] and r1[1].tobytes() == r0[1].tobytes() and np.array_equal(r1[2], r0[2])
+        oex = oracle.extractor(1000, 1.2, 8, 20, 7)
+        oex.extract(img, (0, 0))
+        for level in range(8):
+            m = ex.pyramid_mirror(level, with_border=True)
+            assert np.array_equal(m, ex.pyramid_level(level, with_border=True)), level
+            assert np.array_equal(m, oex.pyramid_level(level, with_border=True)), level
+            assert np.array_equal(ex.pyramid_mirror(level), plain.pyramid_level(level))
+    ex.set_pyramid_mirror(False)
+    ex(synth.image(15, 752, 480))
+
+
+def test_reference_frame_call_site_against_the_adapter():
+    """The reference's own call site — src/Frame.cc:111-127 (stereo Frame constructor: accessor block + the two ExtractORB
+    threads) and 420-455 (extractorParenthesis, Frame::ExtractORB) — compiled UNCHANGED against csrc/adapter/ORBextractor.h
+    (oracle/build_ref.sh slices it at build time; the binary travels with the snapshot) must fill mvKeys / mDescriptors /
+    mvKeysRight / mDescriptorsRight / monoLeft / monoRight and the scale tables exactly as the C ABI does."""
+    import math
+    import os
+    import re
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "oracle", "_ref", "frame_callsite_test")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/frame_callsite_test not built (needs /root/reference at build time)")
+    out = subprocess.check_output([exe, "31", "1200"], text=True)
+    lines = [ln for ln in out.splitlines() if ln.startswith("rep=")]
+    assert len(lines) == 2, out
+
+    def fnv(h, data):
+        for b in bytes(data):
+            h = ((h ^ b) * 1099511628211) & 0xFFFFFFFFFFFFFFFF
+        return h
+    L, R = synth.image(31, 752, 480, view=0, max_disp=40), synth.image(31, 752, 480, view=1, max_disp=40)
+    exL = orbx.ORBextractor(1200, 1.2, 8, 20, 7); exR = orbx.ORBextractor(1200, 1.2, 8, 20, 7)
+    nmL, kL, dL = exL(L, None, (0, 0)); nmR, kR, dR = exR(R, None, (0, 0))
+    hl = fnv(fnv(1469598103934665603, kL.tobytes()), dL.tobytes())
+    hr = fnv(fnv(1469598103934665603, kR.tobytes()), dR.tobytes())
+    ht = 1469598103934665603
+    for t in (exL.GetScaleFactors(), exL.GetInverseScaleFactors(), exL.GetScaleSigmaSquares(), exL.GetInverseScaleSigmaSquares()):
+        ht = fnv(ht, np.asarray(t, np.float32).tobytes())
+    for ln in lines:
+        m = re.search(r"N=(\d+) Nright=(\d+) monoLeft=(-?\d+) monoRight=(-?\d+) levels=(\d+) scale=([\d.]+) logscale=([\d.]+) left=([0-9a-f]+) "
+                      r"right=([0-9a-f]+) tables=([0-9a-f]+)", ln)
+        assert m, ln
+        assert int(m.group(1)) == len(kL) and int(m.group(2)) == len(kR) and int(m.group(3)) == nmL and int(m.group(4)) == nmR
+        assert int(m.group(5)) == 8 and abs(float(m.group(6)) - 1.2000000477) < 1e-7
+        assert abs(float(m.group(7)) - math.log(np.float32(1.2))) < 1e-6
+        assert m.group(8) == "%016x" % hl and m.group(9) == "%016x" % hr and m.group(10) == "%016x" % ht

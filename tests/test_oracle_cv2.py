@@ -172,6 +172,30 @@ def test_descriptor_and_angle_match_cv2_orb(oracle):
     assert nbits.max() <= 3 and (nbits == 0).mean() > 0.6, np.bincount(nbits)
 
 
+@pytest.mark.parametrize("cols,rows,seed", [(752, 480, 200), (1241, 376, 201), (331, 277, 202), (160, 120, 203)])
+def test_ic_angle_pinned_against_cv2_orb_icangles(oracle, cols, rows, seed):
+    """SURVEY.md §8 row A7.  The fork deleted the CPU IC_Angle (only `using cv::fastAtan2` survives at src/ORBextractor.cc:85)
+    and its OpenCL kernel has no reduction (src/OpenCL/Kernel/Angle.cl:55-60), so the reference holds nothing to pin the
+    orientation against.  ORB-SLAM's IC_Angle is OpenCV's ICAngles (same umax table, same u/v summation, same fastAtan2), and
+    cv2.ORB with ONE level runs ICAngles on the image itself at the integer FAST positions: the oracle's IC_Angle must give
+    the same float32, bit for bit, at every keypoint cv2 detects (two FAST thresholds: ~40 000 keypoints over the shapes)."""
+    img = synth.image(seed, cols, rows)
+    total = 0
+    for fast_th in (20, 7):
+        orb = cv2.ORB_create(nfeatures=20000, scaleFactor=1.2, nlevels=1, edgeThreshold=19, firstLevel=0, WTA_K=2, patchSize=31,
+                             fastThreshold=fast_th)
+        kps = orb.detect(img, None)
+        assert len(kps) > 100
+        for kp in kps:
+            x, y = kp.pt
+            assert x == int(x) and y == int(y)                 # level 0 of a one-level pyramid: integer FAST positions
+            assert 19 <= x < cols - 19 and 19 <= y < rows - 19
+            got = np.float32(oracle.ic_angle(img, int(x), int(y)))
+            assert got == np.float32(kp.angle), (x, y, got, kp.angle)
+            total += 1
+    assert total > 500
+
+
 def test_descriptor_against_numpy_restatement(oracle):
     """Independent numpy float32 restatement of computeOrbDescriptor on cv2.GaussianBlur output."""
     pat = np.array([int(v) for l in open("wut_cuda_orb_slam3_b200/csrc/brief_pattern.inc") if not l.startswith("//")

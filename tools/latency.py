@@ -7,10 +7,12 @@ import wut_cuda_orb_slam3_b200 as orbx
 from wut_cuda_orb_slam3_b200 import synth
 from wut_cuda_orb_slam3_b200.capi import lib, ptr, check
 
-def measure(cols, rows, nf, reps=200):
+def measure(cols, rows, nf, reps=200, mirror=False):
     img_t = torch.empty((rows, cols), dtype=torch.uint8).pin_memory()
     img_t.copy_(torch.from_numpy(synth.image(77, cols, rows)))
     ex = orbx.ORBextractor(nf, 1.2, 8, 20, 7, max_cols=cols, max_rows=rows, max_batch=1)
+    if mirror:
+        ex.set_pyramid_mirror(True)
     cap = ex.max_keypoints()
     kps = torch.empty((cap, 7), dtype=torch.float32).pin_memory(); desc = torch.empty((cap, 32), dtype=torch.uint8).pin_memory()
     n = C.c_int(0); nm = C.c_int(0)
@@ -48,6 +50,9 @@ if __name__ == "__main__":
     for (c, r, nf) in [(752, 480, 1000), (1241, 376, 2000), (1280, 720, 2000)]:
         med, p95, n = measure(c, r, nf)
         print("%dx%d nfeatures=%d: median %.1f us, p95 %.1f us, %d keypoints" % (c, r, nf, med, p95, n))
+    for (c, r, nf) in [(752, 480, 1000), (1280, 720, 2000)]:
+        med, p95, n = measure(c, r, nf, mirror=True)
+        print("%dx%d nfeatures=%d with the host mirror of mvImagePyramid (8 bordered levels to pinned memory during the call): median %.1f us, p95 %.1f us" % (c, r, nf, med, p95))
     for (c, r, nf) in [(752, 480, 1200), (1241, 376, 2000)]:
         med, p95, nl, nr, m = measure_stereo(c, r, nf)
         print("stereo pair %dx%d nfeatures=%d (orbx_extract_stereo: 2 extractions + ComputeStereoMatches, host images in, everything out): "

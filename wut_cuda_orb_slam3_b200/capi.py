@@ -48,6 +48,8 @@ SIGNATURES = {
     "orbx_extract_batch_device": (_i, [_vp, _vp, _sz, _i, _i, _i, _sz, _i, _i, _vp, _vp, _i, _vp, _vp, _vp]),
     "orbx_sync": (_i, [_vp]),
     "orbx_get_pyramid_level": (_i, [_vp, _i, _i, _vp, _sz, _i]),
+    "orbx_set_pyramid_mirror": (_i, [_vp, _i]),
+    "orbx_get_pyramid_mirror": (_i, [_vp, _i, _vp, _vp, _vp, _vp]),
     "orbx_get_blurred_level": (_i, [_vp, _i, _i, _vp, _sz]),
     "orbx_get_candidates": (_i, [_vp, _i, _i, _vp, _vp, _vp, _i]),
     "orbx_get_level_keypoints": (_i, [_vp, _i, _i, _vp, _vp, _i]),

@@ -37,7 +37,7 @@ public:
         check(orbx_get_tables(handle, mvScaleFactor.data(), mvInvScaleFactor.data(), mvLevelSigma2.data(), mvInvLevelSigma2.data(),
                               mnFeaturesPerLevel.data()), "orbx_get_tables");
         mvImagePyramid.resize(nlevels);
-        pyramidStorage.resize(nlevels);
+        check(orbx_set_pyramid_mirror(handle, 1), "orbx_set_pyramid_mirror");
     }
     ~ORBextractor() { orbx_destroy(handle); }
     ORBextractor(const ORBextractor&) = delete;
@@ -50,23 +50,34 @@ public:
         if (_image.empty()) return -1;
         cv::Mat image = _image.getMat();
         assert(image.type() == CV_8UC1);
+        if (bDownloadPyramid != mirrorOn) {      // the host copy of the pyramid rides along with the extraction (no blocking copies)
+            mirrorOn = bDownloadPyramid;
+            check(orbx_set_pyramid_mirror(handle, mirrorOn ? 1 : 0), "orbx_set_pyramid_mirror");
+        }
         const int cap = orbx_max_keypoints_for(handle, image.rows, image.cols);
-        std::vector<cv::KeyPoint> kps(cap);
-        std::vector<unsigned char> desc((size_t)cap * 32);
+        // results land directly in the caller's vector (resized to the bound, trimmed to n) and in a reusable descriptor slab
+        _keypoints.resize(cap);
+        if ((int)descScratch.size() < cap * 32) descScratch.resize((size_t)cap * 32);
         int n = 0, nMono = 0;
         const int lap0 = vLappingArea.size() > 0 ? vLappingArea[0] : 0, lap1 = vLappingArea.size() > 1 ? vLappingArea[1] : 0;
-        check(orbx_extract(handle, image.data, image.rows, image.cols, (size_t)image.step, lap0, lap1,
-                           reinterpret_cast<orbx_keypoint*>(kps.data()), desc.data(), cap, &n, &nMono), "orbx_extract");
-        kps.resize(n);
-        _keypoints = kps;
+        const int rc = orbx_extract(handle, image.data, image.rows, image.cols, (size_t)image.step, lap0, lap1,
+                                    reinterpret_cast<orbx_keypoint*>(_keypoints.data()), descScratch.data(), cap, &n, &nMono);
+        if (rc != ORBX_OK) { _keypoints.clear(); check(rc, "orbx_extract"); }
+        _keypoints.resize(n);
         if (n == 0) {
             _descriptors.release();
         } else {
             _descriptors.create(n, 32, CV_8U);
             cv::Mat d = _descriptors.getMat();
-            for (int i = 0; i < n; ++i) std::copy(desc.begin() + (size_t)i * 32, desc.begin() + (size_t)(i + 1) * 32, d.ptr(i));
+            for (int i = 0; i < n; ++i) std::copy(descScratch.begin() + (size_t)i * 32, descScratch.begin() + (size_t)(i + 1) * 32, d.ptr(i));
         }
-        if (bDownloadPyramid) downloadPyramid(image.cols, image.rows);
+        if (mirrorOn) {
+            for (int l = 0; l < nlevels; ++l) {
+                const uint8_t* base = nullptr; size_t step = 0; int w = 0, h = 0;
+                check(orbx_get_pyramid_mirror(handle, l, &base, &step, &w, &h), "orbx_get_pyramid_mirror");
+                mvImagePyramid[l] = cv::Mat(h, w, CV_8UC1, const_cast<uint8_t*>(base) + (size_t)ORBX_EDGE_THRESHOLD * step + ORBX_EDGE_THRESHOLD, step);
+            }
+        }
         return nMono;
     }
 
@@ -77,26 +88,16 @@ public:
     std::vector<float> inline GetScaleSigmaSquares() { return mvLevelSigma2; }
     std::vector<float> inline GetInverseScaleSigmaSquares() { return mvInvLevelSigma2; }
 
-    // Interior views into bordered host copies, valid until the next call (reference: include/ORBextractor.h:92).
-    // Frame::ComputeStereoMatches reads them on the host (src/Frame.cc:848, 938-953); callers that use
-    // orbx_stereo_match instead can set bDownloadPyramid = false and skip the device->host copy.
+    // Interior views into the bordered host mirror the library keeps in pinned memory (filled level by level while the later
+    // stages run), valid until the next call (reference: include/ORBextractor.h:92).  Frame::ComputeStereoMatches reads them on
+    // the host (src/Frame.cc:848, 938-953); callers that use orbx_stereo_match / orbx_extract_stereo instead can set
+    // bDownloadPyramid = false and skip the copy altogether.
     std::vector<cv::Mat> mvImagePyramid;
     bool bDownloadPyramid = true;
 
     orbx_extractor* nativeHandle() { return handle; }
 
 protected:
-    void downloadPyramid(int cols, int rows)
-    {
-        for (int l = 0; l < nlevels; ++l) {
-            int w = 0, h = 0;
-            check(orbx_level_size(handle, cols, rows, l, &w, &h), "orbx_level_size");
-            const int bw = w + 2 * ORBX_EDGE_THRESHOLD, bh = h + 2 * ORBX_EDGE_THRESHOLD;
-            pyramidStorage[l].resize((size_t)bw * bh);
-            check(orbx_get_pyramid_level(handle, 0, l, pyramidStorage[l].data(), (size_t)bw, 1), "orbx_get_pyramid_level");
-            mvImagePyramid[l] = cv::Mat(h, w, CV_8UC1, pyramidStorage[l].data() + (size_t)ORBX_EDGE_THRESHOLD * bw + ORBX_EDGE_THRESHOLD, (size_t)bw);
-        }
-    }
     static void check(int rc, const char* what)
     {
         if (rc != ORBX_OK) throw std::runtime_error(std::string(what) + ": " + orbx_last_error());
@@ -109,7 +110,8 @@ protected:
     int minThFAST;
     std::vector<int> mnFeaturesPerLevel;
     std::vector<float> mvScaleFactor, mvInvScaleFactor, mvLevelSigma2, mvInvLevelSigma2;
-    std::vector<std::vector<unsigned char>> pyramidStorage;
+    std::vector<unsigned char> descScratch;
+    bool mirrorOn = true;
     orbx_extractor* handle = nullptr;
 };
 

@@ -171,15 +171,23 @@ struct orbx_extractor {
     struct GraphKey {
         int rows = 0, cols = 0, lap0 = 0, lap1 = 0, capacity = 0, cap_frames = 0;
         const void* pyr = nullptr; const void* d_in = nullptr; const void* d_kps = nullptr; const void* cand = nullptr;
-        const void* d_n = nullptr; const void* tables = nullptr;
+        const void* d_n = nullptr; const void* tables = nullptr; const void* mirror = nullptr;
         bool operator==(const GraphKey& o) const
         {
-            return rows == o.rows && cols == o.cols && lap0 == o.lap0 && lap1 == o.lap1 && capacity == o.capacity && cap_frames == o.cap_frames &&
+            return mirror == o.mirror && rows == o.rows && cols == o.cols && lap0 == o.lap0 && lap1 == o.lap1 && capacity == o.capacity && cap_frames == o.cap_frames &&
                    pyr == o.pyr && d_in == o.d_in && d_kps == o.d_kps && cand == o.cand && d_n == o.d_n && tables == o.tables;
         }
     } graph_key;
     cudaGraphExec_t graph_exec = nullptr;
     int single_calls = 0;          // the first single-frame call runs un-captured (lazy one-time initialisation inside the launchers)
+    int graph_launches = 0;        // kernel launches one replay of the captured graph stands for
+    // host mirror of the bordered pyramid (std::vector<cv::Mat> mvImagePyramid of the reference, read on the host by
+    // Frame::ComputeStereoMatches): pinned storage, filled level by level on a copy branch while FAST / octree run
+    bool mirror = false;
+    uint8_t* h_mirror = nullptr; size_t h_mirror_bytes = 0;
+    size_t mirror_off[ORBX_MAX_LEVELS] = {0};
+    cudaStream_t mirror_stream = nullptr;
+    cudaEvent_t ev_mirror = nullptr;
     bool force_eager = false;      // debug hooks that patch the workspace (orbx_debug_octree_timing) must not replay a captured graph
     // fork / join of the single-frame pipeline: FAST + octree of level l run on side[l] as soon as level l of the pyramid exists
     cudaStream_t side[ORBX_MAX_LEVELS] = {nullptr};
@@ -558,9 +566,10 @@ static int run_chunk(orbx_extractor* ex, Slot& s, const uint8_t* d_images, size_
     if ((rc = prof_mark(ex, st))) return rc;
     CU(launch_octree(fg, s.ws, frames, st));
     if ((rc = prof_mark(ex, st))) return rc;
-    CU(launch_orient_describe(fg, s.ws, frames, st));
+    bool fused = false;
+    CU(launch_orient_describe(fg, s.ws, frames, st, lap0, lap1, d_kps, d_desc, capacity, d_n, d_nm, &fused));
     if ((rc = prof_mark(ex, st))) return rc;
-    CU(launch_pack(fg, s.ws, frames, lap0, lap1, d_kps, d_desc, capacity, d_n, d_nm, st));
+    if (!fused) CU(launch_pack(fg, s.ws, frames, lap0, lap1, d_kps, d_desc, capacity, d_n, d_nm, st));
     if ((rc = prof_mark(ex, st))) return rc;
     return ORBX_OK;
 }
@@ -582,6 +591,13 @@ static int run_single_forked(orbx_extractor* ex, Slot& s, const uint8_t* d_image
     for (int l = 0; l < fg.nlevels; ++l) {
         CU(launch_pyramid(fg, s.ws, d_image, pitch * fg.rows, pitch, 1, st, l, l + 1));
         CU(cudaEventRecord(ex->ev_lvl[l], st));
+        if (ex->mirror) {           // the level goes home while the later stages run
+            const LevelGeom& g = fg.L[l];
+            const size_t bw = (size_t)g.w + 2 * kEdge;
+            CU(cudaStreamWaitEvent(ex->mirror_stream, ex->ev_lvl[l], 0));
+            CU(cudaMemcpy2DAsync(ex->h_mirror + ex->mirror_off[l], bw, s.ws.pyr + g.pyr_off + (kXPad - kEdge), g.pitch, bw, (size_t)g.rows_alloc,
+                                 cudaMemcpyDeviceToHost, ex->mirror_stream));
+        }
         CU(cudaStreamWaitEvent(ex->side[l], ex->ev_lvl[l], 0));
         CU(launch_fast(fg, s.ws, 1, ex->side[l], l, l + 1));
         CU(launch_octree(fg, s.ws, 1, ex->side[l], l, l + 1));
@@ -589,8 +605,10 @@ static int run_single_forked(orbx_extractor* ex, Slot& s, const uint8_t* d_image
     }
     CU(launch_blur(fg, s.ws, 1, st));
     for (int l = 0; l < fg.nlevels; ++l) CU(cudaStreamWaitEvent(st, ex->ev_side[l], 0));
-    CU(launch_orient_describe(fg, s.ws, 1, st));
-    CU(launch_pack(fg, s.ws, 1, lap0, lap1, d_kps, d_desc, capacity, d_n, d_nm, st));
+    bool fused = false;
+    CU(launch_orient_describe(fg, s.ws, 1, st, lap0, lap1, d_kps, d_desc, capacity, d_n, d_nm, &fused));
+    if (!fused) CU(launch_pack(fg, s.ws, 1, lap0, lap1, d_kps, d_desc, capacity, d_n, d_nm, st));
+    if (ex->mirror) { CU(cudaEventRecord(ex->ev_mirror, ex->mirror_stream)); CU(cudaStreamWaitEvent(st, ex->ev_mirror, 0)); }
     return ORBX_OK;
 }
 
@@ -608,25 +626,44 @@ static int enqueue_single(orbx_extractor* ex, const uint8_t* image, int rows, in
     if (s.d_in_bytes < dframe || s.out_cap < (size_t)capacity || s.out_frames < 1) CU(cudaStreamSynchronize(s.stream));
     if ((rc = ensure_host_staging(s, dframe, 1, capacity))) return rc;
     cudaStream_t st = s.stream;
+    if (ex->mirror) {
+        if (!ex->mirror_stream) CU(cudaStreamCreateWithFlags(&ex->mirror_stream, cudaStreamNonBlocking));
+        if (!ex->ev_mirror) CU(cudaEventCreateWithFlags(&ex->ev_mirror, cudaEventDisableTiming));
+        size_t need = 0;
+        for (int l = 0; l < ex->fg.nlevels; ++l) {
+            ex->mirror_off[l] = need;
+            need += align_up(((size_t)ex->fg.L[l].w + 2 * kEdge) * (size_t)ex->fg.L[l].rows_alloc, 256);
+        }
+        if (ex->h_mirror_bytes < need) {
+            CU(cudaStreamSynchronize(st));
+            if (ex->h_mirror) cudaFreeHost(ex->h_mirror);
+            ex->h_mirror = nullptr; ex->h_mirror_bytes = 0;
+            CU(cudaMallocHost((void**)&ex->h_mirror, need));
+            ex->h_mirror_bytes = need;
+        }
+    }
     if (step == (size_t)cols) CU(cudaMemcpyAsync(s.d_in, image, dframe, cudaMemcpyHostToDevice, st));
     else CU(cudaMemcpy2DAsync(s.d_in, dpitch, image, step, cols, rows, cudaMemcpyHostToDevice, st));
     static const bool graphs = !(getenv("ORBX_GRAPH") && atoi(getenv("ORBX_GRAPH")) == 0);
     static const bool forked = !(getenv("ORBX_SINGLE_FORK") && atoi(getenv("ORBX_SINGLE_FORK")) == 0);   // A/B switch
     auto body = [&](cudaStream_t cs) -> int {
-        if (forked && !ex->profiling) return run_single_forked(ex, s, s.d_in, dpitch, lap0, lap1, s.d_kps, s.d_desc, capacity, s.d_n, s.d_nm, cs);
+        if ((forked && !ex->profiling) || ex->mirror) return run_single_forked(ex, s, s.d_in, dpitch, lap0, lap1, s.d_kps, s.d_desc, capacity, s.d_n, s.d_nm, cs);
         return run_chunk(ex, s, s.d_in, dframe, dpitch, 1, lap0, lap1, s.d_kps, s.d_desc, capacity, s.d_n, s.d_nm, cs);
     };
     if (graphs && !ex->profiling && !ex->force_eager && ex->single_calls++ > 0) {
         orbx_extractor::GraphKey key;
         key.rows = rows; key.cols = cols; key.lap0 = lap0; key.lap1 = lap1; key.capacity = capacity;
         key.pyr = s.ws.pyr; key.d_in = s.d_in; key.d_kps = s.d_kps; key.cand = s.ws.cand;
-        key.cap_frames = s.cap_frames; key.d_n = s.d_n; key.tables = ex->d_tables;
+        key.cap_frames = s.cap_frames; key.d_n = s.d_n; key.tables = ex->d_tables; key.mirror = ex->mirror ? ex->h_mirror : nullptr;
         if (!ex->graph_exec || !(key == ex->graph_key)) {
             if (ex->graph_exec) { cudaGraphExecDestroy(ex->graph_exec); ex->graph_exec = nullptr; }
             cudaGraph_t g = nullptr;
+            const long long l0 = g_launches.load();
             CU(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
             rc = body(st);
             cudaError_t ce = cudaStreamEndCapture(st, &g);
+            ex->graph_launches = (int)(g_launches.load() - l0);
+            count_launch(-ex->graph_launches);              // captured, not launched: the replay below counts them
             if (rc) { if (g) cudaGraphDestroy(g); cudaGetLastError(); return rc; }
             if (ce != cudaSuccess) return fail(ORBX_ERR_CUDA, "graph capture: %s", cudaGetErrorString(ce));
             ce = cudaGraphInstantiate(&ex->graph_exec, g, 0);
@@ -635,7 +672,7 @@ static int enqueue_single(orbx_extractor* ex, const uint8_t* image, int rows, in
             ex->graph_key = key;
         }
         CU(cudaGraphLaunch(ex->graph_exec, st));
-        count_launch(forked ? 3 * ex->fg.nlevels + 3 : 15);
+        count_launch(ex->graph_launches);
     } else if ((rc = body(st))) return rc;
     ex->last_frames = 1;
     return ORBX_OK;
@@ -751,6 +788,9 @@ void orbx_destroy(orbx_extractor* ex)
         if (ex->slots[i].ev_in) { cudaEventDestroy(ex->slots[i].ev_in); cudaEventDestroy(ex->slots[i].ev_done); cudaEventDestroy(ex->slots[i].ev_out); }
     }
     if (ex->ev_user) { cudaEventSynchronize(ex->ev_user); cudaEventDestroy(ex->ev_user); }
+    if (ex->mirror_stream) { cudaStreamSynchronize(ex->mirror_stream); cudaStreamDestroy(ex->mirror_stream); }
+    if (ex->ev_mirror) cudaEventDestroy(ex->ev_mirror);
+    if (ex->h_mirror) cudaFreeHost(ex->h_mirror);
     for (int l = 0; l < ORBX_MAX_LEVELS; ++l) {
         if (ex->side[l]) { cudaStreamSynchronize(ex->side[l]); cudaStreamDestroy(ex->side[l]); }
         if (ex->ev_lvl[l]) cudaEventDestroy(ex->ev_lvl[l]);
@@ -972,6 +1012,26 @@ int orbx_extract(orbx_extractor* ex, const uint8_t* image, int rows, int cols, s
     CU(cudaMemcpyAsync(n_mono, s.d_nm, sizeof(int), cudaMemcpyDeviceToHost, s.stream));
     CU(cudaStreamSynchronize(s.stream));
     if (*n_out > capacity) return fail(ORBX_ERR_CAPACITY, "frame has %d keypoints, capacity %d", *n_out, capacity);
+    return ORBX_OK;
+}
+
+int orbx_set_pyramid_mirror(orbx_extractor* ex, int enable)
+{
+    if (!ex) return fail(ORBX_ERR_INVALID_ARG, "extractor is NULL");
+    ex->mirror = enable != 0;
+    return ORBX_OK;
+}
+
+int orbx_get_pyramid_mirror(orbx_extractor* ex, int level, const uint8_t** bordered, size_t* step, int* level_cols, int* level_rows)
+{
+    if (!ex || !ex->geom_valid || !ex->mirror || !ex->h_mirror || ex->last_frames < 1)
+        return fail(ORBX_ERR_INVALID_ARG, "no mirrored pyramid: enable orbx_set_pyramid_mirror before orbx_extract");
+    if (level < 0 || level >= ex->nlevels) return fail(ORBX_ERR_INVALID_ARG, "level out of range");
+    const LevelGeom& g = ex->fg.L[level];
+    if (bordered) *bordered = ex->h_mirror + ex->mirror_off[level];
+    if (step) *step = (size_t)g.w + 2 * kEdge;
+    if (level_cols) *level_cols = g.w;
+    if (level_rows) *level_rows = g.h;
     return ORBX_OK;
 }
 

@@ -325,8 +325,17 @@ __global__ void __launch_bounds__(32 * kBpWarps) blur_pipe_kernel(const __grid_c
     }
 }
 
+// The packing of operator() (src/ORBextractor.cc:1283-1306) fused into the descriptor kernel for the two cases in which a
+// keypoint's output row follows from its level-major index t alone: no keypoint lies in the lapping area (vLappingArea =
+// {0, 0}: stereo / RGB-D, src/Frame.cc:124-125, 224) -> row t; every keypoint does ({0, 1000} on images up to 1000 px wide:
+// monocular, src/Frame.cc:313) -> row nkp - 1 - t.  Anything else (a fisheye lapping area) takes pack_kernel.
+struct FusedPack {
+    int mode;                 // 0 = separate pack kernel, 1 = nothing lapping, 2 = everything lapping
+    orbx_keypoint* kps; uint8_t* desc; int capacity; int* n_out; int* n_mono;
+};
+
 // grid = (ceil(kp_slots / 8), n_frames), 8 warps per CTA, one warp per keypoint slot.
-__global__ void __launch_bounds__(256) orient_describe_kernel(const __grid_constant__ FrameGeom fg, Workspace ws)
+__global__ void __launch_bounds__(256) orient_describe_kernel(const __grid_constant__ FrameGeom fg, Workspace ws, FusedPack fp)
 {
     const int lane = threadIdx.x & 31;
     const int slot = blockIdx.x * 8 + (threadIdx.x >> 5);
@@ -338,7 +347,27 @@ __global__ void __launch_bounds__(256) orient_describe_kernel(const __grid_const
         if (slot >= fg.L[l].kp_base) level = l;
     const LevelGeom& g = fg.L[level];
     const int i = slot - g.kp_base;
-    if (i >= ws.lvl_n[(size_t)frame * fg.nlevels + level]) return;
+    int n_level, t_out = 0, nkp = 0;
+    if (fp.mode) {
+        // per-level counts -> this level's offset and the frame total (one load per lane + a shuffle scan)
+        const int c = lane < fg.nlevels ? ws.lvl_n[(size_t)frame * fg.nlevels + lane] : 0;
+        int incl = c;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += t;
+        }
+        n_level = __shfl_sync(0xffffffffu, c, level);
+        t_out = __shfl_sync(0xffffffffu, incl - c, level) + i;
+        nkp = __shfl_sync(0xffffffffu, incl, 31);
+        if (slot == 0 && lane == 0) {                       // the frame's counters (src 1306: the return value is monoIndex)
+            fp.n_out[frame] = nkp;
+            fp.n_mono[frame] = nkp > fp.capacity ? -1 : (fp.mode == 1 ? nkp : 0);
+        }
+    } else {
+        n_level = ws.lvl_n[(size_t)frame * fg.nlevels + level];
+    }
+    if (i >= n_level) return;
     const uint32_t key = ws.lvl_kp[(size_t)frame * fg.kp_slots + slot];
     const int x = (int)(key & 0xfff) + kWinBorder, y = (int)((key >> 12) & 0xfff) + kWinBorder;
 
@@ -405,6 +434,25 @@ __global__ void __launch_bounds__(256) orient_describe_kernel(const __grid_const
     }
     ws.lvl_desc[((size_t)frame * fg.kp_slots + slot) * 32 + lane] = (uint8_t)val;
     if (lane == 0) ws.lvl_angle[(size_t)frame * fg.kp_slots + slot] = angle;
+    if (fp.mode && nkp <= fp.capacity) {
+        const int dst = fp.mode == 1 ? t_out : nkp - 1 - t_out;
+        fp.desc[((size_t)frame * fp.capacity + dst) * 32 + lane] = (uint8_t)val;
+        if (lane < 7) {                                     // the 28-byte keypoint, one 32-bit field per lane
+            float px = (float)x, py = (float)y;
+            if (level != 0) { px = __fmul_rn(px, g.scale); py = __fmul_rn(py, g.scale); }       // src 1289-1291
+            uint32_t w;
+            switch (lane) {
+                case 0: w = __float_as_uint(px); break;
+                case 1: w = __float_as_uint(py); break;
+                case 2: w = __float_as_uint(g.kp_size); break;
+                case 3: w = __float_as_uint(angle); break;
+                case 4: w = __float_as_uint((float)(key >> 24)); break;
+                case 5: w = (uint32_t)level; break;
+                default: w = 0xffffffffu; break;            // class_id = -1
+            }
+            reinterpret_cast<uint32_t*>(fp.kps + (size_t)frame * fp.capacity + dst)[lane] = w;
+        }
+    }
 }
 
 // grid = n_frames, T threads: src/ORBextractor.cc:1283-1306.  T = 256 for batches (one CTA per frame, hundreds of frames in
@@ -554,8 +602,20 @@ static cudaError_t fill_describe_tables()
     return cudaMemcpyToSymbol(d_mom_mask, mask, sizeof mask);
 }
 
-cudaError_t launch_orient_describe(const FrameGeom& fg, const Workspace& ws, int n_frames, cudaStream_t st)
+// With d_kps != nullptr the packing is fused when the lapping area allows it; *fused tells the caller whether pack_kernel is
+// still needed.
+cudaError_t launch_orient_describe(const FrameGeom& fg, const Workspace& ws, int n_frames, cudaStream_t st, int lap0, int lap1,
+                                   orbx_keypoint* d_kps, uint8_t* d_desc, int capacity, int* d_n_out, int* d_n_mono, bool* fused)
 {
+    FusedPack fp{};
+    static const bool no_fuse = getenv("ORBX_NO_FUSED_PACK") != nullptr;        // A/B switch
+    if (d_kps && d_desc && d_n_out && d_n_mono && !no_fuse && fg.kp_slots > 0) {
+        // output x = level x * scale lies in [19, cols): the lapping test px >= lap0 && px <= lap1 is decided by the bounds
+        if (lap1 < kEdge || lap0 >= fg.cols || lap0 > lap1) fp.mode = 1;
+        else if (lap0 <= kEdge && lap1 >= fg.cols) fp.mode = 2;
+        fp.kps = d_kps; fp.desc = d_desc; fp.capacity = capacity; fp.n_out = d_n_out; fp.n_mono = d_n_mono;
+    }
+    if (fused) *fused = fp.mode != 0;
     static bool filled[64] = {false};      // per device (the tables are __device__ symbols, one copy per context)
     static std::mutex mu;                  // the left / right extractors launch from two host threads
     int dev = 0;
@@ -567,7 +627,7 @@ cudaError_t launch_orient_describe(const FrameGeom& fg, const Workspace& ws, int
         filled[dev & 63] = true;
     }
     dim3 grid((fg.kp_slots + 7) / 8, n_frames);
-    orient_describe_kernel<<<grid, 256, 0, st>>>(fg, ws);
+    orient_describe_kernel<<<grid, 256, 0, st>>>(fg, ws, fp);
     count_launch();
     return cudaGetLastError();
 }

@@ -60,6 +60,24 @@ __device__ __forceinline__ void csa(uint32_t a, uint32_t b, uint32_t c, uint32_t
     carry = lop3_maj(a, b, c);
 }
 
+// The same distance plus `bias`: the caller passes bias = -d2 (minus the query's current second-best), so the sign of the
+// result says whether the row enters the top 2 — the subtraction rides in the three-input add of the popcounts for free.
+__device__ __forceinline__ int hamming256_csa_biased(const uint32_t (&q)[8], const uint4& a, const uint4& b, int bias)
+{
+    const uint32_t x0 = q[0] ^ a.x, x1 = q[1] ^ a.y, x2 = q[2] ^ a.z, x3 = q[3] ^ a.w;
+    const uint32_t x4 = q[4] ^ b.x, x5 = q[5] ^ b.y, x6 = q[6] ^ b.z, x7 = q[7] ^ b.w;
+    uint32_t c1, s1, c2, s2, c3, s3, d1, t1;
+    csa(x0, x1, x2, c1, s1);
+    csa(x3, x4, x5, c2, s2);
+    csa(s1, s2, x6, c3, s3);
+    csa(c1, c2, c3, d1, t1);
+    // one three-input add on the ALU pipe, the two weighted terms as multiply-adds on the (idle) FMA pipe
+    int acc = __popc(s3) + __popc(x7) + bias, r;
+    asm("mad.lo.s32 %0, %1, 2, %2;" : "=r"(r) : "r"(__popc(t1)), "r"(acc));
+    asm("mad.lo.s32 %0, %1, 4, %2;" : "=r"(acc) : "r"(__popc(d1)), "r"(r));
+    return acc;
+}
+
 __device__ __forceinline__ int hamming256_csa(const uint32_t (&q)[8], const uint4& a, const uint4& b)
 {
     const uint32_t x0 = q[0] ^ a.x, x1 = q[1] ^ a.y, x2 = q[2] ^ a.z, x3 = q[3] ^ a.w;
@@ -100,6 +118,7 @@ __global__ void __launch_bounds__(KNN_THREADS) knn2_kernel(const uint32_t* __res
 
     uint32_t qw[KNN_QT][8];
     int d1[KNN_QT], i1[KNN_QT], d2[KNN_QT], i2[KNN_QT];
+    int nd2[KNN_QT];                               // -d2: the hot loop computes dist - d2 directly
 #pragma unroll
     for (int j = 0; j < KNN_QT; ++j) {
         const int qi = q0 + j * KNN_THREADS + tid;
@@ -108,6 +127,7 @@ __global__ void __launch_bounds__(KNN_THREADS) knn2_kernel(const uint32_t* __res
         qw[j][0] = a.x; qw[j][1] = a.y; qw[j][2] = a.z; qw[j][3] = a.w;
         qw[j][4] = b.x; qw[j][5] = b.y; qw[j][6] = b.z; qw[j][7] = b.w;
         d1[j] = INT_MAX; d2[j] = INT_MAX; i1[j] = -1; i2[j] = -1;
+        nd2[j] = -INT_MAX;
     }
 
     // software pipeline: prefetch tile t+1 into registers while computing tile t
@@ -137,10 +157,22 @@ __global__ void __launch_bounds__(KNN_THREADS) knn2_kernel(const uint32_t* __res
         for (int r = 0; r < rows; ++r) {
             const uint4 a = tile[buf][2 * r], b = tile[buf][2 * r + 1];
             const int gi = index_base + (int)(base + r);
+            // ONE guard per row for the thread's four queries: t[j] = dist_j - d2_j, and a row matters only if some t[j] < 0,
+            // i.e. if the OR of the four has its sign bit set (after the first few thousand rows that is rare)
+            int t[KNN_QT];
 #pragma unroll
-            for (int j = 0; j < KNN_QT; ++j) {
-                const int dist = hamming256_csa(qw[j], a, b);
-                top2_update(dist, gi, d1[j], i1[j], d2[j], i2[j]);
+            for (int j = 0; j < KNN_QT; ++j) t[j] = hamming256_csa_biased(qw[j], a, b, nd2[j]);
+            int any = t[0];
+#pragma unroll
+            for (int j = 1; j < KNN_QT; ++j) any |= t[j];
+            if (any < 0) {
+#pragma unroll
+                for (int j = 0; j < KNN_QT; ++j)
+                    if (t[j] < 0) {
+                        const int4 rr = top2_insert(t[j] - nd2[j], gi, make_int4(d1[j], i1[j], d2[j], i2[j]));
+                        d1[j] = rr.x; i1[j] = rr.y; d2[j] = rr.z; i2[j] = rr.w;
+                        nd2[j] = -rr.z;
+                    }
             }
         }
         if (t + 1 < ntiles) stash(buf ^ 1);

@@ -128,7 +128,9 @@ cudaError_t launch_cvt_gray(const uint8_t* d_src, size_t src_pitch, size_t src_f
 cudaError_t launch_fast(const FrameGeom& fg, const Workspace& ws, int n_frames, cudaStream_t st, int level_lo = 0, int level_hi = 0);
 cudaError_t launch_blur(const FrameGeom& fg, const Workspace& ws, int n_frames, cudaStream_t st);
 cudaError_t launch_octree(const FrameGeom& fg, const Workspace& ws, int n_frames, cudaStream_t st, int level_lo = 0, int level_hi = 0);
-cudaError_t launch_orient_describe(const FrameGeom& fg, const Workspace& ws, int n_frames, cudaStream_t st);
+cudaError_t launch_orient_describe(const FrameGeom& fg, const Workspace& ws, int n_frames, cudaStream_t st, int lap0 = 0, int lap1 = 0,
+                                   orbx_keypoint* d_kps = nullptr, uint8_t* d_desc = nullptr, int capacity = 0, int* d_n_out = nullptr,
+                                   int* d_n_mono = nullptr, bool* fused = nullptr);
 cudaError_t launch_pack(const FrameGeom& fg, const Workspace& ws, int n_frames, int lap0, int lap1,
                         orbx_keypoint* d_kps, uint8_t* d_desc, int capacity, int* d_n_out, int* d_n_mono,
                         cudaStream_t st);

@@ -163,6 +163,18 @@ class ORBextractor:
         check(lib().orbx_get_pyramid_level(self._h, frame, level, ptr(out), out.strides[0], int(with_border)))
         return out
 
+    def set_pyramid_mirror(self, enable=True):
+        """Keep a pinned host mirror of the bordered pyramid current (filled on a copy branch during every __call__)."""
+        check(lib().orbx_set_pyramid_mirror(self._h, int(enable)))
+
+    def pyramid_mirror(self, level, with_border=False):
+        """mvImagePyramid[level] from the host mirror (a copy of the library's pinned storage)."""
+        base = C.c_void_p(); step = C.c_size_t(); w = C.c_int(); h = C.c_int()
+        check(lib().orbx_get_pyramid_mirror(self._h, level, C.byref(base), C.byref(step), C.byref(w), C.byref(h)))
+        bw, bh = w.value + 38, h.value + 38
+        buf = np.ctypeslib.as_array(C.cast(base, C.POINTER(C.c_uint8)), shape=(bh * step.value,)).reshape(bh, step.value)[:, :bw]
+        return buf.copy() if with_border else buf[19:19 + h.value, 19:19 + w.value].copy()
+
     def blurred_level(self, level, frame=0):
         rows, cols = self._shape
         w, h = self.level_size(cols, rows, level)
