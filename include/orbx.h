@@ -216,6 +216,25 @@ int orbx_rotation_consistency(const float* angle_a, const float* angle_b, int n,
  * (int)(0.5*(N-1)) of the sorted row, first row with the least median.  Host (N is a handful of observations). */
 int orbx_distinctive_descriptor(const uint8_t* descriptors, int n, int* best_idx);
 
+/* The same for MANY map points in one call, on the GPU (one warp per map point): the observations of point p are the
+ * descriptors [offsets[p], offsets[p + 1]) of `descriptors` (HOST, rows of 32 bytes; offsets[0] == 0).  best_idx[p] = index
+ * INSIDE the point's own list, -1 for a point without observations.  What LocalMapping does point by point after every key
+ * frame (src/LocalMapping.cc -> MapPoint::ComputeDistinctiveDescriptors, src/MapPoint.cc:329-401). */
+int orbx_distinctive_descriptors(int device, const uint8_t* descriptors, const int32_t* offsets, int n_points, int32_t* best_idx);
+
+/* ---- the on-disk form of descriptors and key points --------------------------------------------------
+ * serializeMatrix / serializeVectorKeyPoints of include/SerializationUtils.h:76-153 as applied to KeyFrame::mDescriptors,
+ * MapPoint::mDescriptor, KeyFrame::mvKeys / mvKeysUn / mvKeysRight (include/KeyFrame.h:120-128, 180, include/MapPoint.h:92) by
+ * System::SaveAtlas / LoadAtlas (src/System.cc:1339-1475).  `text` != 0: the primitive stream of a boost text archive
+ * (space-separated tokens), else of a boost binary archive (native little-endian).  Only the stream these two helpers emit is
+ * produced / parsed — the archive header and class records around it are boost's.  Writers return the stream length (call
+ * with dst == NULL to size it); readers return the bytes consumed; negative = orbx_status. */
+int64_t orbx_serialize_matrix_u8(int text, const uint8_t* data, int rows, int cols, size_t step, uint8_t* dst, size_t dst_capacity);
+int64_t orbx_deserialize_matrix_u8(int text, const uint8_t* src, size_t src_len, int* rows, int* cols, uint8_t* dst, size_t dst_step,
+                                   size_t dst_capacity);
+int64_t orbx_serialize_keypoints(int text, const orbx_keypoint* kps, int n, uint8_t* dst, size_t dst_capacity);
+int64_t orbx_deserialize_keypoints(int text, const uint8_t* src, size_t src_len, int* n_out, orbx_keypoint* kps, int capacity);
+
 /* void Frame::ComputeStereoMatches() — src/Frame.cc:841-1011.  Uses the un-blurred pyramids of frame `frameL` /
  * `frameR` of the LAST calls on exL / exR (which must live on the same device; they may be the same handle) and
  * HOST keypoints/descriptors as returned by orbx_extract.  bf = mbf; maxD = mbf/mb is explicit because the

@@ -242,3 +242,36 @@ def test_reference_frame_call_site_against_the_adapter():
         assert int(m.group(5)) == 8 and abs(float(m.group(6)) - 1.2000000477) < 1e-7
         assert abs(float(m.group(7)) - math.log(np.float32(1.2))) < 1e-6
         assert m.group(8) == "%016x" % hl and m.group(9) == "%016x" % hr and m.group(10) == "%016x" % ht
+
+
+def test_batched_distinctive_descriptors_vs_oracle_and_reference(oracle):
+    """orbx_distinctive_descriptors (one warp per map point) against the oracle's restatement and — where libref.so travelled
+    with the snapshot — the reference's own compiled core of MapPoint::ComputeDistinctiveDescriptors (src/MapPoint.cc:368-397):
+    ties between medians (first row wins), N = 1, N = 2, empty points, N up to 64 on the GPU and beyond (host path)."""
+    rng = np.random.default_rng(5)
+    counts = [0, 1, 2, 3, 5, 8, 13, 33, 64, 65, 100, 0, 7] + [int(x) for x in rng.integers(1, 40, 300)]
+    descs, offsets = [], [0]
+    for n in counts:
+        base = synth.descriptors(1000 + len(offsets), max(n, 1))[:n].copy()
+        if n >= 4:                                     # near-duplicates and exact duplicates: equal medians
+            base[1] = base[0]
+            base[3] = base[2]; base[3, 0] ^= 1
+        descs.append(base)
+        offsets.append(offsets[-1] + n)
+    allD = np.concatenate(descs) if offsets[-1] else np.zeros((0, 32), np.uint8)
+    best = orbx.distinctive_descriptors(allD, np.array(offsets, np.int32))
+    ref = None
+    try:
+        from tests import ref_lib
+        ref = ref_lib.load()
+    except Exception:
+        ref = None
+    for p, n in enumerate(counts):
+        if n == 0:
+            assert best[p] == -1
+            continue
+        exp = oracle.distinctive_descriptor(descs[p])
+        assert best[p] == exp, (p, n, best[p], exp)
+        assert orbx.distinctive_descriptor(descs[p]) == exp
+        if ref is not None and p < 40:
+            assert ref.distinctive_descriptor(descs[p]) == exp

@@ -11,7 +11,8 @@ from .extractor import ORBextractor, compute_tables, distribute_octree  # noqa: 
 from .prep import Rectifier, undistort_keypoints  # noqa: F401
 from .projection import (FrameView, projection_rounds, search_by_projection_kf, search_by_projection_last,  # noqa: F401
                          search_by_projection_map)
-from .matcher import (ORBmatcher, ShardedMatcher, compute_stereo_matches, distinctive_descriptor, extract_stereo,  # noqa: F401
+from . import io  # noqa: F401
+from .matcher import (ORBmatcher, ShardedMatcher, compute_stereo_matches, distinctive_descriptor, distinctive_descriptors, extract_stereo,  # noqa: F401
                       knn2_device, knn2_merge_device, measure_popc_peak, rotation_consistency)
 
 lib()  # fail loudly at import time if the CUDA extension is missing

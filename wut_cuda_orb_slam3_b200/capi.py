@@ -61,6 +61,11 @@ SIGNATURES = {
     "orbx_ratio_test": (_i, [_vp, _i, _f, _i, _i, _vp]),
     "orbx_rotation_consistency": (_i, [_vp, _vp, _i, _vp]),
     "orbx_distinctive_descriptor": (_i, [_vp, _i, _vp]),
+    "orbx_distinctive_descriptors": (_i, [_i, _vp, _vp, _i, _vp]),
+    "orbx_serialize_matrix_u8": (_i64, [_i, _vp, _i, _i, _sz, _vp, _sz]),
+    "orbx_deserialize_matrix_u8": (_i64, [_i, _vp, _sz, _vp, _vp, _vp, _sz, _sz]),
+    "orbx_serialize_keypoints": (_i64, [_i, _vp, _i, _vp, _sz]),
+    "orbx_deserialize_keypoints": (_i64, [_i, _vp, _sz, _vp, _vp, _i]),
     "orbx_stereo_match": (_i, [_vp, _i, _vp, _i, _vp, _vp, _i, _vp, _vp, _i, _f, _f, _vp, _vp]),
     "orbx_stereo_match_device": (_i, [_vp, _i, _vp, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp, _i, _f, _f, _vp, _vp, _vp]),
     "orbx_extract_stereo": (_i, [_vp, _vp, _vp, _vp, _i, _i, _sz, _vp, _vp, _vp, _vp, _vp, _vp, _i, _f, _f, _vp, _vp]),

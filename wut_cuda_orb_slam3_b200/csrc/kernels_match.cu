@@ -7,6 +7,7 @@
 //  * stereo kernels:     Frame::ComputeStereoMatches (src/Frame.cc:841-1011).
 //  * popc_bench_kernel:  POPC issue-rate microbenchmark (roofline denominator for the matcher).
 #include <limits.h>
+#include <stdlib.h>
 
 #include "orbx_internal.cuh"
 #include "synth.h"
@@ -104,7 +105,8 @@ __device__ __forceinline__ void top2_merge(int dist, int idx, int& d1, int& i1, 
 
 // grid = (query tiles, db chunks).  Each thread owns KNN_QT queries in registers; the CTA streams its database chunk
 // through shared memory (every lane reads the same row -> broadcast LDS.128) and keeps (d1,i1,d2,i2) per query.
-__global__ void __launch_bounds__(KNN_THREADS) knn2_kernel(const uint32_t* __restrict__ q, int nq,
+template <int MINB>
+__global__ void __launch_bounds__(KNN_THREADS, MINB) knn2_kernel(const uint32_t* __restrict__ q, int nq,
                                                           const uint4* __restrict__ db, long long ndb, int index_base,
                                                           long long rows_per_chunk, int32_t* __restrict__ out_idx,
                                                           int32_t* __restrict__ out_dist)
@@ -255,9 +257,14 @@ cudaError_t launch_knn2(const uint8_t* d_q, int nq, const uint8_t* d_db, long lo
         p_dist = p_idx + (size_t)chunks * nq * 2;
     }
     dim3 grid(qtiles, chunks);
-    knn2_kernel<<<grid, KNN_THREADS, 0, st>>>(reinterpret_cast<const uint32_t*>(d_q), nq,
-                                              reinterpret_cast<const uint4*>(d_db), ndb, index_base, rows_per_chunk, p_idx,
-                                              p_dist);
+    // register budget for 5 or 6 CTAs per SM (ORBX_KNN_MINB: A/B switch for measurements)
+    static const int minb = getenv("ORBX_KNN_MINB") ? atoi(getenv("ORBX_KNN_MINB")) : 5;
+    if (minb == 6)
+        knn2_kernel<6><<<grid, KNN_THREADS, 0, st>>>(reinterpret_cast<const uint32_t*>(d_q), nq, reinterpret_cast<const uint4*>(d_db), ndb,
+                                                     index_base, rows_per_chunk, p_idx, p_dist);
+    else
+        knn2_kernel<5><<<grid, KNN_THREADS, 0, st>>>(reinterpret_cast<const uint32_t*>(d_q), nq, reinterpret_cast<const uint4*>(d_db), ndb,
+                                                     index_base, rows_per_chunk, p_idx, p_dist);
     count_launch();
     if (chunks > 1) {
         knn2_merge_kernel<<<(nq + 255) / 256, 256, 0, st>>>(p_idx, p_dist, chunks, nq, d_idx, d_dist, (size_t)nq * 2);

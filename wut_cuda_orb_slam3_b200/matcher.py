@@ -55,6 +55,16 @@ def distinctive_descriptor(descriptors):
     return best.value
 
 
+def distinctive_descriptors(descriptors, offsets, device=0):
+    """MapPoint::ComputeDistinctiveDescriptors for many map points in one GPU call: observations of point p are rows
+    offsets[p]:offsets[p+1]; returns the index inside each point's own list (-1 for a point without observations)."""
+    d = np.ascontiguousarray(descriptors, np.uint8).reshape(-1, 32)
+    off = np.ascontiguousarray(offsets, np.int32)
+    best = np.zeros(len(off) - 1, np.int32)
+    check(lib().orbx_distinctive_descriptors(device, ptr(d), ptr(off), len(off) - 1, ptr(best)))
+    return best
+
+
 def knn2_device(d_q, nq, d_db, ndb, d_idx, d_dist, index_base=0, device=0, stream=None):
     check(lib().orbx_knn2_device(device, ptr(d_q), nq, ptr(d_db), ndb, index_base, ptr(d_idx), ptr(d_dist), ptr(stream) if stream else None))
 
