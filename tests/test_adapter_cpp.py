@@ -106,3 +106,67 @@ def test_matcher_adapter_matches_oracle(oracle, tmp_path, mode):
         want, wnm = oracle.search_by_projection_last(kp, desc, ur, occ, bg, SCALE, mbf, P["valid"], P["x"], P["y"], P["invz"], P["level"],
                                                      P["angle"], P["n_obs"], P["desc"], 15.0, False, False, True)
     assert nm == wnm and nm > 50 and np.array_equal(got, want)
+
+
+CSRC = os.path.join(ROOT, "tests", "cpp", "orbmatcher_class_test.cpp")
+CEXE = os.path.join(ROOT, "build", "orbmatcher_class_test")
+
+
+def build_class_exe():
+    os.makedirs(os.path.dirname(CEXE), exist_ok=True)
+    subprocess.check_call(["g++", "-std=c++17", "-O2", "-I" + os.path.join(ROOT, "tests", "cpp", "cv_stub"), "-I" + os.path.join(ROOT, "include"),
+                           "-I" + os.path.join(ROOT, "wut_cuda_orb_slam3_b200", "csrc", "adapter"), "-o", CEXE, CSRC,
+                           "-L" + os.path.join(ROOT, "wut_cuda_orb_slam3_b200"), "-lorbx",
+                           "-Wl,-rpath," + os.path.join(ROOT, "wut_cuda_orb_slam3_b200")])
+
+
+def test_orbmatcher_class_compiles():
+    """CPU: csrc/adapter/ORBmatcher.h (class ORBmatcher with the reference's declarations, include/ORBmatcher.h:36-60) compiles
+    against Frame / KeyFrame / MapPoint stand-ins, all four search overloads instantiated, and links."""
+    build_class_exe()
+    assert os.path.exists(CEXE)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode", [0, 1])
+def test_orbmatcher_class_search_by_bow(oracle, tmp_path, mode):
+    """ORBmatcher::SearchByBoW(KeyFrame*, Frame&, ...) / (KeyFrame*, KeyFrame*, ...) through the C++ class (std::map feature
+    vectors, MapPoint* outputs) against the oracle's restatement of src/ORBmatcher1.cc:225-427 / src/ORBmatcher2.cc:36-171."""
+    import wut_cuda_orb_slam3_b200 as orbx
+    from tests import bow_synth
+    build_class_exe()
+    parent, desc, weights = bow_synth.make_vocab(11, 10, 4)
+    voc = orbx.ORBVocabulary(parent, desc, weights, 10, 4)
+    P = bow_synth.make_pair(1300 + mode, desc, parent, 1500, 1600)
+    _, fva = voc.transform(P["desc_a"], 2)
+    _, fvb = voc.transform(P["desc_b"], 2)
+    ratio, check_ori = 0.75, True
+    rng = np.random.default_rng(3)
+    # bit 0: the key frame holds a map point for the feature, bit 1: that map point isBad()
+    va = (P["valid_a"] | ((rng.random(len(P["valid_a"])) < 0.05).astype(np.uint8) << 1)).astype(np.uint8)
+    vb = (P["valid_b"] | ((rng.random(len(P["valid_b"])) < 0.05).astype(np.uint8) << 1)).astype(np.uint8)
+    ok_a = ((va & 1) != 0) & ((va & 2) == 0); ok_b = ((vb & 1) != 0) & ((vb & 2) == 0)
+    scene = tmp_path / "scene.bin"; result = tmp_path / "result.bin"
+
+    def fv_bytes(fv):
+        nodes, off, idx = fv.node_ids, fv.offsets, fv.indices
+        return np.array([len(nodes)], np.int32).tobytes() + nodes.astype(np.uint32).tobytes() + off.astype(np.int32).tobytes() + idx.astype(np.uint32).tobytes()
+    with open(scene, "wb") as f:
+        f.write(np.array([mode, len(P["desc_a"]), len(P["desc_b"]), int(check_ori)], np.int32).tobytes())
+        f.write(np.array([ratio], np.float32).tobytes())
+        f.write(P["desc_a"].tobytes()); f.write(P["desc_b"].tobytes())
+        f.write(P["angle_a"].astype(np.float32).tobytes()); f.write(P["angle_b"].astype(np.float32).tobytes())
+        f.write(va.tobytes()); f.write(vb.tobytes())
+        f.write(fv_bytes(fva)); f.write(fv_bytes(fvb))
+    subprocess.check_call([CEXE, str(scene), str(result), "instantiate"])
+    raw = np.fromfile(result, np.int32)
+    nm, d01, got = int(raw[0]), int(raw[1]), raw[2:]
+    fv_t = lambda fv: (fv.node_ids, fv.offsets, fv.indices)
+    if mode == 0:
+        want, wnm = oracle.search_by_bow_kf_frame(P["desc_a"], P["angle_a"], ok_a.astype(np.uint8), fv_t(fva), P["desc_b"], P["angle_b"], fv_t(fvb),
+                                                  -1, ratio, check_ori)
+    else:
+        want, wnm = oracle.search_by_bow_kf_kf(P["desc_a"], P["angle_a"], ok_a.astype(np.uint8), fv_t(fva), P["desc_b"], P["angle_b"],
+                                               ok_b.astype(np.uint8), fv_t(fvb), ratio, check_ori)
+    assert nm == wnm and nm > 50 and np.array_equal(got, want)
+    assert d01 == oracle.hamming(P["desc_a"][0], P["desc_a"][1], swar=True)

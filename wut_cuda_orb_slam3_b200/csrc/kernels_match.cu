@@ -258,7 +258,7 @@ cudaError_t launch_knn2(const uint8_t* d_q, int nq, const uint8_t* d_db, long lo
     }
     dim3 grid(qtiles, chunks);
     // register budget for 5 or 6 CTAs per SM (ORBX_KNN_MINB: A/B switch for measurements)
-    static const int minb = getenv("ORBX_KNN_MINB") ? atoi(getenv("ORBX_KNN_MINB")) : 5;
+    static const int minb = getenv("ORBX_KNN_MINB") ? atoi(getenv("ORBX_KNN_MINB")) : 6;     // measured: 8.29e11 (6) vs 8.07e11 (5) compares/s
     if (minb == 6)
         knn2_kernel<6><<<grid, KNN_THREADS, 0, st>>>(reinterpret_cast<const uint32_t*>(d_q), nq, reinterpret_cast<const uint4*>(d_db), ndb,
                                                      index_base, rows_per_chunk, p_idx, p_dist);

@@ -335,70 +335,86 @@ __global__ void __launch_bounds__(T, 1024 / T) octree_kernel(const __grid_consta
     }
 
     // ---- 0./1. counting sort of the level's candidates by the leading bits of their path codes -----------------------
-    // A candidate's identity is its slot in the FAST staging area, flat = cell * cell_cap + i: monotone in the reference's
-    // vToDistributeKeys order (cells row-major, (y, x) inside a cell), which is all the retain rule needs.
+    // A candidate's identity is its rank k in the reference's vToDistributeKeys order (cells row-major, (y, x) inside a cell):
+    // k = (candidates in earlier cells) + slot, which is all the retain rule needs.  The passes are arranged so that a warp
+    // waits for as few dependent global round trips as possible (the kernel is latency-bound): cell counts first (one trip),
+    // then the candidates of eight cells per warp iteration (one trip each), then dense key-parallel passes.
     const int Dsort = octree_sort_depth(g.depth, g.root_bits);
     const int nb = 1 << (g.root_bits + 2 * Dsort);
     uint32_t* scratch = ws.oct + (size_t)frame * fg.oct_frame_stride + g.oct_off;
     const int nmax = g.cand_max;
-    uint32_t* K = scratch;                                       // payload: flat staging slot | score << 24, bin-sorted
-    uint32_t* Bst = scratch + nmax;                              // per staging slot: bin | score << 24 (count pass -> scatter pass)
-    const int* cell_count = ws.cell_count + (size_t)frame * fg.total_cells + g.cell_base;
+    uint32_t* K = scratch;                                       // rank k | score << 24, bin-sorted
+    uint32_t* K2 = scratch + nmax;                               // the packed candidate (x | y << 12 | score << 24), same order
+    uint32_t* stash = scratch + 2 * (size_t)nmax;                // packed candidates in rank order
+    uint32_t* binst = scratch + 3 * (size_t)nmax;                // their bins
+    int* coff = (int*)(scratch + 5 * (size_t)nmax);              // [ncells] candidates in earlier cells
+    const int* __restrict__ cell_count = ws.cell_count + (size_t)frame * fg.total_cells + g.cell_base;
     const uint32_t* __restrict__ cand = ws.cand + (size_t)frame * fg.cand_frame_stride + g.cand_off;
     for (int i = tid; i <= nb; i += T) S.bstart[i] = 0;
+    for (int c = tid; c < ncells; c += T) coff[c] = __ldg(cell_count + c);
     __syncthreads();
-    // warp = 4 cells per iteration so that the dependent global loads (count -> candidates) of several cells overlap.  Only
-    // the Dsort leading depths of the path are evaluated (the deeper bits are needed by the rare splits below depth Dsort,
-    // which work them out on demand), once: the bin travels to the scatter pass through Bst.
-    for (int c0 = warp * 4; c0 < ncells; c0 += (T / 32) * 4) {
-        int cnt[4];
-        uint32_t k[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) cnt[u] = c0 + u < ncells ? cell_count[c0 + u] : 0;
-#pragma unroll
-        for (int u = 0; u < 4; ++u) k[u] = lane < cnt[u] ? cand[(size_t)(c0 + u) * g.cell_cap + lane] : 0u;
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            if (lane < cnt[u]) {
-                const uint32_t bin = path_code_top((int)(k[u] & 0xfff), (int)((k[u] >> 12) & 0xfff), g, winH, Dsort);
-                atomicAdd(&S.bstart[bin], 1);
-                Bst[(size_t)(c0 + u) * g.cell_cap + lane] = bin | (k[u] & 0xff000000u);
-            }
-            for (int i = lane + 32; i < cnt[u]; i += 32) {           // cells with more than 32 candidates (rare)
-                const uint32_t kk = cand[(size_t)(c0 + u) * g.cell_cap + i];
-                const uint32_t bin = path_code_top((int)(kk & 0xfff), (int)((kk >> 12) & 0xfff), g, winH, Dsort);
-                atomicAdd(&S.bstart[bin], 1);
-                Bst[(size_t)(c0 + u) * g.cell_cap + i] = bin | (kk & 0xff000000u);
-            }
-        }
-    }
-    __syncthreads();
-    const int n = block_exclusive_scan_raking<T>(S.bstart, nb, S.warp_tmp);
-    if (tid == 0) { *out_ncand = n; S.bstart[nb] = n; }
+    const int n = block_exclusive_scan_raking<T>(coff, ncells, S.warp_tmp);
+    if (tid == 0) *out_ncand = n;
     if (n == 0) {
         if (tid == 0) *out_n = 0;
         return;
     }
+    // gather: the candidates of eight cells per warp iteration, all loads of an iteration in flight together
+    for (int c0 = warp * 8; c0 < ncells; c0 += (T / 32) * 8) {
+        int cnt[8], o[8];
+        uint32_t k[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const bool in = c0 + u < ncells;
+            cnt[u] = in ? __ldg(cell_count + c0 + u) : 0;
+            o[u] = in ? coff[c0 + u] : 0;
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) k[u] = lane < cnt[u] ? cand[(size_t)(c0 + u) * g.cell_cap + lane] : 0u;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            if (lane < cnt[u]) stash[o[u] + lane] = k[u];
+            for (int i = lane + 32; i < cnt[u]; i += 32) stash[o[u] + i] = cand[(size_t)(c0 + u) * g.cell_cap + i];   // > 32 candidates (rare)
+        }
+    }
+    __syncthreads();
+    // bins, dense over the keys (every lane busy).  Only the Dsort leading depths of the path are evaluated (the deeper bits
+    // are needed by the rare splits below depth Dsort, which work them out on demand), once: binst carries the bin on.
+    for (int k0 = tid; k0 < n; k0 += 4 * T) {
+        uint32_t kk[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) kk[u] = k0 + u * T < n ? stash[k0 + u * T] : 0u;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int k = k0 + u * T;
+            if (k < n) {
+                const uint32_t bin = path_code_top((int)(kk[u] & 0xfff), (int)((kk[u] >> 12) & 0xfff), g, winH, Dsort);
+                atomicAdd(&S.bstart[bin], 1);
+                binst[k] = bin;
+            }
+        }
+    }
+    __syncthreads();
+    block_exclusive_scan_raking<T>(S.bstart, nb, S.warp_tmp);
+    if (tid == 0) S.bstart[nb] = n;
     for (int i = tid; i < nb; i += T) S.cursor[i] = S.bstart[i];
     __syncthreads();
     OCT_MARK(0);
-    for (int c0 = warp * 4; c0 < ncells; c0 += (T / 32) * 4) {
-        int cnt[4];
-        uint32_t bs[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) cnt[u] = c0 + u < ncells ? cell_count[c0 + u] : 0;
-#pragma unroll
-        for (int u = 0; u < 4; ++u) bs[u] = lane < cnt[u] ? Bst[(size_t)(c0 + u) * g.cell_cap + lane] : 0u;
+    for (int k0 = tid; k0 < n; k0 += 4 * T) {                    // dense: four independent keys per thread in flight
+        uint32_t kk[4], bb[4];
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-            if (lane < cnt[u]) {
-                const int pos = atomicAdd(&S.cursor[bs[u] & 0xffffffu], 1);
-                K[pos] = (uint32_t)((c0 + u) * g.cell_cap + lane) | (bs[u] & 0xff000000u);
-            }
-            for (int i = lane + 32; i < cnt[u]; i += 32) {
-                const uint32_t b2 = Bst[(size_t)(c0 + u) * g.cell_cap + i];
-                const int pos = atomicAdd(&S.cursor[b2 & 0xffffffu], 1);
-                K[pos] = (uint32_t)((c0 + u) * g.cell_cap + i) | (b2 & 0xff000000u);
+            const int k = k0 + u * T;
+            kk[u] = k < n ? stash[k] : 0u;
+            bb[u] = k < n ? binst[k] : 0u;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int k = k0 + u * T;
+            if (k < n) {
+                const int pos = atomicAdd(&S.cursor[bb[u]], 1);
+                K[pos] = (uint32_t)k | (kk[u] & 0xff000000u);
+                K2[pos] = kk[u];
             }
         }
     }
@@ -428,8 +444,7 @@ __global__ void __launch_bounds__(T, 1024 / T) octree_kernel(const __grid_consta
     }
 
     // 2-bit quadrant of the key with payload `pl` at depth `dep` of its path (dep >= Dsort: not part of the sorted prefix)
-    auto quadrant_at = [&](uint32_t pl, int dep) -> uint32_t {
-        const uint32_t kk = cand[pl & 0xffffffu];
+    auto quadrant_at = [&](uint32_t kk, int dep) -> uint32_t {
         return path_code_top((int)(kk & 0xfff), (int)((kk >> 12) & 0xfff), g, winH, dep + 1) & 3u;
     };
 
@@ -456,7 +471,7 @@ __global__ void __launch_bounds__(T, 1024 / T) octree_kernel(const __grid_consta
             // (a phase-2 split that was computed but cut off) is a no-op.
             uint32_t c4[4] = {0, 0, 0, 0};
             for (uint32_t i = beg; i < e; ++i) {
-                const uint32_t d = quadrant_at(K[i], dep);
+                const uint32_t d = quadrant_at(K2[i], dep);
                 c4[0] += d == 0; c4[1] += d == 1; c4[2] += d == 2; c4[3] += d == 3;
             }
             b1 = beg + c4[0]; b2 = b1 + c4[1]; b3 = b2 + c4[2];
@@ -464,13 +479,13 @@ __global__ void __launch_bounds__(T, 1024 / T) octree_kernel(const __grid_consta
             const uint32_t end0 = b1, end1 = b2, end2 = b3;
             auto place = [&](uint32_t i, uint32_t d) {     // swap element i with the head of bucket d, advance that head
                 uint32_t& h = d == 0 ? nx0 : (d == 1 ? nx1 : (d == 2 ? nx2 : nx3));
-                const uint32_t tk = K[i];
-                K[i] = K[h]; K[h] = tk;
+                const uint32_t tk = K[i], tk2 = K2[i];
+                K[i] = K[h]; K[h] = tk; K2[i] = K2[h]; K2[h] = tk2;
                 ++h;
             };
-            while (nx0 < end0) { const uint32_t d = quadrant_at(K[nx0], dep); if (d == 0) ++nx0; else place(nx0, d); }
-            while (nx1 < end1) { const uint32_t d = quadrant_at(K[nx1], dep); if (d == 1) ++nx1; else place(nx1, d); }
-            while (nx2 < end2) { const uint32_t d = quadrant_at(K[nx2], dep); if (d == 2) ++nx2; else place(nx2, d); }
+            while (nx0 < end0) { const uint32_t d = quadrant_at(K2[nx0], dep); if (d == 0) ++nx0; else place(nx0, d); }
+            while (nx1 < end1) { const uint32_t d = quadrant_at(K2[nx1], dep); if (d == 1) ++nx1; else place(nx1, d); }
+            while (nx2 < end2) { const uint32_t d = quadrant_at(K2[nx2], dep); if (d == 2) ++nx2; else place(nx2, d); }
         }
         const uint32_t c0 = b1 - beg, c1 = b2 - b1, c2 = b3 - b2, c3 = e - b3;
         S.cc[4 * p] = c0; S.cc[4 * p + 1] = c1; S.cc[4 * p + 2] = c2; S.cc[4 * p + 3] = c3;
@@ -632,19 +647,34 @@ __global__ void __launch_bounds__(T, 1024 / T) octree_kernel(const __grid_consta
     }
 
     // ---- 4. retain the best key per node, in list order (src 756-771) ------------------------------------------------
+    // The segment is ordered by sub-path, not by original position, so "first key with maximal response" (src 758-768) = max
+    // score, then min rank: the reduction runs on (score << 24 | 0xffffff - rank) << 32 | packed candidate, whose low word is
+    // the answer — no dependent look-up.  Four nodes per warp iteration keep four independent loads in flight.
     const int nL = s_nL;
-    for (int i = warp; i < nL; i += T / 32) {
-        const uint32_t beg = S.nbeg[a][i], cnt = S.ncnt[a][i];
-        // The segment is ordered by sub-path, not by original position, so "first key with maximal response" (src 758-768)
-        // = max score, then min ORIGINAL index: (score << 24) | (0xffffff - original index).
-        uint32_t best = 0;
-        for (uint32_t j = lane; j < cnt; j += 32) {
-            const uint32_t pl = K[beg + j];                      // staging slot (monotone in the original index) | score << 24
-            best = max(best, (pl & 0xff000000u) | (0xffffffu - (pl & 0xffffffu)));
+    for (int i0 = warp * 4; i0 < nL; i0 += (T / 32) * 4) {
+        unsigned long long best[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            best[u] = 0ull;
+            const int i = i0 + u;
+            if (i < nL) {
+                const uint32_t beg = S.nbeg[a][i], cnt = S.ncnt[a][i];
+                for (uint32_t j = lane; j < cnt; j += 32) {
+                    const uint32_t pl = K[beg + j], kk = K2[beg + j];
+                    const unsigned long long v = ((unsigned long long)((pl & 0xff000000u) | (0xffffffu - (pl & 0xffffffu))) << 32) | kk;
+                    best[u] = v > best[u] ? v : best[u];
+                }
+            }
         }
 #pragma unroll
-        for (int d = 16; d >= 1; d >>= 1) best = max(best, __shfl_xor_sync(0xffffffffu, best, d));
-        if (lane == 0) out_kp[i] = cand[0xffffffu - (best & 0xffffffu)];
+        for (int u = 0; u < 4; ++u) {
+#pragma unroll
+            for (int d = 16; d >= 1; d >>= 1) {
+                const unsigned long long o = __shfl_xor_sync(0xffffffffu, best[u], d);
+                best[u] = o > best[u] ? o : best[u];
+            }
+            if (lane == 0 && i0 + u < nL) out_kp[i0 + u] = (uint32_t)best[u];
+        }
     }
     if (tid == 0) *out_n = nL;
     OCT_MARK(6);
@@ -655,6 +685,8 @@ __global__ void __launch_bounds__(T, 1024 / T) octree_kernel(const __grid_consta
 cudaError_t octree_prepare()
 {
     cudaError_t e = cudaFuncSetAttribute(octree_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(octree_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(octree_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (e != cudaSuccess) return e;
@@ -706,7 +738,7 @@ cudaError_t launch_octree(const FrameGeom& fg, const Workspace& ws, int n_frames
     // A few frames: the level-0 CTA is the critical path of the whole extraction, so give it more lanes.
     static const int t_override = getenv("ORBX_OCTREE_THREADS") ? atoi(getenv("ORBX_OCTREE_THREADS")) : 0;
     int T = n_frames >= 8 ? 256 : 1024;
-    if (t_override == 128 || t_override == 256 || t_override == 512 || t_override == 1024) T = t_override;
+    if (t_override == 64 || t_override == 128 || t_override == 256 || t_override == 512 || t_override == 1024) T = t_override;
     const size_t smem = octree_smem_bytes(M, NB);
     if (smem > 200 * 1024) return cudaErrorInvalidConfiguration;
     int dev = 0;
@@ -723,7 +755,8 @@ cudaError_t launch_octree(const FrameGeom& fg, const Workspace& ws, int n_frames
         }
     }
     dim3 grid(n_frames, level_hi - level_lo);
-    if (T == 128) octree_kernel<128><<<grid, 128, smem, st>>>(fg, ws, M, NB, level_lo, g_err_flag[dev & 63]);
+    if (T == 64) octree_kernel<64><<<grid, 64, smem, st>>>(fg, ws, M, NB, level_lo, g_err_flag[dev & 63]);
+    else if (T == 128) octree_kernel<128><<<grid, 128, smem, st>>>(fg, ws, M, NB, level_lo, g_err_flag[dev & 63]);
     else if (T == 1024) octree_kernel<1024><<<grid, 1024, smem, st>>>(fg, ws, M, NB, level_lo, g_err_flag[dev & 63]);
     else if (T == 512) octree_kernel<512><<<grid, 512, smem, st>>>(fg, ws, M, NB, level_lo, g_err_flag[dev & 63]);
     else octree_kernel<256><<<grid, 256, smem, st>>>(fg, ws, M, NB, level_lo, g_err_flag[dev & 63]);
