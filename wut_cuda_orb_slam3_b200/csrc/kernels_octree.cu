@@ -226,6 +226,7 @@ __device__ __forceinline__ uint32_t path_code_top(int x, int y, const LevelGeom&
     int ulx = (int)__fmul_rn(g.hX, (float)r), urx = (int)__fmul_rn(g.hX, (float)(r + 1));   // src 602-603
     int uly = 0, bry = winH;
     uint32_t code = (uint32_t)r;
+#pragma unroll 1
     for (int d = 0; d < levels; ++d) {
         const int mx = ulx + ((urx - ulx + 1) >> 1);                   // UL.x + ceil((UR.x-UL.x)/2)   (src 517)
         const int my = uly + ((bry - uly + 1) >> 1);
@@ -360,19 +361,20 @@ __global__ void __launch_bounds__(T, 1024 / T) octree_kernel(const __grid_consta
         return;
     }
     // gather: the candidates of eight cells per warp iteration, all loads of an iteration in flight together
-    for (int c0 = warp * 8; c0 < ncells; c0 += (T / 32) * 8) {
-        int cnt[8], o[8];
-        uint32_t k[8];
+    constexpr int GU = T >= 512 ? 2 : 8;          // cells per warp iteration (a big CTA has the warps instead of the unrolling)
+    for (int c0 = warp * GU; c0 < ncells; c0 += (T / 32) * GU) {
+        int cnt[GU], o[GU];
+        uint32_t k[GU];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
+        for (int u = 0; u < GU; ++u) {
             const bool in = c0 + u < ncells;
             cnt[u] = in ? __ldg(cell_count + c0 + u) : 0;
             o[u] = in ? coff[c0 + u] : 0;
         }
 #pragma unroll
-        for (int u = 0; u < 8; ++u) k[u] = lane < cnt[u] ? cand[(size_t)(c0 + u) * g.cell_cap + lane] : 0u;
+        for (int u = 0; u < GU; ++u) k[u] = lane < cnt[u] ? cand[(size_t)(c0 + u) * g.cell_cap + lane] : 0u;
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
+        for (int u = 0; u < GU; ++u) {
             if (lane < cnt[u]) stash[o[u] + lane] = k[u];
             for (int i = lane + 32; i < cnt[u]; i += 32) stash[o[u] + i] = cand[(size_t)(c0 + u) * g.cell_cap + i];   // > 32 candidates (rare)
         }
@@ -380,12 +382,13 @@ __global__ void __launch_bounds__(T, 1024 / T) octree_kernel(const __grid_consta
     __syncthreads();
     // bins, dense over the keys (every lane busy).  Only the Dsort leading depths of the path are evaluated (the deeper bits
     // are needed by the rare splits below depth Dsort, which work them out on demand), once: binst carries the bin on.
-    for (int k0 = tid; k0 < n; k0 += 4 * T) {
-        uint32_t kk[4];
+    constexpr int KU = T >= 512 ? 1 : 4;          // keys per thread in flight
+    for (int k0 = tid; k0 < n; k0 += KU * T) {
+        uint32_t kk[KU];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) kk[u] = k0 + u * T < n ? stash[k0 + u * T] : 0u;
+        for (int u = 0; u < KU; ++u) kk[u] = k0 + u * T < n ? stash[k0 + u * T] : 0u;
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < KU; ++u) {
             const int k = k0 + u * T;
             if (k < n) {
                 const uint32_t bin = path_code_top((int)(kk[u] & 0xfff), (int)((kk[u] >> 12) & 0xfff), g, winH, Dsort);
@@ -400,16 +403,16 @@ __global__ void __launch_bounds__(T, 1024 / T) octree_kernel(const __grid_consta
     for (int i = tid; i < nb; i += T) S.cursor[i] = S.bstart[i];
     __syncthreads();
     OCT_MARK(0);
-    for (int k0 = tid; k0 < n; k0 += 4 * T) {                    // dense: four independent keys per thread in flight
-        uint32_t kk[4], bb[4];
+    for (int k0 = tid; k0 < n; k0 += KU * T) {                   // dense: independent keys per thread in flight
+        uint32_t kk[KU], bb[KU];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < KU; ++u) {
             const int k = k0 + u * T;
             kk[u] = k < n ? stash[k] : 0u;
             bb[u] = k < n ? binst[k] : 0u;
         }
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < KU; ++u) {
             const int k = k0 + u * T;
             if (k < n) {
                 const int pos = atomicAdd(&S.cursor[bb[u]], 1);
@@ -557,93 +560,85 @@ __global__ void __launch_bounds__(T, 1024 / T) octree_kernel(const __grid_consta
     __syncthreads();
     OCT_MARK(2);
     // ---- 3. main loop (src 635-753) ---------------------------------------------------------------------------------
-    bool finish = false;
+    // One loop body serves both kinds of rounds (one copy of the split / apply code: a single CTA per level is bound by
+    // instruction fetch, so the kernel is kept small): a phase-1 sweep processes every expandable node in list order, a
+    // phase-2 round processes the std::sort-ed expandable nodes from the back and stops at the split that reaches N.
+    bool finish = false, phase2 = false;
+    unsigned long long* vprev = S.vec;      // expandable nodes created by the previous round (creation order)
+    unsigned long long* vnext = S.vec2;
+    int nToExpand = 0;
     while (!finish) {
-        if (dbg) dbg[7] += 1;
-        int nL = s_nL;
-        const int prevSize = nL;
+        const int prevSize = s_nL;
+        if (dbg) { if (phase2) { dbg[8] += 1; if (nToExpand > dbg[10]) dbg[10] = nToExpand; } else dbg[7] += 1; }
+        bool small = false;
+        uint32_t* s32 = reinterpret_cast<uint32_t*>(S.sd);
+        if (phase2) {
+            // std::sort(compareNodes) (src 709).  For the usual few hundred nodes the replay runs on 32-bit items
+            // (dense rank of (count, UL.x) << 16 | creation index): one shared-memory word per move/compare.
+            const int m = nToExpand;
+            small = m <= 512;
+            if (small) {
+                for (int i = tid; i < m; i += T) {
+                    const unsigned long long ki = vprev[i] >> orbx_sort::kPayloadBits;
+                    int rank = 0;
+                    for (int j = 0; j < m; ++j) rank += (vprev[j] >> orbx_sort::kPayloadBits) < ki;
+                    s32[i] = ((uint32_t)rank << 16) | (uint32_t)i;
+                }
+                __syncthreads();
+                sort_replay_parallel<T>(s32, m, reinterpret_cast<uint32_t*>(S.sa), reinterpret_cast<uint32_t*>(S.sb),
+                                        reinterpret_cast<uint32_t*>(S.sc), S.sort_stk);
+            } else {
+                if (tid == 0) orbx_sort::sort_replay(vprev, m);
+            }
+            __syncthreads();
+            OCT_MARK(4);
+        }
         if (warp == 0) {
-            // phase-1 sweep: every node with more than one key, in list order
-            for (int i = lane; i < nL; i += 32) S.sc[i] = S.ncnt[a][i] > 1 ? 1 : 0;
-            __syncwarp();
-            const int nS = warp_exclusive_scan(S.sc, nL, lane);
-            for (int i = lane; i < nL; i += 32)
-                if (S.ncnt[a][i] > 1) S.procpos[S.sc[i]] = i;
+            const int nL = prevSize;
+            int nS;
+            if (!phase2) {
+                // every node with more than one key, in list order
+                for (int i = lane; i < nL; i += 32) S.sc[i] = S.ncnt[a][i] > 1 ? 1 : 0;
+                __syncwarp();
+                nS = warp_exclusive_scan(S.sc, nL, lane);
+                for (int i = lane; i < nL; i += 32)
+                    if (S.ncnt[a][i] > 1) S.procpos[S.sc[i]] = i;
+            } else {
+                // processing order p = 0..m-1 walks the sorted vector from the back (src 710).  s32 lives in sd, which
+                // apply_splits reuses: the positions are taken out first.
+                nS = nToExpand;
+                for (int p = lane; p < nS; p += 32)
+                    S.procpos[p] = (int)orbx_sort::payload(small ? vprev[s32[nS - 1 - p] & 0xffffu] : vprev[nS - 1 - p]);
+            }
             __syncwarp();
             for (int p = lane; p < nS; p += 32) {
                 const int r = split_counts(p, S.procpos[p]);
                 S.sa[p] = r & 0xff; S.sb[p] = r >> 8;
+                S.sc[p] = (r & 0xff) - 1;                               // list growth of this split
             }
             __syncwarp();
-            apply_splits(nL, nS, S.vec);
+            int cut = nS;
+            if (phase2) {
+                // cut-off: stop right after the first split that makes size >= N (src 745-746)
+                warp_exclusive_scan(S.sc, nS, lane);                    // sc[p] = growth before p
+                for (int p = lane; p < nS; p += 32) {
+                    const int before = nL + S.sc[p];
+                    const int after = before + (S.sa[p] - 1);
+                    if (after >= N && before < N) cut = p + 1;          // at most one p satisfies this (growth >= 0)
+                }
+#pragma unroll
+                for (int d = 16; d >= 1; d >>= 1) cut = min(cut, __shfl_xor_sync(0xffffffffu, cut, d));
+            }
+            apply_splits(nL, cut, vnext);
         }
         a ^= 1;
         __syncthreads();
-        nL = s_nL;
-        int nToExpand = s_total;
-        OCT_MARK(3);
-        if (nL >= N || nL == prevSize) {
-            finish = true;
-        } else if (nL + nToExpand * 3 > N) {
-            // phase 2
-            unsigned long long* vprev = S.vec;
-            unsigned long long* vnext = S.vec2;
-            while (!finish) {
-                const int prev2 = nL;
-                const int m = nToExpand;
-                if (dbg) { dbg[8] += 1; if (m > dbg[10]) dbg[10] = m; }
-                // std::sort(compareNodes) (src 709).  For the usual few hundred nodes the replay runs on 32-bit items
-                // (dense rank of (count, UL.x) << 16 | creation index): one shared-memory word per move/compare.
-                const bool small = m <= 512;
-                uint32_t* s32 = reinterpret_cast<uint32_t*>(S.sd);
-                if (small) {
-                    for (int i = tid; i < m; i += T) {
-                        const unsigned long long ki = vprev[i] >> orbx_sort::kPayloadBits;
-                        int rank = 0;
-                        for (int j = 0; j < m; ++j) rank += (vprev[j] >> orbx_sort::kPayloadBits) < ki;
-                        s32[i] = ((uint32_t)rank << 16) | (uint32_t)i;
-                    }
-                    __syncthreads();
-                    sort_replay_parallel<T>(s32, m, reinterpret_cast<uint32_t*>(S.sa), reinterpret_cast<uint32_t*>(S.sb),
-                                            reinterpret_cast<uint32_t*>(S.sc), S.sort_stk);
-                } else {
-                    if (tid == 0) orbx_sort::sort_replay(vprev, m);
-                }
-                __syncthreads();
-                OCT_MARK(4);
-                if (warp == 0) {
-                    // processing order p = 0..m-1 walks the sorted vector from the back (src 710).  s32 lives in sd, which
-                    // apply_splits reuses: the positions are taken out first.
-                    for (int p = lane; p < m; p += 32)
-                        S.procpos[p] = (int)orbx_sort::payload(small ? vprev[s32[m - 1 - p] & 0xffffu] : vprev[m - 1 - p]);
-                    __syncwarp();
-                    for (int p = lane; p < m; p += 32) {
-                        const int r = split_counts(p, S.procpos[p]);
-                        S.sa[p] = r & 0xff; S.sb[p] = r >> 8;
-                        S.sc[p] = (r & 0xff) - 1;                               // list growth of this split
-                    }
-                    __syncwarp();
-                    // cut-off: stop right after the first split that makes size >= N (src 745-746)
-                    warp_exclusive_scan(S.sc, m, lane);                        // sc[p] = growth before p
-                    int cut = m;
-                    for (int p = lane; p < m; p += 32) {
-                        const int before = prev2 + S.sc[p];
-                        const int after = before + (S.sa[p] - 1);
-                        if (after >= N && before < N) cut = p + 1;             // at most one p satisfies this (growth >= 0)
-                    }
-#pragma unroll
-                    for (int d = 16; d >= 1; d >>= 1) cut = min(cut, __shfl_xor_sync(0xffffffffu, cut, d));
-                    apply_splits(prev2, cut, vnext);
-                }
-                a ^= 1;
-                __syncthreads();
-                nL = s_nL;
-                nToExpand = s_total;
-                unsigned long long* t = vprev; vprev = vnext; vnext = t;
-                if (nL >= N || nL == prev2) finish = true;
-                OCT_MARK(5);
-            }
-        }
+        const int nL = s_nL;
+        nToExpand = s_total;
+        { unsigned long long* t = vprev; vprev = vnext; vnext = t; }
+        OCT_MARK(phase2 ? 5 : 3);
+        if (nL >= N || nL == prevSize) finish = true;                   // src 697-698, 751-752
+        else if (!phase2 && nL + nToExpand * 3 > N) phase2 = true;      // src 699: the rest of the work is phase-2 rounds
     }
 
     // ---- 4. retain the best key per node, in list order (src 756-771) ------------------------------------------------
@@ -651,10 +646,11 @@ __global__ void __launch_bounds__(T, 1024 / T) octree_kernel(const __grid_consta
     // score, then min rank: the reduction runs on (score << 24 | 0xffffff - rank) << 32 | packed candidate, whose low word is
     // the answer — no dependent look-up.  Four nodes per warp iteration keep four independent loads in flight.
     const int nL = s_nL;
-    for (int i0 = warp * 4; i0 < nL; i0 += (T / 32) * 4) {
-        unsigned long long best[4];
+    constexpr int RU = T >= 512 ? 1 : 4;
+    for (int i0 = warp * RU; i0 < nL; i0 += (T / 32) * RU) {
+        unsigned long long best[RU];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < RU; ++u) {
             best[u] = 0ull;
             const int i = i0 + u;
             if (i < nL) {
@@ -667,7 +663,7 @@ __global__ void __launch_bounds__(T, 1024 / T) octree_kernel(const __grid_consta
             }
         }
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < RU; ++u) {
 #pragma unroll
             for (int d = 16; d >= 1; d >>= 1) {
                 const unsigned long long o = __shfl_xor_sync(0xffffffffu, best[u], d);
