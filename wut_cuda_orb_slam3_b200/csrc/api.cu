@@ -108,6 +108,7 @@ struct Slot {
     Workspace ws{};
     cudaStream_t stream = nullptr;
     cudaEvent_t ev_in = nullptr, ev_done = nullptr, ev_out = nullptr;   // H2D complete / compute complete / D2H complete (serial-compute pipeline)
+    cudaEvent_t ev_cnt = nullptr;                                       // the chunk's per-frame counts have reached the host
     int cap_frames = 0;
     // staging for the host-buffer API
     uint8_t* d_in = nullptr; size_t d_in_bytes = 0;
@@ -426,6 +427,7 @@ static int ensure_slot(orbx_extractor* ex, Slot& s, int frames)
         CU(cudaEventCreateWithFlags(&s.ev_in, cudaEventDisableTiming));
         CU(cudaEventCreateWithFlags(&s.ev_done, cudaEventDisableTiming));
         CU(cudaEventCreateWithFlags(&s.ev_out, cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&s.ev_cnt, cudaEventDisableTiming));
     }
     if (s.cap_frames >= frames) return ORBX_OK;
     cudaStreamSynchronize(s.stream);
@@ -785,7 +787,7 @@ void orbx_destroy(orbx_extractor* ex)
         if (ex->slots[i].stream) cudaStreamSynchronize(ex->slots[i].stream);
         free_slot(ex->slots[i]);
         if (ex->slots[i].stream) cudaStreamDestroy(ex->slots[i].stream);
-        if (ex->slots[i].ev_in) { cudaEventDestroy(ex->slots[i].ev_in); cudaEventDestroy(ex->slots[i].ev_done); cudaEventDestroy(ex->slots[i].ev_out); }
+        if (ex->slots[i].ev_in) { cudaEventDestroy(ex->slots[i].ev_in); cudaEventDestroy(ex->slots[i].ev_done); cudaEventDestroy(ex->slots[i].ev_out); cudaEventDestroy(ex->slots[i].ev_cnt); }
     }
     if (ex->ev_user) { cudaEventSynchronize(ex->ev_user); cudaEventDestroy(ex->ev_user); }
     if (ex->mirror_stream) { cudaStreamSynchronize(ex->mirror_stream); cudaStreamDestroy(ex->mirror_stream); }
@@ -933,8 +935,12 @@ int orbx_extract_batch(orbx_extractor* ex, const uint8_t* const* images, int n_f
         if ((rc = ensure_host_staging(ex->slots[i], dframe * max_chunk, max_chunk, capacity))) return rc;
     // ORBX_TRACE_BATCH=1: per-chunk timeline (H2D start/end, compute end, D2H end; ms since the first H2D) on stderr
     static const bool trace = getenv("ORBX_TRACE_BATCH") != nullptr;
-    std::vector<cudaEvent_t> tev;
-    auto mark = [&](cudaStream_t st) { if (trace) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, st); tev.push_back(e); } };
+    std::vector<cudaEvent_t> tev;                    // [chunk][4]: H2D start / end, compute end (= D2H may start), D2H end
+    auto mark = [&](cudaStream_t st, int chunk, int k) {
+        if (!trace) return;
+        if (tev.empty()) tev.assign((size_t)4 * sched.size(), nullptr);
+        cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, st); tev[(size_t)4 * chunk + k] = e;
+    };
     // Two pipelines.  Small chunks (< 128 frames) run whole on their slot's stream, so that chunks overlap each other (a small
     // chunk under-fills the GPU: its octree is one partial wave).  Large chunks compute on ONE stream in order: interleaving the
     // kernels of two big chunks costs ~20 % (measured: 80 k vs 98 k frames/s at 256-frame chunks).  The serial pipeline uses
@@ -951,15 +957,44 @@ int orbx_extract_batch(orbx_extractor* ex, const uint8_t* const* images, int n_f
     }
     if (serial)      // earlier work of this extractor on the slot streams (single-frame calls, small batches) must be complete
         for (int i = 0; i < nslots; ++i) CU(cudaStreamSynchronize(ex->slots[i].stream));
+    // Results go home trimmed: a chunk's per-frame counts are copied first (a few hundred bytes), the host reads them and
+    // then asks for the keypoint / descriptor rows every frame of the chunk actually has — one strided copy per array, row
+    // count = the chunk's largest n_out — instead of `capacity` rows per frame.  The host looks at the counts of chunk c - 2
+    // after it has queued chunk c, so two chunks of compute are always queued behind the one it waits for and the next
+    // upload never starts late.  ORBX_D2H_FULL=1 copies whole slabs as before (A/B switch).
+    static const bool d2h_full = getenv("ORBX_D2H_FULL") && atoi(getenv("ORBX_D2H_FULL")) != 0;
+    auto finish = [&](int c) -> int {
+        Slot& s = ex->slots[c % nslots];
+        const int f0 = sched[c].first, nf = sched[c].second;
+        cudaStream_t ost = serial ? ex->copy_out : s.stream;
+        int rows_out = capacity;
+        if (!d2h_full) {
+            CU(cudaEventSynchronize(s.ev_cnt));
+            int mx = 0;
+            for (int f = 0; f < nf; ++f) mx = std::max(mx, n_out[f0 + f]);
+            rows_out = std::min(mx, capacity);         // a frame over capacity wrote nothing: the call fails below
+        }
+        if (rows_out > 0) {
+            CU(cudaMemcpy2DAsync(keypoints + (size_t)f0 * capacity, sizeof(orbx_keypoint) * (size_t)capacity, s.d_kps,
+                                 sizeof(orbx_keypoint) * (size_t)capacity, sizeof(orbx_keypoint) * (size_t)rows_out, nf, cudaMemcpyDeviceToHost, ost));
+            CU(cudaMemcpy2DAsync(descriptors + (size_t)f0 * capacity * 32, (size_t)capacity * 32, s.d_desc, (size_t)capacity * 32,
+                                 (size_t)rows_out * 32, nf, cudaMemcpyDeviceToHost, ost));
+        }
+        mark(ost, c, 3);
+        if (serial) CU(cudaEventRecord(s.ev_out, ost));
+        return ORBX_OK;
+    };
+    const int lag = 2;
     for (int c = 0; c < nchunks; ++c) {
         Slot& s = ex->slots[c % nslots];
         const int f0 = sched[c].first, nf = sched[c].second;
         cudaStream_t cst = serial ? ex->compute : s.stream;
         cudaStream_t ist = serial ? ex->copy_in : s.stream, ost = serial ? ex->copy_out : s.stream;
         // reuse of a slot: its input staging is free once the chunk that used it has been computed, its output staging once
-        // that chunk's D2H has completed (one slot stream orders all of this by itself in the other pipeline)
+        // that chunk's D2H has completed (one slot stream orders all of this by itself in the other pipeline).  The D2H of
+        // chunk c - nslots was queued when chunk c - nslots + lag was (nslots > lag whenever a slot is reused).
         if (serial && c >= nslots) { CU(cudaStreamWaitEvent(ist, s.ev_done, 0)); CU(cudaStreamWaitEvent(cst, s.ev_out, 0)); }
-        mark(ist);
+        mark(ist, c, 0);
         bool contiguous = step == (size_t)cols;
         for (int f = 1; f < nf && contiguous; ++f) contiguous = images[f0 + f] == images[f0 + f - 1] + dframe;
         if (contiguous) {
@@ -968,28 +1003,28 @@ int orbx_extract_batch(orbx_extractor* ex, const uint8_t* const* images, int n_f
             for (int f = 0; f < nf; ++f)
                 CU(cudaMemcpy2DAsync(s.d_in + (size_t)f * dframe, dpitch, images[f0 + f], step, cols, rows, cudaMemcpyHostToDevice, ist));
         }
-        mark(ist);
+        mark(ist, c, 1);
         if (serial) { CU(cudaEventRecord(s.ev_in, ist)); CU(cudaStreamWaitEvent(cst, s.ev_in, 0)); }
         if ((rc = run_chunk(ex, s, s.d_in, dframe, dpitch, nf, lap0, lap1, s.d_kps, s.d_desc, capacity, s.d_n, s.d_nm, cst))) return rc;
         if (serial) { CU(cudaEventRecord(s.ev_done, cst)); CU(cudaStreamWaitEvent(ost, s.ev_done, 0)); }
-        mark(ost);
-        CU(cudaMemcpyAsync(keypoints + (size_t)f0 * capacity, s.d_kps, sizeof(orbx_keypoint) * (size_t)nf * capacity, cudaMemcpyDeviceToHost, ost));
-        CU(cudaMemcpyAsync(descriptors + (size_t)f0 * capacity * 32, s.d_desc, (size_t)nf * capacity * 32, cudaMemcpyDeviceToHost, ost));
+        mark(ost, c, 2);
         CU(cudaMemcpyAsync(n_out + f0, s.d_n, sizeof(int) * nf, cudaMemcpyDeviceToHost, ost));
         CU(cudaMemcpyAsync(n_mono + f0, s.d_nm, sizeof(int) * nf, cudaMemcpyDeviceToHost, ost));
-        mark(ost);
-        if (serial) CU(cudaEventRecord(s.ev_out, ost));
+        CU(cudaEventRecord(s.ev_cnt, ost));
         if (c % nslots == 0) ex->last_frames = nf;
+        if (c >= lag && (rc = finish(c - lag))) return rc;
     }
+    for (int c = std::max(nchunks - lag, 0); c < nchunks; ++c)
+        if ((rc = finish(c))) return rc;
     if (serial) { CU(cudaStreamSynchronize(ex->copy_out)); CU(cudaStreamSynchronize(ex->compute)); CU(cudaStreamSynchronize(ex->copy_in)); }
     for (int i = 0; i < nslots; ++i) CU(cudaStreamSynchronize(ex->slots[i].stream));
     if (trace) {
         for (int c = 0; c < nchunks; ++c) {
             float t[4];
-            for (int k = 0; k < 4; ++k) cudaEventElapsedTime(&t[k], tev[0], tev[4 * c + k]);
+            for (int k = 0; k < 4; ++k) cudaEventElapsedTime(&t[k], tev[0], tev[4 * c + k]);      // (all four marks of every chunk exist)
             fprintf(stderr, "[orbx] chunk %2d frames %3d: h2d %.3f-%.3f compute-end %.3f d2h-end %.3f ms\n", c, sched[c].second, t[0], t[1], t[2], t[3]);
         }
-        for (cudaEvent_t e : tev) cudaEventDestroy(e);
+        for (cudaEvent_t e : tev) if (e) cudaEventDestroy(e);
     }
     for (int f = 0; f < n_frames; ++f)
         if (n_out[f] > capacity) return fail(ORBX_ERR_CAPACITY, "frame %d has %d keypoints, capacity %d", f, n_out[f], capacity);
