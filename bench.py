@@ -136,6 +136,58 @@ def cpu_oracle_throughput(n_frames, threads, seed0=5000):
     return n_frames / dt, dt, counter["kp"] / max(n_frames, 1)
 
 
+def cpu_cv2_hybrid(n_frames=24, seed0=5000):
+    """How fast could the CPU path be with OpenCV's SIMD kernels where the reference calls OpenCV?  One thread: the oracle's
+    own stage times for the reference-owned stages (octree + orientation, descriptors + packing) plus cv2's times for the
+    OpenCV-owned ones — the resize / copyMakeBorder chain, cv2.FastFeatureDetector (ONE call per level at iniThFAST with NMS:
+    a lower bound of the reference's ~700 per-cell calls plus minThFAST retries) and the eight GaussianBlur calls.  Reported as
+    frames/s per thread and, optimistically, times the host threads.  None if cv2 is not importable."""
+    try:
+        import cv2
+    except Exception:
+        return None
+    import numpy as np
+    from tests import oracle_lib
+    o = oracle_lib.load()
+    cv2.setNumThreads(1)
+    ex = o.extractor(NFEAT, SCALE, NLEVELS, INI_TH, MIN_TH)
+    imgs = [o.synth_image(seed0 + i, COLS, ROWS) for i in range(4)]
+    ex.extract(imgs[0], (0, 0)); ex.stage_times(reset=True)
+    t0 = time.perf_counter()
+    for i in range(n_frames):
+        ex.extract(imgs[i % 4], (0, 0))
+    total_ms = (time.perf_counter() - t0) * 1e3 / n_frames
+    st = {k: v / n_frames for k, v in ex.stage_times().items()}
+    inv = o.tables(NFEAT, SCALE, NLEVELS)["inv"]
+    sizes = [(int(np.rint(np.float32(COLS) * inv[l])), int(np.rint(np.float32(ROWS) * inv[l]))) for l in range(NLEVELS)]
+    fast = cv2.FastFeatureDetector_create(threshold=INI_TH, nonmaxSuppression=True)
+    t_pyr = t_fast = t_blur = 0.0
+    for i in range(n_frames):
+        img = imgs[i % 4]
+        a = time.perf_counter()
+        levels = [cv2.copyMakeBorder(img, 19, 19, 19, 19, cv2.BORDER_REFLECT_101)]
+        cur = img
+        for l in range(1, NLEVELS):
+            cur = cv2.resize(cur, sizes[l], interpolation=cv2.INTER_LINEAR)
+            levels.append(cv2.copyMakeBorder(cur, 19, 19, 19, 19, cv2.BORDER_REFLECT_101))
+        b = time.perf_counter()
+        for l in range(NLEVELS):
+            w, h = sizes[l]
+            fast.detect(levels[l][3:h + 35, 3:w + 35])            # the FAST window [16, w - 16) plus its 3-px ring
+        c = time.perf_counter()
+        for l in range(NLEVELS):
+            w, h = sizes[l]
+            cv2.GaussianBlur(levels[l][19:19 + h, 19:19 + w], (7, 7), 2, 2, borderType=cv2.BORDER_REFLECT_101)
+        d = time.perf_counter()
+        t_pyr += b - a; t_fast += c - b; t_blur += d - c
+    cvst = {"pyramid": 1e3 * t_pyr / n_frames, "fast": 1e3 * t_fast / n_frames, "blur": 1e3 * t_blur / n_frames}
+    hybrid_ms = cvst["pyramid"] + cvst["fast"] + cvst["blur"] + st["octree_orient"] + st["describe"]
+    return {"ms_per_frame_one_thread": hybrid_ms, "frames_per_s_one_thread": 1e3 / hybrid_ms,
+            "oracle_ms_per_frame_one_thread": total_ms, "oracle_stage_ms": st, "cv2_stage_ms": cvst, "cv2_version": cv2.__version__,
+            "what": "cv2 (SIMD, 1 thread) for pyramid / FAST (one call per level at iniThFAST: a lower bound of the reference's per-cell calls) / "
+                    "blur + the oracle's octree, orientation and descriptor stages: an upper bound on a tuned CPU path per thread"}
+
+
 def run_reference(args, rank, world):
     if rank != 0:
         return
@@ -352,6 +404,10 @@ def run_ours(args, rank, world, local_rank):
         cpu = {"value": fps, "unit": "frames/s", "cores": threads, "kind": "port",
                "sample": "%d frames of the same 752x480/1000kp workload in %.1f s on %d threads (single thread: %.1f frames/s)" % (nfr, dt, threads, fps1),
                "single_thread_value": fps1}
+        hyb = cpu_cv2_hybrid()
+        if hyb is not None:
+            hyb["frames_per_s_all_threads_if_it_scaled_perfectly"] = hyb["frames_per_s_one_thread"] * threads
+            cpu["cv2_simd_hybrid"] = hyb
 
     if rank == 0:
         line = {

@@ -25,6 +25,7 @@
 #include <cstring>
 #include <list>
 #include <utility>
+#include <chrono>
 #include <vector>
 
 namespace {
@@ -566,7 +567,15 @@ struct Extractor {
     std::vector<std::vector<Cand>> cands;        // per level, window-relative
     std::vector<std::vector<KeyPoint>> levelKps; // per level, level coordinates (border added, angle set)
     std::vector<std::vector<uint8_t>> levelDesc;
+    // wall time per stage of the calls so far (bench.py's cpu_baseline breaks the frame time down with it): pyramid, cell FAST,
+    // octree + border + orientation, blur, descriptors + packing
+    double stage_ms[5] = {0, 0, 0, 0, 0};
 };
+
+static inline double now_ms()
+{
+    return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
 
 }  // namespace
 
@@ -670,7 +679,9 @@ int orbo_extract(void* h, const uint8_t* img, int rows, int cols, size_t step, i
     Extractor& e = *(Extractor*)h;
     const Tables& t = e.t;
     if (!img || rows <= 0 || cols <= 0) return -1;
+    double t0 = now_ms(), t1;
     compute_pyramid(t, img, rows, cols, step, e.pyr);
+    t1 = now_ms(); e.stage_ms[0] += t1 - t0; t0 = t1;
     e.cands.assign(t.nlevels, {});
     e.levelKps.assign(t.nlevels, {});
     e.levelDesc.assign(t.nlevels, {});
@@ -680,6 +691,7 @@ int orbo_extract(void* h, const uint8_t* img, int rows, int cols, size_t step, i
         const int maxBorderX = L.w - EDGE_THRESHOLD + 3;
         const int maxBorderY = L.h - EDGE_THRESHOLD + 3;
         cell_fast(L.interior(), L.w, L.h, L.step, t.iniTh, t.minTh, e.cands[level]);
+        t1 = now_ms(); e.stage_ms[1] += t1 - t0; t0 = t1;
         std::vector<int> keep;
         distribute_octree(e.cands[level], border, maxBorderX, border, maxBorderY, t.nfeat[level], keep);
         const int scaledPatchSize = (int)(PATCH_SIZE * t.scale[level]);
@@ -695,6 +707,7 @@ int orbo_extract(void* h, const uint8_t* img, int rows, int cols, size_t step, i
             kp.angle = ic_angle(L.interior(), L.step, (int)kp.x, (int)kp.y, t.umax);
             e.levelKps[level].push_back(kp);
         }
+        t1 = now_ms(); e.stage_ms[2] += t1 - t0; t0 = t1;
     }
     int nkeypoints = 0;
     for (int level = 0; level < t.nlevels; ++level) nkeypoints += (int)e.levelKps[level].size();
@@ -706,7 +719,9 @@ int orbo_extract(void* h, const uint8_t* img, int rows, int cols, size_t step, i
         if (v.empty()) continue;
         Level& L = e.pyr[level];
         L.blurred.resize((size_t)L.w * L.h);
+        t0 = now_ms();
         gaussian_blur7(L.interior(), L.w, L.h, L.step, L.blurred.data(), L.w);
+        t1 = now_ms(); e.stage_ms[3] += t1 - t0; t0 = t1;
         e.levelDesc[level].resize(v.size() * 32);
         for (size_t i = 0; i < v.size(); ++i)
             orb_descriptor(L.blurred.data(), L.w, cvRoundF(v[i].x), cvRoundF(v[i].y), v[i].angle, &e.levelDesc[level][i * 32]);
@@ -720,9 +735,17 @@ int orbo_extract(void* h, const uint8_t* img, int rows, int cols, size_t step, i
             kps[dst] = kp;
             memcpy(desc + (size_t)dst * 32, &e.levelDesc[level][i * 32], 32);
         }
+        t1 = now_ms(); e.stage_ms[4] += t1 - t0;
     }
     *n_mono = monoIndex;
     return 0;
+}
+
+// accumulated wall time per stage (ms) since creation / the last reset: pyramid, FAST, octree + orientation, blur, descriptors
+void orbo_stage_times(void* h, double* ms5, int reset)
+{
+    Extractor& e = *(Extractor*)h;
+    for (int i = 0; i < 5; ++i) { ms5[i] = e.stage_ms[i]; if (reset) e.stage_ms[i] = 0; }
 }
 
 int orbo_level_size(void* h, int level, int* w, int* hh)

@@ -396,6 +396,14 @@ class OracleExtractor:
         assert rc == 0, rc
         return kps[:n.value].copy(), desc[:n.value].copy(), nm.value
 
+    def stage_times(self, reset=True):
+        """Accumulated wall ms per stage of this extractor's calls: pyramid, FAST, octree + orientation, blur, descriptors."""
+        ms = np.zeros(5, np.float64)
+        self.o.lib.orbo_stage_times.argtypes = [_vp, _vp, C.c_int]
+        self.o.lib.orbo_stage_times.restype = None
+        self.o.lib.orbo_stage_times(self.h, _ptr(ms), int(reset))
+        return dict(zip(("pyramid", "fast", "octree_orient", "blur", "describe"), ms.tolist()))
+
     def level_size(self, level):
         w = C.c_int(0); h = C.c_int(0)
         self.o.lib.orbo_level_size(self.h, level, C.byref(w), C.byref(h))
