@@ -275,3 +275,58 @@ def test_batched_distinctive_descriptors_vs_oracle_and_reference(oracle):
         assert orbx.distinctive_descriptor(descs[p]) == exp
         if ref is not None and p < 40:
             assert ref.distinctive_descriptor(descs[p]) == exp
+
+
+def test_left_right_extractors_on_two_host_threads(oracle):
+    """The reference runs the left and the right extractor on two std::threads (src/Frame.cc:124-127): two handles, two host
+    threads, 150 frames each through the captured forked graph, different shapes per side, every result equal to the
+    single-threaded answer of a third handle (and a sample to the oracle)."""
+    shapes = [(752, 480, 1200), (640, 400, 900)]
+    frames = [[synth.image(100 * t + i, c, r) for i in range(6)] for t, (c, r, _) in enumerate(shapes)]
+    want = []
+    for t, (c, r, nf) in enumerate(shapes):
+        ex = orbx.ORBextractor(nf, 1.2, 8, 20, 7)
+        want.append([ex(im, None, (0, 1000) if t else (0, 0)) for im in frames[t]])
+    errors = []
+
+    def worker(t):
+        try:
+            c, r, nf = shapes[t]
+            ex = orbx.ORBextractor(nf, 1.2, 8, 20, 7)
+            for it in range(150):
+                k = it % 6
+                nm, kp, d = ex(frames[t][k], None, (0, 1000) if t else (0, 0))
+                w = want[t][k]
+                if nm != w[0] or kp.tobytes() != w[1].tobytes() or not np.array_equal(d, w[2]):
+                    errors.append((t, it))
+                    return
+        except Exception as e:          # noqa: BLE001
+            errors.append((t, repr(e)))
+
+    ths = [threading.Thread(target=worker, args=(t,)) for t in range(2)]
+    for th in ths:
+        th.start()
+    for th in ths:
+        th.join()
+    assert not errors, errors
+    oex = oracle.extractor(1200, 1.2, 8, 20, 7)
+    ok, od, onm = oex.extract(frames[0][0], (0, 0))
+    assert want[0][0][0] == onm and np.array_equal(want[0][0][1]["x"], ok["x"]) and np.array_equal(want[0][0][2], od)
+
+
+@pytest.mark.parametrize("lapping", [(0, 1000), (300, 500), (0, 0)])
+def test_lapping_area_in_batches_and_single_frames_agree(oracle, lapping):
+    """The packing is fused into the descriptor kernel for a few frames when the lapping area decides the row (all / none) and
+    is a separate kernel otherwise and for batches: the three paths must agree with each other and with the oracle."""
+    imgs = np.stack([synth.image(300 + f, 752, 480) for f in range(9)])
+    single = orbx.ORBextractor(1000, 1.2, 8, 20, 7)
+    batch = orbx.ORBextractor(1000, 1.2, 8, 20, 7)
+    nm, n, kps, desc = batch.extract_batch(imgs, lapping)
+    oex = oracle.extractor(1000, 1.2, 8, 20, 7)
+    for f in range(9):
+        m1, k1, d1 = single(imgs[f], None, lapping)
+        assert int(nm[f]) == m1 and int(n[f]) == len(k1)
+        assert kps[f, :n[f]].tobytes() == k1.tobytes() and np.array_equal(desc[f, :n[f]], d1)
+        if f < 2:
+            ok, od, onm = oex.extract(imgs[f], lapping)
+            assert m1 == onm and np.array_equal(k1["x"], ok["x"]) and np.array_equal(k1["y"], ok["y"]) and np.array_equal(d1, od)

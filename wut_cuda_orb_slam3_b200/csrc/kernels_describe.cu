@@ -541,17 +541,18 @@ cudaError_t launch_blur(const FrameGeom& fg, const Workspace& ws, int n_frames, 
         for (int l = 0; l < fg.nlevels; ++l) ipf += ((fg.L[l].w + 127) / 128) * ((fg.L[l].h + 31) / 32);
         const long long total = (long long)ipf * n_frames;
         if (total > 0 && total < (1LL << 31)) {
-            static int n_sm = 0;
-            static bool attr_set = false;
+            static int n_sm_dev[64] = {0};               // per device (a process may drive several GPUs)
             const int smem = kBpWarps * kBpStages * kBpStageBytes;
-            if (!attr_set) {
-                int dev = 0;
-                cudaGetDevice(&dev);
-                cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+            int dev = 0;
+            cudaGetDevice(&dev);
+            if (n_sm_dev[dev & 63] == 0) {
+                int n = 0;
+                cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
                 cudaError_t e = cudaFuncSetAttribute(blur_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
                 if (e != cudaSuccess) return e;
-                attr_set = true;
+                n_sm_dev[dev & 63] = n > 0 ? n : 148;
             }
+            const int n_sm = n_sm_dev[dev & 63];
             const int ctas = (int)std::min<long long>((total + kBpWarps - 1) / kBpWarps, (long long)n_sm * 9);
             blur_pipe_kernel<<<ctas, 32 * kBpWarps, smem, st>>>(fg, ws, ipf, (int)total);
             count_launch();

@@ -564,11 +564,13 @@ template <int PA>
 static cudaError_t launch_fast_warp(const FrameGeom& fg, const Workspace& ws, int n_frames, const WarpLaunch& wlc, cudaStream_t st)
 {
     const size_t smem = (size_t)warp_smem(wlc.rows_alloc, PA, wlc.list_cap).total * kWarpsPerCta;
-    static size_t configured = 0;       // per instantiation; grows monotonically (benign race: the attribute is idempotent)
-    if (smem > configured) {
+    static size_t configured[64] = {0};  // per instantiation and device; grows monotonically (benign race: the attribute is idempotent)
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (smem > configured[dev & 63]) {
         cudaError_t e = cudaFuncSetAttribute(fast_cells_warp_kernel<PA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        configured = smem;
+        configured[dev & 63] = smem;
     }
     dim3 grid((wlc.cell_hi - wlc.cell_lo + kWarpsPerCta - 1) / kWarpsPerCta, n_frames);
     fast_cells_warp_kernel<PA><<<grid, 32 * kWarpsPerCta, smem, st>>>(fg, ws, wlc);
