@@ -23,17 +23,18 @@ def run(n_cases, seed0):
       ini, mn = int(rng.integers(10, 40)), int(rng.integers(3, 10))
       seed = int(rng.integers(0, 1 << 30))
       nb = int(rng.choice([1, 1, 9, 17]))
+      lap = [(0, 0), (0, 1000), (cols // 3, 2 * cols // 3)][int(rng.integers(0, 3))]     # stereo / mono / fisheye-style lapping areas
       imgs = np.stack([synth.image(seed + f, cols, rows) for f in range(nb)])
       ex = orbx.ORBextractor(nf, sf, nl, ini, mn)
       oex = o.extractor(nf, sf, nl, ini, mn)
       if nb == 1:
-          nm, kps, desc = ex(imgs[0])
+          nm, kps, desc = ex(imgs[0], None, lap)
           res = [(nm, kps, desc)]
       else:
-          nmv, nv, kb, db = ex.extract_batch(imgs)
+          nmv, nv, kb, db = ex.extract_batch(imgs, lap)
           res = [(int(nmv[f]), kb[f][:nv[f]], db[f][:nv[f]]) for f in range(nb)]
       for f in range(nb):
-          ko, do, nmo = oex.extract(imgs[f], (0, 0))
+          ko, do, nmo = oex.extract(imgs[f], lap)
           nm, kps, desc = res[f]
           ok = nm == nmo and len(kps) == len(ko)
           if ok:
@@ -43,7 +44,7 @@ def run(n_cases, seed0):
               ok = ok and dang.max(initial=0) <= 1e-3 and (len(desc) == 0 or (desc == do).all(axis=1).mean() >= 0.995)
           if not ok:
               bad += 1
-              print("MISMATCH case", case, dict(cols=cols, rows=rows, nf=nf, nl=nl, sf=sf, ini=ini, mn=mn, seed=seed, nb=nb, frame=f), flush=True)
+              print("MISMATCH case", case, dict(cols=cols, rows=rows, nf=nf, nl=nl, sf=sf, ini=ini, mn=mn, seed=seed, nb=nb, lap=lap, frame=f), flush=True)
       ex.close()
   print("fuzz: %d cases, %d mismatching frames (env %s)" % (n_cases, bad, {k: v for k, v in os.environ.items() if k.startswith("ORBX_")}))
   return bad
