@@ -419,6 +419,15 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta) fast_cells_warp_kernel(cons
     }
     __syncwarp();
 
+    // The two thresholds are two passes over the staged cell, exactly as the reference runs them (src/ORBextractor.cc:908-925):
+    // FAST at iniThFAST and, only if that yields no keypoint, FAST at minThFAST.  Three quarters of the cells of a textured
+    // frame stop after the first pass, whose pre-test lets a quarter as many pixels through as the minThFAST one (11 % against
+    // 42 % over the levels of the synthetic frames) — the score, the NMS and the list handling shrink with it.  (Round 1
+    // scored everything once at minThFAST and selected afterwards: the score does not depend on the threshold.)  A second pass
+    // starts from a clean plane (the first pass's score bytes are cleared) and recomputes the same values for a superset.
+    int ns = 0;
+#pragma unroll 1
+    for (int th = iniTh;; th = minTh) {
     // 2. pre-test on the 8 even circle points, FOUR pixels (two u16x2 pairs at x, x+2; x a multiple of 4) per lane: every
     //    9-arc contains one point of each opposite pair, so a corner needs max_p min(r_a, r_b) < v - t (bright) or
     //    min_p max(r_a, r_b) > v + t (dark).  Survivors are ballot-compacted into `list` (plane positions; order irrelevant).
@@ -429,7 +438,7 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta) fast_cells_warp_kernel(cons
         const int nItems = eh * nQ;
         const uint32_t magic = 0xFFFFFFFFu / (uint32_t)nQ + 1u; // exact floor(i / nQ) for i < 2^16 (nQ >= 2)
         // per half: 0x200 + v - M1 - t (bright) and 0x200 + M2 - v - t (dark) never borrow across halves: plain 32-bit adds
-        const uint32_t K = 0x02000200u - (uint32_t)minTh * 0x00010001u;
+        const uint32_t K = 0x02000200u - (uint32_t)th * 0x00010001u;
         uint32_t wl = list_s;
         const uint32_t ltmask = (1u << lane) - 1u;
         for (int i0 = 0; i0 < nItems; i0 += 32) {
@@ -494,15 +503,17 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta) fast_cells_warp_kernel(cons
         const uint32_t pos1 = two ? lds_u16(list_s + 2 * (i + 32)) : pos0;
         const int s0 = fast_score16<PA>(A_s + pos0 * 2);
         const int s1 = fast_score16<PA>(A_s + pos1 * 2);
-        if (s0 >= minTh) sts_u8(A_s + pos0 * 2 + 1, (uint32_t)s0);
-        if (two && s1 >= minTh) sts_u8(A_s + pos1 * 2 + 1, (uint32_t)s1);
+        if (s0 >= th) sts_u8(A_s + pos0 * 2 + 1, (uint32_t)s0);
+        if (two && s1 >= th) sts_u8(A_s + pos1 * 2 + 1, (uint32_t)s1);
     }
     __syncwarp();
 
     // 4. 3x3 strict NMS inside the cell (pixels outside the evaluated region keep score 0 = cv::FAST's zeroed buffer).  The
     //    list is sorted by plane position (the pre-test compacts lane-major, lanes walk the cell row-major), so a ballot
-    //    compaction of the survivors IN PLACE keeps (y, x) order: no bitmaps, no atomics.  nh counts the survivors >= iniTh.
-    int ns = 0, nh = 0;
+    //    compaction of the survivors IN PLACE keeps (y, x) order: no bitmaps, no atomics.  Only scores >= th count: a pixel
+    //    scored in the first pass that this pass's pre-test does not reach is not in the list, and every listed pixel's byte
+    //    holds either 0 or a score >= the threshold of the pass that wrote it (>= th in both passes for listed pixels).
+    ns = 0;
     {
         const uint32_t ltmask = (1u << lane) - 1u;
         for (int base = 0; base < nl; base += 32) {
@@ -524,16 +535,22 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta) fast_cells_warp_kernel(cons
                 keep = s > max(max(max(n0, n1), max(n2, n3)), max(max(n4, n5), max(n6, n7)));
             }
             const uint32_t mk = __ballot_sync(0xffffffffu, keep);
-            nh += __popc(__ballot_sync(0xffffffffu, keep && (int)s >= iniTh));
             // every entry of this iteration is in registers and ns <= base: the in-place write cannot hit an unread entry
             if (keep) sts_u16(list_s + 2 * (ns + __popc(mk & ltmask)), pos);
             ns += __popc(mk);
         }
     }
     __syncwarp();
+    if (ns > 0 || th == minTh) break;          // src/ORBextractor.cc:918: retry with minThFAST only if the cell stayed empty
+    // The cell stayed empty although the pass may have stored scores (equal maxima next to each other suppress one another):
+    // the pre-test of the next pass reads the plane as u16 pixels, so the score bytes go back to 0 first.  ns == 0: the in-place
+    // compaction wrote nothing, the list still holds all nl entries of this pass.
+    for (int i = lane; i < nl; i += 32) sts_u8(A_s + lds_u16(list_s + 2 * i) * 2 + 1, 0u);
+    __syncwarp();
+    }
 
-    // 5. per-cell threshold selection (ini if it yields anything, else min) and ordered output
-    const int total = nh > 0 ? nh : ns;
+    // 5. ordered output of the pass that produced keypoints
+    const int total = ns;
     if (lane == 0) *count_out = total;
     if (total == 0) return;
     uint32_t* out = ws.cand + (size_t)frame * fg.cand_frame_stride + g.cand_off + (size_t)cell * g.cell_cap;
@@ -548,7 +565,7 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta) fast_cells_warp_kernel(cons
             if (i < ns) {
                 pos = lds_u16(list_s + 2 * i);
                 sc8 = lds_u8(A_s + pos * 2 + 1);
-                sel = nh == 0 || (int)sc8 >= iniTh;
+                sel = true;
             }
             const uint32_t mk = __ballot_sync(0xffffffffu, sel);
             if (sel) {
