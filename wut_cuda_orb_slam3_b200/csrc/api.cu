@@ -185,6 +185,7 @@ struct orbx_extractor {
     // host mirror of the bordered pyramid (std::vector<cv::Mat> mvImagePyramid of the reference, read on the host by
     // Frame::ComputeStereoMatches): pinned storage, filled level by level on a copy branch while FAST / octree run
     bool mirror = false;
+    bool mirror_valid = false;     // the mirror holds the pyramid of the LAST call (single-frame calls fill it, batch calls do not)
     uint8_t* h_mirror = nullptr; size_t h_mirror_bytes = 0;
     size_t mirror_off[ORBX_MAX_LEVELS] = {0};
     cudaStream_t mirror_stream = nullptr;
@@ -272,6 +273,7 @@ static int configure(orbx_extractor* ex, int rows, int cols)
     // configure() first and probes / stereo matching check geom_valid), never half-built with the previous shape's flag set.
     ex->geom_valid = false;
     ex->last_frames = 0;
+    ex->mirror_valid = false;
     wait_user_work(ex);
     if (ex->graph_exec) { cudaGraphExecDestroy(ex->graph_exec); ex->graph_exec = nullptr; }
     for (int i = 0; i < orbx_extractor::kSlots; ++i) {
@@ -559,6 +561,7 @@ static int run_chunk(orbx_extractor* ex, Slot& s, const uint8_t* d_images, size_
 {
     const FrameGeom& fg = ex->fg;
     int rc;
+    ex->mirror_valid = false;          // only the forked single-frame pipeline sends the levels home
     if ((rc = prof_mark(ex, st))) return rc;
     CU(launch_pyramid(fg, s.ws, d_images, frame_stride, pitch, frames, st));
     if ((rc = prof_mark(ex, st))) return rc;
@@ -611,6 +614,29 @@ static int run_single_forked(orbx_extractor* ex, Slot& s, const uint8_t* d_image
     CU(launch_orient_describe(fg, s.ws, 1, st, lap0, lap1, d_kps, d_desc, capacity, d_n, d_nm, &fused));
     if (!fused) CU(launch_pack(fg, s.ws, 1, lap0, lap1, d_kps, d_desc, capacity, d_n, d_nm, st));
     if (ex->mirror) { CU(cudaEventRecord(ex->ev_mirror, ex->mirror_stream)); CU(cudaStreamWaitEvent(st, ex->ev_mirror, 0)); }
+    ex->mirror_valid = ex->mirror;
+    return ORBX_OK;
+}
+
+// Pinned host storage + copy stream of the mvImagePyramid mirror for the current geometry (no-op when the mirror is off).
+static int ensure_mirror(orbx_extractor* ex, cudaStream_t st)
+{
+    if (ex->mirror) {
+        if (!ex->mirror_stream) CU(cudaStreamCreateWithFlags(&ex->mirror_stream, cudaStreamNonBlocking));
+        if (!ex->ev_mirror) CU(cudaEventCreateWithFlags(&ex->ev_mirror, cudaEventDisableTiming));
+        size_t need = 0;
+        for (int l = 0; l < ex->fg.nlevels; ++l) {
+            ex->mirror_off[l] = need;
+            need += align_up(((size_t)ex->fg.L[l].w + 2 * kEdge) * (size_t)ex->fg.L[l].rows_alloc, 256);
+        }
+        if (ex->h_mirror_bytes < need) {
+            CU(cudaStreamSynchronize(st));
+            if (ex->h_mirror) cudaFreeHost(ex->h_mirror);
+            ex->h_mirror = nullptr; ex->h_mirror_bytes = 0;
+            CU(cudaMallocHost((void**)&ex->h_mirror, need));
+            ex->h_mirror_bytes = need;
+        }
+    }
     return ORBX_OK;
 }
 
@@ -628,22 +654,7 @@ static int enqueue_single(orbx_extractor* ex, const uint8_t* image, int rows, in
     if (s.d_in_bytes < dframe || s.out_cap < (size_t)capacity || s.out_frames < 1) CU(cudaStreamSynchronize(s.stream));
     if ((rc = ensure_host_staging(s, dframe, 1, capacity))) return rc;
     cudaStream_t st = s.stream;
-    if (ex->mirror) {
-        if (!ex->mirror_stream) CU(cudaStreamCreateWithFlags(&ex->mirror_stream, cudaStreamNonBlocking));
-        if (!ex->ev_mirror) CU(cudaEventCreateWithFlags(&ex->ev_mirror, cudaEventDisableTiming));
-        size_t need = 0;
-        for (int l = 0; l < ex->fg.nlevels; ++l) {
-            ex->mirror_off[l] = need;
-            need += align_up(((size_t)ex->fg.L[l].w + 2 * kEdge) * (size_t)ex->fg.L[l].rows_alloc, 256);
-        }
-        if (ex->h_mirror_bytes < need) {
-            CU(cudaStreamSynchronize(st));
-            if (ex->h_mirror) cudaFreeHost(ex->h_mirror);
-            ex->h_mirror = nullptr; ex->h_mirror_bytes = 0;
-            CU(cudaMallocHost((void**)&ex->h_mirror, need));
-            ex->h_mirror_bytes = need;
-        }
-    }
+    if ((rc = ensure_mirror(ex, st))) return rc;
     if (step == (size_t)cols) CU(cudaMemcpyAsync(s.d_in, image, dframe, cudaMemcpyHostToDevice, st));
     else CU(cudaMemcpy2DAsync(s.d_in, dpitch, image, step, cols, rows, cudaMemcpyHostToDevice, st));
     static const bool graphs = !(getenv("ORBX_GRAPH") && atoi(getenv("ORBX_GRAPH")) == 0);
@@ -677,6 +688,7 @@ static int enqueue_single(orbx_extractor* ex, const uint8_t* image, int rows, in
         count_launch(ex->graph_launches);
     } else if ((rc = body(st))) return rc;
     ex->last_frames = 1;
+    ex->mirror_valid = ex->mirror;     // (a graph replay does not pass through run_single_forked)
     return ORBX_OK;
 }
 
@@ -1059,8 +1071,8 @@ int orbx_set_pyramid_mirror(orbx_extractor* ex, int enable)
 
 int orbx_get_pyramid_mirror(orbx_extractor* ex, int level, const uint8_t** bordered, size_t* step, int* level_cols, int* level_rows)
 {
-    if (!ex || !ex->geom_valid || !ex->mirror || !ex->h_mirror || ex->last_frames < 1)
-        return fail(ORBX_ERR_INVALID_ARG, "no mirrored pyramid: enable orbx_set_pyramid_mirror before orbx_extract");
+    if (!ex || !ex->geom_valid || !ex->mirror || !ex->h_mirror || !ex->mirror_valid)
+        return fail(ORBX_ERR_INVALID_ARG, "no mirrored pyramid: enable orbx_set_pyramid_mirror before a single-frame orbx_extract");
     if (level < 0 || level >= ex->nlevels) return fail(ORBX_ERR_INVALID_ARG, "level out of range");
     const LevelGeom& g = ex->fg.L[level];
     if (bordered) *bordered = ex->h_mirror + ex->mirror_off[level];
@@ -1105,7 +1117,11 @@ int orbx_extract_color(orbx_extractor* ex, const uint8_t* image, int rows, int c
     }
     CU(cudaMemcpy2DAsync(s.d_color, cpitch, image, step, (size_t)cols * channels, rows, cudaMemcpyHostToDevice, s.stream));
     CU(launch_cvt_gray(s.d_color, cpitch, 0, channels, rgb, 1, rows, cols, s.d_in, gpitch, 0, s.stream));
-    if ((rc = run_chunk(ex, s, s.d_in, gpitch * rows, gpitch, 1, lap0, lap1, s.d_kps, s.d_desc, capacity, s.d_n, s.d_nm, s.stream))) return rc;
+    // same per-level fork / join as orbx_extract (launched eagerly: the colour staging buffer is not part of the captured graph)
+    if ((rc = ensure_mirror(ex, s.stream))) return rc;
+    if (ex->profiling) rc = run_chunk(ex, s, s.d_in, gpitch * rows, gpitch, 1, lap0, lap1, s.d_kps, s.d_desc, capacity, s.d_n, s.d_nm, s.stream);
+    else rc = run_single_forked(ex, s, s.d_in, gpitch, lap0, lap1, s.d_kps, s.d_desc, capacity, s.d_n, s.d_nm, s.stream);
+    if (rc) return rc;
     CU(cudaMemcpyAsync(keypoints, s.d_kps, sizeof(orbx_keypoint) * (size_t)capacity, cudaMemcpyDeviceToHost, s.stream));
     CU(cudaMemcpyAsync(descriptors, s.d_desc, (size_t)capacity * 32, cudaMemcpyDeviceToHost, s.stream));
     CU(cudaMemcpyAsync(n_out, s.d_n, sizeof(int), cudaMemcpyDeviceToHost, s.stream));
