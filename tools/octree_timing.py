@@ -18,3 +18,4 @@ for level in (0, 3, 7):
     print("level", level, "total cycles", tot, "= %.1f us @1.9GHz" % (tot / 1.9e3))
     for i, nme in enumerate(names):
         print("   %-14s %10d %s" % (nme, out[i], ("%.1f%%" % (100.0 * out[i] / tot)) if i < 7 else ""))
+    print("   first phase in detail (cycles): zero + cell counts %d, cell-offset scan %d, gather %d, bins %d, bin scan %d" % tuple(out[11:16]))

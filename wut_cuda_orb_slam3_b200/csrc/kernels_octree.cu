@@ -298,6 +298,8 @@ __global__ void __launch_bounds__(T, 1024 / T) octree_kernel(const __grid_consta
     long long* dbg = (ws.dbg && frame == 0 && level == ws.dbg_level && tid == 0) ? ws.dbg : nullptr;
     long long t_prev = dbg ? clock64() : 0;
 #define OCT_MARK(slot) do { if (dbg) { const long long t_now = clock64(); dbg[slot] += t_now - t_prev; t_prev = t_now; } } while (0)
+    long long t_fine = t_prev;          // finer split of the first phase (slots 11..15), independent of the slots above
+#define OCT_FINE(slot) do { if (dbg) { const long long t_now = clock64(); dbg[slot] += t_now - t_fine; t_fine = t_now; } } while (0)
     const int winW = g.w - 2 * kWinBorder, winH = g.h - 2 * kWinBorder;
 
     Smem S;
@@ -354,7 +356,9 @@ __global__ void __launch_bounds__(T, 1024 / T) octree_kernel(const __grid_consta
     for (int i = tid; i <= nb; i += T) S.bstart[i] = 0;
     for (int c = tid; c < ncells; c += T) coff[c] = __ldg(cell_count + c);
     __syncthreads();
+    OCT_FINE(11);
     const int n = block_exclusive_scan_raking<T>(coff, ncells, S.warp_tmp);
+    OCT_FINE(12);
     if (tid == 0) *out_ncand = n;
     if (n == 0) {
         if (tid == 0) *out_n = 0;
@@ -380,6 +384,7 @@ __global__ void __launch_bounds__(T, 1024 / T) octree_kernel(const __grid_consta
         }
     }
     __syncthreads();
+    OCT_FINE(13);
     // bins, dense over the keys (every lane busy).  Only the Dsort leading depths of the path are evaluated (the deeper bits
     // are needed by the rare splits below depth Dsort, which work them out on demand), once: binst carries the bin on.
     constexpr int KU = T >= 512 ? 1 : 4;          // keys per thread in flight
@@ -398,7 +403,9 @@ __global__ void __launch_bounds__(T, 1024 / T) octree_kernel(const __grid_consta
         }
     }
     __syncthreads();
+    OCT_FINE(14);
     block_exclusive_scan_raking<T>(S.bstart, nb, S.warp_tmp);
+    OCT_FINE(15);
     if (tid == 0) S.bstart[nb] = n;
     for (int i = tid; i < nb; i += T) S.cursor[i] = S.bstart[i];
     __syncthreads();
@@ -676,6 +683,7 @@ __global__ void __launch_bounds__(T, 1024 / T) octree_kernel(const __grid_consta
     OCT_MARK(6);
     if (dbg) dbg[9] = n;
 #undef OCT_MARK
+#undef OCT_FINE
 }
 
 cudaError_t octree_prepare()
