@@ -330,3 +330,26 @@ def test_lapping_area_in_batches_and_single_frames_agree(oracle, lapping):
         if f < 2:
             ok, od, onm = oex.extract(imgs[f], lapping)
             assert m1 == onm and np.array_equal(k1["x"], ok["x"]) and np.array_equal(k1["y"], ok["y"]) and np.array_equal(d1, od)
+
+
+@pytest.mark.parametrize("cols,rows,nlevels,scale", [(752, 480, 8, 1.2), (1241, 376, 8, 1.2), (640, 480, 5, 1.44), (333, 211, 6, 1.3),
+                                                     (1300, 100, 4, 1.2), (97, 83, 3, 1.15), (520, 390, 4, 1.5)])
+def test_batch_pyramid_streaming_kernel_is_bit_exact(oracle, cols, rows, nlevels, scale):
+    """ComputePyramid on batches (src/ORBextractor.cc:1309-1329) takes the warp-streaming resize kernel (bordered items, IDP.2A
+    horizontal pass): every byte of every bordered level of every frame equals the oracle's, and a single frame (tiled kernel)
+    gives the same bytes."""
+    F = 9
+    imgs = np.stack([synth.image(500 + f, cols, rows) for f in range(F)])
+    ex = orbx.ORBextractor(300, scale, nlevels, 20, 7, max_batch=F)
+    ex.extract_batch(imgs)
+    got = [[ex.pyramid_level(l, frame=f, with_border=True) for l in range(nlevels)] for f in (0, 4, F - 1)]
+    for k, f in enumerate((0, 4, F - 1)):
+        oex = oracle.extractor(300, scale, nlevels, 20, 7)
+        oex.extract(imgs[f], (0, 0))
+        for l in range(nlevels):
+            want = oex.pyramid_level(l, with_border=True)
+            assert got[k][l].shape == want.shape
+            assert np.array_equal(got[k][l], want), (f, l, np.argwhere(got[k][l] != want)[:4])
+    ex(imgs[4])
+    for l in range(nlevels):
+        assert np.array_equal(ex.pyramid_level(l, with_border=True), got[1][l]), l

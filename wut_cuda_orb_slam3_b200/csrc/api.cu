@@ -389,6 +389,26 @@ static int configure(orbx_extractor* ex, int rows, int cols)
         }
         fg.L[l].tma_box_w = (int)align_up((size_t)bw, 16);
         fg.L[l].tma_box_h = bh;
+        // the warp-streaming kernel (kernels_pyramid.cu: pyr_resize_pipe_kernel) works on the BORDERED level: items of 128 buffer
+        // columns (from column kXPad - kEdge - 1, word aligned) x 16 bordered rows; a border pixel takes the taps of its mirror
+        // image, so the window of an item at the rim is a little larger than 16 * scale rows
+        int rw = 0, rh = 0;
+        const int wb = d.w + 2 * kEdge, hb = d.h + 2 * kEdge;
+        for (int c0 = -1; c0 < wb; c0 += 128) {
+            int lo = INT_MAX, hi = 0;
+            for (int c = c0; c < c0 + 128; ++c) {
+                const uint2 e = xt[std::min(std::max(c, 0), wb - 1)];
+                lo = std::min(lo, (int)(e.x & 0xffff)); hi = std::max(hi, (int)(e.x & 0xffff));
+            }
+            rw = std::max(rw, hi + 2 - (lo & ~15));
+        }
+        for (int r0 = 0; r0 < hb; r0 += 16) {
+            int lo = INT_MAX, hi = 0;
+            for (int r = r0; r < std::min(r0 + 16, hb); ++r) { lo = std::min(lo, (int)(yt[r].x & 0xffff)); hi = std::max(hi, (int)(yt[r].x & 0xffff)); }
+            rh = std::max(rh, hi + 2 - lo);
+        }
+        fg.L[l].rp_box_w = (int)align_up((size_t)rw, 16);
+        fg.L[l].rp_box_h = rh;
     }
     fg.total_cells = cell_base;
     fg.kp_slots = kp_base;
@@ -453,10 +473,10 @@ static int ensure_slot(orbx_extractor* ex, Slot& s, int frames)
     if ((rc = dev_alloc(s, &s.ws.lvl_angle, (size_t)fg.kp_slots * frames))) return rc;
     if ((rc = dev_alloc(s, &s.ws.lvl_desc, (size_t)fg.kp_slots * frames * 32))) return rc;
     // TMA descriptors of the bordered pyramid levels (3-D: byte column, row, frame)
-    s.ws.tmap_resize = nullptr; s.ws.tmap_blur = nullptr;
+    s.ws.tmap_resize = nullptr; s.ws.tmap_blur = nullptr; s.ws.tmap_rpipe = nullptr;
     if (EncodeTiledFn enc = get_encode_tiled()) {
-        std::vector<CUtensorMap> maps(2 * kMaxLevels);
-        bool ok_resize = true, ok_blur = true;
+        std::vector<CUtensorMap> maps(3 * kMaxLevels);
+        bool ok_resize = true, ok_blur = true, ok_rpipe = true;
         for (int l = 0; l < fg.nlevels; ++l) {
             const LevelGeom& g = fg.L[l];
             const cuuint64_t dims[3] = {(cuuint64_t)g.pitch, (cuuint64_t)g.rows_alloc, (cuuint64_t)frames};
@@ -470,6 +490,13 @@ static int ensure_slot(orbx_extractor* ex, Slot& s, int frames)
                                  CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
                     ok_resize = false;
             }
+            if (l + 1 < fg.nlevels) {
+                const bool fits = g.rp_box_w >= 16 && g.rp_box_w <= 256 && g.rp_box_h > 0 && g.rp_box_h <= 256;
+                const cuuint32_t box[3] = {(cuuint32_t)std::max(g.rp_box_w, 16), (cuuint32_t)std::max(g.rp_box_h, 1), 1};
+                if (!fits || enc(&maps[2 * kMaxLevels + l], CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                 CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+                    ok_rpipe = false;
+            }
             const cuuint32_t bbox[3] = {160, 38, 1};
             if (enc(&maps[kMaxLevels + l], CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, base, dims, strides, bbox, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                     CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
@@ -481,6 +508,7 @@ static int ensure_slot(orbx_extractor* ex, Slot& s, int frames)
         static const bool no_tma = getenv("ORBX_NO_TMA") != nullptr;      // A/B switch for measurements
         if (ok_resize && !no_tma) s.ws.tmap_resize = d_maps;
         if (ok_blur && !no_tma) s.ws.tmap_blur = d_maps + kMaxLevels;
+        if (ok_rpipe && !no_tma) s.ws.tmap_rpipe = d_maps + 2 * kMaxLevels;
     }
     CU(cudaMemsetAsync(s.ws.pyr, 0, pyr + 256, s.stream));
     CU(cudaMemsetAsync(s.ws.lvl_n, 0, sizeof(int) * (size_t)fg.nlevels * frames, s.stream));

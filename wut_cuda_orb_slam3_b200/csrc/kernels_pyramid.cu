@@ -311,6 +311,130 @@ __global__ void __launch_bounds__(PT_THREADS, PT_MINB) pyr_resize_tiled_kernel(c
     resize_tile_passes<PT_H>(g, ws, src, hbuf, outt, ytl, xt, tid, tx, x0, y0, frame, tw, th, cbase, spitch, symin, nrows);
 }
 
+// ---- warp-streaming resize (the batch path) ------------------------------------------------------------------------------------
+// The tiled kernel above spends 44 lane-instructions per pixel: two byte gathers per horizontal sum, a u16 plane in shared memory
+// between the passes, a staged output tile, and byte-wise border mirrors on most tiles.  Here a WARP owns an item of 128 buffer
+// columns x 16 rows of the BORDERED level (the resize tables are indexed by bordered coordinates, so a border pixel is an ordinary
+// output whose taps are those of its mirror image: no mirror pass), a lane owns 4 adjacent columns = one aligned 32-bit word per row:
+//   * source window of the item: one TMA box (cp.async.bulk.tensor.3d -> mbarrier) into the warp's own shared-memory stage; warps
+//     are persistent and never meet at a CTA barrier (the blur kernel's scheme: the round trip of a warp's copy hides behind the
+//     other ~30 resident warps);
+//   * horizontal pass of one source row: the lane's 8 taps lie in two aligned 8-byte windows (outputs 0-1, outputs 2-3; fixed for
+//     the item): 4 LDS.32, one PRMT per pair with a per-lane selector puts (s0, s0+1, s1, s1+1) in one word, and one IDP.2A per
+//     output forms a0*s[x] + a1*s[x+1] with the table's (a0 | a1 << 16) word as it is;
+//   * vertical pass: the sums of the last two source rows stay in registers (output rows walk the source rows in order; a jump —
+//     the mirrored rows of the border — recomputes both), ((b0*(r0>>4))>>16) + ((b1*(r1>>4))>>16) + 2 is two IMAD.HI with the
+//     addend riding along, the four pixels leave as one coalesced 32-bit store.
+// Same integer arithmetic as the kernels above, so the result is bit-identical (tests/test_gpu_parity.py pyramid probes).
+constexpr int kRpWarps = 4;
+constexpr int kRpRows = 16;                         // bordered output rows per item
+constexpr int kRpCol0 = kXPad - kEdge - 1;          // first buffer column of column tile 0 (12: word aligned; bordered column -1)
+
+__global__ void __launch_bounds__(32 * kRpWarps) pyr_resize_pipe_kernel(const __grid_constant__ FrameGeom fg, Workspace ws, int level,
+                                                                        int stage_bytes, int ntx, int nstrips, int total_items)
+{
+    extern __shared__ __align__(128) uint8_t rp_smem[];
+    __shared__ __align__(8) uint64_t bars[kRpWarps];
+    __shared__ uint2 ysched[kRpWarps][kRpRows];
+    const LevelGeom& g = fg.L[level];
+    const LevelGeom& p = fg.L[level - 1];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint8_t* stage = rp_smem + (size_t)warp * stage_bytes;
+    const uint32_t stage_s = (uint32_t)__cvta_generic_to_shared(stage);
+    if (lane == 0) mbar_init(&bars[warp], 1);
+    __syncwarp();
+    const int gw = blockIdx.x * kRpWarps + warp, nw = gridDim.x * kRpWarps;
+    const int bw = p.rp_box_w, bh = p.rp_box_h;
+    const int wb = g.w + 2 * kEdge, hb = g.h + 2 * kEdge;
+    const int per_frame = ntx * nstrips;
+    uint32_t phase = 0;
+    for (int item = gw; item < total_items; item += nw) {
+        const int frame = item / per_frame;
+        const int t = item - frame * per_frame;
+        const int strip = t / ntx, ct = t - strip * ntx;
+        // columns: bordered column of the lane's first pixel (buffer column - 13); entries clamped into the table
+        const int bc0 = ct * 128 + 4 * lane - 1;
+        uint2 xt[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) xt[j] = __ldg(g.xtab + min(max(bc0 + j, 0), wb - 1));
+        int c[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) c[j] = (int)(xt[j].x & 0xffff);
+        const int cbase = __reduce_min_sync(0xffffffffu, min(min(c[0], c[1]), min(c[2], c[3]))) & ~15;    // 16-byte aligned box start
+        // rows
+        const int br0 = strip * kRpRows;
+        const int nrows = min(kRpRows, hb - br0);
+        const uint2 yt = __ldg(g.ytab + min(br0 + (lane & (kRpRows - 1)), hb - 1));
+        const int symin = __reduce_min_sync(0xffffffffu, (int)(yt.x & 0xffff));
+        if (lane < kRpRows) ysched[warp][lane] = make_uint2((yt.x & 0xffff) - (uint32_t)symin, yt.y);
+        if (lane == 0) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            mbar_expect_tx(&bars[warp], (uint32_t)(bw * bh));
+            tma_load_3d(stage, ws.tmap_rpipe + (level - 1), &bars[warp], kXPad + cbase, kEdge + symin, frame);
+        }
+        __syncwarp();
+        // the two 8-byte windows of the lane and the selectors that pull (s0, s0+1, s1, s1+1) out of them
+        uint32_t aA, aB, selA, selB;
+        {
+            const int mA = min(c[0], c[1]) - cbase, mB = min(c[2], c[3]) - cbase;
+            const int qA = mA & ~3, qB = mB & ~3;
+            const int i0 = c[0] - cbase - qA, i1 = c[1] - cbase - qA, i2 = c[2] - cbase - qB, i3 = c[3] - cbase - qB;
+            selA = (uint32_t)(i0 | ((i0 + 1) << 4) | (i1 << 8) | ((i1 + 1) << 12));
+            selB = (uint32_t)(i2 | ((i2 + 1) << 4) | (i3 << 8) | ((i3 + 1) << 12));
+            aA = stage_s + qA; aB = stage_s + qB;
+        }
+        // word of the lane in the bordered row; bytes outside the bordered level stay 0 (padding)
+        const int wcol = kRpCol0 + ct * 128 + 4 * lane;
+        uint32_t keep = 0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) keep |= (bc0 + j >= 0 && bc0 + j < wb) ? (0xffu << (8 * j)) : 0u;
+        const bool store = keep != 0;
+        uint8_t* out = ws.pyr + g.pyr_off + (size_t)frame * g.pyr_frame_stride + (size_t)br0 * g.pitch + wcol;
+        const int pitch = g.pitch;
+        auto hrow = [&](int r, uint32_t h[4]) {
+            uint32_t w0, w1, w2, w3;
+            const uint32_t ra = aA + r * bw, rb = aB + r * bw;
+            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w0) : "r"(ra));
+            asm volatile("ld.shared.u32 %0, [%1+4];" : "=r"(w1) : "r"(ra));
+            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w2) : "r"(rb));
+            asm volatile("ld.shared.u32 %0, [%1+4];" : "=r"(w3) : "r"(rb));
+            const uint32_t pa = __byte_perm(w0, w1, selA), pb = __byte_perm(w2, w3, selB);
+            h[0] = __dp2a_lo(xt[0].y, pa, 0u) >> 4; h[1] = __dp2a_hi(xt[1].y, pa, 0u) >> 4;
+            h[2] = __dp2a_lo(xt[2].y, pb, 0u) >> 4; h[3] = __dp2a_hi(xt[3].y, pb, 0u) >> 4;
+        };
+        mbar_wait(&bars[warp], phase);
+        phase ^= 1u;
+        uint32_t hp[4] = {0, 0, 0, 0}, hc[4] = {0, 0, 0, 0};
+        int hr = -4;                                   // source row (relative to the box) held in hc; hp holds hr - 1
+        for (int i = 0; i < nrows; ++i) {
+            const uint2 ys = ysched[warp][i];          // {first source row - symin, b0 | b1 << 16}; warp-uniform
+            const int rel = (int)ys.x;
+            if (rel != hr - 1) {
+                if (rel == hr) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) hp[j] = hc[j];
+                    hrow(hr + 1, hc);
+                    hr += 1;
+                } else {
+                    hrow(rel, hp);
+                    hrow(rel + 1, hc);
+                    hr = rel + 1;
+                }
+            }
+            const uint32_t b0 = ys.y << 16, b1 = ys.y & 0xffff0000u;
+            uint32_t u[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) u[j] = __umulhi(b1, hc[j]) + (__umulhi(b0, hp[j]) + 2u);     // <= 1022
+            // (u >> 2) of four pixels -> one word: pack pairs as u16x2, shift both halves at once, pick the low bytes
+            const uint32_t x01 = __byte_perm(u[0], u[1], 0x5410) >> 2, x23 = __byte_perm(u[2], u[3], 0x5410) >> 2;
+            const uint32_t o = __byte_perm(x01, x23, 0x6420) & keep;
+            if (store) *reinterpret_cast<uint32_t*>(out) = o;
+            out += pitch;
+        }
+        __syncwarp();                                  // every lane is done with the stage before lane 0 refills it
+    }
+}
+
 // ---- ComputePyramid as ONE launch -------------------------------------------------------------------------------------------
 // All levels in one cooperative kernel: the CTAs walk the 128 x 32 tiles of level 0 (copy + border), meet at a grid-wide
 // barrier, walk the tiles of level 1 (source windows of level 0 staged by TMA: cp.async.bulk.tensor + mbarrier, one mbarrier per
@@ -438,6 +562,40 @@ static bool launch_pyramid_multilevel(const FrameGeom& fg, const Workspace& ws, 
     return true;
 }
 
+// One level with the warp-streaming kernel; false = not applicable (the caller falls back to the tiled kernel).
+static bool launch_resize_pipe(const FrameGeom& fg, const Workspace& ws, int level, int n_frames, cudaStream_t st)
+{
+    const LevelGeom& g = fg.L[level];
+    const LevelGeom& p = fg.L[level - 1];
+    if (p.rp_box_w < 16 || p.rp_box_h < 2) return false;
+    // + 8: a lane's second 4-byte word may start at the end of the last staged row (its bytes are then not selected)
+    const int stage_bytes = (p.rp_box_w * p.rp_box_h + 8 + 127) & ~127;
+    const int smem = kRpWarps * stage_bytes;
+    if (smem > 64 * 1024) return false;
+    const int ntx = (g.w + 2 * kEdge + 1 + 127) / 128, nstrips = (g.h + 2 * kEdge + kRpRows - 1) / kRpRows;
+    const long long total = (long long)ntx * nstrips * n_frames;
+    if (total <= 0 || total >= (1LL << 31)) return false;
+    static int n_sm_dev[64] = {0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (n_sm_dev[dev & 63] == 0) {
+        int n = 0;
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        if (cudaFuncSetAttribute(pyr_resize_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024) != cudaSuccess) {
+            cudaGetLastError();
+            n_sm_dev[dev & 63] = -1;
+        } else {
+            n_sm_dev[dev & 63] = n > 0 ? n : 148;
+        }
+    }
+    if (n_sm_dev[dev & 63] < 0) return false;
+    static const char* per_env = getenv("ORBX_PYR_PIPE_CTAS");
+    int per_sm = std::min(per_env ? atoi(per_env) : 9, std::max(1, (200 * 1024) / (smem + 1024)));
+    const int ctas = (int)std::min<long long>((total + kRpWarps - 1) / kRpWarps, (long long)n_sm_dev[dev & 63] * per_sm);
+    pyr_resize_pipe_kernel<<<ctas, 32 * kRpWarps, smem, st>>>(fg, ws, level, stage_bytes, ntx, nstrips, (int)total);
+    return true;
+}
+
 // Levels [level_lo, level_hi) (level_hi <= 0: all); level l >= 1 reads level l - 1, which must be complete on `st`.
 cudaError_t launch_pyramid(const FrameGeom& fg, const Workspace& ws, const uint8_t* d_images, size_t frame_stride,
                            size_t pitch, int n_frames, cudaStream_t st, int level_lo, int level_hi)
@@ -468,7 +626,11 @@ cudaError_t launch_pyramid(const FrameGeom& fg, const Workspace& ws, const uint8
             // source footprint of a tile must fit the staged window: scale <= 1.5 -> 128x32 tiles, <= 2 -> 128x16 tiles
             const bool s15 = 2LL * p.w <= 3LL * g.w && 2LL * p.h <= 3LL * g.h;
             const bool s20 = (long long)p.w <= 2LL * g.w && (long long)p.h <= 2LL * g.h;
-            if (big && s15) {
+            static const char* rp_env = getenv("ORBX_PYR_PIPE");               // A/B switch: 0 = tiled kernel for batches too
+            const bool want_pipe = rp_env ? atoi(rp_env) != 0 : n_frames >= 8;
+            if (big && s15 && !g.area2x && want_pipe && ws.tmap_rpipe && launch_resize_pipe(fg, ws, l, n_frames, st)) {
+                // launched
+            } else if (big && s15) {
                 dim3 tgrid((g.w + PT_W - 1) / PT_W, (g.h + 31) / 32, n_frames);
                 pyr_resize_tiled_kernel<32, 52, 224><<<tgrid, PT_THREADS, 0, st>>>(fg, ws, l);
             } else if (big && s20) {

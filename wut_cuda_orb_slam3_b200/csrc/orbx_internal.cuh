@@ -48,6 +48,7 @@ struct LevelGeom {
     float inv_scale;          // mvInvScaleFactor[level]
     float kp_size;            // (float)(int)(31*scale)
     int tma_box_w, tma_box_h; // box of THIS level's resize-source descriptor (when it is the source of level+1)
+    int rp_box_w, rp_box_h;   // the same for the warp-streaming resize kernel (128-column x 16-row items of the BORDERED level + 1)
 };
 
 struct FrameGeom {
@@ -77,6 +78,7 @@ struct Workspace {
     long long* dbg;           // optional octree phase timing (nullptr in production)
     const CUtensorMap* tmap_resize;   // [nlevels] TMA descriptors of the pyramid levels, box = resize source window (or nullptr)
     const CUtensorMap* tmap_blur;     // [nlevels] TMA descriptors of the pyramid levels, box = blur input tile (or nullptr)
+    const CUtensorMap* tmap_rpipe;    // [nlevels] TMA descriptors of the pyramid levels, box = source window of pyr_resize_pipe_kernel (or nullptr)
     int dbg_level;
 };
 
