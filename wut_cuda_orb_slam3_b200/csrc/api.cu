@@ -374,6 +374,8 @@ static int configure(orbx_extractor* ex, int rows, int cols)
         }
     }
     // TMA box of level l when it is the SOURCE of level l+1 (128x32 output tiles): the largest source window any tile needs
+    std::vector<uint2> rp_tables;
+    std::vector<size_t> rp_x_off(ex->nlevels + 1, 0), rp_y_off(ex->nlevels + 1, 0);
     for (int l = 0; l + 1 < ex->nlevels; ++l) {
         const LevelGeom& d = fg.L[l + 1];
         const uint2* xt = tables.data() + xtab_off[l + 1];
@@ -391,25 +393,77 @@ static int configure(orbx_extractor* ex, int rows, int cols)
         fg.L[l].tma_box_h = bh;
         // the warp-streaming kernel (kernels_pyramid.cu: pyr_resize_pipe_kernel) works on the BORDERED level: items of 128 buffer
         // columns (from column kXPad - kEdge - 1, word aligned) x 16 bordered rows; a border pixel takes the taps of its mirror
-        // image, so the window of an item at the rim is a little larger than 16 * scale rows
-        int rw = 0, rh = 0;
+        // image, so the window of an item at the rim is a little larger than 16 * scale rows.  Everything an item needs is
+        // tabulated here: per (column tile, lane) the four coefficient words, the two 8-byte windows of the lane and the byte
+        // selectors; per row strip the source rows in ascending order with the output row(s) each pair of rows produces (two at
+        // the rim: a border row and its mirror image are the same bytes).
+        fg.L[l].rp_box_w = fg.L[l].rp_box_h = 0;
+        rp_x_off[l + 1] = rp_y_off[l + 1] = 0;
+        if (d.area2x) continue;
         const int wb = d.w + 2 * kEdge, hb = d.h + 2 * kEdge;
-        for (int c0 = -1; c0 < wb; c0 += 128) {
+        const int ntx = (wb + 1 + 127) / 128, nstrips = (hb + 15) / 16;
+        int rw = 0, rh = 0;
+        bool ok = true;
+        std::vector<uint2> xl, ys;
+        for (int ct = 0; ct < ntx; ++ct) {
+            auto col = [&](int c) { return xt[std::min(std::max(c, 0), wb - 1)]; };
             int lo = INT_MAX, hi = 0;
-            for (int c = c0; c < c0 + 128; ++c) {
-                const uint2 e = xt[std::min(std::max(c, 0), wb - 1)];
+            for (int c = ct * 128 - 1; c < ct * 128 + 127; ++c) {
+                const uint2 e = col(c);
                 lo = std::min(lo, (int)(e.x & 0xffff)); hi = std::max(hi, (int)(e.x & 0xffff));
+                if ((e.x >> 16) != (e.x & 0xffff) + 1 && (e.y >> 16) != 0) ok = false;     // second tap = first + 1 unless its weight is 0
             }
-            rw = std::max(rw, hi + 2 - (lo & ~15));
+            const int cbase = lo & ~15;
+            rw = std::max(rw, hi + 2 - cbase);
+            for (int lane = 0; lane < 32; ++lane) {
+                const int bc0 = ct * 128 + 4 * lane - 1;
+                int c[4]; uint32_t a[4], keep = 0;
+                for (int j = 0; j < 4; ++j) {
+                    c[j] = (int)(col(bc0 + j).x & 0xffff) - cbase; a[j] = col(bc0 + j).y;
+                    if (bc0 + j >= 0 && bc0 + j < wb) keep |= 0xffu << (8 * j);
+                }
+                const int qA = std::min(c[0], c[1]) & ~3, qB = std::min(c[2], c[3]) & ~3;
+                const int i0 = c[0] - qA, i1 = c[1] - qA, i2 = c[2] - qB, i3 = c[3] - qB;
+                if (std::max(std::max(i0, i1), std::max(i2, i3)) > 6) ok = false;
+                const uint32_t selA = (uint32_t)(i0 | ((i0 + 1) << 4) | (i1 << 8) | ((i1 + 1) << 12));
+                const uint32_t selB = (uint32_t)(i2 | ((i2 + 1) << 4) | (i3 << 8) | ((i3 + 1) << 12));
+                xl.push_back(make_uint2(a[0], a[1])); xl.push_back(make_uint2(a[2], a[3]));
+                xl.push_back(make_uint2(selA | (selB << 16), (uint32_t)qA | ((uint32_t)qB << 16))); xl.push_back(make_uint2(keep, (uint32_t)cbase));
+            }
         }
-        for (int r0 = 0; r0 < hb; r0 += 16) {
+        std::vector<std::vector<uint2>> strips(nstrips);
+        for (int sidx = 0; sidx < nstrips; ++sidx) {
+            const int r0 = sidx * 16, r1 = std::min(r0 + 16, hb);
             int lo = INT_MAX, hi = 0;
-            for (int r = r0; r < std::min(r0 + 16, hb); ++r) { lo = std::min(lo, (int)(yt[r].x & 0xffff)); hi = std::max(hi, (int)(yt[r].x & 0xffff)); }
-            rh = std::max(rh, hi + 2 - lo);
+            for (int r = r0; r < r1; ++r) {
+                lo = std::min(lo, (int)(yt[r].x & 0xffff)); hi = std::max(hi, (int)(yt[r].x & 0xffff));
+                if ((yt[r].x >> 16) != (yt[r].x & 0xffff) + 1 && (yt[r].y >> 16) != 0) ok = false;
+            }
+            const int nbox = hi + 2 - lo;
+            rh = std::max(rh, nbox);
+            // entry k describes the pair of source rows (lo + k - 1, lo + k): weights, output rows (0xff = none)
+            std::vector<uint2> e((size_t)nbox, make_uint2(0u, 0xffffu));
+            for (int r = r0; r < r1; ++r) {
+                const int k = (int)(yt[r].x & 0xffff) - lo + 1;
+                uint2& slot = e[k];
+                if ((slot.y & 0xff) == 0xff) { slot.x = yt[r].y; slot.y = (uint32_t)(r - r0) | 0xff00u; }
+                else if ((slot.y >> 8) == 0xff && slot.x == yt[r].y) slot.y = (slot.y & 0xff) | ((uint32_t)(r - r0) << 8);
+                else ok = false;
+            }
+            strips[sidx].push_back(make_uint2((uint32_t)lo, (uint32_t)nbox));
+            strips[sidx].insert(strips[sidx].end(), e.begin(), e.end());
         }
+        if (!ok || rh > 31) continue;
+        for (auto& sv : strips) { sv.resize((size_t)rh + 1, make_uint2(0u, 0xffffu)); ys.insert(ys.end(), sv.begin(), sv.end()); }
         fg.L[l].rp_box_w = (int)align_up((size_t)rw, 16);
         fg.L[l].rp_box_h = rh;
+        if (rp_tables.size() & 1) rp_tables.push_back(make_uint2(0, 0));            // 16-byte aligned lane records
+        rp_x_off[l + 1] = rp_tables.size(); rp_tables.insert(rp_tables.end(), xl.begin(), xl.end());
+        rp_y_off[l + 1] = rp_tables.size(); rp_tables.insert(rp_tables.end(), ys.begin(), ys.end());
     }
+    if (tables.size() & 1) tables.push_back(make_uint2(0, 0));
+    const size_t rp_base = tables.size();
+    tables.insert(tables.end(), rp_tables.begin(), rp_tables.end());
     fg.total_cells = cell_base;
     fg.kp_slots = kp_base;
     fg.cand_frame_stride = cand_off + 16;
@@ -431,6 +485,8 @@ static int configure(orbx_extractor* ex, int rows, int cols)
         for (int l = 1; l < ex->nlevels; ++l) {
             fg.L[l].xtab = ex->d_tables + xtab_off[l];
             fg.L[l].ytab = ex->d_tables + ytab_off[l];
+            fg.L[l].rp_xlane = fg.L[l - 1].rp_box_w > 0 ? ex->d_tables + rp_base + rp_x_off[l] : nullptr;
+            fg.L[l].rp_ysched = fg.L[l - 1].rp_box_w > 0 ? ex->d_tables + rp_base + rp_y_off[l] : nullptr;
         }
         fg.cell_tab = reinterpret_cast<const uint32_t*>(ex->d_tables + cell_tab_off);
     }

@@ -322,116 +322,117 @@ __global__ void __launch_bounds__(PT_THREADS, PT_MINB) pyr_resize_tiled_kernel(c
 //   * horizontal pass of one source row: the lane's 8 taps lie in two aligned 8-byte windows (outputs 0-1, outputs 2-3; fixed for
 //     the item): 4 LDS.32, one PRMT per pair with a per-lane selector puts (s0, s0+1, s1, s1+1) in one word, and one IDP.2A per
 //     output forms a0*s[x] + a1*s[x+1] with the table's (a0 | a1 << 16) word as it is;
-//   * vertical pass: the sums of the last two source rows stay in registers (output rows walk the source rows in order; a jump —
-//     the mirrored rows of the border — recomputes both), ((b0*(r0>>4))>>16) + ((b1*(r1>>4))>>16) + 2 is two IMAD.HI with the
-//     addend riding along, the four pixels leave as one coalesced 32-bit store.
-// Same integer arithmetic as the kernels above, so the result is bit-identical (tests/test_gpu_parity.py pyramid probes).
+//   * vertical pass: the source rows of the box are walked once, top to bottom; the sums of the last two rows stay in registers
+//     (two register sets that swap roles, the loop is unrolled by two) and the pair (r-1, r) produces the output row the host's
+//     schedule names — or two rows at the rim, where a border row and its mirror image are the same bytes;
+//     ((b0*(r0>>4))>>16) + ((b1*(r1>>4))>>16) is two IMAD.HI with the addend riding along, +2 and >>2 are applied to two pixels
+//     at a time, the four pixels leave as one coalesced 32-bit store.
+// Everything that depends on the item's position only (coefficients, windows, selectors, row schedule) is tabulated on the host
+// (api.cu: configure), so an item starts with three 16-byte loads.  Same integer arithmetic as the kernels above: bit-identical
+// (tests/test_gpu_round2.py::test_batch_pyramid_streaming_kernel_is_bit_exact, bench.py's cfg4 checksum).
 constexpr int kRpWarps = 4;
 constexpr int kRpRows = 16;                         // bordered output rows per item
 constexpr int kRpCol0 = kXPad - kEdge - 1;          // first buffer column of column tile 0 (12: word aligned; bordered column -1)
 
+__device__ __forceinline__ uint32_t mulhi_u32(uint32_t a, uint32_t b)
+{
+    uint32_t d;
+    asm("mul.hi.u32 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+    return d;
+}
+__device__ __forceinline__ uint32_t madhi_u32(uint32_t a, uint32_t b, uint32_t c)
+{
+    uint32_t d;
+    asm("mad.hi.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+
 __global__ void __launch_bounds__(32 * kRpWarps) pyr_resize_pipe_kernel(const __grid_constant__ FrameGeom fg, Workspace ws, int level,
-                                                                        int stage_bytes, int ntx, int nstrips, int total_items)
+                                                                        int stage_bytes, int ntx, int nstrips, int total_items,
+                                                                        uint32_t magic_frame, uint32_t magic_ntx)
 {
     extern __shared__ __align__(128) uint8_t rp_smem[];
     __shared__ __align__(8) uint64_t bars[kRpWarps];
-    __shared__ uint2 ysched[kRpWarps][kRpRows];
+    __shared__ uint2 sched[kRpWarps][32];
     const LevelGeom& g = fg.L[level];
     const LevelGeom& p = fg.L[level - 1];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint8_t* stage = rp_smem + (size_t)warp * stage_bytes;
     const uint32_t stage_s = (uint32_t)__cvta_generic_to_shared(stage);
+    const uint32_t sched_s = (uint32_t)__cvta_generic_to_shared(&sched[warp][0]);
     if (lane == 0) mbar_init(&bars[warp], 1);
     __syncwarp();
     const int gw = blockIdx.x * kRpWarps + warp, nw = gridDim.x * kRpWarps;
     const int bw = p.rp_box_w, bh = p.rp_box_h;
-    const int wb = g.w + 2 * kEdge, hb = g.h + 2 * kEdge;
     const int per_frame = ntx * nstrips;
+    const int pitch = g.pitch;
     uint32_t phase = 0;
     for (int item = gw; item < total_items; item += nw) {
-        const int frame = item / per_frame;
-        const int t = item - frame * per_frame;
-        const int strip = t / ntx, ct = t - strip * ntx;
-        // columns: bordered column of the lane's first pixel (buffer column - 13); entries clamped into the table
-        const int bc0 = ct * 128 + 4 * lane - 1;
-        uint2 xt[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) xt[j] = __ldg(g.xtab + min(max(bc0 + j, 0), wb - 1));
-        int c[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) c[j] = (int)(xt[j].x & 0xffff);
-        const int cbase = __reduce_min_sync(0xffffffffu, min(min(c[0], c[1]), min(c[2], c[3]))) & ~15;    // 16-byte aligned box start
-        // rows
-        const int br0 = strip * kRpRows;
-        const int nrows = min(kRpRows, hb - br0);
-        const uint2 yt = __ldg(g.ytab + min(br0 + (lane & (kRpRows - 1)), hb - 1));
-        const int symin = __reduce_min_sync(0xffffffffu, (int)(yt.x & 0xffff));
-        if (lane < kRpRows) ysched[warp][lane] = make_uint2((yt.x & 0xffff) - (uint32_t)symin, yt.y);
+        // item -> (frame, strip, column tile): quotients by multiplication with floor(2^32 / d), one correction step
+        int frame = (int)__umulhi((uint32_t)item, magic_frame);
+        int t = item - frame * per_frame;
+        if (t >= per_frame) { t -= per_frame; ++frame; }
+        int strip = (int)__umulhi((uint32_t)t, magic_ntx);
+        int ct = t - strip * ntx;
+        if (ct >= ntx) { ct -= ntx; ++strip; }
+        const uint4* xl = reinterpret_cast<const uint4*>(g.rp_xlane) + ((size_t)ct * 32 + lane) * 2;
+        const uint4 A = __ldg(xl), Q = __ldg(xl + 1);          // a0..a3 | selectors, windows, keep mask, box start column
+        const uint2* ys = g.rp_ysched + (size_t)strip * (bh + 1);
+        const uint2 hd = __ldg(ys);                            // {first source row of the box, rows used}
+        const uint2 e = __ldg(ys + 1 + min(lane, bh - 1));
+        asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(sched_s + 8 * lane), "r"(e.x), "r"(e.y) : "memory");
         if (lane == 0) {
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             mbar_expect_tx(&bars[warp], (uint32_t)(bw * bh));
-            tma_load_3d(stage, ws.tmap_rpipe + (level - 1), &bars[warp], kXPad + cbase, kEdge + symin, frame);
+            tma_load_3d(stage, ws.tmap_rpipe + (level - 1), &bars[warp], kXPad + (int)Q.w, kEdge + (int)hd.x, frame);
         }
         __syncwarp();
-        // the two 8-byte windows of the lane and the selectors that pull (s0, s0+1, s1, s1+1) out of them
-        uint32_t aA, aB, selA, selB;
-        {
-            const int mA = min(c[0], c[1]) - cbase, mB = min(c[2], c[3]) - cbase;
-            const int qA = mA & ~3, qB = mB & ~3;
-            const int i0 = c[0] - cbase - qA, i1 = c[1] - cbase - qA, i2 = c[2] - cbase - qB, i3 = c[3] - cbase - qB;
-            selA = (uint32_t)(i0 | ((i0 + 1) << 4) | (i1 << 8) | ((i1 + 1) << 12));
-            selB = (uint32_t)(i2 | ((i2 + 1) << 4) | (i3 << 8) | ((i3 + 1) << 12));
-            aA = stage_s + qA; aB = stage_s + qB;
-        }
-        // word of the lane in the bordered row; bytes outside the bordered level stay 0 (padding)
-        const int wcol = kRpCol0 + ct * 128 + 4 * lane;
-        uint32_t keep = 0;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) keep |= (bc0 + j >= 0 && bc0 + j < wb) ? (0xffu << (8 * j)) : 0u;
+        const uint32_t selA = Q.x & 0xffffu, selB = Q.x >> 16, keep = Q.z;
+        uint32_t ra = stage_s + (Q.y & 0xffffu), rb = stage_s + (Q.y >> 16);
         const bool store = keep != 0;
-        uint8_t* out = ws.pyr + g.pyr_off + (size_t)frame * g.pyr_frame_stride + (size_t)br0 * g.pitch + wcol;
-        const int pitch = g.pitch;
-        auto hrow = [&](int r, uint32_t h[4]) {
+        uint8_t* out = ws.pyr + g.pyr_off + (size_t)frame * g.pyr_frame_stride + (size_t)(strip * kRpRows) * pitch + (kRpCol0 + ct * 128 + 4 * lane);
+        const int nbox = (int)hd.y;
+        auto hrow = [&](uint32_t h[4]) {                       // horizontal sums (>> 4) of the next source row
             uint32_t w0, w1, w2, w3;
-            const uint32_t ra = aA + r * bw, rb = aB + r * bw;
             asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w0) : "r"(ra));
             asm volatile("ld.shared.u32 %0, [%1+4];" : "=r"(w1) : "r"(ra));
             asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w2) : "r"(rb));
             asm volatile("ld.shared.u32 %0, [%1+4];" : "=r"(w3) : "r"(rb));
+            ra += bw; rb += bw;
             const uint32_t pa = __byte_perm(w0, w1, selA), pb = __byte_perm(w2, w3, selB);
-            h[0] = __dp2a_lo(xt[0].y, pa, 0u) >> 4; h[1] = __dp2a_hi(xt[1].y, pa, 0u) >> 4;
-            h[2] = __dp2a_lo(xt[2].y, pb, 0u) >> 4; h[3] = __dp2a_hi(xt[3].y, pb, 0u) >> 4;
+            h[0] = __dp2a_lo(A.x, pa, 0u) >> 4; h[1] = __dp2a_hi(A.y, pa, 0u) >> 4;
+            h[2] = __dp2a_lo(A.z, pb, 0u) >> 4; h[3] = __dp2a_hi(A.w, pb, 0u) >> 4;
+        };
+        auto emit = [&](int k, const uint32_t h0[4], const uint32_t h1[4]) {     // the output row(s) of source rows (k - 1, k)
+            uint32_t wgt, rows;
+            asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(wgt), "=r"(rows) : "r"(sched_s + 8 * k));
+            const uint32_t rowA = rows & 0xffu, rowB = (rows >> 8) & 0xffu;
+            if (rowA == 0xffu) return;                         // warp-uniform
+            const uint32_t b0 = wgt << 16, b1 = wgt & 0xffff0000u;
+            uint32_t u[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) u[j] = madhi_u32(b1, h1[j], mulhi_u32(b0, h0[j]));        // <= 1020
+            const uint32_t x01 = (__byte_perm(u[0], u[1], 0x5410) + 0x00020002u) >> 2, x23 = (__byte_perm(u[2], u[3], 0x5410) + 0x00020002u) >> 2;
+            const uint32_t o = __byte_perm(x01, x23, 0x6420) & keep;
+            if (store) {
+                *reinterpret_cast<uint32_t*>(out + (size_t)rowA * (uint32_t)pitch) = o;
+                if (rowB != 0xffu) *reinterpret_cast<uint32_t*>(out + (size_t)rowB * (uint32_t)pitch) = o;
+            }
         };
         mbar_wait(&bars[warp], phase);
         phase ^= 1u;
-        uint32_t hp[4] = {0, 0, 0, 0}, hc[4] = {0, 0, 0, 0};
-        int hr = -4;                                   // source row (relative to the box) held in hc; hp holds hr - 1
-        for (int i = 0; i < nrows; ++i) {
-            const uint2 ys = ysched[warp][i];          // {first source row - symin, b0 | b1 << 16}; warp-uniform
-            const int rel = (int)ys.x;
-            if (rel != hr - 1) {
-                if (rel == hr) {
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) hp[j] = hc[j];
-                    hrow(hr + 1, hc);
-                    hr += 1;
-                } else {
-                    hrow(rel, hp);
-                    hrow(rel + 1, hc);
-                    hr = rel + 1;
-                }
+        uint32_t ha[4], hb[4];
+        hrow(ha);                                              // source row 0 of the box
+#pragma unroll 1
+        for (int k = 1; k < nbox; k += 2) {
+            hrow(hb);
+            emit(k, ha, hb);
+            if (k + 1 < nbox) {
+                hrow(ha);
+                emit(k + 1, hb, ha);
             }
-            const uint32_t b0 = ys.y << 16, b1 = ys.y & 0xffff0000u;
-            uint32_t u[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) u[j] = __umulhi(b1, hc[j]) + (__umulhi(b0, hp[j]) + 2u);     // <= 1022
-            // (u >> 2) of four pixels -> one word: pack pairs as u16x2, shift both halves at once, pick the low bytes
-            const uint32_t x01 = __byte_perm(u[0], u[1], 0x5410) >> 2, x23 = __byte_perm(u[2], u[3], 0x5410) >> 2;
-            const uint32_t o = __byte_perm(x01, x23, 0x6420) & keep;
-            if (store) *reinterpret_cast<uint32_t*>(out) = o;
-            out += pitch;
         }
-        __syncwarp();                                  // every lane is done with the stage before lane 0 refills it
+        __syncwarp();                                          // every lane is done with the stage and the schedule
     }
 }
 
@@ -567,7 +568,7 @@ static bool launch_resize_pipe(const FrameGeom& fg, const Workspace& ws, int lev
 {
     const LevelGeom& g = fg.L[level];
     const LevelGeom& p = fg.L[level - 1];
-    if (p.rp_box_w < 16 || p.rp_box_h < 2) return false;
+    if (p.rp_box_w < 16 || p.rp_box_h < 2 || p.rp_box_h > 31 || !g.rp_xlane || !g.rp_ysched) return false;
     // + 8: a lane's second 4-byte word may start at the end of the last staged row (its bytes are then not selected)
     const int stage_bytes = (p.rp_box_w * p.rp_box_h + 8 + 127) & ~127;
     const int smem = kRpWarps * stage_bytes;
@@ -592,7 +593,9 @@ static bool launch_resize_pipe(const FrameGeom& fg, const Workspace& ws, int lev
     static const char* per_env = getenv("ORBX_PYR_PIPE_CTAS");
     int per_sm = std::min(per_env ? atoi(per_env) : 9, std::max(1, (200 * 1024) / (smem + 1024)));
     const int ctas = (int)std::min<long long>((total + kRpWarps - 1) / kRpWarps, (long long)n_sm_dev[dev & 63] * per_sm);
-    pyr_resize_pipe_kernel<<<ctas, 32 * kRpWarps, smem, st>>>(fg, ws, level, stage_bytes, ntx, nstrips, (int)total);
+    const uint32_t magic_frame = (uint32_t)((1ULL << 32) / (uint64_t)(ntx * nstrips)), magic_ntx = (uint32_t)((1ULL << 32) / (uint64_t)ntx);
+    pyr_resize_pipe_kernel<<<ctas, 32 * kRpWarps, smem, st>>>(fg, ws, level, stage_bytes, ntx, nstrips, (int)total,
+                                                              ntx * nstrips > 1 ? magic_frame : 0xffffffffu, ntx > 1 ? magic_ntx : 0xffffffffu);
     return true;
 }
 

@@ -48,7 +48,10 @@ struct LevelGeom {
     float inv_scale;          // mvInvScaleFactor[level]
     float kp_size;            // (float)(int)(31*scale)
     int tma_box_w, tma_box_h; // box of THIS level's resize-source descriptor (when it is the source of level+1)
-    int rp_box_w, rp_box_h;   // the same for the warp-streaming resize kernel (128-column x 16-row items of the BORDERED level + 1)
+    int rp_box_w, rp_box_h;   // the same for the warp-streaming resize kernel (128-column x 16-row items of the BORDERED level + 1); 0 = not applicable
+    // tables of the warp-streaming resize kernel for THIS level as the destination (api.cu: configure)
+    const uint2* rp_xlane;    // [column tile][lane] 32-byte records: a0..a3 | selA + selB << 16, qA + qB << 16 | keep mask, box start column
+    const uint2* rp_ysched;   // [strip][rp_box_h + 1]: {first source row, rows in the box}, then per pair of source rows {b0 + b1 << 16, out rows}
 };
 
 struct FrameGeom {
