@@ -441,20 +441,24 @@ static int configure(orbx_extractor* ex, int rows, int cols)
             }
             const int nbox = hi + 2 - lo;
             rh = std::max(rh, nbox);
-            // entry k describes the pair of source rows (lo + k - 1, lo + k): weights, output rows (0xff = none)
-            std::vector<uint2> e((size_t)nbox, make_uint2(0u, 0xffffu));
+            // entry k (two uint2) describes the pair of source rows (lo + k - 1, lo + k): {b0, b1}, {first output row | (second + 1) << 16, 0};
+            // first = 0xffff: the pair produces nothing
+            std::vector<uint2> e((size_t)nbox * 2, make_uint2(0u, 0u));
+            for (int k = 0; k < nbox; ++k) e[2 * k + 1].x = 0xffffu;
             for (int r = r0; r < r1; ++r) {
                 const int k = (int)(yt[r].x & 0xffff) - lo + 1;
-                uint2& slot = e[k];
-                if ((slot.y & 0xff) == 0xff) { slot.x = yt[r].y; slot.y = (uint32_t)(r - r0) | 0xff00u; }
-                else if ((slot.y >> 8) == 0xff && slot.x == yt[r].y) slot.y = (slot.y & 0xff) | ((uint32_t)(r - r0) << 8);
+                uint2& wgt = e[2 * k]; uint2& rows = e[2 * k + 1];
+                const uint2 b = make_uint2(yt[r].y & 0xffffu, yt[r].y >> 16);
+                if (rows.x == 0xffffu) { wgt = b; rows.x = (uint32_t)(r - r0); }
+                else if ((rows.x >> 16) == 0 && wgt.x == b.x && wgt.y == b.y) rows.x |= (uint32_t)(r - r0 + 1) << 16;
                 else ok = false;
             }
             strips[sidx].push_back(make_uint2((uint32_t)lo, (uint32_t)nbox));
+            strips[sidx].push_back(make_uint2(0u, 0u));
             strips[sidx].insert(strips[sidx].end(), e.begin(), e.end());
         }
         if (!ok || rh > 31) continue;
-        for (auto& sv : strips) { sv.resize((size_t)rh + 1, make_uint2(0u, 0xffffu)); ys.insert(ys.end(), sv.begin(), sv.end()); }
+        for (auto& sv : strips) { sv.resize(2 * ((size_t)rh + 1), make_uint2(0xffffu, 0u)); ys.insert(ys.end(), sv.begin(), sv.end()); }
         fg.L[l].rp_box_w = (int)align_up((size_t)rw, 16);
         fg.L[l].rp_box_h = rh;
         if (rp_tables.size() & 1) rp_tables.push_back(make_uint2(0, 0));            // 16-byte aligned lane records

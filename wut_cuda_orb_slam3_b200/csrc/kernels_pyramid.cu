@@ -325,8 +325,8 @@ __global__ void __launch_bounds__(PT_THREADS, PT_MINB) pyr_resize_tiled_kernel(c
 //   * vertical pass: the source rows of the box are walked once, top to bottom; the sums of the last two rows stay in registers
 //     (two register sets that swap roles, the loop is unrolled by two) and the pair (r-1, r) produces the output row the host's
 //     schedule names — or two rows at the rim, where a border row and its mirror image are the same bytes;
-//     ((b0*(r0>>4))>>16) + ((b1*(r1>>4))>>16) is two IMAD.HI with the addend riding along, +2 and >>2 are applied to two pixels
-//     at a time, the four pixels leave as one coalesced 32-bit store.
+//     (b*(r>>4))>>16 is the upper half of a 32-bit IMAD (the product has 27 bits), PRMT gathers the upper halves of two pixels,
+//     the sum, +2 and >>2 act on two pixels at a time, the four pixels leave as one coalesced 32-bit store.
 // Everything that depends on the item's position only (coefficients, windows, selectors, row schedule) is tabulated on the host
 // (api.cu: configure), so an item starts with three 16-byte loads.  Same integer arithmetic as the kernels above: bit-identical
 // (tests/test_gpu_round2.py::test_batch_pyramid_streaming_kernel_is_bit_exact, bench.py's cfg4 checksum).
@@ -334,26 +334,13 @@ constexpr int kRpWarps = 4;
 constexpr int kRpRows = 16;                         // bordered output rows per item
 constexpr int kRpCol0 = kXPad - kEdge - 1;          // first buffer column of column tile 0 (12: word aligned; bordered column -1)
 
-__device__ __forceinline__ uint32_t mulhi_u32(uint32_t a, uint32_t b)
-{
-    uint32_t d;
-    asm("mul.hi.u32 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
-    return d;
-}
-__device__ __forceinline__ uint32_t madhi_u32(uint32_t a, uint32_t b, uint32_t c)
-{
-    uint32_t d;
-    asm("mad.hi.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
-    return d;
-}
-
 __global__ void __launch_bounds__(32 * kRpWarps) pyr_resize_pipe_kernel(const __grid_constant__ FrameGeom fg, Workspace ws, int level,
                                                                         int stage_bytes, int ntx, int nstrips, int total_items,
                                                                         uint32_t magic_frame, uint32_t magic_ntx)
 {
     extern __shared__ __align__(128) uint8_t rp_smem[];
     __shared__ __align__(8) uint64_t bars[kRpWarps];
-    __shared__ uint2 sched[kRpWarps][32];
+    __shared__ uint4 sched[kRpWarps][32];
     const LevelGeom& g = fg.L[level];
     const LevelGeom& p = fg.L[level - 1];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -365,7 +352,7 @@ __global__ void __launch_bounds__(32 * kRpWarps) pyr_resize_pipe_kernel(const __
     const int gw = blockIdx.x * kRpWarps + warp, nw = gridDim.x * kRpWarps;
     const int bw = p.rp_box_w, bh = p.rp_box_h;
     const int per_frame = ntx * nstrips;
-    const int pitch = g.pitch;
+    const uint32_t pitch = (uint32_t)g.pitch;
     uint32_t phase = 0;
     for (int item = gw; item < total_items; item += nw) {
         // item -> (frame, strip, column tile): quotients by multiplication with floor(2^32 / d), one correction step
@@ -377,10 +364,10 @@ __global__ void __launch_bounds__(32 * kRpWarps) pyr_resize_pipe_kernel(const __
         if (ct >= ntx) { ct -= ntx; ++strip; }
         const uint4* xl = reinterpret_cast<const uint4*>(g.rp_xlane) + ((size_t)ct * 32 + lane) * 2;
         const uint4 A = __ldg(xl), Q = __ldg(xl + 1);          // a0..a3 | selectors, windows, keep mask, box start column
-        const uint2* ys = g.rp_ysched + (size_t)strip * (bh + 1);
-        const uint2 hd = __ldg(ys);                            // {first source row of the box, rows used}
-        const uint2 e = __ldg(ys + 1 + min(lane, bh - 1));
-        asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(sched_s + 8 * lane), "r"(e.x), "r"(e.y) : "memory");
+        const uint4* ys = reinterpret_cast<const uint4*>(g.rp_ysched) + (size_t)strip * (bh + 1);
+        const uint4 hd = __ldg(ys);                            // {first source row of the box, rows used, -, -}
+        const uint4 e = __ldg(ys + 1 + min(lane, bh - 1));
+        asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(sched_s + 16 * lane), "r"(e.x), "r"(e.y), "r"(e.z), "r"(e.w) : "memory");
         if (lane == 0) {
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             mbar_expect_tx(&bars[warp], (uint32_t)(bw * bh));
@@ -389,8 +376,9 @@ __global__ void __launch_bounds__(32 * kRpWarps) pyr_resize_pipe_kernel(const __
         __syncwarp();
         const uint32_t selA = Q.x & 0xffffu, selB = Q.x >> 16, keep = Q.z;
         uint32_t ra = stage_s + (Q.y & 0xffffu), rb = stage_s + (Q.y >> 16);
-        const bool store = keep != 0;
-        uint8_t* out = ws.pyr + g.pyr_off + (size_t)frame * g.pyr_frame_stride + (size_t)(strip * kRpRows) * pitch + (kRpCol0 + ct * 128 + 4 * lane);
+        unsigned long long out = (unsigned long long)(ws.pyr + g.pyr_off + (size_t)frame * g.pyr_frame_stride + (size_t)(strip * kRpRows) * pitch +
+                                                      (kRpCol0 + ct * 128 + 4 * lane));
+        asm volatile("" : "+l"(out));                          // one finished base pointer: a row address is a single mad.wide
         const int nbox = (int)hd.y;
         auto hrow = [&](uint32_t h[4]) {                       // horizontal sums (>> 4) of the next source row
             uint32_t w0, w1, w2, w3;
@@ -404,32 +392,36 @@ __global__ void __launch_bounds__(32 * kRpWarps) pyr_resize_pipe_kernel(const __
             h[2] = __dp2a_lo(A.z, pb, 0u) >> 4; h[3] = __dp2a_hi(A.w, pb, 0u) >> 4;
         };
         auto emit = [&](int k, const uint32_t h0[4], const uint32_t h1[4]) {     // the output row(s) of source rows (k - 1, k)
-            uint32_t wgt, rows;
-            asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(wgt), "=r"(rows) : "r"(sched_s + 8 * k));
-            const uint32_t rowA = rows & 0xffu, rowB = (rows >> 8) & 0xffu;
-            if (rowA == 0xffu) return;                         // warp-uniform
-            const uint32_t b0 = wgt << 16, b1 = wgt & 0xffff0000u;
-            uint32_t u[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) u[j] = madhi_u32(b1, h1[j], mulhi_u32(b0, h0[j]));        // <= 1020
-            const uint32_t x01 = (__byte_perm(u[0], u[1], 0x5410) + 0x00020002u) >> 2, x23 = (__byte_perm(u[2], u[3], 0x5410) + 0x00020002u) >> 2;
+            uint32_t b0, b1, rows, unused;
+            asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(b0), "=r"(b1), "=r"(rows), "=r"(unused) : "r"(sched_s + 16 * k));
+            if ((rows & 0xffffu) == 0xffffu) return;           // warp-uniform
+            // b <= 2048 and h < 2^15: the products fit 32 bits, so (b * h) >> 16 is the upper half of a plain IMAD (IMAD.HI runs at
+            // a quarter of its rate); PRMT pulls the upper halves of two pixels into one word, +2 and >> 2 act on both halves
+            const uint32_t p01 = __byte_perm(b0 * h0[0], b0 * h0[1], 0x7632), q01 = __byte_perm(b1 * h1[0], b1 * h1[1], 0x7632);
+            const uint32_t p23 = __byte_perm(b0 * h0[2], b0 * h0[3], 0x7632), q23 = __byte_perm(b1 * h1[2], b1 * h1[3], 0x7632);
+            const uint32_t x01 = (p01 + q01 + 0x00020002u) >> 2, x23 = (p23 + q23 + 0x00020002u) >> 2;       // halves <= 1022
             const uint32_t o = __byte_perm(x01, x23, 0x6420) & keep;
-            if (store) {
-                *reinterpret_cast<uint32_t*>(out + (size_t)rowA * (uint32_t)pitch) = o;
-                if (rowB != 0xffu) *reinterpret_cast<uint32_t*>(out + (size_t)rowB * (uint32_t)pitch) = o;
+            unsigned long long addr;
+            asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(addr) : "r"(rows & 0xffffu), "r"(pitch), "l"(out));
+            asm volatile("st.global.u32 [%0], %1;" ::"l"(addr), "r"(o) : "memory");
+            if (rows >= 0x10000u) {                            // the mirror image of a border row: same bytes
+                asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(addr) : "r"((rows >> 16) - 1u), "r"(pitch), "l"(out));
+                asm volatile("st.global.u32 [%0], %1;" ::"l"(addr), "r"(o) : "memory");
             }
         };
         mbar_wait(&bars[warp], phase);
         phase ^= 1u;
-        uint32_t ha[4], hb[4];
-        hrow(ha);                                              // source row 0 of the box
+        if (keep != 0) {                                       // lanes right of the bordered level have nothing to do
+            uint32_t ha[4], hb[4];
+            hrow(ha);                                          // source row 0 of the box
 #pragma unroll 1
-        for (int k = 1; k < nbox; k += 2) {
-            hrow(hb);
-            emit(k, ha, hb);
-            if (k + 1 < nbox) {
-                hrow(ha);
-                emit(k + 1, hb, ha);
+            for (int k = 1; k < nbox; k += 2) {
+                hrow(hb);
+                emit(k, ha, hb);
+                if (k + 1 < nbox) {
+                    hrow(ha);
+                    emit(k + 1, hb, ha);
+                }
             }
         }
         __syncwarp();                                          // every lane is done with the stage and the schedule

@@ -51,7 +51,7 @@ struct LevelGeom {
     int rp_box_w, rp_box_h;   // the same for the warp-streaming resize kernel (128-column x 16-row items of the BORDERED level + 1); 0 = not applicable
     // tables of the warp-streaming resize kernel for THIS level as the destination (api.cu: configure)
     const uint2* rp_xlane;    // [column tile][lane] 32-byte records: a0..a3 | selA + selB << 16, qA + qB << 16 | keep mask, box start column
-    const uint2* rp_ysched;   // [strip][rp_box_h + 1]: {first source row, rows in the box}, then per pair of source rows {b0 + b1 << 16, out rows}
+    const uint2* rp_ysched;   // [strip][rp_box_h + 1] 16-byte records: {first source row, rows in the box, 0, 0}, then per pair of source rows {b0, b1, out rows, 0}
 };
 
 struct FrameGeom {
