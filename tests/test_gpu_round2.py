@@ -353,3 +353,24 @@ def test_batch_pyramid_streaming_kernel_is_bit_exact(oracle, cols, rows, nlevels
     ex(imgs[4])
     for l in range(nlevels):
         assert np.array_equal(ex.pyramid_level(l, with_border=True), got[1][l]), l
+
+
+def test_tiled_pyramid_kernel_matches_streaming_kernel():
+    """ORBX_PYR_PIPE=0 selects the tiled resize kernel (the fallback of the streaming one, e.g. without tensor maps): a child
+    process with the switch set must produce the same bordered pyramid bytes as this process (streaming kernel, compared with
+    the oracle in the tests above)."""
+    import hashlib, os, subprocess, sys
+    code = ("import hashlib, numpy as np, wut_cuda_orb_slam3_b200 as orbx\n"
+            "from wut_cuda_orb_slam3_b200 import synth\n"
+            "h = hashlib.sha1()\n"
+            "for cols, rows, scale in ((752, 480, 1.2), (333, 211, 1.3)):\n"
+            "    ex = orbx.ORBextractor(500, scale, 6, 20, 7)\n"
+            "    ex(synth.image(77, cols, rows))\n"
+            "    for l in range(6): h.update(ex.pyramid_level(l, with_border=True).tobytes())\n"
+            "print(h.hexdigest())\n")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    digests = []
+    for v in ("0", "1"):
+        env = dict(os.environ, ORBX_PYR_PIPE=v, PYTHONPATH=root + os.pathsep + os.environ.get("PYTHONPATH", ""))
+        digests.append(subprocess.check_output([sys.executable, "-c", code], env=env, text=True, cwd=root).strip().splitlines()[-1])
+    assert digests[0] == digests[1]
