@@ -533,10 +533,10 @@ static int ensure_slot(orbx_extractor* ex, Slot& s, int frames)
     if ((rc = dev_alloc(s, &s.ws.lvl_angle, (size_t)fg.kp_slots * frames))) return rc;
     if ((rc = dev_alloc(s, &s.ws.lvl_desc, (size_t)fg.kp_slots * frames * 32))) return rc;
     // TMA descriptors of the bordered pyramid levels (3-D: byte column, row, frame)
-    s.ws.tmap_resize = nullptr; s.ws.tmap_blur = nullptr; s.ws.tmap_rpipe = nullptr;
+    s.ws.tmap_resize = nullptr; s.ws.tmap_blur = nullptr; s.ws.tmap_rpipe = nullptr; s.ws.tmap_desc = nullptr;
     if (EncodeTiledFn enc = get_encode_tiled()) {
-        std::vector<CUtensorMap> maps(3 * kMaxLevels);
-        bool ok_resize = true, ok_blur = true, ok_rpipe = true;
+        std::vector<CUtensorMap> maps(4 * kMaxLevels);
+        bool ok_resize = true, ok_blur = true, ok_rpipe = true, ok_desc = true;
         for (int l = 0; l < fg.nlevels; ++l) {
             const LevelGeom& g = fg.L[l];
             const cuuint64_t dims[3] = {(cuuint64_t)g.pitch, (cuuint64_t)g.rows_alloc, (cuuint64_t)frames};
@@ -557,6 +557,15 @@ static int ensure_slot(orbx_extractor* ex, Slot& s, int frames)
                                  CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
                     ok_rpipe = false;
             }
+            {   // blurred level (no border): the window around a keypoint's descriptor patch
+                const cuuint64_t bdims[3] = {(cuuint64_t)g.bpitch, (cuuint64_t)g.h, (cuuint64_t)frames};
+                const cuuint64_t bstrides[2] = {(cuuint64_t)g.bpitch, (cuuint64_t)g.blur_frame_stride};
+                const cuuint32_t dbox[3] = {64, 40, 1};
+                if (enc(&maps[3 * kMaxLevels + l], CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, s.ws.blur + g.blur_off, bdims, bstrides, dbox, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+                    ok_desc = false;
+            }
             const cuuint32_t bbox[3] = {160, 38, 1};
             if (enc(&maps[kMaxLevels + l], CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, base, dims, strides, bbox, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                     CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
@@ -569,6 +578,7 @@ static int ensure_slot(orbx_extractor* ex, Slot& s, int frames)
         if (ok_resize && !no_tma) s.ws.tmap_resize = d_maps;
         if (ok_blur && !no_tma) s.ws.tmap_blur = d_maps + kMaxLevels;
         if (ok_rpipe && !no_tma) s.ws.tmap_rpipe = d_maps + 2 * kMaxLevels;
+        if (ok_desc && !no_tma) s.ws.tmap_desc = d_maps + 3 * kMaxLevels;
     }
     CU(cudaMemsetAsync(s.ws.pyr, 0, pyr + 256, s.stream));
     CU(cudaMemsetAsync(s.ws.lvl_n, 0, sizeof(int) * (size_t)fg.nlevels * frames, s.stream));

@@ -335,8 +335,17 @@ struct FusedPack {
 };
 
 // grid = (ceil(kp_slots / 8), n_frames), 8 warps per CTA, one warp per keypoint slot.
-__global__ void __launch_bounds__(256) orient_describe_kernel(const __grid_constant__ FrameGeom fg, Workspace ws, FusedPack fp)
+constexpr int kDescBoxW = 64, kDescBoxH = 40;     // window of the blurred level staged per keypoint: |dx|, |dy| <= 19 + 16-byte alignment
+constexpr int kOdStage = kDescBoxW * kDescBoxH;   // bytes per warp
+#ifndef ORBX_OD_MINB
+#define ORBX_OD_MINB 5          // 47 registers, no spills; 6 and 8 CTAs per SM (40 / 32 registers, spills) measure the same, 1 (61 registers) 6 % slower
+#endif
+
+template <bool STAGED>
+__global__ void __launch_bounds__(256, STAGED ? ORBX_OD_MINB : 1) orient_describe_kernel(const __grid_constant__ FrameGeom fg, Workspace ws, FusedPack fp)
 {
+    extern __shared__ __align__(128) uint8_t od_smem[];      // [8 warps][64 x 40] when the blurred levels have tensor maps
+    __shared__ __align__(8) uint64_t od_bar[8];
     const int lane = threadIdx.x & 31;
     const int slot = blockIdx.x * 8 + (threadIdx.x >> 5);
     const int frame = blockIdx.y;
@@ -370,6 +379,22 @@ __global__ void __launch_bounds__(256) orient_describe_kernel(const __grid_const
     if (i >= n_level) return;
     const uint32_t key = ws.lvl_kp[(size_t)frame * fg.kp_slots + slot];
     const int x = (int)(key & 0xfff) + kWinBorder, y = (int)((key >> 12) & 0xfff) + kWinBorder;
+
+    // The rBRIEF tests gather 512 bytes of the blurred level from a 39 x 39 window in an order set by the rotated pattern: as global
+    // loads every warp instruction touches ~20 different lines.  With a tensor map the window is staged by ONE bulk copy issued
+    // here, before the orientation is computed (the copy overlaps IC_Angle), and the gathers become shared-memory byte loads.
+    constexpr bool staged = STAGED;
+    const int warp = threadIdx.x >> 5;
+    const int x0 = (x - 19) & ~15;                            // 16-byte aligned box start; x >= 19
+    const uint32_t stage_s = (uint32_t)__cvta_generic_to_shared(od_smem) + (uint32_t)warp * kOdStage;
+    if (staged) {
+        if (lane == 0) {
+            mbar_init(&od_bar[warp], 1);
+            mbar_expect_tx(&od_bar[warp], kDescBoxW * kDescBoxH);
+            tma_load_3d(od_smem + warp * kOdStage, ws.tmap_desc + level, &od_bar[warp], x0, y - 20, frame);
+        }
+        __syncwarp();
+    }
 
     // ---- IC_Angle on the un-blurred level: lane <-> patch row v = lane - 15 ----
     // The row's 31 bytes arrive as 9 aligned 32-bit words, realigned with funnel shifts (the misalignment is the same for
@@ -422,6 +447,22 @@ __global__ void __launch_bounds__(256) orient_describe_kernel(const __grid_const
     const float kMagic = 12582912.0f;
     const int kMagicBits = 0x4B400000;
     uint32_t val = 0;
+    if (staged) {
+        mbar_wait(&od_bar[warp], 0);
+        const uint32_t cb = stage_s + 20 * kDescBoxW + (uint32_t)(x - x0);      // the keypoint's byte in the staged window
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const float4 q = d_pattern_f[k][lane];
+            const int iy0 = __float_as_int(__fadd_rn(__fadd_rn(__fmul_rn(q.x, b), __fmul_rn(q.y, a)), kMagic)) - kMagicBits;
+            const int ix0 = __float_as_int(__fadd_rn(__fsub_rn(__fmul_rn(q.x, a), __fmul_rn(q.y, b)), kMagic)) - kMagicBits;
+            const int iy1 = __float_as_int(__fadd_rn(__fadd_rn(__fmul_rn(q.z, b), __fmul_rn(q.w, a)), kMagic)) - kMagicBits;
+            const int ix1 = __float_as_int(__fadd_rn(__fsub_rn(__fmul_rn(q.z, a), __fmul_rn(q.w, b)), kMagic)) - kMagicBits;
+            uint32_t t0, t1;
+            asm volatile("ld.shared.u8 %0, [%1];" : "=r"(t0) : "r"(cb + (uint32_t)(iy0 * kDescBoxW + ix0)));
+            asm volatile("ld.shared.u8 %0, [%1];" : "=r"(t1) : "r"(cb + (uint32_t)(iy1 * kDescBoxW + ix1)));
+            val |= (uint32_t)(t0 < t1) << k;
+        }
+    } else
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
         const float4 q = d_pattern_f[k][lane];          // (x0, y0, x1, y1) of test 8 * lane + k
@@ -630,7 +671,9 @@ cudaError_t launch_orient_describe(const FrameGeom& fg, const Workspace& ws, int
         filled[dev & 63] = true;
     }
     dim3 grid((fg.kp_slots + 7) / 8, n_frames);
-    orient_describe_kernel<<<grid, 256, 0, st>>>(fg, ws, fp);
+    static const char* od_env = getenv("ORBX_DESC_STAGED");           // A/B switch: 0 = global gathers
+    if (ws.tmap_desc && (od_env ? atoi(od_env) != 0 : true)) orient_describe_kernel<true><<<grid, 256, 8 * kOdStage, st>>>(fg, ws, fp);
+    else orient_describe_kernel<false><<<grid, 256, 0, st>>>(fg, ws, fp);
     count_launch();
     return cudaGetLastError();
 }

@@ -82,6 +82,7 @@ struct Workspace {
     const CUtensorMap* tmap_resize;   // [nlevels] TMA descriptors of the pyramid levels, box = resize source window (or nullptr)
     const CUtensorMap* tmap_blur;     // [nlevels] TMA descriptors of the pyramid levels, box = blur input tile (or nullptr)
     const CUtensorMap* tmap_rpipe;    // [nlevels] TMA descriptors of the pyramid levels, box = source window of pyr_resize_pipe_kernel (or nullptr)
+    const CUtensorMap* tmap_desc;     // [nlevels] TMA descriptors of the BLURRED levels, box = the 64 x 40 window around a keypoint's rBRIEF patch (or nullptr)
     int dbg_level;
 };
 
