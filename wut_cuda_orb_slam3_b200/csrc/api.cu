@@ -560,7 +560,7 @@ static int ensure_slot(orbx_extractor* ex, Slot& s, int frames)
             {   // blurred level (no border): the window around a keypoint's descriptor patch
                 const cuuint64_t bdims[3] = {(cuuint64_t)g.bpitch, (cuuint64_t)g.h, (cuuint64_t)frames};
                 const cuuint64_t bstrides[2] = {(cuuint64_t)g.bpitch, (cuuint64_t)g.blur_frame_stride};
-                const cuuint32_t dbox[3] = {64, 40, 1};
+                const cuuint32_t dbox[3] = {kDescBoxW, kDescBoxH, 1};
                 if (enc(&maps[3 * kMaxLevels + l], CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, s.ws.blur + g.blur_off, bdims, bstrides, dbox, estr,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)

@@ -335,7 +335,6 @@ struct FusedPack {
 };
 
 // grid = (ceil(kp_slots / 8), n_frames), 8 warps per CTA, one warp per keypoint slot.
-constexpr int kDescBoxW = 64, kDescBoxH = 40;     // window of the blurred level staged per keypoint: |dx|, |dy| <= 19 + 16-byte alignment
 constexpr int kOdStage = kDescBoxW * kDescBoxH;   // bytes per warp
 #ifndef ORBX_OD_MINB
 #define ORBX_OD_MINB 5          // 47 registers, no spills; 6 and 8 CTAs per SM (40 / 32 registers, spills) measure the same, 1 (61 registers) 6 % slower
@@ -404,12 +403,22 @@ __global__ void __launch_bounds__(256, STAGED ? ORBX_OD_MINB : 1) orient_describ
     {
         const int v = lane - kHalfPatch;
         if (lane < 31) {
+            // three 16-byte loads per row instead of nine 4-byte ones: a warp instruction touches 31 different lines either way,
+            // and the L1 data pipe is this kernel's limiter (one wavefront per line per instruction)
             const uint8_t* rowp = level_interior((const uint8_t*)ws.pyr, g, frame) + (ptrdiff_t)(y + v) * g.pitch + (x - kHalfPatch);
-            const int mis = (int)((uintptr_t)rowp & 3);
-            const uint32_t* rw = reinterpret_cast<const uint32_t*>(rowp - mis);
-            uint32_t w[9];
+            const int mis16 = (int)((uintptr_t)rowp & 15);                  // the same for every row: the pitch is a multiple of 16
+            const int mis = mis16 & 3;
+            const uint4* rq = reinterpret_cast<const uint4*>(rowp - mis16);
+            const uint4 q0 = __ldg(rq), q1 = __ldg(rq + 1), q2 = __ldg(rq + 2);
+            uint32_t w[12] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w};
+            if (mis16 & 4) {                                                // warp-uniform: drop the leading words
 #pragma unroll
-            for (int j = 0; j < 9; ++j) w[j] = __ldg(rw + j);
+                for (int j = 0; j < 11; ++j) w[j] = w[j + 1];
+            }
+            if (mis16 & 8) {
+#pragma unroll
+                for (int j = 0; j < 10; ++j) w[j] = w[j + 2];
+            }
             const int av = v < 0 ? -v : v;
             const uint4 ma = d_mom_mask[av][0], mb = d_mom_mask[av][1];
             const uint32_t mk[8] = {ma.x, ma.y, ma.z, ma.w, mb.x, mb.y, mb.z, mb.w};

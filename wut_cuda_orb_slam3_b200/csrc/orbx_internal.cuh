@@ -15,6 +15,9 @@ constexpr int kMaxLevels = ORBX_MAX_LEVELS;
 constexpr int kMaxCellDim = 70;               // wCell/hCell < 70 whenever the grid has >= 1 cell
 constexpr int kMaxDim = 4128;                 // packed 12-bit window coordinates
 constexpr int kHalfPatch = 15;
+// window of a blurred level staged per keypoint for rBRIEF: |dx|, |dy| <= 19, + 15 bytes of alignment; a row pitch of 80 bytes spreads
+// the rows over 8 shared-memory bank offsets (64 bytes: 2)
+constexpr int kDescBoxW = 80, kDescBoxH = 40;
 
 // Geometry of one pyramid level for the current image shape (host-computed, passed to kernels by value).
 struct LevelGeom {
