@@ -470,6 +470,7 @@ static int configure(orbx_extractor* ex, int rows, int cols)
     tables.insert(tables.end(), rp_tables.begin(), rp_tables.end());
     fg.total_cells = cell_base;
     fg.kp_slots = kp_base;
+    for (int l = ex->nlevels; l < kMaxLevels; ++l) fg.L[l].kp_base = INT_MAX;      // slot -> level is a binary search over all kMaxLevels entries
     fg.cand_frame_stride = cand_off + 16;
     fg.oct_frame_stride = oct_off + 16;
     ex->max_kp = kp_base;

@@ -349,10 +349,11 @@ __global__ void __launch_bounds__(256, STAGED ? ORBX_OD_MINB : 1) orient_describ
     const int slot = blockIdx.x * 8 + (threadIdx.x >> 5);
     const int frame = blockIdx.y;
     if (slot >= fg.kp_slots) return;
-    int level = 0;
-#pragma unroll 1
-    for (int l = 1; l < fg.nlevels; ++l)
-        if (slot >= fg.L[l].kp_base) level = l;
+    static_assert((kMaxLevels & (kMaxLevels - 1)) == 0, "binary search over a power of two");
+    int level = 0;                                   // the level whose slot range holds `slot`: kp_base ascends, unused levels hold INT_MAX
+#pragma unroll
+    for (int step = kMaxLevels / 2; step >= 1; step >>= 1)
+        if (slot >= fg.L[level + step].kp_base) level += step;
     const LevelGeom& g = fg.L[level];
     const int i = slot - g.kp_base;
     int n_level, t_out = 0, nkp = 0;
