@@ -768,7 +768,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=512, help="frames per GPU per step")
     ap.add_argument("--e2e-batch", type=int, default=8192, help="frames per host-API call (as many as configs[3] streams)")
-    ap.add_argument("--e2e-chunk", type=int, default=384, help="pipeline chunk of the host API (max_batch of its extractor)")
+    ap.add_argument("--e2e-chunk", type=int, default=256, help="pipeline chunk of the host API (max_batch of its extractor)")
     ap.add_argument("--no-knn2", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-other", action="store_true", help="skip the short measurements of the other BASELINE configs")

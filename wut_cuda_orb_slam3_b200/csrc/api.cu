@@ -1034,7 +1034,12 @@ int orbx_extract_batch(orbx_extractor* ex, const uint8_t* const* images, int n_f
         } else {
             const int ramp[2] = {std::max(chunk / 4, 1), std::max(chunk / 2, 1)};
             for (int r = 0; r < 2 && n_frames - f0 > 2 * chunk; ++r) { sched.emplace_back(f0, ramp[r]); f0 += ramp[r]; }
-            while (f0 < n_frames) { const int nf = std::min(chunk, n_frames - f0); sched.emplace_back(f0, nf); f0 += nf; }
+            // ... and ramps down the same way: the compute of a chunk trails its upload, so what is left after the LAST upload
+            // is one chunk of compute + its download — a quarter chunk instead of a full one (trace of a 4096-frame call:
+            // 2.8 ms of tail behind 27.3 ms of back-to-back uploads)
+            const int tail = n_frames - f0 > 3 * chunk ? ramp[0] + ramp[1] : 0;
+            while (f0 < n_frames - tail) { const int nf = std::min(chunk, n_frames - tail - f0); sched.emplace_back(f0, nf); f0 += nf; }
+            if (tail) { sched.emplace_back(f0, ramp[1]); f0 += ramp[1]; sched.emplace_back(f0, ramp[0]); f0 += ramp[0]; }
         }
     }
     const int nchunks = (int)sched.size();
