@@ -664,11 +664,32 @@ static int run_chunk(orbx_extractor* ex, Slot& s, const uint8_t* d_images, size_
     if ((rc = prof_mark(ex, st))) return rc;
     CU(launch_pyramid(fg, s.ws, d_images, frame_stride, pitch, frames, st));
     if ((rc = prof_mark(ex, st))) return rc;
-    CU(launch_fast(fg, s.ws, frames, st));
-    if ((rc = prof_mark(ex, st))) return rc;
-    CU(launch_blur(fg, s.ws, frames, st));
-    if ((rc = prof_mark(ex, st))) return rc;
-    CU(launch_octree(fg, s.ws, frames, st));
+    // The blur depends on the pyramid only: for batches it runs on a side stream beside FAST and the octree.  While a FAST launch
+    // is at full occupancy there is no room for a blur CTA (shared memory and registers are taken), but each of FAST's three
+    // launches ends with a tail of half-empty SMs, and the blur's persistent CTAs fill those: 3.163 -> 3.088 ms per 512 frames.
+    // (The blur beside the octree instead: no gain — the octree's four CTAs hold the whole register file of an SM.)  Not while
+    // profiling (the per-stage events assume one stream), not for a few frames (run_single_forked forks per level);
+    // ORBX_BATCH_FORK=0 keeps everything on one stream.
+    static const char* fork_env = getenv("ORBX_BATCH_FORK");
+    const bool fork = (fork_env ? atoi(fork_env) != 0 : true) && !ex->profiling && frames >= 8;
+    if (fork) {
+        if (!ex->side[0]) CU(cudaStreamCreateWithFlags(&ex->side[0], cudaStreamNonBlocking));
+        if (!ex->ev_lvl[0]) CU(cudaEventCreateWithFlags(&ex->ev_lvl[0], cudaEventDisableTiming));
+        if (!ex->ev_side[0]) CU(cudaEventCreateWithFlags(&ex->ev_side[0], cudaEventDisableTiming));
+        CU(cudaEventRecord(ex->ev_lvl[0], st));
+        CU(cudaStreamWaitEvent(ex->side[0], ex->ev_lvl[0], 0));
+        CU(launch_fast(fg, s.ws, frames, st));
+        CU(launch_blur(fg, s.ws, frames, ex->side[0]));
+        CU(cudaEventRecord(ex->ev_side[0], ex->side[0]));
+        CU(launch_octree(fg, s.ws, frames, st));
+        CU(cudaStreamWaitEvent(st, ex->ev_side[0], 0));
+    } else {
+        CU(launch_fast(fg, s.ws, frames, st));
+        if ((rc = prof_mark(ex, st))) return rc;
+        CU(launch_blur(fg, s.ws, frames, st));
+        if ((rc = prof_mark(ex, st))) return rc;
+        CU(launch_octree(fg, s.ws, frames, st));
+    }
     if ((rc = prof_mark(ex, st))) return rc;
     bool fused = false;
     CU(launch_orient_describe(fg, s.ws, frames, st, lap0, lap1, d_kps, d_desc, capacity, d_n, d_nm, &fused));

@@ -336,7 +336,10 @@ __device__ __forceinline__ int fast_score16(uint32_t c /* byte address of the ce
     return max(bright, dark) - 1;
 }
 
-constexpr int kWarpsPerCta = 1;
+#ifndef ORBX_FAST_WPC
+#define ORBX_FAST_WPC 1
+#endif
+constexpr int kWarpsPerCta = ORBX_FAST_WPC;
 
 // per-warp shared-memory carve-up for a plane of `rows` x PA pixels and `list_cap` pre-test survivors
 struct WarpSmem {
