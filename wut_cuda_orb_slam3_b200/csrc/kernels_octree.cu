@@ -282,8 +282,11 @@ size_t octree_smem_bytes(int M, int NB)
 }
 
 // grid = (n_frames, levels of this launch); dynamic smem sized for the largest level's node capacity M and bin count NB.
+#ifndef ORBX_OCT_THREADS_PER_SM
+#define ORBX_OCT_THREADS_PER_SM 1024      // resident threads per SM the register budget is set for (64 registers)
+#endif
 template <int T>
-__global__ void __launch_bounds__(T, 1024 / T) octree_kernel(const __grid_constant__ FrameGeom fg, Workspace ws, int M, int NB,
+__global__ void __launch_bounds__(T, ORBX_OCT_THREADS_PER_SM / T) octree_kernel(const __grid_constant__ FrameGeom fg, Workspace ws, int M, int NB,
                                                    int level_base, int* __restrict__ err_flag)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
