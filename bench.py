@@ -317,20 +317,24 @@ def run_ours(args, rank, world, local_rank):
 
     def h2d_ceiling():
         """Pinned host -> device copy bandwidth with ALL ranks copying at once (the box's ceiling for the host-fed path):
-        256 MB per copy, 6 copies per rank after a barrier, device-timed, max over ranks; returns the aggregate GB/s."""
+        256 MB per copy, 6 copies per rank after a barrier, device-timed, max over ranks; the best of 4 such rounds (a single
+        round now and then comes out 20 % low — a ceiling must not) as the aggregate GB/s."""
         nbytes = 256 << 20
         h = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
         d = torch.empty(nbytes, dtype=torch.uint8, device=dev)
         d.copy_(h, non_blocking=True)
-        barrier()
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        for _ in range(6):
-            d.copy_(h, non_blocking=True)
-        b.record()
-        torch.cuda.synchronize()
-        t = max_over_ranks(a.elapsed_time(b))
-        return world * 6 * nbytes / (t * 1e-3) / 1e9
+        best = 0.0
+        for _round in range(4):
+            barrier()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(6):
+                d.copy_(h, non_blocking=True)
+            b.record()
+            torch.cuda.synchronize()
+            t = max_over_ranks(a.elapsed_time(b))
+            best = max(best, world * 6 * nbytes / (t * 1e-3) / 1e9)
+        return best
 
     Be = args.e2e_batch
     e2e_value = run_e2e(Be, args.e2e_chunk)
@@ -339,7 +343,7 @@ def run_ours(args, rank, world, local_rank):
            "d2h_bytes_per_step": Be * cap * 60 + Be * 8, "frames_per_step": Be, "pipeline_chunk": args.e2e_chunk,
            "api": "orbx_extract_batch (pinned host buffers; one call = one step)",
            "h2d_ceiling_gbs": ceil_gbs, "h2d_achieved_gbs": e2e_value * ROWS * COLS / 1e9,
-           "h2d_ceiling_note": "aggregate pinned host->device bandwidth with all %d rank(s) copying at once (measured here, 256 MB copies)" % world}
+           "h2d_ceiling_note": "aggregate pinned host->device bandwidth with all %d rank(s) copying at once (measured here, 256 MB copies, best of 4 rounds)" % world}
     e2e_small = None
     if Be > B:      # the same call with only as many frames as the resident step, for comparison
         e2e_small = {"value": run_e2e(B, 64), "unit": "frames/s", "frames_per_step": B, "pipeline_chunk": 64}
