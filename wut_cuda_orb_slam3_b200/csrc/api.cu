@@ -667,7 +667,8 @@ static int run_chunk(orbx_extractor* ex, Slot& s, const uint8_t* d_images, size_
     // The blur depends on the pyramid only: for batches it runs on a side stream beside FAST and the octree.  While a FAST launch
     // is at full occupancy there is no room for a blur CTA (shared memory and registers are taken), but each of FAST's three
     // launches ends with a tail of half-empty SMs, and the blur's persistent CTAs fill those: 3.163 -> 3.088 ms per 512 frames.
-    // (The blur beside the octree instead: no gain — the octree's four CTAs hold the whole register file of an SM.)  Not while
+    // (The blur beside the octree instead: no gain — the octree's four CTAs hold the whole register file of an SM.  FAST's three
+    // launches alternating between two streams: 3.17 ms.  The octree of the first FAST group's levels beside the later FAST launches: 3.13 ms.)  Not while
     // profiling (the per-stage events assume one stream), not for a few frames (run_single_forked forks per level);
     // ORBX_BATCH_FORK=0 keeps everything on one stream.
     static const char* fork_env = getenv("ORBX_BATCH_FORK");
