@@ -149,8 +149,12 @@ constexpr int PT_W = 128, PT_THREADS = 256;
 constexpr int L0_H = 32;                     // level-0 copy tile height
 
 // One 128 x 32 tile of level 0 (copy + the border mirrors it owns); t = L0_H * PT_W bytes of shared memory.  No trailing barrier.
+// `aligned`: image base, frame stride and pitch are multiples of 16 (16-byte loads).  Otherwise (e.g. 1241-pixel KITTI rows at
+// pitch = cols) a 16-byte segment is read as its 4 - 5 covering aligned words and realigned with funnel shifts; the misalignment
+// differs from row to row.  `img_end` = one past the last image byte: the fifth word is only read when it lies inside the images.
 __device__ __forceinline__ void level0_tile(const LevelGeom& g, const Workspace& ws, const uint8_t* __restrict__ images, size_t frame_stride,
-                                            size_t in_pitch, uint8_t* t, int tid, int x0, int y0, int frame)
+                                            size_t in_pitch, uint8_t* t, int tid, int x0, int y0, int frame, bool aligned = true,
+                                            const uint8_t* img_end = nullptr)
 {
     const int tw = min(PT_W, g.w - x0), th = min(L0_H, g.h - y0);
     const uint8_t* S = images + (size_t)frame * frame_stride;
@@ -161,7 +165,21 @@ __device__ __forceinline__ void level0_tile(const LevelGeom& g, const Workspace&
             const uint8_t* sp = S + (size_t)(y0 + ty) * in_pitch + x0 + v * 16;
             uint8_t* dp = D + (size_t)(y0 + ty) * g.pitch + x0 + v * 16;
             if (v * 16 + 16 <= tw) {
-                const uint4 q = __ldg(reinterpret_cast<const uint4*>(sp));
+                uint4 q;
+                if (aligned) {
+                    q = __ldg(reinterpret_cast<const uint4*>(sp));
+                } else {
+                    const int mis = (int)((uintptr_t)sp & 3);
+                    const uint32_t* wp = reinterpret_cast<const uint32_t*>(sp - mis);
+                    const uint32_t w0 = __ldg(wp), w1 = __ldg(wp + 1), w2 = __ldg(wp + 2), w3 = __ldg(wp + 3);
+                    uint32_t w4 = 0;
+                    if (mis) {
+                        if (reinterpret_cast<const uint8_t*>(wp + 5) <= img_end) w4 = __ldg(wp + 4);
+                        else for (int b = 0; b < mis; ++b) w4 |= (uint32_t)__ldg(sp + 16 - mis + b) << (8 * b);
+                    }
+                    const int sh = 8 * mis;
+                    q = make_uint4(__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh), __funnelshift_r(w2, w3, sh), __funnelshift_r(w3, w4, sh));
+                }
                 *reinterpret_cast<uint4*>(t + ty * PT_W + v * 16) = q;
                 *reinterpret_cast<uint4*>(dp) = q;
             } else {
@@ -176,10 +194,11 @@ __device__ __forceinline__ void level0_tile(const LevelGeom& g, const Workspace&
 }
 
 __global__ void __launch_bounds__(PT_THREADS) pyr_level0_tiled_kernel(const __grid_constant__ FrameGeom fg, Workspace ws,
-                                                                     const uint8_t* __restrict__ images, size_t frame_stride, size_t in_pitch)
+                                                                     const uint8_t* __restrict__ images, size_t frame_stride, size_t in_pitch,
+                                                                     int aligned, const uint8_t* img_end)
 {
     __shared__ __align__(16) uint8_t t[L0_H * PT_W];
-    level0_tile(fg.L[0], ws, images, frame_stride, in_pitch, t, threadIdx.x, blockIdx.x * PT_W, blockIdx.y * L0_H, blockIdx.z);
+    level0_tile(fg.L[0], ws, images, frame_stride, in_pitch, t, threadIdx.x, blockIdx.x * PT_W, blockIdx.y * L0_H, blockIdx.z, aligned != 0, img_end);
 }
 
 // The two fixed-point passes, the interior stores and the border mirrors of one 128 x PT_H tile whose source window is already
@@ -614,7 +633,9 @@ cudaError_t launch_pyramid(const FrameGeom& fg, const Workspace& ws, const uint8
         if (l == 0) {
             const bool aligned = ((uintptr_t)d_images & 15) == 0 && (frame_stride & 15) == 0 && (pitch & 15) == 0;
             dim3 tgrid((g.w + PT_W - 1) / PT_W, (g.h + L0_H - 1) / L0_H, n_frames);
-            if (big && aligned) pyr_level0_tiled_kernel<<<tgrid, PT_THREADS, 0, st>>>(fg, ws, d_images, frame_stride, pitch);
+            // one past the last byte the caller's images hold (the last row of the last frame ends at its last pixel)
+            const uint8_t* img_end = d_images + (size_t)(n_frames - 1) * frame_stride + (size_t)(g.h - 1) * pitch + g.w;
+            if (big) pyr_level0_tiled_kernel<<<tgrid, PT_THREADS, 0, st>>>(fg, ws, d_images, frame_stride, pitch, aligned ? 1 : 0, img_end);
             else pyr_level0_kernel<<<grid, 128, 0, st>>>(fg, ws, d_images, frame_stride, pitch);
         } else {
             const LevelGeom& p = fg.L[l - 1];
