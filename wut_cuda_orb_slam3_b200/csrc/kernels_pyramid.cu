@@ -8,8 +8,18 @@
 // at its reflected interior coordinate.
 //
 // Data layout: every level is a bordered buffer [rows+38][pitch] per frame, interior pixel (0,0) at byte
-// 19*pitch + 32 (16-byte aligned), frames strided by pyr_frame_stride, levels by pyr_off.  Each thread produces one
-// aligned 32-bit word (4 pixels) of a bordered row, so stores are fully coalesced 128-byte lines per warp.
+// 19*pitch + 32 (16-byte aligned), frames strided by pyr_frame_stride, levels by pyr_off.
+//
+// Kernels in this file (launch_pyramid picks per level):
+//   pyr_level0_tiled_kernel   level 0: 128 x 32 tiles, 16-byte loads / stores (realigned word loads for unaligned rows), the
+//                             tile that owns the mirrored pixels writes the reflect-101 border
+//   pyr_resize_pipe_kernel    levels >= 1, the production path: one warp per 128 x 16 item of the BORDERED level, source window
+//                             by TMA into the warp's stage, IDP.2A horizontal pass, row sums in registers (scale <= 1.5)
+//   pyr_resize_tiled_kernel   levels >= 1 without tensor maps / scale in (1.5, 2]: 128 x 32 (128 x 16) tiles, u16 sum plane
+//   pyr_multilevel_kernel     all levels in one cooperative launch (opt-in, slower on batches)
+//   pyr_level0_kernel, pyr_resize_kernel   generic per-word fallbacks (tiny levels, scale > 2): each thread produces one aligned
+//                             32-bit word of a bordered row
+//   cvt_gray_kernel           cv::cvtColor RGB/BGR(A) -> grey of Tracking::GrabImage*
 #include <limits.h>
 #include <stdlib.h>
 
