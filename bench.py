@@ -659,6 +659,31 @@ def _hbm_peak():
     return 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
 
 
+IMMA_PEAK_TOPS = 1139.9     # legacy warp-level int8 MMA (IMMA.16832.U8.U8) issue rate of one B200: tools/micro/imma_rate.cu, profiles/r02g_imma_rate.txt
+
+
+def knn2_roofline(per_gpu, popc_peak):
+    """The matcher's roofline block.  Default kernel = int8 tensor-core dot products on {0,1}-expanded descriptors (8 m16n8k32 MMAs
+    per 16 x 8 tile of compares = 512 int8 ops per compare); ORBX_KNN_IMMA=0 = the carry-save POPC kernel of round 1."""
+    if os.environ.get("ORBX_KNN_IMMA", "1") != "0":
+        tops = per_gpu * 512 / 1e12
+        return {"bound": "tensor (warp-level int8 MMA, mma.sync m16n8k32 u8 -> SASS IMMA.16832.U8.U8)", "achieved": tops, "peak": IMMA_PEAK_TOPS,
+                "unit": "dense int8 TOPS per GPU", "frac": tops / IMMA_PEAK_TOPS,
+                "algorithmic_popc_frac": per_gpu * 8 / popc_peak if popc_peak > 0 else None,
+                "note": "Hamming(a, b) = popc(a) + popc(b) - 2 a.b on descriptors expanded to {0,1} bytes in registers; peak = the "
+                        "measured issue rate of that MMA on a B200 of this pool (tools/micro/imma_rate.cu, profiles/r02g_imma_rate.txt; "
+                        "Blackwell has no 1-bit MMA and tcgen05 kind::i8 is not used here); algorithmic_popc_frac relates the same "
+                        "throughput to the 8-POPC-per-compare integer roofline of SURVEY.md §8(d) (POPC peak measured on this GPU) — "
+                        "the carry-save POPC kernel (ORBX_KNN_IMMA=0) reaches 1.47 of it, this kernel more because it does not use that pipe"}
+    return {"bound": "int-pipe POPC", "achieved": per_gpu * 8, "peak": popc_peak, "unit": "POPC.b32/s per GPU",
+            "frac": per_gpu * 8 / popc_peak if popc_peak > 0 else None,
+            "frac_issued": per_gpu * 4 / popc_peak if popc_peak > 0 else None,
+            "note": "frac counts the ALGORITHMIC 8 POPC per 256-bit compare (SURVEY.md §8(d)) and can exceed 1: the kernel's "
+                    "carry-save front end (16 LOP3) issues only 4 POPC per compare — frac_issued is the POPC pipe's real "
+                    "utilisation; the co-limiter is the ALU pipe (LOP3/ISETP, ~78 % in ncu: profiles/*knn2_ncu_summary.txt). "
+                    "peak = orbx_measure_popc_peak microbenchmark on this GPU"}
+
+
 def run_knn2(args, rank, world, local_rank, dev, barrier, max_over_ranks):
     """BASELINE.json configs[4]: 100k queries x 10M database rows, database sharded over the ranks.  The whole exchange is inside
     the C ABI: orbx_knn2_sharded = local scan + ONE ncclAllGather of the packed candidates + merge (csrc/api_shard.cu); torch
@@ -760,18 +785,12 @@ def run_knn2(args, rank, world, local_rank, dev, barrier, max_over_ranks):
     per_gpu = cps / world
     return {"metric": "hamming_2nn_compares_per_s", "value": cps, "unit": "compares/s", "nq": nq, "ndb": ndb, "n_gpus": world,
             "scaling": "strong", "ms_per_pass": ms / reps, "gpu_launches": int(launches),
-            "api": "orbx_knn2_sharded (C ABI: knn2_kernel + one ncclAllGather of 16 B/query + knn2_merge_kernel)", "nccl_version": nccl_version,
+            "api": "orbx_knn2_sharded (C ABI: knn2_imma_kernel + one ncclAllGather of 16 B/query + knn2_merge_kernel)", "nccl_version": nccl_version,
             "verified": planted_ok and sample_ok and torch_ok,
             "verification": {"planted_queries_hit_their_row_within_k": planted_ok, "planted_queries": int(qs.numel()),
                              "sample_vs_single_rank_full_scan": sample_ok, "sample_queries": ns,
                              "four_queries_vs_torch_bruteforce": torch_ok},
-            "roofline": {"bound": "int-pipe POPC", "achieved": per_gpu * 8, "peak": popc_peak, "unit": "POPC.b32/s per GPU",
-                         "frac": per_gpu * 8 / popc_peak if popc_peak > 0 else None,
-                         "frac_issued": per_gpu * 4 / popc_peak if popc_peak > 0 else None,
-                         "note": "frac counts the ALGORITHMIC 8 POPC per 256-bit compare (SURVEY.md §8(d)) and can exceed 1: the kernel's "
-                                 "carry-save front end (16 LOP3) issues only 4 POPC per compare — frac_issued is the POPC pipe's real "
-                                 "utilisation; the co-limiter is the ALU pipe (LOP3/ISETP, ~78 % in ncu: profiles/*knn2_ncu_summary.txt). "
-                                 "peak = orbx_measure_popc_peak microbenchmark on this GPU"}}
+            "roofline": knn2_roofline(per_gpu, popc_peak)}
 
 
 def main():

@@ -191,6 +191,149 @@ __global__ void __launch_bounds__(KNN_THREADS, MINB) knn2_kernel(const uint32_t*
     }
 }
 
+// ---- the same search on the tensor cores (the default; ORBX_KNN_IMMA=0 selects the CSA kernel above) ---------------------------
+// Blackwell has no 1-bit MMA (mma.sync b1 compiles into bit-plane LOP3s + IMMA), but Hamming(a, b) = popc(a) + popc(b) - 2 a.b
+// with the bits of a and b expanded to {0,1} bytes, and a.b over 256 bytes is eight m16n8k32 u8 MMAs (SASS IMMA.16832.U8.U8,
+// 1.39e11 per second on one B200: tools/micro/imma_rate.cu).  A warp keeps the expanded fragments of 32 queries (two m16
+// tiles, 64 registers) for the whole chunk; the CTA streams the database through shared memory as the CSA kernel does, every
+// warp expands the 8 rows of a group — lane t of a row takes the bits 8 j + t and 8 j + t + 4 of every word, (w >> t) & 0x01010101
+// and ((w >> t) >> 4) & 0x01010101: two shifts and two ANDs per word — and issues 16 MMAs per group = 256 compares.  Which bit
+// lands on which k index is the same function of (word, lane) for queries and database rows, which is all the dot product needs.  popc(b) per row is computed once per CTA while the tile is stashed.
+// Accumulator layout (PTX m16n8k32): c0, c1 = row lane/4, columns 2 (lane%4), +1; c2, c3 = row lane/4 + 8: a thread keeps a top-2
+// state per (tile, row half) = 4 states, sees its columns in ascending index order (strict < keeps the earlier row on ties, as
+// the reference's scan does), and the four lanes that share a row merge lexicographically at the end.
+constexpr int KI_WARPS = 8, KI_QTILE = KI_WARPS * 32, KI_DT = 128;
+#ifndef ORBX_KI_UNROLL
+#define ORBX_KI_UNROLL 8          // groups of 8 rows in flight per warp: 1 -> 1.40e12, 2 -> 1.48e12, 4 -> 1.51e12, 8 -> 1.53e12 compares/s
+#endif
+constexpr int kKiUnroll = ORBX_KI_UNROLL;
+
+__device__ __forceinline__ void imma_16832_u8(int (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1)
+{
+    asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.u8.u8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+r"(c[0]), "+r"(c[1]), "+r"(c[2]), "+r"(c[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+__global__ void __launch_bounds__(32 * KI_WARPS, 2) knn2_imma_kernel(const uint32_t* __restrict__ q, int nq, const uint4* __restrict__ db,
+                                                                    long long ndb, int index_base, long long rows_per_chunk,
+                                                                    int32_t* __restrict__ out_idx, int32_t* __restrict__ out_dist)
+{
+    __shared__ uint4 tile[2][KI_DT * 2];
+    __shared__ __align__(16) uint32_t pdq[2][KI_DT * 2];        // popcount of every staged uint4 (two per row)
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    const long long r_begin = (long long)blockIdx.y * rows_per_chunk;
+    long long r_end = r_begin + rows_per_chunk;
+    if (r_end > ndb) r_end = ndb;
+    const int qw0 = blockIdx.x * KI_QTILE + warp * 32;
+
+    // query fragments: tile T, k-step s: a[T][s][0..3] = rows (g, g+8) x bit sets (8j + t, 8j + t + 4) of word s
+    uint32_t a[2][8][4];
+    int pq[2][2];
+#pragma unroll
+    for (int T = 0; T < 2; ++T)
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int qi = qw0 + T * 16 + h * 8 + g;
+            const uint4* p = reinterpret_cast<const uint4*>(q + (size_t)(qi < nq ? qi : 0) * 8);
+            const uint4 x = __ldg(p), y = __ldg(p + 1);
+            const uint32_t w[8] = {x.x, x.y, x.z, x.w, y.x, y.y, y.z, y.w};
+            int pc = 0;
+#pragma unroll
+            for (int sidx = 0; sidx < 8; ++sidx) {
+                pc += __popc(w[sidx]);
+                const uint32_t v = w[sidx] >> t;
+                a[T][sidx][h] = v & 0x01010101u;
+                a[T][sidx][2 + h] = (v >> 4) & 0x01010101u;
+            }
+            pq[T][h] = pc;
+        }
+    // top-2 state per (tile, row half), thresholds in "e space": e = popc(b) - 2 a.b = dist - popc(a)
+    int d1[2][2], i1[2][2], d2[2][2], i2[2][2], thr[2][2];
+#pragma unroll
+    for (int T = 0; T < 2; ++T)
+#pragma unroll
+        for (int h = 0; h < 2; ++h) { d1[T][h] = INT_MAX; d2[T][h] = INT_MAX; i1[T][h] = -1; i2[T][h] = -1; thr[T][h] = 1 << 20; }
+
+    const long long ntiles = (r_end - r_begin + KI_DT - 1) / KI_DT;
+    uint4 pre;
+    auto fetch = [&](long long tl) {
+        const long long row = r_begin + tl * KI_DT + (tid >> 1);
+        pre = row < r_end ? __ldg(db + row * 2 + (tid & 1)) : make_uint4(0, 0, 0, 0);
+    };
+    auto stash = [&](int buf) {
+        tile[buf][tid] = pre;
+        pdq[buf][tid] = (uint32_t)(__popc(pre.x) + __popc(pre.y) + __popc(pre.z) + __popc(pre.w));
+    };
+    if (ntiles > 0) { fetch(0); stash(0); }
+    __syncthreads();
+    for (long long tl = 0; tl < ntiles; ++tl) {
+        const int buf = (int)(tl & 1);
+        if (tl + 1 < ntiles) fetch(tl + 1);
+        const long long base = r_begin + tl * KI_DT;
+#pragma unroll kKiUnroll
+        for (int g8 = 0; g8 < KI_DT / 8; ++g8) {
+            const uint4 wa = tile[buf][(8 * g8 + g) * 2], wb = tile[buf][(8 * g8 + g) * 2 + 1];
+            const uint4 pd4 = *reinterpret_cast<const uint4*>(&pdq[buf][(8 * g8) * 2 + 4 * t]);
+            const uint32_t w[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
+            int cA[4] = {0, 0, 0, 0}, cB[4] = {0, 0, 0, 0};
+#pragma unroll
+            for (int sidx = 0; sidx < 8; ++sidx) {
+                const uint32_t v = w[sidx] >> t;
+                const uint32_t b0 = v & 0x01010101u, b1 = (v >> 4) & 0x01010101u;
+                imma_16832_u8(cA, a[0][sidx], b0, b1);
+                imma_16832_u8(cB, a[1][sidx], b0, b1);
+            }
+            const int pd0 = (int)(pd4.x + pd4.y), pd1 = (int)(pd4.z + pd4.w);      // rows base + 8 g8 + 2t, + 1
+            int e[2][2][2];                                                      // [tile][row half][column]
+            e[0][0][0] = pd0 - 2 * cA[0]; e[0][0][1] = pd1 - 2 * cA[1]; e[0][1][0] = pd0 - 2 * cA[2]; e[0][1][1] = pd1 - 2 * cA[3];
+            e[1][0][0] = pd0 - 2 * cB[0]; e[1][0][1] = pd1 - 2 * cB[1]; e[1][1][0] = pd0 - 2 * cB[2]; e[1][1][1] = pd1 - 2 * cB[3];
+            int any = 0;
+#pragma unroll
+            for (int T = 0; T < 2; ++T)
+#pragma unroll
+                for (int h = 0; h < 2; ++h) any |= min(e[T][h][0], e[T][h][1]) - thr[T][h];
+            if (any < 0) {
+                const long long row0 = base + 8 * g8 + 2 * t;
+#pragma unroll
+                for (int T = 0; T < 2; ++T)
+#pragma unroll
+                    for (int h = 0; h < 2; ++h)
+#pragma unroll
+                        for (int c = 0; c < 2; ++c)
+                            if (e[T][h][c] < thr[T][h] && row0 + c < r_end) {
+                                const int4 rr = top2_insert(e[T][h][c] + pq[T][h], index_base + (int)(row0 + c),
+                                                            make_int4(d1[T][h], i1[T][h], d2[T][h], i2[T][h]));
+                                d1[T][h] = rr.x; i1[T][h] = rr.y; d2[T][h] = rr.z; i2[T][h] = rr.w;
+                                if (rr.z != INT_MAX) thr[T][h] = rr.z - pq[T][h];
+                            }
+            }
+        }
+        if (tl + 1 < ntiles) stash(buf ^ 1);
+        __syncthreads();
+    }
+    // the four lanes of a row hold disjoint column sets: lexicographic merge, lane t == 0 writes
+#pragma unroll
+    for (int T = 0; T < 2; ++T)
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            int md1 = d1[T][h], mi1 = i1[T][h], md2 = d2[T][h], mi2 = i2[T][h];
+#pragma unroll
+            for (int x = 1; x <= 2; x <<= 1) {
+                const int od1 = __shfl_xor_sync(0xffffffffu, md1, x), oi1 = __shfl_xor_sync(0xffffffffu, mi1, x);
+                const int od2 = __shfl_xor_sync(0xffffffffu, md2, x), oi2 = __shfl_xor_sync(0xffffffffu, mi2, x);
+                top2_merge(od1, oi1, md1, mi1, md2, mi2);
+                top2_merge(od2, oi2, md1, mi1, md2, mi2);
+            }
+            const int qi = qw0 + T * 16 + h * 8 + g;
+            if (t == 0 && qi < nq) {
+                const size_t o = ((size_t)blockIdx.y * nq + qi) * 2;
+                out_idx[o] = mi1; out_idx[o + 1] = mi2;
+                out_dist[o] = md1; out_dist[o + 1] = md2;
+            }
+        }
+}
+
 // shard s holds its [nq][2] candidates at idx_sh + s * shard_stride / dist_sh + s * shard_stride (int32 elements)
 __global__ void knn2_merge_kernel(const int32_t* __restrict__ idx_sh, const int32_t* __restrict__ dist_sh, int n_shards,
                                   int nq, int32_t* __restrict__ idx, int32_t* __restrict__ dist, size_t shard_stride)
@@ -208,9 +351,16 @@ __global__ void knn2_merge_kernel(const int32_t* __restrict__ idx_sh, const int3
 }
 
 // Database chunking of one launch: a few thousand CTAs, every chunk long enough to amortise the query load / result store.
+static bool knn2_use_imma()
+{
+    // default: the tensor-core kernel (1.5e12 compares/s against 8.3e11 of the CSA kernel on 100 k x 10 M); ORBX_KNN_IMMA=0 = CSA kernel
+    static const bool on = getenv("ORBX_KNN_IMMA") ? atoi(getenv("ORBX_KNN_IMMA")) != 0 : true;
+    return on;
+}
+
 static void knn2_plan(int nq, long long ndb, int& qtiles, int& chunks, long long& rows_per_chunk)
 {
-    qtiles = (nq + KNN_QTILE - 1) / KNN_QTILE;
+    qtiles = (nq + (knn2_use_imma() ? KI_QTILE : KNN_QTILE) - 1) / (knn2_use_imma() ? KI_QTILE : KNN_QTILE);
     chunks = 1;
     if (ndb > 0) {
         const long long target_ctas = 148LL * 16;
@@ -259,7 +409,10 @@ cudaError_t launch_knn2(const uint8_t* d_q, int nq, const uint8_t* d_db, long lo
     dim3 grid(qtiles, chunks);
     // register budget for 5 or 6 CTAs per SM (ORBX_KNN_MINB: A/B switch for measurements)
     static const int minb = getenv("ORBX_KNN_MINB") ? atoi(getenv("ORBX_KNN_MINB")) : 6;     // measured: 8.29e11 (6) vs 8.07e11 (5) compares/s
-    if (minb == 6)
+    if (knn2_use_imma())
+        knn2_imma_kernel<<<grid, 32 * KI_WARPS, 0, st>>>(reinterpret_cast<const uint32_t*>(d_q), nq, reinterpret_cast<const uint4*>(d_db), ndb,
+                                                         index_base, rows_per_chunk, p_idx, p_dist);
+    else if (minb == 6)
         knn2_kernel<6><<<grid, KNN_THREADS, 0, st>>>(reinterpret_cast<const uint32_t*>(d_q), nq, reinterpret_cast<const uint4*>(d_db), ndb,
                                                      index_base, rows_per_chunk, p_idx, p_dist);
     else
