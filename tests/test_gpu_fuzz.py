@@ -16,3 +16,13 @@ def test_random_configurations(seed):
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)
     assert mod.run(20, seed) == 0
+
+
+@pytest.mark.parametrize("seed", [5, 4711])
+def test_random_knn2_sizes(seed):
+    """tools/knn2_fuzz.py: the brute-force 2-NN (tensor-core matcher by default) against the oracle on random, ragged and tiny
+    (nq, ndb) pairs with duplicated rows (ties -> lower index) and exact / near copies of database rows as queries."""
+    spec = importlib.util.spec_from_file_location("knn2_fuzz", os.path.join(ROOT, "tools", "knn2_fuzz.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    assert mod.run(40, seed) == 0
